@@ -1,0 +1,4 @@
+"""gtf_b200 -- B200-native Gaussian-mixture message passing for track finding.
+
+Drop-in for the message-passing hot path of nishalad95/GNN-track-finding."""
+from . import fields, synth, nxio  # noqa: F401

@@ -1,0 +1,203 @@
+"""networkx <-> flat structure-of-arrays ("host batch") conversion.
+
+This is the data half of the drop-in boundary: the reference's
+stages exchange `list[nx.DiGraph]` whose node attributes hold Python dicts of
+numpy 3-vectors / 3x3 matrices (schema: helper.py:432-441, 497-508;
+extrapolate_merged_states.py:375-385).  The B200 path keeps the same
+information as flat arrays:
+
+* nodes in *graph iteration order*, sub-graphs concatenated (order is data: the
+  reference's results depend on it, SURVEY.md §7 "Order as data");
+* in-CSR by destination: one *slot* per (neighbour -> node) entry, slots in the
+  insertion order of the node's `track_state_estimates` dict (helper.py:375);
+* out-CSR by source: the slot ids of a node's out-edges in `G.successors(u)` order
+  (extrapolate_merged_states.py:430 iterates in this order);
+* `updated_track_states` dict order is dynamic -> stored as `uts_rank` per slot.
+
+Covariances are stored as the 4 numbers (p00, p01, p11, p22) the reference's
+matrices actually carry (row/col 2 are zeroed, helper.py:423-425,
+extrapolate_merged_states.py:363-365; p10 is p01 up to rounding).
+"""
+import numpy as np
+
+F64_FIELDS_TSE = ("a", "b", "c", "tau", "p00", "p01", "p11", "p22", "prior", "w")
+F64_FIELDS_UTS = ("a", "b", "c", "tau", "p00", "p01", "p11", "p22", "lik", "prior", "w", "lrn")
+NODE_MERGED = ("m_a", "m_b", "m_c", "m_p00", "m_p01", "m_p11", "m_p22", "m_prior")
+
+
+def empty_host_batch(N, E, S):
+    hb = {
+        "x": np.zeros(N), "y": np.zeros(N), "z": np.zeros(N), "r": np.zeros(N),
+        "layer": np.zeros(N, np.int32), "volume": np.zeros(N, np.int32),
+        "truth": np.zeros(N, np.int64), "orig_id": np.zeros(N, np.int64),
+        "sub": np.zeros(N, np.int32), "alive": np.ones(N, np.uint8),
+        "sub_off": np.zeros(S + 1, np.int32), "sub_event": np.zeros(S, np.int32),
+        "in_off": np.zeros(N + 1, np.int32), "in_src": np.zeros(E, np.int32),
+        "out_off": np.zeros(N + 1, np.int32), "out_slot": np.zeros(E, np.int32),
+        "rev_slot": np.full(E, -1, np.int32), "slot_dst": np.zeros(E, np.int32),
+        "active": np.zeros(E, np.uint8), "edge_w": np.full(E, np.nan),
+        "tse_present": np.zeros(E, np.uint8),
+        "uts_present": np.zeros(E, np.uint8), "uts_rank": np.full(E, -1, np.int32),
+        "uts_side": np.zeros(E, np.int8),
+        "has_merged": np.zeros(N, np.uint8), "degree": np.zeros(N, np.int32),
+        "has_uts": np.zeros(N, np.uint8), "in_key": np.zeros(E, np.int64),
+    }
+    for f in F64_FIELDS_TSE:
+        hb["tse_" + f] = np.full(E, np.nan)
+    for f in F64_FIELDS_UTS:
+        hb["uts_" + f] = np.full(E, np.nan)
+    for f in NODE_MERGED:
+        hb[f] = np.full(N, np.nan)
+    return hb
+
+
+def _put_state(hb, prefix, s, ent):
+    sv = ent["edge_state_vector"]
+    jv = ent["joint_vector"]
+    cov = ent["joint_vector_covariance"]
+    hb[prefix + "a"][s] = sv[0]
+    hb[prefix + "b"][s] = sv[1]
+    hb[prefix + "c"][s] = sv[2]
+    hb[prefix + "tau"][s] = jv[2]
+    hb[prefix + "p00"][s] = cov[0, 0]
+    hb[prefix + "p01"][s] = cov[0, 1]
+    hb[prefix + "p11"][s] = cov[1, 1]
+    hb[prefix + "p22"][s] = cov[2, 2]
+    if "prior" in ent:
+        hb[prefix + "prior"][s] = ent["prior"]
+    if "mixture_weight" in ent:
+        hb[prefix + "w"][s] = ent["mixture_weight"]
+
+
+def graphs_to_host(graphs, events=None):
+    """Flatten a list of reference-schema DiGraphs.
+
+    Slot order at a node = key order of its `track_state_estimates` dict when present,
+    else predecessor order.  Every predecessor must have a slot.
+    """
+    N = sum(g.number_of_nodes() for g in graphs)
+    S = len(graphs)
+    index = {}
+    pos = 0
+    per_graph_nodes = []
+    for gi, g in enumerate(graphs):
+        nodes = list(g.nodes())
+        per_graph_nodes.append(nodes)
+        for n in nodes:
+            index[(gi, n)] = pos
+            pos += 1
+    # slots
+    slot_keys = []
+    E = 0
+    for gi, g in enumerate(graphs):
+        for n in per_graph_nodes[gi]:
+            attr = g.nodes[n]
+            if "track_state_estimates" in attr:
+                keys = list(attr["track_state_estimates"].keys())
+                for p in g.predecessors(n):
+                    if p not in attr["track_state_estimates"]:
+                        keys.append(p)
+                if "updated_track_states" in attr:
+                    for p in attr["updated_track_states"].keys():
+                        if p not in keys:
+                            keys.append(p)
+            else:
+                keys = list(g.predecessors(n))
+            slot_keys.append(keys)
+            E += len(keys)
+    hb = empty_host_batch(N, E, S)
+    slot_of = {}
+    s = 0
+    i = 0
+    for gi, g in enumerate(graphs):
+        hb["sub_off"][gi] = i
+        hb["sub_event"][gi] = 0 if events is None else events[gi]
+        for n in per_graph_nodes[gi]:
+            attr = g.nodes[n]
+            gm = attr["GNN_Measurement"]
+            hb["x"][i], hb["y"][i], hb["z"][i], hb["r"][i] = gm.x, gm.y, gm.z, gm.r
+            hb["layer"][i] = attr["in_volume_layer_id"]
+            hb["volume"][i] = attr["volume_id"]
+            hb["truth"][i] = attr["truth_particle"]
+            hb["orig_id"][i] = n
+            hb["sub"][i] = gi
+            hb["degree"][i] = attr.get("degree", 0)
+            hb["in_off"][i] = s
+            tse = attr.get("track_state_estimates", {})
+            uts = attr.get("updated_track_states", None)
+            hb["has_uts"][i] = uts is not None
+            uts_pos = {} if uts is None else {k: r for r, k in enumerate(uts.keys())}
+            for k in slot_keys[i]:
+                slot_of[(gi, k, n)] = s
+                # a key whose node was removed from the graph keeps its slot; src = -1
+                hb["in_src"][s] = index.get((gi, k), -1)
+                hb["slot_dst"][s] = i
+                hb["in_key"][s] = k
+                if g.has_edge(k, n):
+                    ed = g[k][n]
+                    hb["active"][s] = ed.get("activated", 0)
+                    if "mixture_weight" in ed:
+                        hb["edge_w"][s] = ed["mixture_weight"]
+                if k in tse:
+                    hb["tse_present"][s] = 1
+                    _put_state(hb, "tse_", s, tse[k])
+                if uts is not None and k in uts:
+                    ent = uts[k]
+                    hb["uts_present"][s] = 1
+                    hb["uts_rank"][s] = uts_pos[k]
+                    _put_state(hb, "uts_", s, ent)
+                    hb["uts_lik"][s] = ent["likelihood"]
+                    if "lr_layer_norm" in ent:
+                        hb["uts_lrn"][s] = ent["lr_layer_norm"]
+                    if "side" in ent:
+                        hb["uts_side"][s] = 1 if ent["side"] == "left" else 2
+                s += 1
+            if "merged_state" in attr:
+                hb["has_merged"][i] = 1
+                ms, mc = attr["merged_state"], attr["merged_cov"]
+                hb["m_a"][i], hb["m_b"][i], hb["m_c"][i] = ms[0], ms[1], ms[2]
+                hb["m_p00"][i], hb["m_p01"][i] = mc[0, 0], mc[0, 1]
+                hb["m_p11"][i], hb["m_p22"][i] = mc[1, 1], mc[2, 2]
+                hb["m_prior"][i] = attr["merged_prior"]
+            i += 1
+    hb["sub_off"][S] = N
+    hb["in_off"][N] = E
+    # out-CSR in successor order, and reverse-slot cross index
+    o = 0
+    i = 0
+    for gi, g in enumerate(graphs):
+        for n in per_graph_nodes[gi]:
+            hb["out_off"][i] = o
+            for v in g.successors(n):
+                hb["out_slot"][o] = slot_of[(gi, n, v)]
+                o += 1
+            i += 1
+    hb["out_off"][N] = o
+    hb["out_slot"] = hb["out_slot"][:o].copy()
+    for (gi, k, n), s in slot_of.items():
+        hb["rev_slot"][s] = slot_of.get((gi, n, k), -1)
+    return hb
+
+
+def events_to_graphs(ev, event_id=0):
+    """Build the DiGraph the reference's `construct_graph` (helper.py:465-520) would build for a
+    synthetic event dict (synth.py), then split it into weakly-connected sub-graphs exactly like
+    event_conversion.py:76-84.  Needs the reference's GNN_Measurement class on sys.path."""
+    import networkx as nx
+    from GNN_Measurement import GNN_Measurement as gnn
+    G = nx.DiGraph()
+    for i in range(len(ev["x"])):
+        x, y, z, r = float(ev["x"][i]), float(ev["y"][i]), float(ev["z"][i]), float(ev["r"][i])
+        t = int(ev["truth"][i])
+        gm = gnn.GNN_Measurement(x, y, z, r, truth_particle=t, n=i)
+        G.add_node(i, GNN_Measurement=gm, xy=(x, y), zr=(z, r), xyzr=(x, y, z, r),
+                   volume_id=int(ev["volume"][i]), in_volume_layer_id=int(ev["layer"][i]),
+                   vivl_id=(int(ev["volume"][i]), int(ev["layer"][i])),
+                   module_id=np.array([i]), truth_particle=t,
+                   hit_dissociation={"hit_id": np.array([i]), "particle_id": [t]},
+                   tags=[i])
+    for a, b in zip(ev["edge_a"].tolist(), ev["edge_b"].tolist()):
+        G.add_edge(a, b)
+        G.add_edge(b, a)
+    G = nx.DiGraph(G)
+    return [G.subgraph(c).copy() for c in nx.weakly_connected_components(G)]

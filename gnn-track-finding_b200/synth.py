@@ -1,0 +1,193 @@
+"""Seeded synthetic events.
+
+Two generators, both deterministic in `seed` (numpy `default_rng`):
+
+* `barrel_event`  -- TrackML-shaped 10-layer barrel event: helical tracks from a
+  smeared beam-spot, doublet edges l->l+1 and l->l+2 inside a d-phi window and a
+  z0-extrapolation window.  This is the cfg2/cfg3/cfg4 workload of BASELINE.json.
+* `toy_event`     -- restatement of the reference's 2-D toy simulator
+  (/root/reference/src/toyMC_model/track_simulation_xy.py:36-160): 88 straight
+  radial tracks x 10 hits, Gaussian smear 0.05, edges by layer gap / distance /
+  intercept cuts.  z = r = 0 there, so it is only an edge-topology generator.
+
+An event is a plain dict of numpy arrays:
+  x, y, z, r        f64[N]   hit coordinates (r = sqrt(x^2 + y^2))
+  layer             i32[N]   in_volume_layer_id  (helper.py:18-19 semantics)
+  volume            i32[N]   volume_id
+  truth             i64[N]   truth particle label
+  edge_a, edge_b    i32[M]   undirected doublets in list order; the graph gets
+                             a->b then b->a per row (helper.py:517-518)
+"""
+import numpy as np
+
+BARREL_RADII = np.array([32., 72., 116., 172., 260., 360., 500., 660., 820., 1020.])
+
+
+def _window_pairs(phi_a, phi_b, w):
+    """All (i, j) with |wrap(phi_b[j] - phi_a[i])| < w; vectorised via sort + searchsorted."""
+    order = np.argsort(phi_b, kind="stable")
+    pb = phi_b[order]
+    # pad periodic images so a plain window search handles the wrap-around
+    pb_ext = np.concatenate([pb - 2 * np.pi, pb, pb + 2 * np.pi])
+    idx_ext = np.concatenate([order, order, order])
+    lo = np.searchsorted(pb_ext, phi_a - w, side="right")
+    hi = np.searchsorted(pb_ext, phi_a + w, side="left")
+    cnt = np.maximum(hi - lo, 0)
+    tot = int(cnt.sum())
+    if tot == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    ia = np.repeat(np.arange(len(phi_a)), cnt)
+    start = np.repeat(lo, cnt)
+    within = np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    jb = idx_ext[start + within]
+    return ia, jb
+
+
+def barrel_event(n_tracks=1000, seed=0, eta_max=0.5, dphi_window=None, z0_window=200.0,
+                 target_degree=10.0, n_layers=10):
+    """One synthetic barrel event.
+
+    True doublets (same track, layer gap 1 or 2) are always present; fake doublets are
+    drawn from a d-phi/z0 window and subsampled so the mean in-degree is `target_degree`.
+    """
+    rng = np.random.default_rng(seed)
+    radii = BARREL_RADII[:n_layers]
+    pt = rng.uniform(1.0, 10.0, n_tracks)                 # GeV
+    q = rng.choice(np.array([-1.0, 1.0]), n_tracks)
+    R = pt / 0.6 * 1000.0                                 # mm, B = 2 T
+    phi0 = rng.uniform(-np.pi, np.pi, n_tracks)
+    eta = rng.uniform(-eta_max, eta_max, n_tracks)
+    z0 = rng.normal(0.0, 30.0, n_tracks)
+
+    rl = radii[None, :]                                   # (1, L)
+    theta = 2.0 * np.arcsin(rl / (2.0 * R[:, None]))      # turning angle to reach radius r
+    phi_hit = phi0[:, None] - q[:, None] * 0.5 * theta
+    x = rl * np.cos(phi_hit)
+    y = rl * np.sin(phi_hit)
+    z = z0[:, None] + R[:, None] * theta * np.sinh(eta)[:, None]
+    x = x + rng.normal(0.0, 0.05, x.shape)
+    y = y + rng.normal(0.0, 0.05, y.shape)
+    z = z + rng.normal(0.0, 0.05, z.shape)
+
+    # node ids: layer-major so that ids of one layer are contiguous
+    x = x.T.reshape(-1)
+    y = y.T.reshape(-1)
+    z = z.T.reshape(-1)
+    r = np.sqrt(x * x + y * y)
+    layer_idx = np.repeat(np.arange(n_layers), n_tracks)
+    truth = np.tile(np.arange(n_tracks, dtype=np.int64), n_layers)
+    phi = np.arctan2(y, x)
+
+    # true doublets: same track, layer gap 1 or 2 (always kept)
+    # fake doublets: random pairs inside a d-phi window and a z0 window, subsampled so that
+    # the mean in-degree hits `target_degree` ("windows tuned so mean in-degree = target")
+    n_nodes = n_tracks * n_layers
+    n_true = n_tracks * ((n_layers - 1) + (n_layers - 2))
+    n_fake_wanted = max(int(round(target_degree * n_nodes / 2.0)) - n_true, 0)
+    n_pairs_layers = (n_layers - 1) + (n_layers - 2)
+    if dphi_window is None:
+        # candidates per layer pair ~ n_tracks^2 * w / pi * (z acceptance ~ 0.4); ask for ~3x the need
+        per_pair = 3.0 * n_fake_wanted / max(n_pairs_layers, 1)
+        dphi_window = min(max(per_pair * np.pi / (0.4 * max(n_tracks, 1) ** 2), 1e-4), 0.8)
+
+    ea, eb, fa, fb = [], [], [], []
+    for l in range(n_layers):
+        a_ids = np.nonzero(layer_idx == l)[0]
+        for gap in (1, 2):
+            l2 = l + gap
+            if l2 >= n_layers:
+                continue
+            b_ids = np.nonzero(layer_idx == l2)[0]
+            ea.append(a_ids)                              # track t on layer l  -> track t on layer l2
+            eb.append(b_ids)
+            if n_fake_wanted == 0:
+                continue
+            ia, jb = _window_pairs(phi[a_ids], phi[b_ids], dphi_window)
+            a = a_ids[ia]
+            b = b_ids[jb]
+            zz = z[a] - r[a] * (z[b] - z[a]) / (r[b] - r[a])   # doublet extrapolated to r = 0
+            keep = (np.abs(zz) < z0_window) & (truth[a] != truth[b])
+            fa.append(a[keep])
+            fb.append(b[keep])
+    if n_fake_wanted > 0:
+        fa = np.concatenate(fa)
+        fb = np.concatenate(fb)
+        if len(fa) > n_fake_wanted:
+            sel = np.sort(rng.choice(len(fa), n_fake_wanted, replace=False))
+            fa, fb = fa[sel], fb[sel]
+        ea.append(fa)
+        eb.append(fb)
+    ea = np.concatenate(ea)
+    eb = np.concatenate(eb)
+    order = np.lexsort((eb, ea))                          # list order: by first node, then second
+    ea, eb = [ea[order]], [eb[order]]
+    edge_a = np.concatenate(ea).astype(np.int32)
+    edge_b = np.concatenate(eb).astype(np.int32)
+    return {
+        "x": x, "y": y, "z": z, "r": r,
+        "layer": (2 * (layer_idx + 1)).astype(np.int32),
+        "volume": np.full(x.shape, 8, np.int32),
+        "truth": truth,
+        "edge_a": edge_a, "edge_b": edge_b,
+    }
+
+
+def toy_event(seed=0, sigma0=0.05):
+    """2-D toy event (track_simulation_xy.py:36-160), RNG seeded instead of global."""
+    rng = np.random.default_rng(seed)
+    num_hits, radius = 10, 10.0
+    ends = []
+    for i in [0.5, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9.5]:
+        yy = np.sqrt(radius ** 2 - i ** 2)
+        ends += [(i, yy), (yy, i), (-i, -yy), (-yy, -i), (i, -yy), (-yy, i), (-i, yy), (yy, -i)]
+    ends = np.array(ends)
+    n_tracks = len(ends)
+    xs, ys, layers, truth = [], [], [], []
+    for n in range(n_tracks):
+        grad = ends[n, 1] / ends[n, 0]
+        xx = np.linspace(0.0, ends[n, 0], num_hits)
+        yy = grad * xx + sigma0 * rng.normal(0.0, 1.0, num_hits)
+        xs.append(xx)
+        ys.append(yy)
+        layers.append(np.arange(num_hits))
+        truth.append(np.full(num_hits, n))
+    x = np.concatenate(xs)
+    y = np.concatenate(ys)
+    layer = np.concatenate(layers)
+    truth = np.concatenate(truth).astype(np.int64)
+    N = len(x)
+    dx = x[None, :] - x[:, None]
+    dy = y[None, :] - y[:, None]
+    diff = np.abs(layer[None, :] - layer[:, None])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m = dy / dx
+        c = y[None, :] - m * x[None, :]
+        xint = -c / m
+        ok = (diff > 0) & (diff <= 2) & (np.sqrt(dx ** 2 + dy ** 2) <= 3) \
+            & (np.abs(c) <= 1.8) & (np.abs(xint) <= 1.8)
+    ok &= ~np.eye(N, dtype=bool)
+    alive = np.ones(N, bool)
+    alive[np.arange(n_tracks) * num_hits] = False        # collision point removed (:134-135)
+    ok &= alive[:, None] & alive[None, :]
+    ii, jj = np.nonzero(ok & (np.abs(dx) > 0.75))        # nodes on long-dx edges dropped (:155-159)
+    alive[ii] = False
+    alive[jj] = False
+    ok &= alive[:, None] & alive[None, :]
+    ii, jj = np.nonzero(np.triu(ok | ok.T))
+    remap = -np.ones(N, np.int64)
+    remap[alive] = np.arange(int(alive.sum()))
+    z = np.zeros(int(alive.sum()))
+    return {
+        "x": x[alive], "y": y[alive], "z": z, "r": z.copy(),
+        "layer": layer[alive].astype(np.int32),
+        "volume": np.zeros(int(alive.sum()), np.int32),
+        "truth": truth[alive],
+        "edge_a": remap[ii].astype(np.int32), "edge_b": remap[jj].astype(np.int32),
+    }
+
+
+def degree_stats(ev):
+    """(n_nodes, n_directed_edges, mean in-degree, fraction of nodes with 3 <= d <= 15)."""
+    n = len(ev["x"])
+    deg = np.bincount(ev["edge_a"], minlength=n) + np.bincount(ev["edge_b"], minlength=n)
+    return n, 2 * len(ev["edge_a"]), float(deg.mean()), float(((deg >= 3) & (deg <= 15)).mean())

@@ -1,0 +1,122 @@
+"""Helpers to load golden fixtures (tests/golden/*.npz) into host batches and compare states."""
+import os
+import sys
+import numpy as np
+
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, REPO)
+import gtf_b200  # noqa: E402,F401
+from gtf_b200 import fields as F  # noqa: E402
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+STAGES = ("seed", "c1", "x1", "e2", "x2", "m2", "c3", "x3")
+RTOL = 1e-9      # north_star: states / covariances / KL within 1e-9 relative (fp64)
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def stage_batch(fx, stage):
+    """Host batch (dict) = static topology + the mutable arrays recorded after `stage`."""
+    hb = {}
+    for k in fx.files:
+        if k.startswith("topo_"):
+            hb[k[5:]] = fx[k]
+        elif k.startswith(stage + "/"):
+            hb[k[len(stage) + 1:]] = fx[k]
+    for k in ("truth", "orig_id", "in_key", "accepted", "cand_label", "pvals"):
+        hb.pop(k, None)
+    return F.complete_host_batch(hb)
+
+
+def rel_err(a, b):
+    """max relative error over entries where both are finite; inf if NaN patterns differ."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return np.inf
+    m = ~na
+    if not m.any():
+        return 0.0
+    d = np.abs(a[m] - b[m])
+    s = np.maximum(np.abs(a[m]), np.abs(b[m]))
+    s[s == 0] = 1.0
+    return float(np.max(d / s))
+
+
+def edge_exists(hb):
+    src = hb["in_src"]
+    return (hb["alive"][np.maximum(src, 0)] > 0) & (src >= 0) & (hb["alive"][hb["slot_dst"]] > 0)
+
+
+def inplay_nodes(hb):
+    return (hb["alive"] > 0) & (hb["sub_state"][hb["sub"]] == 0)
+
+
+def dict_order(hb, key="uts"):
+    """per-node tuple of slots in dict order, for order comparisons"""
+    out = []
+    for i in range(len(hb["x"])):
+        s0, s1 = hb["in_off"][i], hb["in_off"][i + 1]
+        sl = [s for s in range(s0, s1) if hb[key + "_present"][s]]
+        if key == "uts":
+            sl.sort(key=lambda s: hb["uts_rank"][s])
+        out.append(tuple(sl))
+    return out
+
+
+def compare_states(got, want, what, rtol=RTOL):
+    """Compare two complete host batches on the reference-visible part of the state.
+    Returns list of mismatch strings (empty = parity)."""
+    bad = []
+    ex = edge_exists(want)
+    live = inplay_nodes(want)
+    live_slot = live[want["slot_dst"]]
+    if "alive" in what:
+        for f in ("alive", "sub_state"):
+            if not np.array_equal(got[f], want[f]):
+                bad.append("%s differs at %d places" % (f, int((got[f] != want[f]).sum())))
+    if "active" in what:
+        m = ex & live_slot
+        if not np.array_equal(got["active"][m], want["active"][m]):
+            bad.append("active differs on %d existing edges" % int((got["active"][m] != want["active"][m]).sum()))
+    if "merged" in what:
+        if not np.array_equal(got["has_merged"][live], want["has_merged"][live]):
+            bad.append("has_merged differs at %d nodes" % int((got["has_merged"][live] != want["has_merged"][live]).sum()))
+        m = live & (want["has_merged"] > 0) & (got["has_merged"] > 0)
+        for f in ("m_a", "m_b", "m_c", "m_p00", "m_p01", "m_p11", "m_p22", "m_prior"):
+            e = rel_err(got[f][m], want[f][m])
+            if not e <= rtol:
+                bad.append("%s rel err %.3g" % (f, e))
+    for key in ("tse", "uts"):
+        if key not in what:
+            continue
+        pm = live_slot
+        if not np.array_equal(got[key + "_present"][pm], want[key + "_present"][pm]):
+            bad.append("%s_present differs at %d slots" % (key, int((got[key + "_present"][pm] != want[key + "_present"][pm]).sum())))
+        m = pm & (want[key + "_present"] > 0) & (got[key + "_present"] > 0)
+        names = ["a", "b", "c", "tau", "p00", "p01", "p11", "p22", "prior", "w"]
+        if key == "uts":
+            names += ["lik", "lrn"]
+        for f in names:
+            e = rel_err(got["%s_%s" % (key, f)][m], want["%s_%s" % (key, f)][m])
+            if not e <= rtol:
+                bad.append("%s_%s rel err %.3g" % (key, f, e))
+        if key == "uts":
+            if not np.array_equal(got["uts_side"][m], want["uts_side"][m]):
+                bad.append("uts_side differs")
+            if not np.array_equal(got["has_uts"][live], want["has_uts"][live]):
+                bad.append("has_uts differs")
+            if dict_order(got) != dict_order(want):
+                bad.append("uts dict order differs")
+    if "degree" in what:
+        if not np.array_equal(got["degree"][live], want["degree"][live]):
+            bad.append("degree differs at %d nodes" % int((got["degree"][live] != want["degree"][live]).sum()))
+    if "edge_w" in what:
+        m = ex & live_slot
+        e = rel_err(got["edge_w"][m], want["edge_w"][m])
+        if not e <= rtol:
+            bad.append("edge_w rel err %.3g" % e)
+    return bad
