@@ -1,0 +1,211 @@
+"""EventBatch: device-resident batch of events (flat layout of include/gtf_fields.h) + stage methods.
+
+The methods carry the reference's function names and argument meaning; each is one call
+through the C-ABI.  Reference-side exceptions (ValueError / ZeroDivisionError / KeyError raised by the
+Python reference at the cited lines) are re-raised from the `ref_errors` bits the kernels report."""
+import ctypes
+import numpy as np
+
+from . import fields as F
+from . import lib as L
+
+KEY = {"track_state_estimates": 0, "updated_track_states": 1, 0: 0, 1: 1}
+TOPOLOGY = ("x", "y", "z", "r", "layer", "volume", "sub", "alive", "sub_off", "sub_state", "sub_event",
+            "in_off", "in_src", "slot_dst", "out_off", "out_slot", "rev_slot")
+_REF_EXC = ((1, ValueError, "np.min of an empty array (clustering.py:116,120)"),
+            (2, ValueError, "nan is not in list (clustering.py:117)"),
+            (4, ZeroDivisionError, "1/len({}) (helper.py:90)"),
+            (8, KeyError, "edge of the last dict key no longer exists (helper.py:131,138)"),
+            (16, KeyError, "missing track_state_estimates entry (extrapolate_merged_states.py:384)"))
+
+
+class EventBatch(object):
+    def __init__(self, host_batch, device=0, geom=(0.3, 0.4, 0.6, 550.0), raise_ref_errors=True):
+        hb = F.complete_host_batch(host_batch)
+        self.N, self.E, self.S = len(hb["x"]), len(hb["in_src"]), len(hb["sub_off"]) - 1
+        self.lib = L.lib()
+        self.h = ctypes.c_void_p()
+        L.check(self.lib.gtf_batch_create(self.N, self.E, self.S, device, ctypes.byref(self.h)))
+        self.geom = L.Geom(*geom)
+        self.raise_ref_errors = raise_ref_errors
+        self.last_stats = None
+        self.upload(hb)
+        L.check(self.lib.gtf_batch_finalize(self.h))
+
+    # ---- data movement
+    def upload(self, hb, names=None):
+        for name in (names or [f[0] for f in F.FIELDS]):
+            if name not in hb:
+                continue
+            arr = np.ascontiguousarray(hb[name], dtype=F.FIELD_DTYPE[name])
+            n = F.extent_len(F.FIELD_EXTENT[name], self.N, self.E, self.S)
+            assert arr.shape == (n,), (name, arr.shape, n)
+            if n:
+                L.check(self.lib.gtf_batch_upload(self.h, F.FIELD_ID[name], arr.ctypes.data_as(ctypes.c_void_p)))
+        L.check(self.lib.gtf_batch_sync(self.h))
+
+    def download(self, names=None):
+        out = {}
+        for name in (names or [f[0] for f in F.FIELDS]):
+            n = F.extent_len(F.FIELD_EXTENT[name], self.N, self.E, self.S)
+            arr = np.empty(n, F.FIELD_DTYPE[name])
+            if n:
+                L.check(self.lib.gtf_batch_download(self.h, F.FIELD_ID[name], arr.ctypes.data_as(ctypes.c_void_p)))
+            out[name] = arr
+        return out
+
+    def device_ptr(self, name):
+        p = ctypes.c_void_p()
+        L.check(self.lib.gtf_batch_device_ptr(self.h, F.FIELD_ID[name], ctypes.byref(p)))
+        return p.value
+
+    def stream(self):
+        p = ctypes.c_void_p()
+        L.check(self.lib.gtf_batch_stream(self.h, ctypes.byref(p)))
+        return p.value or 0
+
+    def sync(self):
+        L.check(self.lib.gtf_batch_sync(self.h))
+
+    def device_bytes(self):
+        return int(self.lib.gtf_batch_device_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.gtf_batch_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _done(self, st):
+        self.last_stats = st.as_dict()
+        if self.raise_ref_errors and st.ref_errors:
+            for bit, exc, msg in _REF_EXC:
+                if st.ref_errors & bit:
+                    raise exc(msg)
+        return self.last_stats
+
+    # ---- reference-named stages
+    def compute_track_state_estimates(self):
+        """helper.py:238 (sigmas / endcap boundary come from self.geom)."""
+        L.check(self.lib.gtf_seed(self.h, ctypes.byref(self.geom)))
+
+    def initialize_edge_activation(self):
+        L.check(self.lib.gtf_initialize_edge_activation(self.h))
+
+    def compute_prior_probabilities(self, track_state_key):
+        L.check(self.lib.gtf_compute_prior_probabilities(self.h, KEY[track_state_key]))
+
+    def compute_mixture_weights(self, track_state_key):
+        st = L.Stats()
+        L.check(self.lib.gtf_compute_mixture_weights(self.h, KEY[track_state_key], ctypes.byref(st)))
+        return self._done(st)
+
+    def query_node_degree_in_edges(self):
+        L.check(self.lib.gtf_query_node_degree(self.h))
+
+    def seed(self):
+        """event_conversion.py:87-96: seed, activate, priors, weights, degree."""
+        self.compute_track_state_estimates()
+        self.initialize_edge_activation()
+        self.compute_prior_probabilities(0)
+        self.compute_mixture_weights(0)
+        self.query_node_degree_in_edges()
+
+    def cluster(self, track_state_key, chi2_threshold, KL_threshold, KL_lut=None):
+        st = L.Stats()
+        lut = None
+        if KL_lut is not None:
+            lut = np.ascontiguousarray(KL_lut, np.float64)
+            assert lut.shape == (28,)
+            lut = lut.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        L.check(self.lib.gtf_cluster(self.h, KEY[track_state_key], chi2_threshold, KL_threshold, lut,
+                                     ctypes.byref(self.geom), ctypes.byref(st)))
+        return self._done(st)
+
+    def message_passing(self, chi2CutFactor):
+        st = L.Stats()
+        L.check(self.lib.gtf_message_passing(self.h, chi2CutFactor, ctypes.byref(self.geom), ctypes.byref(st)))
+        return self._done(st)
+
+    def reweight(self, track_state_estimates_key="updated_track_states", threshold=0.1):
+        st = L.Stats()
+        L.check(self.lib.gtf_reweight(self.h, KEY[track_state_estimates_key], threshold, ctypes.byref(st)))
+        return self._done(st)
+
+    def extrapolate_stage(self, chi2CutFactor):
+        st = L.Stats()
+        L.check(self.lib.gtf_extrapolate_stage(self.h, chi2CutFactor, ctypes.byref(self.geom), ctypes.byref(st)))
+        return self._done(st)
+
+    def remove_state_metadata(self):
+        st = L.Stats()
+        L.check(self.lib.gtf_remove_state_metadata(self.h, ctypes.byref(st)))
+        return self._done(st)
+
+    def _iter_params(self, chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, KL_lut):
+        p = L.IterParams(chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, None)
+        if KL_lut is not None:
+            self._lut_keep = np.ascontiguousarray(KL_lut, np.float64)
+            p.kl_lut = self._lut_keep.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        return p
+
+    def iterate(self, max_iter=10, stop_when_converged=True, chi2_cut=2.0, cluster_chi2=1000.0, cluster_kl=100.0,
+                reweight_threshold=0.1, KL_lut=None):
+        """Fused iterations [message_passing, (prior, reweight) x2, cluster(updated states)]."""
+        p = self._iter_params(chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, KL_lut)
+        stats = (L.Stats * max_iter)()
+        n = ctypes.c_int(0)
+        L.check(self.lib.gtf_iterate(self.h, ctypes.byref(p), ctypes.byref(self.geom), max_iter,
+                                     1 if stop_when_converged else 0, stats, ctypes.byref(n)))
+        out = [stats[i].as_dict() for i in range(n.value)]
+        for s in out:
+            if self.raise_ref_errors and s["ref_errors"]:
+                self._done(stats[out.index(s)])
+        return out
+
+    def iterate_dry(self, chi2_cut=2.0, cluster_chi2=1000.0, cluster_kl=100.0, reweight_threshold=0.1, KL_lut=None,
+                    want_stats=False):
+        p = self._iter_params(chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, KL_lut)
+        st = L.Stats()
+        L.check(self.lib.gtf_iterate_dry(self.h, ctypes.byref(p), ctypes.byref(self.geom),
+                                         ctypes.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def CCA(self):
+        """extract_track_candidates.py:332: component label per node (smallest node index; -1 = removed)."""
+        L.check(self.lib.gtf_components(self.h))
+        return self.download(["label"])["label"]
+
+    def extract(self, pval=0.01, numhits=4, sep3d=10.0, merge_dist=8.0):
+        acc = np.zeros(self.N, np.uint8)
+        pxy = np.zeros(self.N)
+        pzr = np.zeros(self.N)
+        n = ctypes.c_int32(0)
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.check(self.lib.gtf_extract(self.h, ctypes.byref(self.geom), pval, numhits, sep3d, merge_dist, ctypes.byref(n),
+                                     acc.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), pxy.ctypes.data_as(dp),
+                                     pzr.ctypes.data_as(dp)))
+        L.check(self.lib.gtf_batch_sync(self.h))
+        return n.value, acc, pxy, pzr
+
+    def tag_propagation(self, tags, threshold=0.1, max_sweeps=1000):
+        tags = np.ascontiguousarray(tags, np.int32).copy()
+        n = ctypes.c_int(0)
+        L.check(self.lib.gtf_tag_propagate(self.h, threshold, tags.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                           max_sweeps, ctypes.byref(n)))
+        return n.value, tags
+
+    def candidates(self):
+        """(event_id, candidate_id, node_index) rows of all nodes accepted so far, sorted."""
+        n = ctypes.c_int64(0)
+        L.check(self.lib.gtf_candidates(self.h, None, 0, ctypes.byref(n)))
+        rows = np.zeros((max(n.value, 1), 3), np.int32)
+        L.check(self.lib.gtf_candidates(self.h, rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), max(n.value, 1),
+                                        ctypes.byref(n)))
+        rows = rows[:n.value]
+        return rows[np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))]

@@ -1,0 +1,791 @@
+// gtf_b200.cu -- C-ABI (include/gtf.h) of the B200 message-passing path: batch object, stage launchers,
+// seeding / component / extraction / tag-propagation kernels.  Built for sm_100a only; no CPU fallback.
+#include <cub/device/device_radix_sort.cuh>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "gtf_tile.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(GTF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+struct FieldInfo { const char *name; int elem; char ext; };
+static const FieldInfo g_fields[GTF_NFIELDS] = {
+#define EXT_N 'N'
+#define EXT_N1 'n'
+#define EXT_E 'E'
+#define EXT_S 'S'
+#define EXT_S1 's'
+#define X(name, type, ext) {#name, (int)sizeof(type), EXT_##ext},
+    GTF_FIELDS(X)
+#undef X
+};
+static int64_t field_count(const gtf_batch *b, int f)
+{
+    switch (g_fields[f].ext) {
+    case 'N': return b->N;
+    case 'n': return (int64_t)b->N + 1;
+    case 'E': return b->E;
+    case 'S': return b->S;
+    default: return (int64_t)b->S + 1;
+    }
+}
+
+extern "C" int gtf_abi_version(void) { return GTF_ABI_VERSION; }
+extern "C" const char *gtf_last_error(void) { return g_err.c_str(); }
+extern "C" int gtf_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int gtf_field_count(void) { return GTF_NFIELDS; }
+extern "C" const char *gtf_field_name(int f) { return (f >= 0 && f < GTF_NFIELDS) ? g_fields[f].name : nullptr; }
+extern "C" int gtf_field_id(const char *name)
+{
+    for (int f = 0; f < GTF_NFIELDS; f++)
+        if (!strcmp(name, g_fields[f].name)) return f;
+    return -1;
+}
+extern "C" int64_t gtf_field_bytes(const gtf_batch *b, int f)
+{
+    if (!b || f < 0 || f >= GTF_NFIELDS) return -1;
+    return field_count(b, f) * g_fields[f].elem;
+}
+
+// ------------------------------------------------------------------------------------------------ batch
+template <typename T> static int dalloc(gtf_batch *b, T **p, int64_t count)
+{
+    size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+    CK(cudaMalloc((void **)p, bytes));
+    CK(cudaMemsetAsync(*p, 0, bytes, b->stream));
+    b->dev_bytes += bytes;
+    return 0;
+}
+#define DA(ptr, count)                         \
+    do {                                       \
+        int r_ = dalloc(b, &(ptr), (count));   \
+        if (r_) return r_;                     \
+    } while (0)
+
+static void sync_dev_view(gtf_batch *b)
+{
+    DevBatch &d = b->d;
+    d.N = b->N; d.E = b->E; d.S = b->S; d.n_tiles = b->n_tiles;
+    int f = 0;
+#define X(name, type, ext) d.name = (type *)b->f[f++];
+    GTF_FIELDS(X)
+#undef X
+    d.tile_begin = b->tile_begin;
+}
+
+extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf_batch **out)
+{
+    if (!out || N < 0 || E < 0 || S < 0) return fail(GTF_E_ARG, "gtf_batch_create: bad sizes");
+    if (gtf_device_count() <= device || device < 0) return fail(GTF_E_CUDA, "gtf_batch_create: no such CUDA device");
+    CK(cudaSetDevice(device));
+    gtf_batch *b = new gtf_batch();
+    memset((void *)b, 0, sizeof(*b));
+    b->N = N; b->E = E; b->S = S; b->device = device;
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    for (int f = 0; f < GTF_NFIELDS; f++) {
+        size_t bytes = (size_t)field_count(b, f) * g_fields[f].elem;
+        if (!bytes) bytes = 8;
+        CK(cudaMalloc(&b->f[f], bytes));
+        CK(cudaMemsetAsync(b->f[f], 0, bytes, b->stream));
+        b->dev_bytes += bytes;
+    }
+    DevBatch &d = b->d;
+    DA(d.sub_nalive, S);
+    DA(d.slot_p11, E); DA(d.slot_vms, E); DA(d.node_p11tot, N);
+    DA(d.active_nx, E); DA(d.has_merged_nx, N);
+    DA(d.m_a_nx, N); DA(d.m_b_nx, N); DA(d.m_c_nx, N); DA(d.m_p00_nx, N); DA(d.m_p01_nx, N);
+    DA(d.m_p11_nx, N); DA(d.m_p22_nx, N); DA(d.m_prior_nx, N);
+    DA(d.counters, GTF_NCOUNTERS);
+    DA(b->accepted_total, N); DA(b->cand_root, N); DA(b->sub_has_inactive, S); DA(b->sub_first, S);
+    DA(b->sort_keys, N); DA(b->sort_vals, N); DA(b->sort_keys2, N); DA(b->sort_vals2, N);
+    DA(b->pv_xy, N); DA(b->pv_zr, N); DA(b->acc_now, N); DA(b->tags_a, N); DA(b->tags_b, N);
+    CK(cudaMallocHost((void **)&b->h_counters, sizeof(unsigned long long) * GTF_NCOUNTERS));
+    sync_dev_view(b);
+    CK(cudaStreamSynchronize(b->stream));
+    *out = b;
+    return 0;
+}
+
+extern "C" int gtf_batch_destroy(gtf_batch *b)
+{
+    if (!b) return 0;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    for (int f = 0; f < GTF_NFIELDS; f++) cudaFree(b->f[f]);
+    DevBatch &d = b->d;
+    void *extra[] = {d.sub_nalive, d.slot_p11, d.slot_vms, d.node_p11tot, d.active_nx, d.has_merged_nx, d.m_a_nx,
+                     d.m_b_nx, d.m_c_nx, d.m_p00_nx, d.m_p01_nx, d.m_p11_nx, d.m_p22_nx, d.m_prior_nx, d.counters,
+                     b->accepted_total, b->cand_root, b->sub_has_inactive, b->sub_first, b->sort_keys, b->sort_vals,
+                     b->sort_keys2, b->sort_vals2, b->pv_xy, b->pv_zr, b->acc_now, b->tags_a, b->tags_b,
+                     b->tile_begin, b->sort_tmp};
+    for (void *p : extra) cudaFree(p);
+    cudaFreeHost(b->h_counters);
+    cudaStreamDestroy(b->stream);
+    delete b;
+    return 0;
+}
+
+extern "C" int gtf_batch_upload(gtf_batch *b, int f, const void *host)
+{
+    if (!b || f < 0 || f >= GTF_NFIELDS || !host) return fail(GTF_E_ARG, "gtf_batch_upload: bad argument");
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpyAsync(b->f[f], host, (size_t)gtf_field_bytes(b, f), cudaMemcpyHostToDevice, b->stream));
+    return 0;
+}
+extern "C" int gtf_batch_download(gtf_batch *b, int f, void *host)
+{
+    if (!b || f < 0 || f >= GTF_NFIELDS || !host) return fail(GTF_E_ARG, "gtf_batch_download: bad argument");
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpyAsync(host, b->f[f], (size_t)gtf_field_bytes(b, f), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+extern "C" int gtf_batch_device_ptr(gtf_batch *b, int f, void **dptr)
+{
+    if (!b || f < 0 || f >= GTF_NFIELDS || !dptr) return fail(GTF_E_ARG, "gtf_batch_device_ptr: bad argument");
+    *dptr = b->f[f];
+    return 0;
+}
+extern "C" int gtf_batch_sync(gtf_batch *b)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+extern "C" int gtf_batch_stream(gtf_batch *b, void **s)
+{
+    if (!b || !s) return fail(GTF_E_ARG, "null");
+    *s = (void *)b->stream;
+    return 0;
+}
+extern "C" int64_t gtf_batch_device_bytes(const gtf_batch *b) { return b ? b->dev_bytes : 0; }
+
+// alive nodes per sub-graph
+__global__ void k_sub_count(DevBatch B)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.N && B.alive[i]) atomicAdd(&B.sub_nalive[B.sub[i]], 1);
+}
+static int recount_subs(gtf_batch *b)
+{
+    CK(cudaMemsetAsync(b->d.sub_nalive, 0, sizeof(int32_t) * (b->S ? b->S : 1), b->stream));
+    if (b->N) k_sub_count<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gtf_batch_finalize(gtf_batch *b)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    CK(cudaSetDevice(b->device));
+    std::vector<int32_t> in_off((size_t)b->N + 1);
+    CK(cudaMemcpyAsync(in_off.data(), b->f[GTF_F_in_off], sizeof(int32_t) * ((size_t)b->N + 1), cudaMemcpyDeviceToHost,
+                       b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    if (b->N && (in_off[0] != 0 || in_off[b->N] != b->E)) return fail(GTF_E_STATE, "gtf_batch_finalize: in_off does not span the slots");
+    std::vector<int32_t> tiles;
+    tiles.push_back(0);
+    int i = 0;
+    while (i < b->N) {
+        int start = i, slots = 0;
+        while (i < b->N && (i - start) < GTF_TILE_NODES) {
+            int d = in_off[i + 1] - in_off[i];
+            if (d < 0) return fail(GTF_E_STATE, "gtf_batch_finalize: in_off not monotone");
+            if (d > GTF_TILE_SLOTS) return fail(GTF_E_DEGREE, "gtf_batch_finalize: node in-degree exceeds GTF_TILE_SLOTS");
+            if (slots + d > GTF_TILE_SLOTS) break;
+            slots += d;
+            i++;
+        }
+        tiles.push_back(i);
+    }
+    b->n_tiles = (int)tiles.size() - 1;
+    if (b->tile_begin) cudaFree(b->tile_begin);
+    CK(cudaMalloc((void **)&b->tile_begin, sizeof(int32_t) * tiles.size()));
+    CK(cudaMemcpyAsync(b->tile_begin, tiles.data(), sizeof(int32_t) * tiles.size(), cudaMemcpyHostToDevice, b->stream));
+    sync_dev_view(b);
+    int r = recount_subs(b);
+    if (r) return r;
+    CK(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CK(cudaStreamSynchronize(b->stream));
+    b->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stats
+static int counters_reset(gtf_batch *b)
+{
+    CK(cudaMemsetAsync(b->d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS, b->stream));
+    return 0;
+}
+static int counters_read(gtf_batch *b, gtf_stats *st)
+{
+    CK(cudaMemcpyAsync(b->h_counters, b->d.counters, sizeof(unsigned long long) * GTF_NCOUNTERS, cudaMemcpyDeviceToHost,
+                       b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    if (st) {
+        st->nodes_merged = (int64_t)b->h_counters[CNT_MERGED];
+        st->edges_deactivated = (int64_t)b->h_counters[CNT_DEACT];
+        st->edges_sent = (int64_t)b->h_counters[CNT_SENT];
+        st->edges_gated = (int64_t)b->h_counters[CNT_GATED];
+        st->edges_reweight_off = (int64_t)b->h_counters[CNT_RWOFF];
+        st->active_edges = (int64_t)b->h_counters[CNT_ACTIVE];
+        st->active_changed = (int64_t)b->h_counters[CNT_CHANGED];
+        st->ref_errors = (int64_t)b->h_counters[CNT_REFERR];
+    }
+    return 0;
+}
+
+static GtfGeom geom_of(const gtf_geom *g)
+{
+    GtfGeom o;
+    o.sigma0xy = g->sigma0xy; o.sigma0rz = g->sigma0rz; o.sigma0rz2 = g->sigma0rz2; o.endcap = g->endcap_boundary;
+    return o;
+}
+static GtfGeom geom_default()
+{
+    GtfGeom o;
+    o.sigma0xy = 0.3; o.sigma0rz = 0.4; o.sigma0rz2 = 0.6; o.endcap = 550.0;
+    return o;
+}
+
+static int launch_tile(gtf_batch *b, const Prog &P, const GtfGeom &g)
+{
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized (call gtf_batch_finalize after uploading the topology)");
+    CK(cudaSetDevice(b->device));
+    if (b->n_tiles == 0) return 0;
+    k_tile<<<b->n_tiles, GTF_TILE_THREADS, sizeof(TileSmem), b->stream>>>(b->d, P, g);
+    CK(cudaGetLastError());
+    return 0;
+}
+static Prog make_prog(int key, int wb, std::initializer_list<int> ops)
+{
+    Prog P;
+    memset(&P, 0, sizeof(P));
+    int k = 0;
+    for (int op : ops) P.ops[k++] = op;
+    P.key = key;
+    P.wb = wb;
+    P.rw_thr = 0.1;
+    return P;
+}
+static int launch_prefix(gtf_batch *b, const GtfGeom &g)
+{
+    if (b->N) k_prefix<<<(b->N + 127) / 128, 128, 0, b->stream>>>(b->d, g);
+    CK(cudaGetLastError());
+    return 0;
+}
+#define TRY(x)              \
+    do {                    \
+        int r_ = (x);       \
+        if (r_) return r_;  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ seeding
+__global__ void k_seed_slots(DevBatch B, GtfGeom g)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B.E) return;
+    int i = B.slot_dst[s], b0 = B.in_off[i], d = B.in_off[i + 1] - b0, k = s - b0;
+    int key = B.in_src[s], other = B.in_src[b0 + d - 1 - k]; // quirk 5: tau of the mirrored neighbour
+    double zA = B.z[i], rA = B.r[i];
+    double dz = B.z[other] - zA, dr = B.r[other] - rA;
+    double vt = gtf_var_tau(dz, dr, zA, B.z[other], g);
+    GtfState o;
+    gtf_seed_entry(B.x[i], B.y[i], zA, rA, B.x[key], B.y[key], B.z[key], B.r[key], dz / dr, vt * vt, g, o);
+    B.tse_present[s] = 1;
+    B.tse_a[s] = o.a; B.tse_b[s] = o.b; B.tse_c[s] = o.c; B.tse_tau[s] = o.tau;
+    B.tse_p00[s] = o.p00; B.tse_p01[s] = o.p01; B.tse_p11[s] = o.p11; B.tse_p22[s] = o.p22;
+}
+// np.var of the xy edge gradients (helper.py:446), in set-iteration order = reversed slot order
+__global__ void k_seed_nodes(DevBatch B)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N) return;
+    int b0 = B.in_off[i], d = B.in_off[i + 1] - b0;
+    double xA = B.x[i], yA = B.y[i], sum = 0.0;
+    for (int q = d - 1; q >= 0; q--) { int nb = B.in_src[b0 + q]; sum += (B.y[nb] - yA) / (B.x[nb] - xA); }
+    double mean = d ? sum / d : NAN, var = 0.0;
+    for (int q = d - 1; q >= 0; q--) {
+        int nb = B.in_src[b0 + q];
+        double t = (B.y[nb] - yA) / (B.x[nb] - xA) - mean;
+        var += t * t;
+    }
+    B.emp_var[i] = d ? var / d : NAN;
+}
+
+extern "C" int gtf_seed(gtf_batch *b, const gtf_geom *g)
+{
+    if (!b || !g) return fail(GTF_E_ARG, "gtf_seed: null argument");
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
+    CK(cudaSetDevice(b->device));
+    GtfGeom gg = geom_of(g);
+    if (b->E) k_seed_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, gg);
+    if (b->N) k_seed_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gtf_initialize_edge_activation(gtf_batch *b)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemsetAsync(b->f[GTF_F_active], 1, (size_t)(b->E ? b->E : 0), b->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stages
+extern "C" int gtf_compute_prior_probabilities(gtf_batch *b, int key)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    Prog P = make_prog(key, WB_PRIOR, {OP_PRIOR});
+    return launch_tile(b, P, geom_default());
+}
+extern "C" int gtf_compute_mixture_weights(gtf_batch *b, int key, gtf_stats *st)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    TRY(counters_reset(b));
+    Prog P = make_prog(key, WB_W, {OP_WEIGHTS});
+    TRY(launch_tile(b, P, geom_default()));
+    return counters_read(b, st);
+}
+extern "C" int gtf_query_node_degree(gtf_batch *b)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    Prog P = make_prog(GTF_KEY_TSE, 0, {OP_DEGREE});
+    return launch_tile(b, P, geom_default());
+}
+extern "C" int gtf_cluster(gtf_batch *b, int key, double chi2_thr, double kl_thr, const double *kl_lut,
+                           const gtf_geom *g, gtf_stats *st)
+{
+    if (!b || !g) return fail(GTF_E_ARG, "gtf_cluster: null argument");
+    TRY(counters_reset(b));
+    Prog P = make_prog(key, WB_ACTIVE | WB_PRIOR | WB_W | WB_COUNT_ACTIVE, {OP_CLUSTER, OP_DEGREE, OP_WEIGHTS, OP_PRIOR});
+    P.cl_chi2 = chi2_thr;
+    P.cl_kl = kl_thr;
+    if (kl_lut) { P.use_lut = 1; memcpy(P.lut, kl_lut, sizeof(double) * 28); }
+    TRY(launch_tile(b, P, geom_of(g)));
+    return counters_read(b, st);
+}
+extern "C" int gtf_message_passing(gtf_batch *b, double chi2_cut, const gtf_geom *g, gtf_stats *st)
+{
+    if (!b || !g) return fail(GTF_E_ARG, "gtf_message_passing: null argument");
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
+    CK(cudaSetDevice(b->device));
+    TRY(counters_reset(b));
+    GtfGeom gg = geom_of(g);
+    TRY(launch_prefix(b, gg));
+    Prog P = make_prog(GTF_KEY_UTS, WB_ACTIVE | WB_PRESENT | WB_STATE | WB_PRIOR | WB_W | WB_UTSX | WB_COUNT_ACTIVE, {OP_E});
+    P.chi2_cut = chi2_cut;
+    TRY(launch_tile(b, P, gg));
+    // the accumulated multiple-scattering term persists on the node attribute (quirk 2)
+    CK(cudaMemcpyAsync(b->d.m_p11, b->d.node_p11tot, sizeof(double) * (size_t)b->N, cudaMemcpyDeviceToDevice, b->stream));
+    return counters_read(b, st);
+}
+extern "C" int gtf_reweight(gtf_batch *b, int key, double threshold, gtf_stats *st)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    TRY(counters_reset(b));
+    if (key == GTF_KEY_UTS) {
+        Prog P = make_prog(key, WB_ACTIVE | WB_W | WB_UTSX | WB_EDGEW | WB_COUNT_ACTIVE, {OP_RW});
+        P.rw_thr = threshold;
+        TRY(launch_tile(b, P, geom_default()));
+    }
+    return counters_read(b, st);
+}
+extern "C" int gtf_extrapolate_stage(gtf_batch *b, double chi2_cut, const gtf_geom *g, gtf_stats *st)
+{
+    if (!b || !g) return fail(GTF_E_ARG, "gtf_extrapolate_stage: null argument");
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
+    CK(cudaSetDevice(b->device));
+    TRY(counters_reset(b));
+    GtfGeom gg = geom_of(g);
+    TRY(launch_prefix(b, gg));
+    Prog P = make_prog(GTF_KEY_UTS,
+                       WB_ACTIVE | WB_PRESENT | WB_STATE | WB_PRIOR | WB_W | WB_UTSX | WB_EDGEW | WB_COUNT_ACTIVE,
+                       {OP_E, OP_PRIOR, OP_RW, OP_PRIOR, OP_RW, OP_DEGREE});
+    P.chi2_cut = chi2_cut;
+    TRY(launch_tile(b, P, gg));
+    CK(cudaMemcpyAsync(b->d.m_p11, b->d.node_p11tot, sizeof(double) * (size_t)b->N, cudaMemcpyDeviceToDevice, b->stream));
+    return counters_read(b, st);
+}
+extern "C" int gtf_remove_state_metadata(gtf_batch *b, gtf_stats *st)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    TRY(counters_reset(b));
+    Prog P1 = make_prog(GTF_KEY_TSE, WB_PRESENT | WB_PRIOR, {OP_POP, OP_PRIOR});
+    TRY(launch_tile(b, P1, geom_default()));
+    Prog P2 = make_prog(GTF_KEY_UTS, WB_ACTIVE | WB_PRESENT | WB_PRIOR | WB_W | WB_UTSX | WB_EDGEW | WB_COUNT_ACTIVE,
+                        {OP_POP, OP_PRIOR, OP_RW});
+    TRY(launch_tile(b, P2, geom_default()));
+    return counters_read(b, st);
+}
+
+// ------------------------------------------------------------------------------------------------ fused iteration
+static Prog fused_prog(const gtf_iter_params *p)
+{
+    Prog P = make_prog(GTF_KEY_UTS,
+                       WB_ACTIVE | WB_PRESENT | WB_STATE | WB_PRIOR | WB_W | WB_UTSX | WB_EDGEW | WB_MERGED_NX | WB_COUNT_ACTIVE,
+                       {OP_E, OP_PRIOR, OP_RW, OP_PRIOR, OP_RW, OP_CLUSTER, OP_DEGREE, OP_WEIGHTS, OP_PRIOR});
+    P.chi2_cut = p->chi2_cut;
+    P.cl_chi2 = p->cluster_chi2;
+    P.cl_kl = p->cluster_kl;
+    P.rw_thr = p->reweight_threshold;
+    if (p->kl_lut) { P.use_lut = 1; memcpy(P.lut, p->kl_lut, sizeof(double) * 28); }
+    return P;
+}
+static void commit_next(gtf_batch *b)
+{
+    DevBatch &d = b->d;
+    std::swap(b->f[GTF_F_active], *(void **)&d.active_nx);
+    std::swap(b->f[GTF_F_has_merged], *(void **)&d.has_merged_nx);
+    std::swap(b->f[GTF_F_m_a], *(void **)&d.m_a_nx);
+    std::swap(b->f[GTF_F_m_b], *(void **)&d.m_b_nx);
+    std::swap(b->f[GTF_F_m_c], *(void **)&d.m_c_nx);
+    std::swap(b->f[GTF_F_m_p00], *(void **)&d.m_p00_nx);
+    std::swap(b->f[GTF_F_m_p01], *(void **)&d.m_p01_nx);
+    std::swap(b->f[GTF_F_m_p11], *(void **)&d.m_p11_nx);
+    std::swap(b->f[GTF_F_m_p22], *(void **)&d.m_p22_nx);
+    std::swap(b->f[GTF_F_m_prior], *(void **)&d.m_prior_nx);
+    sync_dev_view(b);
+}
+extern "C" int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st)
+{
+    if (!b || !p || !g) return fail(GTF_E_ARG, "gtf_iterate_dry: null argument");
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
+    CK(cudaSetDevice(b->device));
+    TRY(counters_reset(b));
+    GtfGeom gg = geom_of(g);
+    TRY(launch_prefix(b, gg));
+    TRY(launch_tile(b, fused_prog(p), gg));
+    if (st) return counters_read(b, st);
+    return 0;
+}
+extern "C" int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, int max_iter, int stop_when_converged,
+                           gtf_stats *stats, int *n_done)
+{
+    if (!b || !p || !g) return fail(GTF_E_ARG, "gtf_iterate: null argument");
+    int it = 0;
+    for (; it < max_iter; it++) {
+        gtf_stats st;
+        TRY(gtf_iterate_dry(b, p, g, &st));
+        commit_next(b);
+        if (stats) stats[it] = st;
+        if (stop_when_converged && st.active_changed == 0) { it++; break; }
+    }
+    if (n_done) *n_done = it;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ components
+__device__ __forceinline__ int uf_find(int32_t *p, int i)
+{
+    int r = i;
+    while (true) {
+        int q = p[r];
+        if (q == r) break;
+        int qq = p[q];
+        if (qq != q) p[r] = qq; // path halving: benign race, qq is still an ancestor of r
+        r = q;
+    }
+    return r;
+}
+__global__ void k_cca_init(DevBatch B, uint8_t *has_inactive, int32_t *first)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.S) { has_inactive[i] = 0; first[i] = 0x7fffffff; }
+    if (i < B.N) B.label[i] = B.alive[i] ? i : -1;
+}
+__global__ void k_cca_first(DevBatch B, int32_t *first)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.N && B.alive[i]) atomicMin(&first[B.sub[i]], i);
+}
+__global__ void k_cca_edges(DevBatch B, uint8_t *has_inactive)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B.E) return;
+    int u = B.in_src[s], v = B.slot_dst[s];
+    if (u < 0 || !B.alive[u] || !B.alive[v]) return;
+    int sg = B.sub[v];
+    if (B.sub_state[sg] != GTF_SUB_INPLAY) return;
+    if (B.active[s] == 0) { has_inactive[sg] = 1; return; } // extract...py:335
+    int32_t *p = B.label;
+    int a = u, c = v;
+    while (true) { // lock-free union: hook the larger root under the smaller one
+        a = uf_find(p, a);
+        c = uf_find(p, c);
+        if (a == c) break;
+        int hi = max(a, c), lo = min(a, c);
+        int old = atomicCAS(&p[hi], hi, lo);
+        if (old == hi) break;
+        a = old; c = lo;
+    }
+}
+__global__ void k_cca_final(DevBatch B, const uint8_t *has_inactive, const int32_t *first)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N || !B.alive[i]) return;
+    int sg = B.sub[i];
+    if (B.sub_state[sg] != GTF_SUB_INPLAY) return;
+    // extract...py:343-344: with no inactive edge the WHOLE sub-graph is one candidate
+    B.label[i] = has_inactive[sg] ? uf_find(B.label, i) : first[sg];
+}
+extern "C" int gtf_components(gtf_batch *b)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
+    CK(cudaSetDevice(b->device));
+    int n = b->N > b->S ? b->N : b->S;
+    if (n == 0) return 0;
+    k_cca_init<<<(n + 255) / 256, 256, 0, b->stream>>>(b->d, b->sub_has_inactive, b->sub_first);
+    if (b->N) k_cca_first<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, b->sub_first);
+    if (b->E) k_cca_edges<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, b->sub_has_inactive);
+    // pointer-jump pass needs the unions finished: separate launch
+    if (b->N) k_cca_final<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, b->sub_has_inactive, b->sub_first);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ extraction
+#define GTF_MAX_CAND 64
+__global__ void k_extract_keys(DevBatch B, int32_t *keys, int32_t *vals)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N) return;
+    bool ok = B.alive[i] && B.sub_state[B.sub[i]] == GTF_SUB_INPLAY;
+    keys[i] = ok ? B.label[i] : 0x7fffffff;
+    vals[i] = i;
+}
+// one thread per component head (extract...py:409-456)
+__global__ void k_extract_gate(DevBatch B, const int32_t *keys, const int32_t *vals, GtfGeom g, double pval_cut,
+                               int numhits, double sep3d, double merge_dist, uint8_t *acc, int32_t *root_out,
+                               double *pv_xy, double *pv_zr)
+{
+    int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= B.N) return;
+    int key = keys[pos];
+    if (key == 0x7fffffff || (pos > 0 && keys[pos - 1] == key)) return;
+    int n = 1;
+    while (pos + n < B.N && keys[pos + n] == key) n++;
+    if (n < numhits || n > GTF_MAX_CAND) return; // :415; > 64 nodes cannot be one-hit-per-layer
+    int mem[GTF_MAX_CAND];
+    int lay[GTF_MAX_CAND];
+    double co[GTF_MAX_CAND][4];
+    for (int k = 0; k < n; k++) {
+        int m = vals[pos + k];
+        mem[k] = m;
+        lay[k] = B.volume[m] * 1000 + B.layer[m];
+        co[k][0] = B.x[m]; co[k][1] = B.y[m]; co[k][2] = B.z[m]; co[k][3] = B.r[m];
+    }
+    // check_close_proximity_nodes (:58-151): at most two layers with exactly two nodes, all others one
+    int n2 = 0, bad = 0;
+    for (int p = 0; p < n; p++) {
+        int cnt = 0, first = 1;
+        for (int q = 0; q < n; q++)
+            if (lay[q] == lay[p]) { cnt++; if (q < p) first = 0; }
+        if (!first) continue;
+        if (cnt == 2) n2++; else if (cnt != 1) bad = 1;
+    }
+    bool dropped[GTF_MAX_CAND];
+    for (int k = 0; k < n; k++) dropped[k] = false;
+    if (n2 > 0) {
+        if (n2 > 2 || bad) return; // duplicates stay -> fails the one-hit-per-layer test (:429)
+        for (int p = 0; p < n; p++)
+            for (int q = p + 1; q < n; q++) {
+                if (lay[q] != lay[p]) continue;
+                double dx = co[p][0] - co[q][0], dy = co[p][1] - co[q][1], dz = co[p][2] - co[q][2];
+                if (!(sqrt(dx * dx + dy * dy + dz * dz) <= merge_dist)) return; // :136-139
+                double xm = (co[p][0] + co[q][0]) / 2, ym = (co[p][1] + co[q][1]) / 2, zm = (co[p][2] + co[q][2]) / 2;
+                co[p][0] = xm; co[p][1] = ym; co[p][2] = zm; co[p][3] = sqrt(xm * xm + ym * ym);
+                dropped[q] = true;
+                break;
+            }
+    } else if (bad)
+        return;
+    int nk = 0;
+    for (int k = 0; k < n; k++)
+        if (!dropped[k]) {
+            if (nk != k) { co[nk][0] = co[k][0]; co[nk][1] = co[k][1]; co[nk][2] = co[k][2]; co[nk][3] = co[k][3]; }
+            nk++;
+        }
+    if (nk < numhits) return;
+    for (int p = 1; p < nk; p++) { // stable sort by r, largest first (:434-436)
+        double t0 = co[p][0], t1 = co[p][1], t2 = co[p][2], t3 = co[p][3];
+        int q = p;
+        while (q > 0 && co[q - 1][3] < t3) {
+            co[q][0] = co[q - 1][0]; co[q][1] = co[q - 1][1]; co[q][2] = co[q - 1][2]; co[q][3] = co[q - 1][3];
+            q--;
+        }
+        co[q][0] = t0; co[q][1] = t1; co[q][2] = t2; co[q][3] = t3;
+    }
+    double pxy, pzr;
+    gtf_track_fit(co, nk, g.sigma0xy, g.sigma0rz, g.endcap, sep3d, pxy, pzr);
+    pv_xy[key] = pxy;
+    pv_zr[key] = pzr;
+    if (pxy >= pval_cut && pzr >= pval_cut) // :442
+        for (int k = 0; k < n; k++) { acc[mem[k]] = 1; root_out[mem[k]] = key; }
+}
+__global__ void k_extract_apply(DevBatch B, const uint8_t *acc, uint8_t *acc_total, unsigned long long *count)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N || !acc[i]) return;
+    B.alive[i] = 0;
+    acc_total[i] = 1;
+    if (B.label[i] == i) atomicAdd(count, 1ull);
+}
+__global__ void k_sub_state(DevBatch B, int numhits)
+{
+    int sg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sg >= B.S || B.sub_state[sg] != GTF_SUB_INPLAY) return;
+    int left = B.sub_nalive[sg];
+    if (left == 0) B.sub_state[sg] = GTF_SUB_EMPTY;            // extract...py:463-467
+    else if (left < numhits) B.sub_state[sg] = GTF_SUB_FRAGMENT;
+}
+__global__ void k_fill_nan(double *a, double *c, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = NAN; c[i] = NAN; }
+}
+
+extern "C" int gtf_extract(gtf_batch *b, const gtf_geom *g, double pval_cut, int numhits, double sep3d, double merge_dist,
+                           int32_t *n_accepted, uint8_t *accepted, double *pval_xy, double *pval_zr)
+{
+    if (!b || !g) return fail(GTF_E_ARG, "gtf_extract: null argument");
+    TRY(gtf_components(b));
+    if (n_accepted) *n_accepted = 0;
+    if (b->N == 0) return 0;
+    int nb = (b->N + 255) / 256;
+    k_extract_keys<<<nb, 256, 0, b->stream>>>(b->d, b->sort_keys, b->sort_vals);
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, need, b->sort_keys, b->sort_keys2, b->sort_vals, b->sort_vals2, b->N, 0, 32,
+                                       b->stream));
+    if (need > b->sort_tmp_bytes) {
+        if (b->sort_tmp) cudaFree(b->sort_tmp);
+        CK(cudaMalloc(&b->sort_tmp, need));
+        b->sort_tmp_bytes = need;
+    }
+    CK(cub::DeviceRadixSort::SortPairs(b->sort_tmp, need, b->sort_keys, b->sort_keys2, b->sort_vals, b->sort_vals2, b->N, 0,
+                                       32, b->stream));
+    CK(cudaMemsetAsync(b->acc_now, 0, (size_t)b->N, b->stream));
+    k_fill_nan<<<nb, 256, 0, b->stream>>>(b->pv_xy, b->pv_zr, b->N);
+    TRY(counters_reset(b));
+    k_extract_gate<<<(b->N + 63) / 64, 64, 0, b->stream>>>(b->d, b->sort_keys2, b->sort_vals2, geom_of(g), pval_cut, numhits,
+                                                           sep3d, merge_dist, b->acc_now, b->cand_root, b->pv_xy, b->pv_zr);
+    k_extract_apply<<<nb, 256, 0, b->stream>>>(b->d, b->acc_now, b->accepted_total, b->d.counters + CNT_MERGED);
+    TRY(recount_subs(b));
+    if (b->S) k_sub_state<<<(b->S + 255) / 256, 256, 0, b->stream>>>(b->d, numhits);
+    CK(cudaGetLastError());
+    if (accepted) CK(cudaMemcpyAsync(accepted, b->acc_now, (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
+    if (pval_xy) CK(cudaMemcpyAsync(pval_xy, b->pv_xy, sizeof(double) * (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
+    if (pval_zr) CK(cudaMemcpyAsync(pval_zr, b->pv_zr, sizeof(double) * (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
+    gtf_stats st;
+    TRY(counters_read(b, &st));
+    if (n_accepted) *n_accepted = (int32_t)st.nodes_merged;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ tag propagation
+__global__ void k_tag_sweep(DevBatch B, const int32_t *tin, int32_t *tout, unsigned long long *cnt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N) return;
+    int32_t t = tin[i];
+    bool work = false;
+    if (B.alive[i] && B.sub_state[B.sub[i]] == GTF_SUB_INPLAY) {
+        double ri = B.r[i];
+        for (int o = B.out_off[i]; o < B.out_off[i + 1]; o++) {
+            int v = B.slot_dst[B.out_slot[o]];
+            if (B.alive[v] && !(B.r[v] > ri)) { // keep successors with radius <= own (tag_propagation.py:99-110)
+                work = true;
+                t = max(t, tin[v]);             // :139-149 (max, although the script calls it "smallest")
+            }
+        }
+    }
+    tout[i] = t;
+    if (work) {
+        atomicAdd(&cnt[0], 1ull);
+        if (t != tin[i]) atomicAdd(&cnt[1], 1ull);
+    }
+}
+extern "C" int gtf_tag_propagate(gtf_batch *b, double threshold, int32_t *tags, int max_sweeps, int *n_sweeps)
+{
+    if (!b || !tags) return fail(GTF_E_ARG, "gtf_tag_propagate: null argument");
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
+    CK(cudaSetDevice(b->device));
+    int sweeps = 0;
+    if (b->N) {
+        CK(cudaMemcpyAsync(b->tags_a, tags, sizeof(int32_t) * (size_t)b->N, cudaMemcpyHostToDevice, b->stream));
+        int32_t *cur = b->tags_a, *nxt = b->tags_b;
+        double frac = 1.0;
+        while (frac > threshold && sweeps < max_sweeps) {
+            TRY(counters_reset(b));
+            k_tag_sweep<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, cur, nxt, b->d.counters);
+            CK(cudaGetLastError());
+            TRY(counters_read(b, nullptr));
+            unsigned long long nwork = b->h_counters[0], flipped = b->h_counters[1];
+            if (nwork == 0) break;
+            std::swap(cur, nxt);
+            frac = (double)flipped / (double)nwork;
+            sweeps++;
+        }
+        CK(cudaMemcpyAsync(tags, cur, sizeof(int32_t) * (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    if (n_sweeps) *n_sweeps = sweeps;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ candidate table
+__global__ void k_cand_rows(DevBatch B, const uint8_t *acc_total, const int32_t *root, int32_t *rows, long long cap,
+                            unsigned long long *count)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N || !acc_total[i]) return;
+    unsigned long long k = atomicAdd(count, 1ull);
+    if ((long long)k < cap) {
+        rows[3 * k + 0] = B.sub_event[B.sub[i]];
+        rows[3 * k + 1] = root[i];
+        rows[3 * k + 2] = i;
+    }
+}
+extern "C" int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_rows, int64_t *n_rows)
+{
+    if (!b || !n_rows) return fail(GTF_E_ARG, "gtf_candidates: null argument");
+    CK(cudaSetDevice(b->device));
+    *n_rows = 0;
+    if (b->N == 0) return 0;
+    int32_t *rows = nullptr;
+    int64_t cap = cap_rows > 0 && table_host ? cap_rows : 0;
+    if (cap) CK(cudaMalloc((void **)&rows, sizeof(int32_t) * 3 * (size_t)cap));
+    TRY(counters_reset(b));
+    k_cand_rows<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, b->accepted_total, b->cand_root, rows, (long long)cap,
+                                                           b->d.counters);
+    CK(cudaGetLastError());
+    TRY(counters_read(b, nullptr));
+    *n_rows = (int64_t)b->h_counters[0];
+    if (cap) {
+        int64_t nw = *n_rows < cap ? *n_rows : cap;
+        CK(cudaMemcpyAsync(table_host, rows, sizeof(int32_t) * 3 * (size_t)nw, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        cudaFree(rows);
+    }
+    return 0;
+}

@@ -1,0 +1,83 @@
+// gtf_dev.cuh -- device-side view of an event batch, op codes of the per-node program, batch object.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gtf.h"
+#include "gtf_math.cuh"
+
+enum {
+#define X(name, type, ext) GTF_F_##name,
+    GTF_FIELDS(X)
+#undef X
+        GTF_NFIELDS
+};
+
+// every array of gtf_fields.h as a typed device pointer + derived / scratch arrays
+struct DevBatch {
+    int N, E, S, n_tiles;
+#define X(name, type, ext) type *name;
+    GTF_FIELDS(X)
+#undef X
+    // derived topology
+    const int32_t *tile_begin;   // [n_tiles + 1] node ranges, <= TILE_SLOTS slots and <= TILE_NODES nodes each
+    int32_t *sub_nalive;         // [S] alive nodes per sub-graph ("len(subGraph.nodes()) == 1: continue")
+    // per-source multiple-scattering prefix (extrapolate_merged_states.py:127-128, quirk 2)
+    double *slot_p11;            // [E] merged_cov[1,1] as seen by this edge
+    double *slot_vms;            // [E] var_ms of this edge
+    double *node_p11tot;         // [N] merged_cov[1,1] after all successors
+    // "next" buffers of the fused iteration (ping-pong with active / has_merged / m_*)
+    uint8_t *active_nx, *has_merged_nx;
+    double *m_a_nx, *m_b_nx, *m_c_nx, *m_p00_nx, *m_p01_nx, *m_p11_nx, *m_p22_nx, *m_prior_nx;
+    unsigned long long *counters; // [GTF_NCOUNTERS]
+};
+
+enum {
+    CNT_MERGED = 0, CNT_DEACT, CNT_SENT, CNT_GATED, CNT_RWOFF, CNT_ACTIVE, CNT_CHANGED, CNT_REFERR, GTF_NCOUNTERS
+};
+
+// per-node program executed by the tile kernel
+enum { OP_END = 0, OP_E, OP_PRIOR, OP_RW, OP_CLUSTER, OP_DEGREE, OP_WEIGHTS, OP_POP };
+
+// write-back masks
+enum {
+    WB_ACTIVE = 1, WB_PRESENT = 2, WB_STATE = 4, WB_PRIOR = 8, WB_W = 16, WB_UTSX = 32 /* lik, lrn, side, rank */,
+    WB_EDGEW = 64, WB_MERGED_NX = 128 /* fused: write every node's merged state to the *_nx buffers */,
+    WB_COUNT_ACTIVE = 256
+};
+
+struct Prog {
+    int ops[12];
+    int key;          // working dict: GTF_KEY_TSE / GTF_KEY_UTS
+    int wb;           // WB_* mask
+    int use_lut;
+    double chi2_cut, cl_chi2, cl_kl, rw_thr;
+    double lut[28];
+};
+
+#define GTF_TILE_SLOTS 384
+#define GTF_TILE_NODES 192
+#define GTF_TILE_THREADS 256
+#define GTF_MAXD 15
+
+struct gtf_batch {
+    int N, E, S, device;
+    cudaStream_t stream;
+    void *f[GTF_NFIELDS];
+    DevBatch d;
+    bool finalized;
+    int n_tiles, n_big;
+    int32_t *tile_begin;
+    unsigned long long *h_counters; // pinned
+    int64_t dev_bytes;
+    // extraction scratch
+    uint8_t *accepted_total;   // [N] nodes accepted by any gtf_extract so far
+    int32_t *cand_root;        // [N] root (candidate id) of accepted nodes
+    uint8_t *sub_has_inactive; // [S]
+    int32_t *sub_first;        // [S]
+    void *sort_tmp;
+    size_t sort_tmp_bytes;
+    int32_t *sort_keys, *sort_vals, *sort_keys2, *sort_vals2;
+    double *pv_xy, *pv_zr;     // [N]
+    uint8_t *acc_now;          // [N]
+    int32_t *tags_a, *tags_b;  // [N]
+};

@@ -1,0 +1,390 @@
+// gtf_math.cuh -- per-edge / per-pair fp64 algebra of the message-passing hot path.
+//
+// Pure functions, usable from device code (kernels in gtf_kernels.cu) and -- for CPU-side unit tests of
+// the algebra against the oracle -- from host code (csrc/gtf_hostmath.cpp compiles this header with g++).
+// Everything is written for the covariance structure the reference actually stores:
+//     [ p00 p01  0  ]
+//     [ p01 p11  0  ]      (row/col 2 zeroed: helper.py:423-425, extrapolate_merged_states.py:363-365)
+//     [  0   0  p22 ]
+// so 3x3 inverses collapse to a closed-form 2x2 inverse plus a reciprocal, and sin/cos(atan2(s, c)) are
+// taken algebraically (s/h, c/h).  Reference line numbers are relative to /root/reference/src.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define GTF_HD __host__ __device__ __forceinline__
+#else
+#define GTF_HD inline
+#endif
+
+struct GtfGeom {
+    double sigma0xy, sigma0rz, sigma0rz2, endcap;
+};
+
+struct GtfState {          // one Gaussian component: parabola (a,b,c), slope tau, block covariance
+    double a, b, c, tau, p00, p01, p11, p22;
+};
+
+GTF_HD double gtf_sq(double v) { return v * v; }
+
+// Highland multiple-scattering variance of the track direction (helper.py:402-415,
+// extrapolate_merged_states.py:114-124, extract_track_candidates.py:244-255).
+// dr, dz: segment; xk: global x of the far hit; endcap_side_z: the z whose |z| >= endcap selects tan(theta).
+GTF_HD double gtf_var_ms(double a, double b, double xk, double dr, double dz, double endcap_side_z, double endcap)
+{
+    double hyp = sqrt(dr * dr + dz * dz);
+    double sin_t = fabs(dr) / hyp;
+    double kb = 2.0 * a * xk + b;
+    double t = 1.0 + kb * kb;
+    double kappa = (2.0 * a) / (t * sqrt(t));
+    double q = (13.6 * 1e-3 * 0.1414213562373095048801688724 * kappa) / 0.3; // sqrt(0.02)
+    double v = sin_t * (q * q);
+    if (fabs(endcap_side_z) >= endcap) v = v * (fabs(dr) / fabs(dz));
+    return v;
+}
+
+// variance of tau = dz/dr from the four measurement errors (helper.py:317-330, extrapolate...py:344-358)
+GTF_HD double gtf_var_tau(double dz, double dr, double z_node, double z_nb, const GtfGeom &g)
+{
+    double sr = g.sigma0rz, sz = g.sigma0rz2, srn = g.sigma0rz, szn = g.sigma0rz2;
+    if (fabs(z_node) >= g.endcap) { sz = g.sigma0rz; sr = g.sigma0rz2; }
+    if (fabs(z_nb) >= g.endcap) { szn = g.sigma0rz; srn = g.sigma0rz2; }
+    double j1 = 1.0 / dr, j3 = dz / (dr * dr);
+    return j1 * j1 * (sz * sz) + j1 * j1 * (szn * szn) + j3 * j3 * (sr * sr) + j3 * j3 * (srn * srn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Seeding: helper.py:354-441 for one (node, key) pair.  `tau`/`var_tau_sq` come from the *mirrored*
+// neighbour (quirk 5: key N[d-1-i] gets the tau of N[i]) and are supplied by the caller.
+GTF_HD void gtf_seed_entry(double xA, double yA, double zA, double rA, double xk, double yk, double zk, double rk,
+                           double tau, double var_tau_sq, const GtfGeom &g, GtfState &o)
+{
+    double rho = sqrt(xA * xA + yA * yA);
+    double ca = rho > 0.0 ? xA / rho : 1.0, sa = rho > 0.0 ? yA / rho : 0.0;
+    double x0 = (0.0 - xA) * ca + (0.0 - yA) * sa;
+    double xB = (xk - xA) * ca + (yk - yA) * sa;
+    double mB = -(xk - xA) * sa + (yk - yA) * ca;
+    // H = [[x0^2/2, x0, 1], [0, 0, 1], [xB^2/2, xB, 1]]; measurement (0, 0, mB)  ->  closed-form inverse
+    double det = 0.5 * x0 * xB * (x0 - xB);          // det of the 2x2 system after subtracting row 1
+    // rows of H^-1:  Hi0 = ( xB, -(xB - x0), -x0) / det ;  Hi1 = (-xB^2/2, (xB^2 - x0^2)/2, x0^2/2) / det ; Hi2 = (0,1,0)
+    double h00 = xB / det, h01 = (x0 - xB) / det, h02 = -x0 / det;
+    double h10 = -0.5 * xB * xB / det, h11 = 0.5 * (xB * xB - x0 * x0) / det, h12 = 0.5 * x0 * x0 / det;
+    o.a = h02 * mB;
+    o.b = h12 * mB;
+    o.c = 0.0 * mB;                                   // Hi2 . (0, 0, mB) = 0 (NaN-propagating like the reference)
+    double sO = 16.0, sA = g.sigma0xy * g.sigma0xy;   // sigmaO = 4 mm (helper.py:243)
+    double var_ms = gtf_var_ms(o.a, o.b, xk, rA - rk, zA - zk, zA, g.endcap);
+    o.p00 = h00 * h00 * sO + h01 * h01 * sA + h02 * h02 * sA;
+    o.p01 = h00 * h10 * sO + h01 * h11 * sA + h02 * h12 * sA;
+    o.p11 = h10 * h10 * sO + h11 * h11 * sA + h12 * h12 * sA + var_ms;
+    o.tau = tau;
+    o.p22 = var_tau_sq + var_ms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Extrapolate + chi2 gate + Kalman update for one edge u -> v (extrapolate_merged_states.py:26-402).
+struct GtfExtrapOut {
+    double chi2, lik, var_ms;
+    GtfState s;        // updated state stored at the receiver
+    int pass;
+};
+
+GTF_HD void gtf_extrapolate(double ux, double uy, double uz, double ur, double vx, double vy, double vz, double vr,
+                            double a, double b, double c, double p00, double p01, double p11_eff, double p22,
+                            double var_ms, double chi2_cut, const GtfGeom &g, GtfExtrapOut &o)
+{
+    // rotation into the source frame (:41,52) -- only x_A is live
+    double rho = sqrt(ux * ux + uy * uy);
+    double ca = rho > 0.0 ? ux / rho : 1.0, sa = rho > 0.0 ? uy / rho : 0.0;
+    double xA = (vx - ux) * ca + (vy - uy) * sa;
+    // phi between the two radius vectors (:59): sin/cos taken algebraically
+    double cr = ux * vy - uy * vx, dt = ux * vx + uy * vy;
+    double h = sqrt(cr * cr + dt * dt);
+    double sp = h > 0.0 ? cr / h : 0.0, cp = h > 0.0 ? dt / h : 1.0;
+    double xp = xA + c * sp, Vx = cp + b * sp, Ax = a * sp;                     // :63-65
+    double Vx2 = Vx * Vx;
+    double s_star = (-xp * (2.0 * Vx2 + Ax * xp)) / (2.0 * Vx2 * Vx);           // :68
+    // ds*/d(a,b,c) (:82-86); numer == xp, denom == Vx
+    double iV = 1.0 / Vx, iV2 = iV * iV;
+    double ds_da = -(sp * xp * xp) * iV2 * iV;
+    double ds_db = (sp * xp) * (1.0 + 3.0 * a * sp * xp * iV2) * iV2;
+    double ds_dc = -sp * (1.0 + 2.0 * a * sp * xp * iV2) * iV;
+    // da'/d. (:89-92)
+    double den = cp + (2.0 * a + b) * sp, id = 1.0 / den, id2 = id * id, id4 = id2 * id2;
+    double f00 = (id2 * id) * (1.0 - (6.0 * a * sp) * (s_star + a * ds_da) * id);
+    double f01 = (-3.0 * a * sp * (2.0 * a * ds_db + 1.0)) * id4;
+    double f02 = (-6.0 * sp * ds_dc * a * a) * id4;
+    // db'/d. (:95-99)
+    double w = 2.0 * a * s_star + b;
+    den = cp + w * sp;
+    id = 1.0 / den;
+    double br = cp - (sp * (-sp + w * cp)) * id;
+    double f10 = (2.0 * (s_star + a * ds_da) * br) * id;
+    double f11 = ((1.0 + 2.0 * a * ds_da) * br) * id;
+    double f12 = (2.0 * a * ds_dc * br) * id;
+    // dc'/d. (:102-105)
+    br = cp * (2.0 * a + b) - sp;
+    double f20 = ds_da * br + s_star * s_star * cp;
+    double f21 = ds_db * br + s_star * cp;
+    double f22 = ds_dc * br + cp;
+
+    // first propagation (:129-130): x_e = F x, P_e = F P F^T with block P (p11 already carries the
+    // accumulated multiple-scattering term, :127-128)
+    double xe0 = f00 * a + f01 * b + f02 * c;
+    double xe1 = f10 * a + f11 * b + f12 * c;
+    double xe2 = f20 * a + f21 * b + f22 * c;
+#define GTF_FPFT(ri0, ri1, ri2, rj0, rj1, rj2) \
+    ((ri0) * (p00 * (rj0) + p01 * (rj1)) + (ri1) * (p01 * (rj0) + p11_eff * (rj1)) + (ri2) * p22 * (rj2))
+    double e00 = GTF_FPFT(f00, f01, f02, f00, f01, f02);
+    double e01 = GTF_FPFT(f00, f01, f02, f10, f11, f12);
+    double e02 = GTF_FPFT(f00, f01, f02, f20, f21, f22);
+    double e11 = GTF_FPFT(f10, f11, f12, f10, f11, f12);
+    double e12 = GTF_FPFT(f10, f11, f12, f20, f21, f22);
+    double e22 = GTF_FPFT(f20, f21, f22, f20, f21, f22);
+#undef GTF_FPFT
+    double R = g.sigma0xy * g.sigma0xy;
+    double res = 0.0 - xe2;                                                     // :137
+    double S = e22 + R;                                                         // :138
+    double chi2 = (res / S) * res;                                              // :140
+    o.chi2 = chi2;
+    o.var_ms = var_ms;
+    o.pass = chi2 <= chi2_cut;                                                  // :298 (NaN -> fail)
+    if (!o.pass) return;
+    o.lik = exp(-0.5 * chi2) / sqrt(2.0 * 3.14159265358979323846 * fabs(S));    // :302-304
+    // filterpy predict(): F applied a second time, + Q = diag(0, var_ms, 0)    (:321)
+    double x0 = f00 * xe0 + f01 * xe1 + f02 * xe2;
+    double x1 = f10 * xe0 + f11 * xe1 + f12 * xe2;
+    double x2 = f20 * xe0 + f21 * xe1 + f22 * xe2;
+    // G = F * P_e (rows), then P' = G F^T ; P_e symmetric
+#define GTF_G(r0, r1, r2, c0, c1, c2) ((r0) * (c0) + (r1) * (c1) + (r2) * (c2))
+    double g00 = GTF_G(f00, f01, f02, e00, e01, e02), g01 = GTF_G(f00, f01, f02, e01, e11, e12),
+           g02 = GTF_G(f00, f01, f02, e02, e12, e22);
+    double g10 = GTF_G(f10, f11, f12, e00, e01, e02), g11 = GTF_G(f10, f11, f12, e01, e11, e12),
+           g12 = GTF_G(f10, f11, f12, e02, e12, e22);
+    double g20 = GTF_G(f20, f21, f22, e00, e01, e02), g21 = GTF_G(f20, f21, f22, e01, e11, e12),
+           g22 = GTF_G(f20, f21, f22, e02, e12, e22);
+    double q00 = GTF_G(g00, g01, g02, f00, f01, f02);
+    double q01 = GTF_G(g00, g01, g02, f10, f11, f12);
+    double q02 = GTF_G(g00, g01, g02, f20, f21, f22);
+    double q11 = GTF_G(g10, g11, g12, f10, f11, f12) + var_ms;
+    double q12 = GTF_G(g10, g11, g12, f20, f21, f22);
+    double q22 = GTF_G(g20, g21, g22, f20, f21, f22);
+#undef GTF_G
+    // filterpy update(z = 0), H = [0 0 1], Joseph form (:322)
+    double y = 0.0 - x2;
+    double SI = 1.0 / (q22 + R);
+    double K0 = q02 * SI, K1 = q12 * SI, K2 = q22 * SI;
+    o.s.a = x0 + K0 * y;
+    o.s.b = x1 + K1 * y;
+    o.s.c = x2 + K2 * y;
+    double t00 = q00 - K0 * q02, t01 = q01 - K0 * q12, t02 = q02 - K0 * q22;
+    double t11 = q11 - K1 * q12, t12 = q12 - K1 * q22;
+    o.s.p00 = t00 - K0 * t02 + K0 * R * K0;
+    o.s.p01 = t01 - K1 * t02 + K0 * R * K1;
+    o.s.p11 = t11 - K1 * t12 + K1 * R * K1;
+    // tau and its variance (:326-365)
+    double dr = vr - ur, dz = vz - uz;
+    o.s.tau = dz / dr;
+    o.s.p22 = gtf_var_tau(dz, dr, uz, vz, g) + var_ms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// clustering.py:11-78 pairwise chi2 of components i ("neighbour1", b) and j ("neighbour2", c) at node a.
+GTF_HD double gtf_pair_chi2(const GtfState &si, const GtfState &sj, double xa, double za, double ra, double xb,
+                            double zb, double rb, double xc, double zc, double rc, const GtfGeom &g)
+{
+    double r0 = si.a - sj.a, r1 = si.b - sj.b;
+    double c00 = si.p00 + sj.p00, c01 = si.p01 + sj.p01, c11 = si.p11 + sj.p11;
+    double det = c00 * c11 - c01 * c01;
+    double d1 = (r0 * r0 * c11 - 2.0 * r0 * r1 * c01 + r1 * r1 * c00) / det;
+    double ib = 1.0 / (rb - ra), ic = 1.0 / (rc - ra);
+    double j2 = ib, j3 = -ic, j1 = -j3 - j2;
+    double j5 = -(zb - za) * ib * ib, j6 = (zc - za) * ic * ic, j4 = -j5 - j6;
+    double sza = g.sigma0rz2, szb = g.sigma0rz2, szc = g.sigma0rz2;
+    double sra = g.sigma0rz, srb = g.sigma0rz, src = g.sigma0rz;
+    if (fabs(xa) >= g.endcap) { sza = g.sigma0rz; sra = g.sigma0rz2; }    // abs(x), not abs(z): clustering.py:49-57
+    if (fabs(xb) >= g.endcap) { szb = g.sigma0rz; srb = g.sigma0rz2; }
+    if (fabs(xc) >= g.endcap) { szc = g.sigma0rz; src = g.sigma0rz2; }
+    double cdt = j1 * j1 * sza * sza + j2 * j2 * szb * szb + j3 * j3 * szc * szc + j4 * j4 * sra * sra +
+                 j5 * j5 * srb * srb + j6 * j6 * src * src;
+    double dtau = (zb - za) * ib - (zc - za) * ic;
+    return d1 + dtau * dtau * (1.0 / cdt);
+}
+
+// inverse of the 2x2 block: returns (i00, i01, i11)
+GTF_HD void gtf_inv2(double p00, double p01, double p11, double &i00, double &i01, double &i11)
+{
+    double id = 1.0 / (p00 * p11 - p01 * p01);
+    i00 = p11 * id;
+    i01 = -p01 * id;
+    i11 = p00 * id;
+}
+
+// clustering.py:97-105 merge_states for BOTH chains at once: (a,b,c) and (a,b,tau) share the covariance
+// (quirk 4: edge_covariance is joint_vector_covariance), so c and tau are both fused with weight 1/p22.
+GTF_HD void gtf_merge(const GtfState &s1, const GtfState &s2, GtfState &m)
+{
+    double a00, a01, a11, b00, b01, b11;
+    gtf_inv2(s1.p00, s1.p01, s1.p11, a00, a01, a11);
+    gtf_inv2(s2.p00, s2.p01, s2.p11, b00, b01, b11);
+    double s00 = a00 + b00, s01 = a01 + b01, s11 = a11 + b11;
+    double m00, m01, m11;
+    gtf_inv2(s00, s01, s11, m00, m01, m11);
+    double v0 = (a00 * s1.a + a01 * s1.b) + (b00 * s2.a + b01 * s2.b);
+    double v1 = (a01 * s1.a + a11 * s1.b) + (b01 * s2.a + b11 * s2.b);
+    double q1 = 1.0 / s1.p22, q2 = 1.0 / s2.p22;
+    double mq = 1.0 / (q1 + q2);
+    GtfState r;
+    r.a = m00 * v0 + m01 * v1;
+    r.b = m01 * v0 + m11 * v1;
+    r.c = mq * (q1 * s1.c + q2 * s2.c);
+    r.tau = mq * (q1 * s1.tau + q2 * s2.tau);
+    r.p00 = m00;
+    r.p01 = m01;
+    r.p11 = m11;
+    r.p22 = mq;
+    m = r;
+}
+
+// clustering.py:90-94 KLDistance on the joint vector (a, b, tau).  The "trace" is of an ELEMENT-WISE
+// product (numpy `*`), i.e. sum_k (c1_kk - c2_kk) * (inv2_kk - inv1_kk): reproduced, pinned by the golden CSV.
+GTF_HD double gtf_kl(const GtfState &s1, const GtfState &s2)
+{
+    double a00, a01, a11, b00, b01, b11;
+    gtf_inv2(s1.p00, s1.p01, s1.p11, a00, a01, a11);
+    gtf_inv2(s2.p00, s2.p01, s2.p11, b00, b01, b11);
+    double q1 = 1.0 / s1.p22, q2 = 1.0 / s2.p22;
+    double tr = (s1.p00 - s2.p00) * (b00 - a00) + (s1.p11 - s2.p11) * (b11 - a11) + (s1.p22 - s2.p22) * (q2 - q1);
+    double d0 = s1.a - s2.a, d1 = s1.b - s2.b, d2 = s1.tau - s2.tau;
+    double s00 = a00 + b00, s01 = a01 + b01, s11 = a11 + b11;
+    return tr + (d0 * d0 * s00 + 2.0 * d0 * d1 * s01 + d1 * d1 * s11 + d2 * d2 * (q1 + q2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Candidate quality gate (extract/extract_track_candidates.py:172-328).
+
+// regularised upper incomplete gamma Q(a, x): power series for x < a + 1, modified-Lentz continued
+// fraction otherwise.  chi2.sf(x, k) = Q(k/2, x/2) (extract...py:321,325 call scipy's chi2.sf).
+GTF_HD double gtf_gammq(double a, double x)
+{
+    if (x != x || a != a) return NAN;
+    if (x <= 0.0) return 1.0;
+    if (isinf(x)) return 0.0;
+    double lead = exp(-x + a * log(x) - lgamma(a));
+    if (x < a + 1.0) {
+        double ap = a, term = 1.0 / a, sum = term;
+        for (int it = 0; it < 2000; it++) {
+            ap += 1.0;
+            term *= x / ap;
+            sum += term;
+            if (fabs(term) < fabs(sum) * 1e-17) break;
+        }
+        return 1.0 - sum * lead;
+    }
+    const double tiny = 1e-300;
+    double bb = x + 1.0 - a, cc = 1.0 / tiny, dd = 1.0 / bb, hh = dd;
+    for (int it = 1; it < 2000; it++) {
+        double an = -it * (it - a);
+        bb += 2.0;
+        dd = an * dd + bb;
+        if (fabs(dd) < tiny) dd = tiny;
+        cc = bb + an / cc;
+        if (fabs(cc) < tiny) cc = tiny;
+        dd = 1.0 / dd;
+        double del = dd * cc;
+        hh *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return lead * hh;
+}
+
+// rotate_track (:172-193) + KF_track_fit_moliere (:209-328).  co[k] = (x, y, z, r) sorted by r, largest
+// first; rotated in place.  xy filter: 3-state OU model; zr filter: 2-state with the scalar process noise
+// broadcast onto all four covariance entries (filterpy semantics of `g.Q = var_ms`).
+GTF_HD void gtf_track_fit(double (*co)[4], int n, double sigma0xy, double sigma0rz, double endcap, double sep3d,
+                          double &pval_xy, double &pval_zr)
+{
+    {
+        const double *p1 = co[n - 1], *p2 = co[n - 2];
+        double d3 = sqrt(gtf_sq(p1[0] - p2[0]) + gtf_sq(p1[1] - p2[1]) + gtf_sq(p1[2] - p2[2]));
+        if (d3 < sep3d) p2 = co[n - 3];
+        double dxy = sqrt(gtf_sq(p2[0] - p1[0]) + gtf_sq(p2[1] - p1[1]));
+        double cxy = dxy > 0.0 ? (p2[0] - p1[0]) / dxy : 1.0, sxy = dxy > 0.0 ? (p2[1] - p1[1]) / dxy : 0.0;
+        double dzr = sqrt(gtf_sq(p2[2] - p1[2]) + gtf_sq(p2[3] - p1[3]));
+        double czr = dzr > 0.0 ? (p2[3] - p1[3]) / dzr : 1.0, szr = dzr > 0.0 ? (p2[2] - p1[2]) / dzr : 0.0;
+        for (int k = 0; k < n; k++) {
+            double x = co[k][0], y = co[k][1], z = co[k][2], r = co[k][3];
+            co[k][0] = x * cxy + y * sxy;
+            co[k][1] = -x * sxy + y * cxy;
+            co[k][3] = r * czr + r * szr;   // :190 (r appears twice in the reference)
+            co[k][2] = -z * szr + z * czr;  // :191
+        }
+    }
+    const double Rxy = sigma0xy * sigma0xy, Rzr = sigma0rz * sigma0rz;
+    double x0 = co[0][1], x1 = 0.0, x2 = 0.0;                               // f.x
+    double P00 = Rxy, P01 = 0, P02 = 0, P11 = 1, P12 = 0, P22 = 1;          // f.P (symmetric)
+    double g0 = co[0][3], g1 = 0.0;                                         // g.x
+    double G00 = Rzr, G01 = 0.0, G10 = 0.0, G11 = 1000.0;                   // g.P (not kept symmetric by the scalar Q)
+    double chi_xy = 0.0, chi_zr = 0.0;
+    for (int i = 0; i + 1 < n; i++) {
+        double xa = co[i][0], ya = co[i][1], xb = co[i + 1][0], yb = co[i + 1][1];
+        // parabola through the origin and the two hits (:202-204 with x1 = y1 = 0)
+        double den = (-xa) * (-xb) * (xa - xb);
+        double pa = (xb * ya - xa * yb) / den;
+        double pb = (-(xb * xb) * ya + (xa * xa) * yb) / den;
+        double dr = co[i + 1][3] - co[i][3], dz = co[i + 1][2] - co[i][2];
+        double var_ms = gtf_var_ms(pa, pb, xb, dr, dz, co[i + 1][2], endcap);
+        double dx = xb - xa, alpha = 0.1;
+        double e1 = exp(-fabs(dx) * alpha), f1 = (1.0 - e1) / alpha, g1f = (fabs(dx) - f1) / alpha;
+        double sw2 = 1e-5 * 1e-5, dx2 = dx * dx, dxw2 = dx2 * sw2;
+        double Q02 = 0.5 * dxw2, Q01 = dx * (var_ms + Q02), Q12 = dx * sw2;
+        double Q00 = dx2 * (var_ms + 0.25 * dxw2), Q11 = var_ms + dxw2, Q22 = sw2;
+        // predict: F = [[1, dx, g1f], [0, 1, f1], [0, 0, e1]]
+        double y0 = x0 + dx * x1 + g1f * x2, y1 = x1 + f1 * x2, y2 = e1 * x2;
+        // A = F P
+        double A00 = P00 + dx * P01 + g1f * P02, A01 = P01 + dx * P11 + g1f * P12, A02 = P02 + dx * P12 + g1f * P22;
+        double A10 = P01 + f1 * P02, A11 = P11 + f1 * P12, A12 = P12 + f1 * P22;
+        double A20 = e1 * P02, A21 = e1 * P12, A22 = e1 * P22;
+        (void)A20; (void)A21; (void)A10;
+        double N00 = A00 + dx * A01 + g1f * A02 + Q00, N01 = A01 + f1 * A02 + Q01, N02 = e1 * A02 + Q02;
+        double N11 = A11 + f1 * A12 + Q11, N12 = e1 * A12 + Q12, N22 = e1 * A22 + Q22;
+        // update with H = [1 0 0]
+        double meas = yb, yres = meas - y0;
+        double SI = 1.0 / (N00 + Rxy);
+        double K0 = N00 * SI, K1 = N01 * SI, K2 = N02 * SI;
+        x0 = y0 + K0 * yres; x1 = y1 + K1 * yres; x2 = y2 + K2 * yres;
+        // Joseph form with I-KH = [[1-K0,0,0],[-K1,1,0],[-K2,0,1]]
+        double c0 = 1.0 - K0;
+        double T00 = c0 * N00, T01 = c0 * N01, T02 = c0 * N02;
+        double T10 = N01 - K1 * N00, T11 = N11 - K1 * N01, T12 = N12 - K1 * N02;
+        double T20 = N02 - K2 * N00, T21 = N12 - K2 * N01, T22 = N22 - K2 * N02;
+        P00 = T00 * c0 + K0 * Rxy * K0;
+        P01 = T00 * (-K1) + T01 + K0 * Rxy * K1;
+        P02 = T00 * (-K2) + T02 + K0 * Rxy * K2;
+        P11 = T10 * (-K1) + T11 + K1 * Rxy * K1;
+        P12 = T10 * (-K2) + T12 + K1 * Rxy * K2;
+        P22 = T20 * (-K2) + T22 + K2 * Rxy * K2;
+        (void)T21;
+        double res = meas - x0;                                  // post-fit residual (:292-296)
+        chi_xy += (res / (P00 + Rxy)) * res;
+        // zr filter: F = [[1, dz], [0, 1]], Q scalar -> + var_ms on every entry (:299-316)
+        double h0 = g0 + dz * g1, h1 = g1;
+        double B00 = G00 + dz * G10, B01 = G01 + dz * G11, B10 = G10, B11 = G11;
+        double M00 = B00 + B01 * dz + var_ms, M01 = B01 + var_ms, M10 = B10 + B11 * dz + var_ms, M11 = B11 + var_ms;
+        double gm = co[i + 1][3], gy = gm - h0;
+        double gSI = 1.0 / (M00 + Rzr);
+        double L0 = M00 * gSI, L1 = M10 * gSI;
+        g0 = h0 + L0 * gy; g1 = h1 + L1 * gy;
+        double d0 = 1.0 - L0;
+        double U00 = d0 * M00, U01 = d0 * M01, U10 = M10 - L1 * M00, U11 = M11 - L1 * M01;
+        G00 = U00 * d0 + L0 * Rzr * L0;
+        G01 = U00 * (-L1) + U01 + L0 * Rzr * L1;
+        G10 = U10 * d0 + L1 * Rzr * L0;
+        G11 = U10 * (-L1) + U11 + L1 * Rzr * L1;
+        double gres = gm - g0;
+        chi_zr += (gres / (G00 + Rzr)) * gres;
+    }
+    double dof = (double)(n - 2);
+    pval_xy = gtf_gammq(0.5 * dof, 0.5 * chi_xy);
+    pval_zr = gtf_gammq(0.5 * dof, 0.5 * chi_zr);
+}

@@ -1,0 +1,559 @@
+// gtf_tile.cuh -- the fused per-iteration kernel (and, with shorter programs, every per-stage kernel).
+//
+// One CTA owns a *tile*: a contiguous range of nodes (hits) and therefore a contiguous range of in-slots
+// (incoming edges / mixture components).  Phases:
+//   1. load     thread-per-slot, coalesced loads of the slot SoA into shared memory; per-slot gathers of the
+//               source hit's coordinates / layer (L2-resident: sources live in the same event)
+//   2. OP_E     thread-per-slot: extrapolate the source's merged state along the edge, chi2 gate, Kalman
+//               update (extrapolate_merged_states.py:26-402) -- full-lane fp64 work, results stay in smem
+//   3. node     warp-per-node over the node's slots in smem: dict-order bookkeeping, priors (helper.py:30-63),
+//               side-norm + reweight + prune (helper.py:99-200), pairwise chi2 + greedy KL clustering
+//               (clustering.py:193-307), degree / mixture weights (helper.py:67-94)
+//   4. store    thread-per-slot coalesced write-back of what the program changed
+// The program (list of OP_*) selects which of these run, so gtf_cluster / gtf_reweight / ... are the same
+// kernel with a one- or two-op program and gtf_iterate is the full list in one launch.
+#pragma once
+#include "gtf_dev.cuh"
+
+#define F_EX 1u      // edge exists (both end nodes alive)
+#define F_ACT 2u     // G[src][dst]['activated'] == 1
+#define F_PRES 4u    // entry present in the working dict
+#define F_NEW 8u     // inserted into the dict by this launch
+#define F_FRESH 16u  // state (re)written by this launch
+#define F_RW 32u     // weight rewritten by reweight in this launch
+#define F_ORIG 64u   // activated flag as loaded
+#define F_TMP 128u   // scratch (reweight eligibility)
+
+#define NF_OK 1u     // node alive and its sub-graph still in play
+#define NF_MULTI 2u  // sub-graph has != 1 nodes
+#define NF_DICT 4u   // node has the working dict
+#define NF_HASUTS 8u
+#define NF_CLUSTERED 16u
+
+struct TileSmem {
+    double st[8][GTF_TILE_SLOTS]; // a b c tau p00 p01 p11 p22 of the working dict entry
+    double prior[GTF_TILE_SLOTS], w[GTF_TILE_SLOTS], lik[GTF_TILE_SLOTS], lrn[GTF_TILE_SLOTS];
+    double srcx[GTF_TILE_SLOTS], srcz[GTF_TILE_SLOTS], srcr[GTF_TILE_SLOTS];
+    int32_t src[GTF_TILE_SLOTS], rank[GTF_TILE_SLOTS], layer[GTF_TILE_SLOTS];
+    uint16_t ordl[GTF_TILE_SLOTS], dstl[GTF_TILE_SLOTS];
+    uint8_t flags[GTF_TILE_SLOTS], side[GTF_TILE_SLOTS];
+    uint16_t nbeg[GTF_TILE_NODES + 1];
+    uint8_t nflags[GTF_TILE_NODES];
+    double D[GTF_TILE_THREADS / 32][GTF_MAXD * (GTF_MAXD - 1) / 2 + 1];
+    unsigned int cnt[GTF_NCOUNTERS];
+};
+
+__device__ __forceinline__ GtfState tile_state(const TileSmem &sm, int ls)
+{
+    GtfState s;
+    s.a = sm.st[0][ls]; s.b = sm.st[1][ls]; s.c = sm.st[2][ls]; s.tau = sm.st[3][ls];
+    s.p00 = sm.st[4][ls]; s.p01 = sm.st[5][ls]; s.p11 = sm.st[6][ls]; s.p22 = sm.st[7][ls];
+    return s;
+}
+__device__ __forceinline__ void tile_put_state(TileSmem &sm, int ls, const GtfState &s)
+{
+    sm.st[0][ls] = s.a; sm.st[1][ls] = s.b; sm.st[2][ls] = s.c; sm.st[3][ls] = s.tau;
+    sm.st[4][ls] = s.p00; sm.st[5][ls] = s.p01; sm.st[6][ls] = s.p11; sm.st[7][ls] = s.p22;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_min_i(int v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned warp_or(unsigned v)
+{
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void pair_decode(int p, int &i, int &j)
+{
+    i = 1;
+    while (i * (i + 1) / 2 <= p) i++;
+    j = p - i * (i - 1) / 2;
+}
+
+// dict order: ordl[b0 + k] = local slot of the k-th entry (ascending rank); returns the entry count
+__device__ __forceinline__ int node_build_order(TileSmem &sm, int b0, int b1, int lane)
+{
+    int n = 0;
+    for (int base = b0; base < b1; base += 32) {
+        int ls = base + lane;
+        bool pres = ls < b1 && (sm.flags[ls] & F_PRES);
+        if (pres) {
+            int r = sm.rank[ls], pos = 0;
+            for (int t = b0; t < b1; t++)
+                if ((sm.flags[t] & F_PRES) && sm.rank[t] < r) pos++;
+            sm.ordl[b0 + pos] = (uint16_t)ls;
+        }
+        n += __popc(__ballot_sync(0xffffffffu, pres));
+    }
+    __syncwarp();
+    return n;
+}
+
+// helper.py:30-63 compute_prior_probabilities for one node
+__device__ __forceinline__ void node_prior(TileSmem &sm, int b0, int b1, int lane)
+{
+    const unsigned m = F_PRES | F_EX | F_ACT;
+    for (int base = b0; base < b1; base += 32) {
+        int ls = base + lane;
+        if (ls < b1 && (sm.flags[ls] & m) == m) {
+            int lay = sm.layer[ls], cnt = 0;
+            for (int t = b0; t < b1; t++)
+                if ((sm.flags[t] & m) == m && sm.layer[t] == lay) cnt++;
+            sm.prior[ls] = 1.0 / cnt;
+        }
+    }
+    __syncwarp();
+}
+
+// helper.py:99-200 calculate_side_norm_factor + reweight for one node
+__device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int n, double nodex, double thr, int lane)
+{
+    const unsigned m = F_PRES | F_EX | F_ACT;
+    int nl = 0, nr = 0, normL = 0, normR = 0;
+    for (int base = b0; base < b1; base += 32) {
+        int ls = base + lane;
+        bool el = ls < b1 && (sm.flags[ls] & m) == m;
+        bool left = el && sm.srcx[ls] < nodex, right = el && !left;
+        bool first = el;
+        if (el) {
+            double xs = sm.srcx[ls];
+            for (int t = b0; t < ls; t++)
+                if ((sm.flags[t] & m) == m && (sm.srcx[t] < nodex) == left && sm.srcx[t] == xs) { first = false; break; }
+            sm.flags[ls] |= F_TMP;
+            sm.side[ls] = left ? 1 : 2;
+        } else if (ls < b1)
+            sm.flags[ls] &= ~F_TMP;
+        nl += __popc(__ballot_sync(0xffffffffu, left));
+        nr += __popc(__ballot_sync(0xffffffffu, right));
+        normL += __popc(__ballot_sync(0xffffffffu, left && first));
+        normR += __popc(__ballot_sync(0xffffffffu, right && first));
+    }
+    __syncwarp();
+    if (nl + nr == 0) return;
+    // stale `neighbour_num`: the LAST key of the dict decides whether the norms apply (helper.py:131,138)
+    unsigned lf = sm.flags[sm.ordl[b0 + n - 1]];
+    if (!(lf & F_EX) && lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_KEY);
+    bool last_active = (lf & (F_EX | F_ACT)) == (F_EX | F_ACT);
+    double denom = 0.0; // helper.py:165-169, dict order
+    for (int k = 0; k < n; k++) {
+        int t = sm.ordl[b0 + k];
+        if (sm.flags[t] & F_TMP) denom += sm.w[t] * sm.lik[t];
+    }
+    int off = 0;
+    for (int base = b0; base < b1; base += 32) {
+        int ls = base + lane;
+        if (ls < b1 && (sm.flags[ls] & F_TMP)) {
+            double norm = last_active ? (double)(sm.side[ls] == 1 ? normL : normR) : 1.0;
+            double rw = (sm.w[ls] * sm.lik[ls] * sm.prior[ls]) / denom;
+            rw = rw / norm;
+            sm.lrn[ls] = norm;
+            sm.w[ls] = rw;
+            unsigned f = sm.flags[ls] | F_RW;
+            if (rw < thr) { f &= ~F_ACT; off++; } else f |= F_ACT;
+            sm.flags[ls] = (uint8_t)f;
+        }
+    }
+    if (off) atomicAdd(&sm.cnt[CNT_RWOFF], (unsigned)off);
+    __syncwarp();
+}
+
+// clustering.py:193-307 for one node.  Returns true and the merged state when a cluster was formed.
+__device__ __forceinline__ bool node_cluster(TileSmem &sm, double *Dw, int b0, int n, double nx, double nz, double nr_,
+                                             double chi2_thr, double kl_thr, const GtfGeom &g, int lane,
+                                             GtfState &merged, double &mprior)
+{
+    if (n < 3 || n > GTF_MAXD) return false; // clustering.py:207
+    const unsigned FULL = 0xffffffffu;
+    int npairs = n * (n - 1) / 2;
+    double best = INFINITY;
+    bool nz_any = false, nan_any = false;
+    for (int p = lane; p < npairs; p += 32) {
+        int i, j;
+        pair_decode(p, i, j);
+        int ei = sm.ordl[b0 + i], ej = sm.ordl[b0 + j];
+        double v = gtf_pair_chi2(tile_state(sm, ei), tile_state(sm, ej), nx, nz, nr_, sm.srcx[ei], sm.srcz[ei],
+                                 sm.srcr[ei], sm.srcx[ej], sm.srcz[ej], sm.srcr[ej], g);
+        Dw[p] = v;
+        if (v != 0.0) {          // np.nonzero keeps NaN, drops +-0 (clustering.py:119)
+            nz_any = true;
+            if (v != v) nan_any = true; else best = fmin(best, v);
+        }
+    }
+    __syncwarp();
+    nz_any = __any_sync(FULL, nz_any);
+    nan_any = __any_sync(FULL, nan_any);
+    if (!nz_any) { // np.min([]) -> ValueError
+        if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_EMPTY_MIN);
+        return false;
+    }
+    if (nan_any) return false; // np.min -> nan, `nan < thr` False
+    best = warp_min(best);
+    if (!(best < chi2_thr)) return false; // clustering.py:228
+    // np.where(distances == smallest): all tied positions in row-major order (clustering.py:122-123)
+    int p1 = 1 << 30, nm = 0;
+    unsigned gone = 0;
+    for (int p = lane; p < npairs; p += 32)
+        if (Dw[p] == best) {
+            int i, j;
+            pair_decode(p, i, j);
+            p1 = min(p1, p);
+            nm++;
+            gone |= (1u << i) | (1u << j);
+        }
+    int pfirst = warp_min_i(p1);
+    for (int o = 16; o > 0; o >>= 1) nm += __shfl_xor_sync(FULL, nm, o);
+    gone = warp_or(gone);
+    int idx0, idx1;
+    pair_decode(pfirst, idx0, idx1); // unique minimum: idx = [row, col]
+    if (nm > 1) {                    // ties: idx = [rows..., cols...] -> idx[1] is the SECOND ROW
+        int p2 = 1 << 30;
+        for (int p = lane; p < npairs; p += 32)
+            if (Dw[p] == best && p > pfirst) p2 = min(p2, p);
+        p2 = warp_min_i(p2);
+        int jj;
+        pair_decode(p2, idx1, jj);
+    }
+    int e0 = sm.ordl[b0 + idx0], e1 = sm.ordl[b0 + idx1];
+    gtf_merge(tile_state(sm, e0), tile_state(sm, e1), merged); // clustering.py:231-233
+    mprior = sm.prior[e0] + sm.prior[e1];                      // :234
+    unsigned rem = ((1u << n) - 1u) & ~gone;
+    if (rem == 0) { // np.min([]) at :252
+        if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_EMPTY_MIN);
+        return false;
+    }
+    GtfState mine = merged;
+    if (lane < n) mine = tile_state(sm, sm.ordl[b0 + lane]);
+    for (;;) {
+        bool have = lane < n && ((rem >> lane) & 1u);
+        double kl = have ? gtf_kl(mine, merged) : INFINITY; // clustering.py:107-112
+        if (__any_sync(FULL, have && kl != kl)) {           // list.index(nan) -> ValueError
+            if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_NAN_INDEX);
+            return false;
+        }
+        double bv = warp_min(kl);
+        int bk = warp_min_i((have && kl == bv) ? lane : 64); // list.index: first occurrence
+        if (bk >= 64 || !(bv < kl_thr)) break;               // clustering.py:261
+        int eb = sm.ordl[b0 + bk];
+        GtfState nm_;
+        gtf_merge(tile_state(sm, eb), merged, nm_);          // :263-265 (entry first, merged second)
+        merged = nm_;
+        mprior = sm.prior[eb] + mprior;                      // :266
+        rem &= ~(1u << bk);
+        if (rem == 0) break;                                 // :283
+    }
+    // un-absorbed components: their in-edge is deactivated (clustering.py:297-321)
+    if (lane < n && ((rem >> lane) & 1u)) {
+        int e = sm.ordl[b0 + lane];
+        if (sm.flags[e] & F_EX) {
+            sm.flags[e] &= ~F_ACT;
+            atomicAdd(&sm.cnt[CNT_DEACT], 1u);
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+__global__ void __launch_bounds__(GTF_TILE_THREADS, 2) k_tile(DevBatch B, Prog P, GtfGeom g)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = B.tile_begin[blockIdx.x], n1 = B.tile_begin[blockIdx.x + 1];
+    const int nn = n1 - n0;
+    const int s0 = B.in_off[n0], ns = B.in_off[n1] - s0;
+    const bool uts = P.key == GTF_KEY_UTS;
+    bool has_E = false;
+    for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) has_E |= P.ops[k] == OP_E;
+
+    if (tid < GTF_NCOUNTERS) sm.cnt[tid] = 0;
+    // ---------------------------------------------------------------- node table
+    for (int ln = tid; ln <= nn; ln += GTF_TILE_THREADS) {
+        sm.nbeg[ln] = (uint16_t)(B.in_off[n0 + ln] - s0);
+        if (ln < nn) {
+            int i = n0 + ln, sg = B.sub[i];
+            unsigned f = 0;
+            if (B.alive[i] && B.sub_state[sg] == GTF_SUB_INPLAY) f |= NF_OK;
+            if (B.sub_nalive[sg] != 1) f |= NF_MULTI;
+            bool hu = B.has_uts[i] != 0;
+            if (hu) f |= NF_HASUTS;
+            if (!uts || hu) f |= NF_DICT;
+            sm.nflags[ln] = (uint8_t)f;
+        }
+    }
+    // ---------------------------------------------------------------- load (thread per slot)
+    const uint8_t *present_in = uts ? B.uts_present : B.tse_present;
+    for (int ls = tid; ls < ns; ls += GTF_TILE_THREADS) {
+        int s = s0 + ls;
+        int src = B.in_src[s], dst = B.slot_dst[s];
+        sm.src[ls] = src;
+        sm.dstl[ls] = (uint16_t)(dst - n0);
+        unsigned f = 0;
+        if (src >= 0 && B.alive[src] && B.alive[dst]) f |= F_EX;
+        if (B.active[s] == 1) f |= F_ACT | F_ORIG;
+        if (present_in[s]) f |= F_PRES;
+        double sx = 0, sz = 0, sr = 0;
+        int lay = -1;
+        if (src >= 0) { sx = B.x[src]; sz = B.z[src]; sr = B.r[src]; lay = B.layer[src]; }
+        sm.srcx[ls] = sx; sm.srcz[ls] = sz; sm.srcr[ls] = sr; sm.layer[ls] = lay;
+        sm.side[ls] = 0;
+        if (f & F_PRES) {
+            if (uts) {
+                sm.st[0][ls] = B.uts_a[s]; sm.st[1][ls] = B.uts_b[s]; sm.st[2][ls] = B.uts_c[s]; sm.st[3][ls] = B.uts_tau[s];
+                sm.st[4][ls] = B.uts_p00[s]; sm.st[5][ls] = B.uts_p01[s]; sm.st[6][ls] = B.uts_p11[s]; sm.st[7][ls] = B.uts_p22[s];
+                sm.prior[ls] = B.uts_prior[s]; sm.w[ls] = B.uts_w[s]; sm.lik[ls] = B.uts_lik[s];
+                sm.lrn[ls] = B.uts_lrn[s]; sm.side[ls] = (uint8_t)B.uts_side[s];
+                sm.rank[ls] = B.uts_rank[s];
+            } else {
+                sm.st[0][ls] = B.tse_a[s]; sm.st[1][ls] = B.tse_b[s]; sm.st[2][ls] = B.tse_c[s]; sm.st[3][ls] = B.tse_tau[s];
+                sm.st[4][ls] = B.tse_p00[s]; sm.st[5][ls] = B.tse_p01[s]; sm.st[6][ls] = B.tse_p11[s]; sm.st[7][ls] = B.tse_p22[s];
+                sm.prior[ls] = B.tse_prior[s]; sm.w[ls] = B.tse_w[s];
+                sm.rank[ls] = ls;
+            }
+        } else
+            sm.rank[ls] = uts ? 0x7fffffff : ls;
+        sm.flags[ls] = (uint8_t)f;
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- OP_E (thread per slot)
+    if (has_E) {
+        unsigned sent = 0, gated = 0;
+        for (int ls = tid; ls < ns; ls += GTF_TILE_THREADS) {
+            unsigned f = sm.flags[ls];
+            unsigned nf = sm.nflags[sm.dstl[ls]];
+            if ((f & (F_EX | F_ACT)) != (F_EX | F_ACT) || (nf & (NF_OK | NF_MULTI)) != (NF_OK | NF_MULTI)) continue;
+            int u = sm.src[ls];
+            if (!B.has_merged[u]) continue; // extrapolate_merged_states.py:425
+            int s = s0 + ls, v = n0 + sm.dstl[ls];
+            GtfExtrapOut o;
+            gtf_extrapolate(sm.srcx[ls], B.y[u], sm.srcz[ls], sm.srcr[ls], B.x[v], B.y[v], B.z[v], B.r[v], B.m_a[u],
+                            B.m_b[u], B.m_c[u], B.m_p00[u], B.m_p01[u], B.slot_p11[s], B.m_p22[u], B.slot_vms[s],
+                            P.chi2_cut, g, o);
+            B.uts_chi2[s] = o.chi2;
+            sent++;
+            if (o.pass) {
+                int rs = B.rev_slot[s];
+                double wv = NAN;
+                if (rs >= 0 && B.tse_present[rs]) wv = B.tse_w[rs]; // :384
+                else atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_NO_TSE);
+                tile_put_state(sm, ls, o.s);
+                sm.lik[ls] = o.lik;
+                sm.w[ls] = wv;
+                sm.prior[ls] = NAN; // a fresh dict entry has no prior / lr_layer_norm / side yet
+                sm.lrn[ls] = NAN;
+                sm.side[ls] = 0;
+                f |= F_FRESH;
+                if (!(f & F_PRES)) f |= F_PRES | F_NEW;
+            } else {
+                f &= ~F_ACT; // :393
+                gated++;
+            }
+            sm.flags[ls] = (uint8_t)f;
+        }
+        if (sent) atomicAdd(&sm.cnt[CNT_SENT], sent);
+        if (gated) atomicAdd(&sm.cnt[CNT_GATED], gated);
+        __syncthreads();
+    }
+
+    // ---------------------------------------------------------------- node programs (warp per node)
+    uint8_t *hm_out = (P.wb & WB_MERGED_NX) ? B.has_merged_nx : B.has_merged;
+    double *ma_o = (P.wb & WB_MERGED_NX) ? B.m_a_nx : B.m_a, *mb_o = (P.wb & WB_MERGED_NX) ? B.m_b_nx : B.m_b,
+           *mc_o = (P.wb & WB_MERGED_NX) ? B.m_c_nx : B.m_c, *m00_o = (P.wb & WB_MERGED_NX) ? B.m_p00_nx : B.m_p00,
+           *m01_o = (P.wb & WB_MERGED_NX) ? B.m_p01_nx : B.m_p01, *m11_o = (P.wb & WB_MERGED_NX) ? B.m_p11_nx : B.m_p11,
+           *m22_o = (P.wb & WB_MERGED_NX) ? B.m_p22_nx : B.m_p22, *mpr_o = (P.wb & WB_MERGED_NX) ? B.m_prior_nx : B.m_prior;
+    for (int ln = warp; ln < nn; ln += GTF_TILE_THREADS / 32) {
+        const int i = n0 + ln, b0 = sm.nbeg[ln], b1 = sm.nbeg[ln + 1];
+        unsigned nf = sm.nflags[ln];
+        int n = -1; // entry count; -1 = order list stale
+        bool clustered = false;
+        GtfState merged;
+        double mprior = 0.0;
+        for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) {
+            const int op = P.ops[k];
+            if (op == OP_E) {
+                // dict insertion order of the new entries = processing order of their sources = ascending
+                // node index (extrapolate_merged_states.py:419-447)
+                int nnew = 0;
+                for (int base = b0; base < b1; base += 32) {
+                    int ls = base + lane;
+                    nnew += __popc(__ballot_sync(0xffffffffu, ls < b1 && (sm.flags[ls] & F_NEW)));
+                }
+                if (nnew) {
+                    int nxt = B.uts_next[i];
+                    for (int base = b0; base < b1; base += 32) {
+                        int ls = base + lane;
+                        if (ls < b1 && (sm.flags[ls] & F_NEW)) {
+                            int before = 0, me = sm.src[ls];
+                            for (int t = b0; t < b1; t++)
+                                if ((sm.flags[t] & F_NEW) && sm.src[t] < me) before++;
+                            sm.rank[ls] = nxt + before;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) { B.uts_next[i] = nxt + nnew; B.has_uts[i] = 1; }
+                    nf |= NF_DICT | NF_HASUTS;
+                    n = -1;
+                    __syncwarp();
+                }
+            } else if (op == OP_POP) {
+                // remove_state_metadata.py:35-47: entries whose key is no longer a successor are popped
+                // from updated_track_states if the node has it, else from track_state_estimates
+                bool mine = (nf & NF_OK) && (uts ? (nf & NF_HASUTS) != 0 : (nf & NF_HASUTS) == 0);
+                if (mine) {
+                    for (int base = b0; base < b1; base += 32) {
+                        int ls = base + lane;
+                        if (ls < b1 && (sm.flags[ls] & F_PRES)) {
+                            bool succ = (sm.flags[ls] & F_EX) && B.rev_slot[s0 + ls] >= 0;
+                            if (!succ) sm.flags[ls] &= ~F_PRES;
+                        }
+                    }
+                    n = -1;
+                    __syncwarp();
+                }
+            } else if (op == OP_PRIOR) {
+                if ((nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT)) node_prior(sm, b0, b1, lane);
+            } else if (op == OP_RW) {
+                if (uts && (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS)) {
+                    if (n < 0) n = node_build_order(sm, b0, b1, lane);
+                    node_reweight(sm, b0, b1, n, B.x[i], P.rw_thr, lane);
+                }
+            } else if (op == OP_CLUSTER) {
+                if ((nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT)) {
+                    if (n < 0) n = node_build_order(sm, b0, b1, lane);
+                    double thr = P.cl_kl;
+                    if (P.use_lut) { // LUT mode: per-node KL threshold from the emp_var bin
+                        double ev = B.emp_var[i];
+                        int bin = (ev == ev) ? (int)floor(ev / 0.05) : 27;
+                        bin = max(0, min(27, bin));
+                        thr = P.lut[bin];
+                    }
+                    clustered = node_cluster(sm, sm.D[warp], b0, n, B.x[i], B.z[i], B.r[i], P.cl_chi2, thr, g, lane,
+                                             merged, mprior);
+                }
+            } else if (op == OP_DEGREE) {
+                int deg = 0;
+                for (int base = b0; base < b1; base += 32) {
+                    int ls = base + lane;
+                    deg += __popc(__ballot_sync(0xffffffffu, ls < b1 && (sm.flags[ls] & (F_EX | F_ACT)) == (F_EX | F_ACT)));
+                }
+                if ((nf & NF_OK) && lane == 0) B.degree[i] = deg;
+            } else if (op == OP_WEIGHTS) {
+                if ((nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT)) {
+                    if (n < 0) n = node_build_order(sm, b0, b1, lane);
+                    if (n == 0) {
+                        if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_ZERO_DIV);
+                    } else {
+                        double mw = 1.0 / n;
+                        for (int base = b0; base < b1; base += 32) {
+                            int ls = base + lane;
+                            if (ls < b1 && (sm.flags[ls] & F_PRES)) sm.w[ls] = mw;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        // merged state of the node: new cluster result, or (fused) carried forward with the accumulated
+        // multiple-scattering term that the reference leaves on the node attribute (quirk 2)
+        if (lane == 0) {
+            if (clustered) {
+                hm_out[i] = 1;
+                ma_o[i] = merged.a; mb_o[i] = merged.b; mc_o[i] = merged.c;
+                m00_o[i] = merged.p00; m01_o[i] = merged.p01; m11_o[i] = merged.p11; m22_o[i] = merged.p22;
+                mpr_o[i] = mprior;
+                atomicAdd(&sm.cnt[CNT_MERGED], 1u);
+            } else if (P.wb & WB_MERGED_NX) {
+                uint8_t h = B.has_merged[i];
+                hm_out[i] = h;
+                if (h) {
+                    ma_o[i] = B.m_a[i]; mb_o[i] = B.m_b[i]; mc_o[i] = B.m_c[i];
+                    m00_o[i] = B.m_p00[i]; m01_o[i] = B.m_p01[i]; m22_o[i] = B.m_p22[i];
+                    m11_o[i] = has_E ? B.node_p11tot[i] : B.m_p11[i];
+                    mpr_o[i] = B.m_prior[i];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- store (thread per slot)
+    uint8_t *act_out = (P.wb & WB_MERGED_NX) ? B.active_nx : B.active;
+    unsigned n_act = 0, n_chg = 0;
+    for (int ls = tid; ls < ns; ls += GTF_TILE_THREADS) {
+        int s = s0 + ls;
+        unsigned f = sm.flags[ls];
+        bool a = f & F_ACT, a0 = f & F_ORIG;
+        if (f & F_EX) {
+            n_act += a;
+            n_chg += a != a0;
+        }
+        if (P.wb & WB_ACTIVE) {
+            if (P.wb & WB_MERGED_NX) act_out[s] = a ? 1 : (a0 ? 0 : B.active[s]);
+            else if (a != a0) act_out[s] = a ? 1 : 0;
+        }
+        if (uts) {
+            if (P.wb & WB_PRESENT) {
+                if (f & F_NEW) B.uts_present[s] = 1;
+                else if (!(f & F_PRES) && present_in[s]) B.uts_present[s] = 0;
+            }
+            if ((P.wb & WB_STATE) && (f & F_FRESH)) {
+                B.uts_a[s] = sm.st[0][ls]; B.uts_b[s] = sm.st[1][ls]; B.uts_c[s] = sm.st[2][ls]; B.uts_tau[s] = sm.st[3][ls];
+                B.uts_p00[s] = sm.st[4][ls]; B.uts_p01[s] = sm.st[5][ls]; B.uts_p11[s] = sm.st[6][ls]; B.uts_p22[s] = sm.st[7][ls];
+                B.uts_lik[s] = sm.lik[ls];
+                if (f & F_NEW) B.uts_rank[s] = sm.rank[ls];
+            }
+            if (f & F_PRES) {
+                if (P.wb & WB_PRIOR) B.uts_prior[s] = sm.prior[ls];
+                if (P.wb & WB_W) B.uts_w[s] = sm.w[ls];
+                if ((P.wb & WB_UTSX) && (f & (F_RW | F_FRESH))) { B.uts_lrn[s] = sm.lrn[ls]; B.uts_side[s] = (int8_t)sm.side[ls]; }
+                if ((P.wb & WB_EDGEW) && (f & F_RW)) B.edge_w[s] = sm.w[ls];
+            }
+        } else {
+            if ((P.wb & WB_PRESENT) && !(f & F_PRES) && present_in[s]) B.tse_present[s] = 0;
+            if (f & F_PRES) {
+                if (P.wb & WB_PRIOR) B.tse_prior[s] = sm.prior[ls];
+                if (P.wb & WB_W) B.tse_w[s] = sm.w[ls];
+            }
+        }
+    }
+    if (P.wb & WB_COUNT_ACTIVE) {
+        if (n_act) atomicAdd(&sm.cnt[CNT_ACTIVE], n_act);
+        if (n_chg) atomicAdd(&sm.cnt[CNT_CHANGED], n_chg);
+    }
+    __syncthreads();
+    if (tid < GTF_NCOUNTERS && sm.cnt[tid]) {
+        if (tid == CNT_REFERR) atomicOr(&B.counters[tid], (unsigned long long)sm.cnt[tid]);
+        else atomicAdd(&B.counters[tid], (unsigned long long)sm.cnt[tid]);
+    }
+}
+
+// per-source sequential multiple-scattering prefix (extrapolate_merged_states.py:114-128, quirk 2):
+// the k-th ACTIVE successor of u sees merged_cov[1,1] + sum_{j<=k} var_ms_j, summed left to right in
+// adjacency order; the total stays on the node.
+__global__ void k_prefix(DevBatch B, GtfGeom g)
+{
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= B.N) return;
+    double p = B.m_p11[u];
+    int sg = B.sub[u];
+    bool ok = B.alive[u] && B.has_merged[u] && B.sub_state[sg] == GTF_SUB_INPLAY && B.sub_nalive[sg] != 1;
+    if (ok) {
+        double a = B.m_a[u], b = B.m_b[u], ur = B.r[u], uz = B.z[u];
+        for (int o = B.out_off[u]; o < B.out_off[u + 1]; o++) {
+            int s = B.out_slot[o], v = B.slot_dst[s];
+            if (!B.alive[v] || B.active[s] != 1) continue;
+            double vms = gtf_var_ms(a, b, B.x[v], B.r[v] - ur, B.z[v] - uz, uz, g.endcap);
+            p += vms;
+            B.slot_p11[s] = p;
+            B.slot_vms[s] = vms;
+        }
+    }
+    B.node_p11tot[u] = p;
+}

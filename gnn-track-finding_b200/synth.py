@@ -191,3 +191,123 @@ def degree_stats(ev):
     n = len(ev["x"])
     deg = np.bincount(ev["edge_a"], minlength=n) + np.bincount(ev["edge_b"], minlength=n)
     return n, 2 * len(ev["edge_a"]), float(deg.mean()), float(((deg >= 3) & (deg <= 15)).mean())
+
+
+# ------------------------------------------------------------------------------------------------
+# native (networkx-free) construction of the flat layout for synthetic events
+
+
+def event_to_host(ev, event_id=0):
+    """Flat host batch (topology + hit arrays) of one synthetic event, no networkx involved.
+
+    Orders are *defined* here (they are inputs of the algorithm, SURVEY.md §7 "Order as data"):
+      * sub-graphs = weakly connected components, ordered by their smallest hit id; nodes inside a
+        sub-graph in ascending hit id
+      * successor order of u = order in which u's out-edges are first added when the doublet list is
+        walked adding a->b then b->a (helper.py:517-518)
+      * slot (state-dict) order at v = order in which v's in-edges are added by the same walk
+    """
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    n = len(ev["x"])
+    a = ev["edge_a"].astype(np.int64)
+    b = ev["edge_b"].astype(np.int64)
+    m = len(a)
+    # directed edges in insertion order: (a0,b0),(b0,a0),(a1,b1),...
+    src = np.empty(2 * m, np.int64)
+    dst = np.empty(2 * m, np.int64)
+    src[0::2], dst[0::2] = a, b
+    src[1::2], dst[1::2] = b, a
+    # drop duplicate directed edges, keeping the first insertion
+    key = src * n + dst
+    _, first = np.unique(key, return_index=True)
+    keep = np.sort(first)
+    src, dst = src[keep], dst[keep]
+    ncomp, comp = connected_components(coo_matrix((np.ones(len(src), np.int8), (src, dst)), shape=(n, n)),
+                                       directed=True, connection="weak")
+    comp_min = np.full(ncomp, n, np.int64)
+    np.minimum.at(comp_min, comp, np.arange(n))
+    comp_rank = np.argsort(np.argsort(comp_min))          # sub-graph index by smallest member
+    sub_of = comp_rank[comp]
+    order = np.lexsort((np.arange(n), sub_of))            # new position -> old id
+    newpos = np.empty(n, np.int64)
+    newpos[order] = np.arange(n)
+    S = ncomp
+    E = len(src)
+    s_new, d_new = newpos[src], newpos[dst]
+    # in-CSR: group by destination, stable in insertion order
+    o_in = np.argsort(d_new, kind="stable")
+    in_src = s_new[o_in]
+    slot_dst = d_new[o_in]
+    in_off = np.zeros(n + 1, np.int64)
+    np.add.at(in_off, d_new + 1, 1)
+    in_off = np.cumsum(in_off)
+    slot_of_edge = np.empty(E, np.int64)
+    slot_of_edge[o_in] = np.arange(E)
+    # out-CSR: group by source, stable in insertion order
+    o_out = np.argsort(s_new, kind="stable")
+    out_slot = slot_of_edge[o_out]
+    out_off = np.zeros(n + 1, np.int64)
+    np.add.at(out_off, s_new + 1, 1)
+    out_off = np.cumsum(out_off)
+    # reverse slot: slot of (dst -> src)
+    fwd_key = s_new * n + d_new
+    rev_key = d_new * n + s_new
+    sorter = np.argsort(fwd_key)
+    pos = np.searchsorted(fwd_key[sorter], rev_key)
+    pos = np.clip(pos, 0, E - 1) if E else pos
+    found = (fwd_key[sorter][pos] == rev_key) if E else np.zeros(0, bool)
+    rev_edge = np.where(found, sorter[pos], -1)
+    rev_slot = np.full(E, -1, np.int64)
+    rev_slot[slot_of_edge] = np.where(rev_edge >= 0, slot_of_edge[np.maximum(rev_edge, 0)], -1)
+    sub_sorted = sub_of[order]
+    sub_off = np.zeros(S + 1, np.int64)
+    np.add.at(sub_off, sub_sorted + 1, 1)
+    sub_off = np.cumsum(sub_off)
+    return {
+        "x": ev["x"][order], "y": ev["y"][order], "z": ev["z"][order], "r": ev["r"][order],
+        "layer": ev["layer"][order].astype(np.int32), "volume": ev["volume"][order].astype(np.int32),
+        "truth": ev["truth"][order], "orig_id": order.astype(np.int64),
+        "sub": sub_sorted.astype(np.int32), "alive": np.ones(n, np.uint8),
+        "sub_off": sub_off.astype(np.int32), "sub_state": np.zeros(S, np.uint8),
+        "sub_event": np.full(S, event_id, np.int32),
+        "in_off": in_off.astype(np.int32), "in_src": in_src.astype(np.int32), "slot_dst": slot_dst.astype(np.int32),
+        "out_off": out_off.astype(np.int32), "out_slot": out_slot.astype(np.int32),
+        "rev_slot": rev_slot.astype(np.int32),
+    }
+
+
+_NODE_IDX = ("in_src", "slot_dst")
+_SLOT_IDX = ("out_slot", "rev_slot")
+
+
+def concat_host_batches(hbs):
+    """Concatenate per-event host batches into one batch (events stay independent sub-graph sets)."""
+    out = {}
+    n_off = e_off = s_off = 0
+    parts = {}
+    for hb in hbs:
+        N, E, S = len(hb["x"]), len(hb["in_src"]), len(hb["sub_off"]) - 1
+        for k, v in hb.items():
+            if k in ("in_off", "out_off"):
+                v = v[:-1].astype(np.int64) + e_off
+            elif k == "sub_off":
+                v = v[:-1].astype(np.int64) + n_off
+            elif k in _NODE_IDX:
+                v = np.where(v >= 0, v.astype(np.int64) + n_off, -1)
+            elif k in _SLOT_IDX:
+                v = np.where(v >= 0, v.astype(np.int64) + e_off, -1)
+            elif k == "sub":
+                v = v.astype(np.int64) + s_off
+            parts.setdefault(k, []).append(v)
+        n_off, e_off, s_off = n_off + N, e_off + E, s_off + S
+    for k, vs in parts.items():
+        arr = np.concatenate(vs)
+        if k in ("in_off", "out_off"):
+            arr = np.concatenate([arr, [e_off]])
+        elif k == "sub_off":
+            arr = np.concatenate([arr, [n_off]])
+        if k in ("in_off", "out_off", "sub_off", "sub", "in_src", "slot_dst", "out_slot", "rev_slot"):
+            arr = arr.astype(np.int32)
+        out[k] = arr
+    return out

@@ -1,0 +1,139 @@
+/* gtf.h -- C-ABI of libgtf_b200.so: the B200 (sm_100a) message-passing hot path of
+ * nishalad95/GNN-track-finding behind plain C entry points.
+ *
+ * The reference has no FFI; its de-facto boundary is "Python function taking a list of nx.DiGraph (or a
+ * directory of {i}_subgraph.gpickle) and mutating it" (SURVEY.md §8b).  Each entry point below names the
+ * reference function (path relative to /root/reference/src) whose effect on the graph attributes it
+ * reproduces on the flat layout of gtf_fields.h.  INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions: every function returns 0 on success or a negative GTF_E_* code (message via
+ * gtf_last_error()).  `host` pointers are plain host memory (pinned or not); the library copies.  A batch
+ * owns its device buffers and one CUDA stream; calls on one batch are not re-entrant.  There is NO CPU
+ * fallback: without a CUDA device every compute call fails with GTF_E_CUDA.
+ */
+#ifndef GTF_H
+#define GTF_H
+#include <stdint.h>
+#include "gtf_fields.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTF_ABI_VERSION 1
+
+#define GTF_E_CUDA (-1)    /* CUDA runtime error / no device */
+#define GTF_E_ARG (-2)     /* bad argument */
+#define GTF_E_STATE (-3)   /* batch not finalized / topology missing */
+#define GTF_E_DEGREE (-4)  /* a node has more in-slots than one tile holds (GTF_TILE_SLOTS) */
+#define GTF_E_NOMEM (-5)
+
+/* bits of gtf_stats.ref_errors: points where the reference itself would raise */
+#define GTF_REF_EMPTY_MIN 1 /* np.min([])                clustering/clustering.py:116,120  ValueError        */
+#define GTF_REF_NAN_INDEX 2 /* list.index(nan)           clustering/clustering.py:117      ValueError        */
+#define GTF_REF_ZERO_DIV 4  /* 1/len({})                 utilities/helper.py:90            ZeroDivisionError */
+#define GTF_REF_KEY 8       /* G[u][v] on a removed edge utilities/helper.py:131,138       KeyError          */
+#define GTF_REF_NO_TSE 16   /* missing seed entry        extrapolate/extrapolate_merged_states.py:384 KeyError */
+
+typedef struct gtf_batch gtf_batch;
+
+typedef struct {
+    double sigma0xy, sigma0rz, sigma0rz2, endcap_boundary; /* run_gnn_trackml_mod.sh:11-21 */
+} gtf_geom;
+
+typedef struct {
+    int64_t nodes_merged;       /* nodes that got a (new) merged state        clustering.py:291-294 */
+    int64_t edges_deactivated;  /* un-absorbed components switched off        clustering.py:311-321 */
+    int64_t edges_sent;         /* extrapolate_validate calls                 extrapolate...py:433  */
+    int64_t edges_gated;        /* chi2 > cut                                 extrapolate...py:393  */
+    int64_t edges_reweight_off; /* weight < threshold                         helper.py:186-187     */
+    int64_t active_edges;       /* existing edges with activated == 1 after the call */
+    int64_t active_changed;     /* edges whose flag changed in the call (convergence test) */
+    int64_t ref_errors;         /* OR of GTF_REF_* */
+} gtf_stats;
+
+typedef struct {
+    double chi2_cut;            /* extrapolation gate            run_gnn_trackml_mod.sh:28  (2.0)   */
+    double cluster_chi2, cluster_kl; /* cluster on updated states run_gnn_trackml_mod.sh:112 (1000, 100) */
+    double reweight_threshold;  /* helper.py:145 (0.1) */
+    const double *kl_lut;       /* host pointer to 28 kl_max values or NULL (scalar threshold) */
+} gtf_iter_params;
+
+int gtf_abi_version(void);
+const char *gtf_last_error(void);
+int gtf_device_count(void);
+
+/* ---- batch life cycle and data movement ------------------------------------------------------- */
+int gtf_batch_create(int32_t n_nodes, int32_t n_slots, int32_t n_subgraphs, int device, gtf_batch **out);
+int gtf_batch_destroy(gtf_batch *b);
+int gtf_field_count(void);
+const char *gtf_field_name(int field_id);
+int gtf_field_id(const char *name);
+int64_t gtf_field_bytes(const gtf_batch *b, int field_id);
+/* host -> device / device -> host copies of one array of gtf_fields.h (async on the batch stream;
+ * download synchronises before returning) */
+int gtf_batch_upload(gtf_batch *b, int field_id, const void *host);
+int gtf_batch_download(gtf_batch *b, int field_id, void *host);
+int gtf_batch_device_ptr(gtf_batch *b, int field_id, void **dptr);
+/* after the topology arrays (in_off, in_src, slot_dst, out_off, out_slot, rev_slot, sub, sub_off,
+ * sub_state, alive) are uploaded: builds the node tiles and per-sub-graph counters */
+int gtf_batch_finalize(gtf_batch *b);
+int gtf_batch_sync(gtf_batch *b);
+int gtf_batch_stream(gtf_batch *b, void **cuda_stream);
+int64_t gtf_batch_device_bytes(const gtf_batch *b);
+
+/* ---- per-stage entry points (same effect as the reference function named) ---------------------- */
+/* utilities/helper.py:238-452 compute_track_state_estimates (slot order supplies the neighbour order) */
+int gtf_seed(gtf_batch *b, const gtf_geom *g);
+/* utilities/helper.py:24-25 initialize_edge_activation */
+int gtf_initialize_edge_activation(gtf_batch *b);
+/* utilities/helper.py:30-63 compute_prior_probabilities(GraphList, key) */
+int gtf_compute_prior_probabilities(gtf_batch *b, int key);
+/* utilities/helper.py:76-94 compute_mixture_weights(GraphList, key) */
+int gtf_compute_mixture_weights(gtf_batch *b, int key, gtf_stats *st);
+/* utilities/helper.py:67-73 query_node_degree_in_edges for every node -> `degree` */
+int gtf_query_node_degree(gtf_batch *b);
+/* clustering/clustering.py:149-376 cluster(): per-node chi2/KL clustering, simultaneous deactivation,
+ * degree, mixture weights, priors.  kl_lut: host pointer to 28 doubles (LUT mode) or NULL. */
+int gtf_cluster(gtf_batch *b, int key, double chi2_threshold, double kl_threshold, const double *kl_lut,
+                const gtf_geom *g, gtf_stats *st);
+/* extrapolate/extrapolate_merged_states.py:406-447 message_passing() */
+int gtf_message_passing(gtf_batch *b, double chi2_cut, const gtf_geom *g, gtf_stats *st);
+/* utilities/helper.py:143-200 reweight(subGraphs, 'updated_track_states') */
+int gtf_reweight(gtf_batch *b, int key, double threshold, gtf_stats *st);
+/* extrapolate/extrapolate_merged_states.py:552-567 main(): message_passing, (prior, reweight) x2, degree */
+int gtf_extrapolate_stage(gtf_batch *b, double chi2_cut, const gtf_geom *g, gtf_stats *st);
+/* update/remove_state_metadata.py:31-53 */
+int gtf_remove_state_metadata(gtf_batch *b, gtf_stats *st);
+
+/* ---- fused iteration: [message_passing, prior, reweight, prior, reweight, cluster(updated states)] --- */
+/* One launch pair per iteration (per-source prefix + fused per-node kernel).  Runs `max_iter` iterations or
+ * stops early when an iteration leaves the active-edge bitmap unchanged (SURVEY.md §8d "converged").
+ * stats[i] receives iteration i's counters (may be NULL); *n_done the number of iterations run. */
+int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, int max_iter, int stop_when_converged,
+                gtf_stats *stats, int *n_done);
+/* the same fused iteration, ONE pass, reading the current state and writing the next state into the
+ * batch's shadow buffers WITHOUT committing it (idempotent: benchmark / profiling entry point) */
+int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st);
+
+/* ---- candidate extraction ------------------------------------------------------------------- */
+/* extract/extract_track_candidates.py:332-346 CCA: weakly connected components over active edges ->
+ * `label` (smallest node index of the component; -1 for removed nodes) */
+int gtf_components(gtf_batch *b);
+/* extract/extract_track_candidates.py:402-467: components -> one-hit-per-layer / close-pair merge /
+ * KF fit p-value gate -> accepted nodes removed, sub-graph states updated.
+ * accepted (u8[N]), pval_xy / pval_zr (f64[N], at the component's root index) are optional host outputs. */
+int gtf_extract(gtf_batch *b, const gtf_geom *g, double pval_cut, int numhits, double sep3d, double merge_dist,
+                int32_t *n_accepted, uint8_t *accepted, double *pval_xy, double *pval_zr);
+/* tag_propagation/tag_propagation.py:64-164: Jacobi max-label propagation from lower-radius successors until
+ * the fraction of flipped tags <= threshold.  tags: host i32[N], in = initial tag, out = final tag. */
+int gtf_tag_propagate(gtf_batch *b, double threshold, int32_t *tags, int max_sweeps, int *n_sweeps);
+/* rows (event_id, candidate_id = root node index, node index) of every node accepted so far; device-side
+ * compaction, table copied to host.  Returns the row count in *n_rows (may exceed cap; only cap rows written). */
+int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_rows, int64_t *n_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

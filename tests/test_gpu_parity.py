@@ -1,0 +1,207 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI
+(libgtf_b200.so via gtf_b200.EventBatch).
+
+Gates (BASELINE.json north_star): activation bitmap, dict membership / order, merged-state existence,
+candidate node sets: bit-exact.  States / covariances / weights / likelihoods / p-values: 1e-9 relative
+per stage on identical inputs (chained runs accumulate through ill-conditioned 2x2 inverses: 1e-7)."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import oracle_lib as ol
+import gtf_b200
+from gtf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ALL = ("alive", "active", "merged", "tse", "uts", "degree", "edge_w")
+FIX = ["barrel25_deg6", "barrel40_eta1"]
+
+
+def gpu_batch(hb):
+    return gtf_b200.EventBatch(hb)
+
+
+def blank_seed(hb):
+    hb = dict(hb)
+    for f in list(hb):
+        if f.startswith("tse_") and f != "tse_present":
+            hb[f] = np.full_like(hb[f], np.nan)
+    hb["tse_present"] = np.zeros_like(hb["tse_present"])
+    hb["active"] = np.zeros_like(hb["active"])
+    return hb
+
+
+def state_of(b):
+    hb = b.download()
+    return hb
+
+
+@pytest.mark.parametrize("name", FIX)
+def test_seed_vs_reference(name):
+    fx = gu.load(name)
+    b = gpu_batch(blank_seed(gu.stage_batch(fx, "seed")))
+    b.seed()
+    assert gu.compare_states(state_of(b), gu.stage_batch(fx, "seed"), ("active", "tse", "degree")) == []
+
+
+STEPS = [
+    ("seed", "c1", lambda b: b.cluster(0, 1.0, 2.0), ALL),
+    ("x1", "e2", lambda b: b.extrapolate_stage(2.0), ALL),
+    ("x2", "m2", lambda b: b.remove_state_metadata(), ALL),
+    ("m2", "c3", lambda b: b.cluster(1, 1000.0, 100.0), ALL),
+]
+
+
+@pytest.mark.parametrize("name", FIX)
+@pytest.mark.parametrize("step", range(len(STEPS)))
+def test_stage_vs_reference(name, step):
+    """one reference stage on the reference's own previous state"""
+    prev, stage, fn, what = STEPS[step]
+    fx = gu.load(name)
+    b = gpu_batch(gu.stage_batch(fx, prev))
+    fn(b)
+    assert gu.compare_states(state_of(b), gu.stage_batch(fx, stage), what) == []
+
+
+@pytest.mark.parametrize("name", FIX)
+def test_message_passing_then_reweight_separately(name):
+    """the un-fused entry points compose to the same result as extrapolate_stage"""
+    fx = gu.load(name)
+    b = gpu_batch(gu.stage_batch(fx, "x1"))
+    b.message_passing(2.0)
+    for _ in range(2):
+        b.compute_prior_probabilities("updated_track_states")
+        b.reweight("updated_track_states")
+    b.query_node_degree_in_edges()
+    assert gu.compare_states(state_of(b), gu.stage_batch(fx, "e2"), ALL) == []
+
+
+@pytest.mark.parametrize("name", FIX)
+@pytest.mark.parametrize("prev,stage", [("c1", "x1"), ("e2", "x2"), ("c3", "x3")])
+def test_extract_vs_reference(name, prev, stage):
+    fx = gu.load(name)
+    b = gpu_batch(gu.stage_batch(fx, prev))
+    n, acc, pxy, pzr = b.extract()
+    assert np.array_equal(acc, fx[stage + "/accepted"])
+    assert gu.compare_states(state_of(b), gu.stage_batch(fx, stage), ("alive",)) == []
+    lab = fx[stage + "/cand_label"]
+    roots = sorted(set(lab[lab >= 0].tolist()))
+    assert n == len(roots)
+    want = fx[stage + "/pvals"]
+    if len(roots):
+        got = np.array([[pxy[r], pzr[r]] for r in roots])
+        assert gu.rel_err(np.sort(got[:, 0]), np.sort(want[:, 0])) <= 1e-8
+        assert gu.rel_err(np.sort(got[:, 1]), np.sort(want[:, 1])) <= 1e-8
+
+
+@pytest.mark.parametrize("name", FIX + ["barrel100_cfg1"])
+def test_full_schedule_vs_reference(name):
+    """run_gnn_trackml_mod.sh schedule end to end on the GPU: decisions bit-exact at every stage"""
+    fx = gu.load(name)
+    b = gpu_batch(blank_seed(gu.stage_batch(fx, "seed")))
+    W = ("alive", "active", "merged", "degree")
+    b.seed()
+
+    def chk(stage, rtol=1e-7):
+        assert gu.compare_states(state_of(b), gu.stage_batch(fx, stage), W, rtol=rtol) == [], stage
+
+    chk("seed")
+    b.cluster("track_state_estimates", 1.0, 2.0)
+    chk("c1")
+    n, acc, _, _ = b.extract()
+    assert np.array_equal(acc, fx["x1/accepted"])
+    chk("x1")
+    b.extrapolate_stage(2.0)
+    chk("e2")
+    n, acc, _, _ = b.extract()
+    assert np.array_equal(acc, fx["x2/accepted"])
+    chk("x2")
+    b.remove_state_metadata()
+    chk("m2")
+    b.cluster("updated_track_states", 1000.0, 100.0)
+    chk("c3")
+    n, acc, _, _ = b.extract()
+    assert np.array_equal(acc, fx["x3/accepted"])
+    chk("x3")
+    rows = b.candidates()
+    total = (fx["x1/accepted"] | fx["x2/accepted"] | fx["x3/accepted"]).sum()
+    assert len(rows) == total
+
+
+def synth_batch(n_events, n_tracks, seed0, **kw):
+    hbs = [synth.event_to_host(synth.barrel_event(n_tracks, seed=seed0 + i, **kw), i) for i in range(n_events)]
+    hb = synth.concat_host_batches(hbs)
+    hb.pop("truth")
+    hb.pop("orig_id")
+    return hb
+
+
+@pytest.mark.parametrize("n_events,n_tracks,eta", [(3, 200, 0.5), (1, 1000, 1.0)])
+def test_fused_iterate_vs_oracle(n_events, n_tracks, eta):
+    """seed -> cluster -> 3 fused iterations on synthetic events (cfg2 shape) vs the oracle chain
+    [message_passing, (prior, reweight) x2, cluster(updated states)]"""
+    hb = synth_batch(n_events, n_tracks, 2000, eta_max=eta)
+    ob = ol.OracleBatch(hb)
+    ob.seed()
+    ob.cluster(0, 1.0, 2.0)
+    b = gpu_batch(hb)
+    b.seed()
+    b.cluster(0, 1.0, 2.0)
+    assert gu.compare_states(state_of(b), ob.hb, ALL) == []
+    for it in range(3):
+        ob.extrapolate_stage(2.0)
+        ob.cluster(1, 1000.0, 100.0)
+        st = b.iterate(max_iter=1, stop_when_converged=False)
+        bad = gu.compare_states(state_of(b), ob.hb, ALL, rtol=1e-7)
+        assert bad == [], (it, bad)
+        assert st[0]["active_edges"] == int((ob.hb["active"][gu.edge_exists(ob.hb)] == 1).sum())
+    lab = b.CCA()
+    assert np.array_equal(lab, ob.cca())
+
+
+def test_iterate_dry_is_idempotent_and_matches_commit():
+    hb = synth_batch(2, 300, 2100)
+    b = gpu_batch(hb)
+    b.seed()
+    b.cluster(0, 1.0, 2.0)
+    s1 = b.iterate_dry(want_stats=True)
+    before = state_of(b)
+    s2 = b.iterate_dry(want_stats=True)
+    assert s1 == s2
+    after = state_of(b)
+    for f in ("active", "has_merged", "m_a", "m_p11"):
+        assert np.array_equal(before[f], after[f], equal_nan=True)
+    s3 = b.iterate(max_iter=1, stop_when_converged=False)[0]
+    assert s3 == s1
+
+
+def test_tag_propagation_vs_oracle():
+    hb = synth_batch(2, 200, 2200)
+    ob = ol.OracleBatch(hb)
+    ob.seed()
+    b = gpu_batch(hb)
+    b.seed()
+    tags0 = np.arange(len(hb["x"]), dtype=np.int32)
+    n_o, t_o = ob.tag_propagation(tags0)
+    n_g, t_g = b.tag_propagation(tags0)
+    assert n_o == n_g and np.array_equal(t_o, t_g)
+
+
+def test_converged_loop_and_candidates_vs_oracle():
+    hb = synth_batch(2, 150, 2300)
+    ob = ol.OracleBatch(hb)
+    ob.seed()
+    ob.cluster(0, 1.0, 2.0)
+    b = gpu_batch(hb)
+    b.seed()
+    b.cluster(0, 1.0, 2.0)
+    stats = b.iterate(max_iter=10, stop_when_converged=True)
+    for _ in range(len(stats)):
+        ob.extrapolate_stage(2.0)
+        ob.cluster(1, 1000.0, 100.0)
+    assert gu.compare_states(state_of(b), ob.hb, ("active", "merged", "degree"), rtol=1e-7) == []
+    n_o, acc_o, pxy_o, pzr_o = ob.extract()
+    n_g, acc_g, pxy_g, pzr_g = b.extract()
+    assert n_o == n_g and np.array_equal(acc_o, acc_g)
+    assert gu.rel_err(pxy_g, pxy_o) <= 1e-7 and gu.rel_err(pzr_g, pzr_o) <= 1e-7
