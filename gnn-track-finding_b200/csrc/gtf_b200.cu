@@ -223,7 +223,8 @@ extern "C" int gtf_batch_finalize(gtf_batch *b)
     sync_dev_view(b);
     int r = recount_subs(b);
     if (r) return r;
-    CK(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CK(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     CK(cudaStreamSynchronize(b->stream));
     b->finalized = true;
     return 0;
@@ -266,12 +267,13 @@ static GtfGeom geom_default()
     return o;
 }
 
-static int launch_tile(gtf_batch *b, const Prog &P, const GtfGeom &g)
+static int launch_tile(gtf_batch *b, const Prog &P, const GtfGeom &g, bool fused = false)
 {
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized (call gtf_batch_finalize after uploading the topology)");
     CK(cudaSetDevice(b->device));
     if (b->n_tiles == 0) return 0;
-    k_tile<<<b->n_tiles, GTF_TILE_THREADS, sizeof(TileSmem), b->stream>>>(b->d, P, g);
+    if (fused) k_tile<true><<<b->n_tiles, GTF_TILE_THREADS, sizeof(TileSmem), b->stream>>>(b->d, P, g);
+    else k_tile<false><<<b->n_tiles, GTF_TILE_THREADS, sizeof(TileSmem), b->stream>>>(b->d, P, g);
     CK(cudaGetLastError());
     return 0;
 }
@@ -473,9 +475,41 @@ extern "C" int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf
     CK(cudaSetDevice(b->device));
     TRY(counters_reset(b));
     GtfGeom gg = geom_of(g);
+    if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
     TRY(launch_prefix(b, gg));
-    TRY(launch_tile(b, fused_prog(p), gg));
+    if (b->timing) CK(cudaEventRecord(b->ev[1], b->stream));
+    TRY(launch_tile(b, fused_prog(p), gg, true));
+    if (b->timing) {
+        CK(cudaEventRecord(b->ev[2], b->stream));
+        CK(cudaEventSynchronize(b->ev[2]));
+        float t0 = 0, t1 = 0;
+        CK(cudaEventElapsedTime(&t0, b->ev[0], b->ev[1]));
+        CK(cudaEventElapsedTime(&t1, b->ev[1], b->ev[2]));
+        b->t_prefix_ms += t0; b->t_tile_ms += t1; b->t_count++;
+    }
     if (st) return counters_read(b, st);
+    return 0;
+}
+// per-kernel timing of the fused iteration with CUDA events on the batch stream (bench.py roofline):
+// enable=1 resets the accumulators; gtf_batch_timing returns the averages since then
+extern "C" int gtf_batch_set_timing(gtf_batch *b, int enable)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    CK(cudaSetDevice(b->device));
+    if (enable && !b->ev[0])
+        for (int k = 0; k < 3; k++) CK(cudaEventCreate(&b->ev[k]));
+    b->timing = enable != 0;
+    b->t_prefix_ms = b->t_tile_ms = 0.0;
+    b->t_count = 0;
+    return 0;
+}
+extern "C" int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms, int *count)
+{
+    if (!b) return fail(GTF_E_ARG, "null batch");
+    int n = b->t_count ? b->t_count : 1;
+    if (prefix_ms) *prefix_ms = b->t_prefix_ms / n;
+    if (tile_ms) *tile_ms = b->t_tile_ms / n;
+    if (count) *count = b->t_count;
     return 0;
 }
 extern "C" int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, int max_iter, int stop_when_converged,
@@ -503,6 +537,16 @@ __device__ __forceinline__ int uf_find(int32_t *p, int i)
         if (q == r) break;
         int qq = p[q];
         if (qq != q) p[r] = qq; // path halving: benign race, qq is still an ancestor of r
+        r = q;
+    }
+    return r;
+}
+__device__ __forceinline__ int uf_find_ro(const int32_t *p, int i)
+{
+    int r = i;
+    while (true) {
+        int q = p[r];
+        if (q == r) break;
         r = q;
     }
     return r;
@@ -546,7 +590,8 @@ __global__ void k_cca_final(DevBatch B, const uint8_t *has_inactive, const int32
     int sg = B.sub[i];
     if (B.sub_state[sg] != GTF_SUB_INPLAY) return;
     // extract...py:343-344: with no inactive edge the WHOLE sub-graph is one candidate
-    B.label[i] = has_inactive[sg] ? uf_find(B.label, i) : first[sg];
+    // read-only find: a compressing find here could overwrite another node's FINAL label with a stale ancestor
+    B.label[i] = has_inactive[sg] ? uf_find_ro(B.label, i) : first[sg];
 }
 extern "C" int gtf_components(gtf_batch *b)
 {

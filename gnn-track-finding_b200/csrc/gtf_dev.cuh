@@ -80,4 +80,9 @@ struct gtf_batch {
     double *pv_xy, *pv_zr;     // [N]
     uint8_t *acc_now;          // [N]
     int32_t *tags_a, *tags_b;  // [N]
+    // optional per-kernel timing of the fused iteration
+    bool timing;
+    cudaEvent_t ev[3];
+    double t_prefix_ms, t_tile_ms;
+    int t_count;
 };

@@ -47,3 +47,9 @@ void gtfh_merge(const double *s1, const double *s2, double *out8)
 }
 double gtfh_kl(const double *s1, const double *s2) { return gtf_kl(st(s1), st(s2)); }
 }
+
+extern "C" void gtfh_track_fit(double *co4, int n, double sigma0xy, double sigma0rz, double endcap, double sep3d,
+                               double *pv2)
+{
+    gtf_track_fit((double (*)[4])co4, n, sigma0xy, sigma0rz, endcap, sep3d, pv2[0], pv2[1]);
+}

@@ -41,6 +41,7 @@ struct TileSmem {
     uint8_t nflags[GTF_TILE_NODES];
     double D[GTF_TILE_THREADS / 32][GTF_MAXD * (GTF_MAXD - 1) / 2 + 1];
     unsigned int cnt[GTF_NCOUNTERS];
+    int next_node, elist_n;
 };
 
 __device__ __forceinline__ GtfState tile_state(const TileSmem &sm, int ls)
@@ -113,7 +114,8 @@ __device__ __forceinline__ void node_prior(TileSmem &sm, int b0, int b1, int lan
 }
 
 // helper.py:99-200 calculate_side_norm_factor + reweight for one node
-__device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int n, double nodex, double thr, int lane)
+__device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int n, double nodex, double thr, int lane,
+                                              double *edge_w_tile)
 {
     const unsigned m = F_PRES | F_EX | F_ACT;
     int nl = 0, nr = 0, normL = 0, normR = 0;
@@ -155,6 +157,7 @@ __device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int 
             rw = rw / norm;
             sm.lrn[ls] = norm;
             sm.w[ls] = rw;
+            edge_w_tile[ls] = rw; // helper.py:180 edge attribute (coalesced: consecutive lanes, consecutive slots)
             unsigned f = sm.flags[ls] | F_RW;
             if (rw < thr) { f &= ~F_ACT; off++; } else f |= F_ACT;
             sm.flags[ls] = (uint8_t)f;
@@ -260,6 +263,272 @@ __device__ __forceinline__ bool node_cluster(TileSmem &sm, double *Dw, int b0, i
     return true;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// generic per-node program (any in-degree; state in shared memory).  Only used for nodes with more than 32
+// in-slots -- everything else runs the register-resident fast path below.
+__device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch &B, const Prog &P, const GtfGeom &g, int i,
+                                                  int ln, int s0, int warp, int lane, bool uts, uint8_t *hm_out,
+                                                  double *const *mo)
+{
+    const int b0 = sm.nbeg[ln], b1 = sm.nbeg[ln + 1];
+    unsigned nf = sm.nflags[ln];
+    int n = -1;
+    bool clustered = false;
+    GtfState merged;
+    double mprior = 0.0;
+    for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) {
+        const int op = P.ops[k];
+        if (op == OP_E) {
+            int nnew = 0;
+            for (int base = b0; base < b1; base += 32) {
+                int ls = base + lane;
+                nnew += __popc(__ballot_sync(0xffffffffu, ls < b1 && (sm.flags[ls] & F_NEW)));
+            }
+            if (nnew) {
+                int nxt = B.uts_next[i];
+                for (int base = b0; base < b1; base += 32) {
+                    int ls = base + lane;
+                    if (ls < b1 && (sm.flags[ls] & F_NEW)) {
+                        int before = 0, me = sm.src[ls];
+                        for (int t = b0; t < b1; t++)
+                            if ((sm.flags[t] & F_NEW) && sm.src[t] < me) before++;
+                        sm.rank[ls] = nxt + before;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { B.uts_next[i] = nxt + nnew; B.has_uts[i] = 1; }
+                nf |= NF_DICT | NF_HASUTS;
+                n = -1;
+                __syncwarp();
+            }
+        } else if (op == OP_POP) {
+            bool mine = (nf & NF_OK) && (uts ? (nf & NF_HASUTS) != 0 : (nf & NF_HASUTS) == 0);
+            if (mine) {
+                for (int base = b0; base < b1; base += 32) {
+                    int ls = base + lane;
+                    if (ls < b1 && (sm.flags[ls] & F_PRES)) {
+                        bool succ = (sm.flags[ls] & F_EX) && B.rev_slot[s0 + ls] >= 0;
+                        if (!succ) sm.flags[ls] &= ~F_PRES;
+                    }
+                }
+                n = -1;
+                __syncwarp();
+            }
+        } else if (op == OP_PRIOR) {
+            if ((nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT)) node_prior(sm, b0, b1, lane);
+        } else if (op == OP_RW) {
+            if (uts && (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS)) {
+                if (n < 0) n = node_build_order(sm, b0, b1, lane);
+                node_reweight(sm, b0, b1, n, B.x[i], P.rw_thr, lane, B.edge_w + s0);
+            }
+        } else if (op == OP_CLUSTER) {
+            if ((nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT)) {
+                if (n < 0) n = node_build_order(sm, b0, b1, lane);
+                double thr = P.cl_kl;
+                if (P.use_lut) {
+                    double ev = B.emp_var[i];
+                    int bin = (ev == ev) ? (int)floor(ev / 0.05) : 27;
+                    thr = P.lut[max(0, min(27, bin))];
+                }
+                clustered = node_cluster(sm, sm.D[warp], b0, n, B.x[i], B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior);
+            }
+        } else if (op == OP_DEGREE) {
+            int deg = 0;
+            for (int base = b0; base < b1; base += 32) {
+                int ls = base + lane;
+                deg += __popc(__ballot_sync(0xffffffffu, ls < b1 && (sm.flags[ls] & (F_EX | F_ACT)) == (F_EX | F_ACT)));
+            }
+            if ((nf & NF_OK) && lane == 0) B.degree[i] = deg;
+        } else if (op == OP_WEIGHTS) {
+            if ((nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT)) {
+                if (n < 0) n = node_build_order(sm, b0, b1, lane);
+                if (n == 0) {
+                    if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_ZERO_DIV);
+                } else {
+                    double mw = 1.0 / n;
+                    for (int base = b0; base < b1; base += 32) {
+                        int ls = base + lane;
+                        if (ls < b1 && (sm.flags[ls] & F_PRES)) sm.w[ls] = mw;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    if (clustered && lane == 0) {
+        hm_out[i] = 1;
+        mo[0][i] = merged.a; mo[1][i] = merged.b; mo[2][i] = merged.c; mo[3][i] = merged.p00;
+        mo[4][i] = merged.p01; mo[5][i] = merged.p11; mo[6][i] = merged.p22; mo[7][i] = mprior;
+        sm.nflags[ln] = (uint8_t)(nf | NF_CLUSTERED);
+        atomicAdd(&sm.cnt[CNT_MERGED], 1u);
+    }
+}
+
+// the op list of the fused iteration (gtf_iterate): known at compile time in k_tile<true>
+__device__ __forceinline__ constexpr int fused_op(int k)
+{
+    return k == 0 ? OP_E : k == 1 ? OP_PRIOR : k == 2 ? OP_RW : k == 3 ? OP_PRIOR : k == 4 ? OP_RW
+         : k == 5 ? OP_CLUSTER : k == 6 ? OP_DEGREE : k == 7 ? OP_WEIGHTS : k == 8 ? OP_PRIOR : OP_END;
+}
+
+// register-resident per-node program for nodes with <= 32 in-slots: lane l owns slot b0 + l; counts,
+// same-layer / same-x groupings and dict positions come from ballots, MATCH.ANY and shuffles instead of
+// O(d^2) shared-memory loops.
+template <bool FUSED>
+__device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &B, const Prog &P, const GtfGeom &g, int i,
+                                                  int ln, int s0, int warp, int lane, bool uts, uint8_t *hm_out,
+                                                  double *const *mo)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int b0 = sm.nbeg[ln], d = sm.nbeg[ln + 1] - b0;
+    const int ls = b0 + lane;
+    const bool valid = lane < d;
+    unsigned nf = sm.nflags[ln];
+    unsigned f = valid ? sm.flags[ls] : 0u;
+    int lay = valid ? sm.layer[ls] : (-100 - lane);
+    int src = valid ? sm.src[ls] : 0, rank = valid ? sm.rank[ls] : 0x7fffffff;
+    double sx = valid ? sm.srcx[ls] + 0.0 : 0.0;
+    double w = 0.0, lik = 0.0, prior = 0.0, lrnv = 0.0;
+    int sidev = 0;
+    if (f & F_PRES) { w = sm.w[ls]; lik = sm.lik[ls]; prior = sm.prior[ls]; }
+    const double nodex = B.x[i];
+    const unsigned lt = (1u << lane) - 1u;
+    int n = -1, pos = 0;
+    bool clustered = false;
+    GtfState merged;
+    double mprior = 0.0;
+    double *scratch = sm.D[warp];
+
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const int op = FUSED ? fused_op(k) : P.ops[k];
+        if (op == OP_END) break;
+        bool need_order = (op == OP_RW || op == OP_CLUSTER || op == OP_WEIGHTS);
+        if (op == OP_E) {
+            // dict insertion order of new entries = ascending source node index (extrapolate...py:419-447)
+            unsigned newmask = __ballot_sync(FULL, (f & F_NEW) != 0);
+            if (newmask) {
+                int nxt = B.uts_next[i], before = 0;
+                for (unsigned m = newmask; m; m &= m - 1) {
+                    int sk = __shfl_sync(FULL, src, __ffs(m) - 1);
+                    before += sk < src;
+                }
+                if (f & F_NEW) rank = nxt + before;
+                __syncwarp();
+                if (lane == 0) { B.uts_next[i] = nxt + __popc(newmask); B.has_uts[i] = 1; }
+                nf |= NF_DICT | NF_HASUTS;
+                n = -1;
+            }
+        } else if (op == OP_POP) {
+            bool mine = (nf & NF_OK) && (uts ? (nf & NF_HASUTS) != 0 : (nf & NF_HASUTS) == 0);
+            if (mine) {
+                if (f & F_PRES) {
+                    bool succ = (f & F_EX) && B.rev_slot[s0 + ls] >= 0;
+                    if (!succ) f &= ~F_PRES;
+                }
+                n = -1;
+            }
+        }
+        if (need_order && n < 0) {
+            unsigned pm = __ballot_sync(FULL, (f & F_PRES) != 0);
+            n = __popc(pm);
+            pos = 0;
+            if (!uts) pos = __popc(pm & lt); // seed dict: slot order
+            else
+                for (unsigned m = pm; m; m &= m - 1) {
+                    int rk = __shfl_sync(FULL, rank, __ffs(m) - 1);
+                    pos += rk < rank;
+                }
+        }
+        if (op == OP_PRIOR) {
+            if ((nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT)) {
+                const unsigned m3 = F_PRES | F_EX | F_ACT;
+                bool el = (f & m3) == m3;
+                unsigned elmask = __ballot_sync(FULL, el);
+                unsigned same = __match_any_sync(FULL, lay);
+                if (el) prior = 1.0 / (double)__popc(same & elmask); // helper.py:61
+            }
+        } else if (op == OP_RW) {
+            if (uts && (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS)) {
+                const unsigned m3 = F_PRES | F_EX | F_ACT;
+                bool el = (f & m3) == m3;
+                bool left = el && sx < nodex;
+                unsigned elmask = __ballot_sync(FULL, el), leftmask = __ballot_sync(FULL, left);
+                if (elmask) {
+                    unsigned samex = __match_any_sync(FULL, __double_as_longlong(sx));
+                    unsigned grp = samex & (left ? leftmask : (elmask & ~leftmask));
+                    bool first = el && (__ffs(grp) - 1 == lane);      // distinct x per side: len(set(coords))
+                    int normL = __popc(__ballot_sync(FULL, first && left));
+                    int normR = __popc(__ballot_sync(FULL, first && !left));
+                    // stale `neighbour_num`: the LAST dict key gates the norms (helper.py:131,138)
+                    unsigned lastm = __ballot_sync(FULL, (f & F_PRES) && pos == n - 1);
+                    unsigned lf = __shfl_sync(FULL, f, __ffs(lastm) - 1);
+                    if (!(lf & F_EX) && lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_KEY);
+                    bool last_active = (lf & (F_EX | F_ACT)) == (F_EX | F_ACT);
+                    // denominator in dict order (helper.py:165-169); adding 0.0 for the others is exact
+                    if (f & F_PRES) scratch[pos] = el ? w * lik : 0.0;
+                    __syncwarp();
+                    double denom = 0.0;
+                    for (int q = 0; q < n; q++) denom += scratch[q];
+                    __syncwarp();
+                    if (el) {
+                        double norm = last_active ? (double)(left ? normL : normR) : 1.0;
+                        double rw = (w * lik * prior) / denom;
+                        rw = rw / norm;
+                        lrnv = norm;
+                        sidev = left ? 1 : 2;
+                        w = rw;
+                        B.edge_w[s0 + ls] = rw; // helper.py:180
+                        f |= F_RW;
+                        if (rw < P.rw_thr) f &= ~F_ACT; else f |= F_ACT;
+                    }
+                    int off = __popc(__ballot_sync(FULL, el && !(f & F_ACT)));
+                    if (off && lane == 0) atomicAdd(&sm.cnt[CNT_RWOFF], (unsigned)off);
+                }
+            }
+        } else if (op == OP_CLUSTER) {
+            if ((nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT) && n >= 3 && n <= GTF_MAXD) {
+                if (valid) { sm.flags[ls] = (uint8_t)f; sm.prior[ls] = prior; }
+                if (f & F_PRES) sm.ordl[b0 + pos] = (uint16_t)ls;
+                __syncwarp();
+                double thr = P.cl_kl;
+                if (P.use_lut) {
+                    double ev = B.emp_var[i];
+                    int bin = (ev == ev) ? (int)floor(ev / 0.05) : 27;
+                    thr = P.lut[max(0, min(27, bin))];
+                }
+                clustered = node_cluster(sm, scratch, b0, n, nodex, B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior);
+                if (valid) f = sm.flags[ls];
+            }
+        } else if (op == OP_DEGREE) {
+            int deg = __popc(__ballot_sync(FULL, (f & (F_EX | F_ACT)) == (F_EX | F_ACT)));
+            if ((nf & NF_OK) && lane == 0) B.degree[i] = deg;
+        } else if (op == OP_WEIGHTS) {
+            if ((nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT)) {
+                if (n == 0) {
+                    if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_ZERO_DIV);
+                } else if (f & F_PRES)
+                    w = 1.0 / (double)n;
+            }
+        }
+    }
+    if (valid) {
+        sm.flags[ls] = (uint8_t)f;
+        sm.rank[ls] = rank;
+        if (f & F_PRES) { sm.w[ls] = w; sm.prior[ls] = prior; }
+        if (f & F_RW) { sm.lrn[ls] = lrnv; sm.side[ls] = (uint8_t)sidev; }
+    }
+    if (clustered && lane == 0) {
+        hm_out[i] = 1;
+        mo[0][i] = merged.a; mo[1][i] = merged.b; mo[2][i] = merged.c; mo[3][i] = merged.p00;
+        mo[4][i] = merged.p01; mo[5][i] = merged.p11; mo[6][i] = merged.p22; mo[7][i] = mprior;
+        sm.nflags[ln] = (uint8_t)(nf | NF_CLUSTERED);
+        atomicAdd(&sm.cnt[CNT_MERGED], 1u);
+    }
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(GTF_TILE_THREADS, 2) k_tile(DevBatch B, Prog P, GtfGeom g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -268,11 +537,14 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, 2) k_tile(DevBatch B, Prog P
     const int n0 = B.tile_begin[blockIdx.x], n1 = B.tile_begin[blockIdx.x + 1];
     const int nn = n1 - n0;
     const int s0 = B.in_off[n0], ns = B.in_off[n1] - s0;
-    const bool uts = P.key == GTF_KEY_UTS;
-    bool has_E = false;
-    for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) has_E |= P.ops[k] == OP_E;
+    const bool uts = FUSED ? true : (P.key == GTF_KEY_UTS);
+    const int wb = FUSED ? (WB_ACTIVE | WB_PRESENT | WB_STATE | WB_PRIOR | WB_W | WB_UTSX | WB_MERGED_NX | WB_COUNT_ACTIVE) : P.wb;
+    bool has_E = FUSED;
+    if (!FUSED)
+        for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) has_E |= P.ops[k] == OP_E;
 
     if (tid < GTF_NCOUNTERS) sm.cnt[tid] = 0;
+    if (tid == 0) { sm.next_node = GTF_TILE_THREADS / 32; sm.elist_n = 0; }
     // ---------------------------------------------------------------- node table
     for (int ln = tid; ln <= nn; ln += GTF_TILE_THREADS) {
         sm.nbeg[ln] = (uint16_t)(B.in_off[n0 + ln] - s0);
@@ -322,22 +594,40 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, 2) k_tile(DevBatch B, Prog P
     }
     __syncthreads();
 
-    // ---------------------------------------------------------------- OP_E (thread per slot)
+    // ---------------------------------------------------------------- OP_E
     if (has_E) {
-        unsigned sent = 0, gated = 0;
-        for (int ls = tid; ls < ns; ls += GTF_TILE_THREADS) {
+        // pass 1: which slots carry a message this iteration -> dense list (so pass 2 runs with full warps)
+        for (int base = 0; base < ns; base += GTF_TILE_THREADS) {
+            int ls = base + tid;
+            bool send = false;
+            if (ls < ns) {
+                unsigned f = sm.flags[ls];
+                unsigned nf = sm.nflags[sm.dstl[ls]];
+                send = (f & (F_EX | F_ACT)) == (F_EX | F_ACT) && (nf & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI) &&
+                       B.has_merged[sm.src[ls]] != 0; // extrapolate_merged_states.py:425,431
+            }
+            unsigned m = __ballot_sync(0xffffffffu, send);
+            if (m) {
+                int basepos = 0;
+                if (lane == 0) basepos = atomicAdd(&sm.elist_n, __popc(m));
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                if (send) sm.ordl[basepos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)ls;
+            }
+        }
+        __syncthreads();
+        const int nsend = sm.elist_n;
+        unsigned gated = 0;
+        // pass 2: thread per message: extrapolate, chi2 gate, Kalman update (extrapolate...py:26-402)
+        for (int q = tid; q < nsend; q += GTF_TILE_THREADS) {
+            int ls = sm.ordl[q];
             unsigned f = sm.flags[ls];
-            unsigned nf = sm.nflags[sm.dstl[ls]];
-            if ((f & (F_EX | F_ACT)) != (F_EX | F_ACT) || (nf & (NF_OK | NF_MULTI)) != (NF_OK | NF_MULTI)) continue;
             int u = sm.src[ls];
-            if (!B.has_merged[u]) continue; // extrapolate_merged_states.py:425
             int s = s0 + ls, v = n0 + sm.dstl[ls];
             GtfExtrapOut o;
             gtf_extrapolate(sm.srcx[ls], B.y[u], sm.srcz[ls], sm.srcr[ls], B.x[v], B.y[v], B.z[v], B.r[v], B.m_a[u],
                             B.m_b[u], B.m_c[u], B.m_p00[u], B.m_p01[u], B.slot_p11[s], B.m_p22[u], B.slot_vms[s],
                             P.chi2_cut, g, o);
             B.uts_chi2[s] = o.chi2;
-            sent++;
             if (o.pass) {
                 int rs = B.rev_slot[s];
                 double wv = NAN;
@@ -357,134 +647,44 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, 2) k_tile(DevBatch B, Prog P
             }
             sm.flags[ls] = (uint8_t)f;
         }
-        if (sent) atomicAdd(&sm.cnt[CNT_SENT], sent);
+        if (tid == 0 && nsend) atomicAdd(&sm.cnt[CNT_SENT], (unsigned)nsend);
         if (gated) atomicAdd(&sm.cnt[CNT_GATED], gated);
         __syncthreads();
     }
 
-    // ---------------------------------------------------------------- node programs (warp per node)
-    uint8_t *hm_out = (P.wb & WB_MERGED_NX) ? B.has_merged_nx : B.has_merged;
-    double *ma_o = (P.wb & WB_MERGED_NX) ? B.m_a_nx : B.m_a, *mb_o = (P.wb & WB_MERGED_NX) ? B.m_b_nx : B.m_b,
-           *mc_o = (P.wb & WB_MERGED_NX) ? B.m_c_nx : B.m_c, *m00_o = (P.wb & WB_MERGED_NX) ? B.m_p00_nx : B.m_p00,
-           *m01_o = (P.wb & WB_MERGED_NX) ? B.m_p01_nx : B.m_p01, *m11_o = (P.wb & WB_MERGED_NX) ? B.m_p11_nx : B.m_p11,
-           *m22_o = (P.wb & WB_MERGED_NX) ? B.m_p22_nx : B.m_p22, *mpr_o = (P.wb & WB_MERGED_NX) ? B.m_prior_nx : B.m_prior;
-    for (int ln = warp; ln < nn; ln += GTF_TILE_THREADS / 32) {
-        const int i = n0 + ln, b0 = sm.nbeg[ln], b1 = sm.nbeg[ln + 1];
-        unsigned nf = sm.nflags[ln];
-        int n = -1; // entry count; -1 = order list stale
-        bool clustered = false;
-        GtfState merged;
-        double mprior = 0.0;
-        for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) {
-            const int op = P.ops[k];
-            if (op == OP_E) {
-                // dict insertion order of the new entries = processing order of their sources = ascending
-                // node index (extrapolate_merged_states.py:419-447)
-                int nnew = 0;
-                for (int base = b0; base < b1; base += 32) {
-                    int ls = base + lane;
-                    nnew += __popc(__ballot_sync(0xffffffffu, ls < b1 && (sm.flags[ls] & F_NEW)));
-                }
-                if (nnew) {
-                    int nxt = B.uts_next[i];
-                    for (int base = b0; base < b1; base += 32) {
-                        int ls = base + lane;
-                        if (ls < b1 && (sm.flags[ls] & F_NEW)) {
-                            int before = 0, me = sm.src[ls];
-                            for (int t = b0; t < b1; t++)
-                                if ((sm.flags[t] & F_NEW) && sm.src[t] < me) before++;
-                            sm.rank[ls] = nxt + before;
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) { B.uts_next[i] = nxt + nnew; B.has_uts[i] = 1; }
-                    nf |= NF_DICT | NF_HASUTS;
-                    n = -1;
-                    __syncwarp();
-                }
-            } else if (op == OP_POP) {
-                // remove_state_metadata.py:35-47: entries whose key is no longer a successor are popped
-                // from updated_track_states if the node has it, else from track_state_estimates
-                bool mine = (nf & NF_OK) && (uts ? (nf & NF_HASUTS) != 0 : (nf & NF_HASUTS) == 0);
-                if (mine) {
-                    for (int base = b0; base < b1; base += 32) {
-                        int ls = base + lane;
-                        if (ls < b1 && (sm.flags[ls] & F_PRES)) {
-                            bool succ = (sm.flags[ls] & F_EX) && B.rev_slot[s0 + ls] >= 0;
-                            if (!succ) sm.flags[ls] &= ~F_PRES;
-                        }
-                    }
-                    n = -1;
-                    __syncwarp();
-                }
-            } else if (op == OP_PRIOR) {
-                if ((nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT)) node_prior(sm, b0, b1, lane);
-            } else if (op == OP_RW) {
-                if (uts && (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS)) {
-                    if (n < 0) n = node_build_order(sm, b0, b1, lane);
-                    node_reweight(sm, b0, b1, n, B.x[i], P.rw_thr, lane);
-                }
-            } else if (op == OP_CLUSTER) {
-                if ((nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT)) {
-                    if (n < 0) n = node_build_order(sm, b0, b1, lane);
-                    double thr = P.cl_kl;
-                    if (P.use_lut) { // LUT mode: per-node KL threshold from the emp_var bin
-                        double ev = B.emp_var[i];
-                        int bin = (ev == ev) ? (int)floor(ev / 0.05) : 27;
-                        bin = max(0, min(27, bin));
-                        thr = P.lut[bin];
-                    }
-                    clustered = node_cluster(sm, sm.D[warp], b0, n, B.x[i], B.z[i], B.r[i], P.cl_chi2, thr, g, lane,
-                                             merged, mprior);
-                }
-            } else if (op == OP_DEGREE) {
-                int deg = 0;
-                for (int base = b0; base < b1; base += 32) {
-                    int ls = base + lane;
-                    deg += __popc(__ballot_sync(0xffffffffu, ls < b1 && (sm.flags[ls] & (F_EX | F_ACT)) == (F_EX | F_ACT)));
-                }
-                if ((nf & NF_OK) && lane == 0) B.degree[i] = deg;
-            } else if (op == OP_WEIGHTS) {
-                if ((nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT)) {
-                    if (n < 0) n = node_build_order(sm, b0, b1, lane);
-                    if (n == 0) {
-                        if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_ZERO_DIV);
-                    } else {
-                        double mw = 1.0 / n;
-                        for (int base = b0; base < b1; base += 32) {
-                            int ls = base + lane;
-                            if (ls < b1 && (sm.flags[ls] & F_PRES)) sm.w[ls] = mw;
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-        }
-        // merged state of the node: new cluster result, or (fused) carried forward with the accumulated
-        // multiple-scattering term that the reference leaves on the node attribute (quirk 2)
-        if (lane == 0) {
-            if (clustered) {
-                hm_out[i] = 1;
-                ma_o[i] = merged.a; mb_o[i] = merged.b; mc_o[i] = merged.c;
-                m00_o[i] = merged.p00; m01_o[i] = merged.p01; m11_o[i] = merged.p11; m22_o[i] = merged.p22;
-                mpr_o[i] = mprior;
-                atomicAdd(&sm.cnt[CNT_MERGED], 1u);
-            } else if (P.wb & WB_MERGED_NX) {
-                uint8_t h = B.has_merged[i];
-                hm_out[i] = h;
-                if (h) {
-                    ma_o[i] = B.m_a[i]; mb_o[i] = B.m_b[i]; mc_o[i] = B.m_c[i];
-                    m00_o[i] = B.m_p00[i]; m01_o[i] = B.m_p01[i]; m22_o[i] = B.m_p22[i];
-                    m11_o[i] = has_E ? B.node_p11tot[i] : B.m_p11[i];
-                    mpr_o[i] = B.m_prior[i];
-                }
-            }
-        }
+    // ---------------------------------------------------------------- node programs (warp per node, dynamic)
+    uint8_t *hm_out = (wb & WB_MERGED_NX) ? B.has_merged_nx : B.has_merged;
+    double *const mo[8] = {(wb & WB_MERGED_NX) ? B.m_a_nx : B.m_a,     (wb & WB_MERGED_NX) ? B.m_b_nx : B.m_b,
+                           (wb & WB_MERGED_NX) ? B.m_c_nx : B.m_c,     (wb & WB_MERGED_NX) ? B.m_p00_nx : B.m_p00,
+                           (wb & WB_MERGED_NX) ? B.m_p01_nx : B.m_p01, (wb & WB_MERGED_NX) ? B.m_p11_nx : B.m_p11,
+                           (wb & WB_MERGED_NX) ? B.m_p22_nx : B.m_p22, (wb & WB_MERGED_NX) ? B.m_prior_nx : B.m_prior};
+    for (int ln = warp; ln < nn;) {
+        const int i = n0 + ln;
+        if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+        else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
+        ln = __shfl_sync(0xffffffffu, nxt, 0);
     }
     __syncthreads();
 
-    // ---------------------------------------------------------------- store (thread per slot)
-    uint8_t *act_out = (P.wb & WB_MERGED_NX) ? B.active_nx : B.active;
+    // ---------------------------------------------------------------- store
+    // merged state of nodes without a new cluster result is carried to the next buffers, with the
+    // multiple-scattering term the reference accumulates on the node attribute (quirk 2)
+    if (wb & WB_MERGED_NX) {
+        for (int ln = tid; ln < nn; ln += GTF_TILE_THREADS) {
+            if (sm.nflags[ln] & NF_CLUSTERED) continue;
+            int i = n0 + ln;
+            uint8_t h = B.has_merged[i];
+            hm_out[i] = h;
+            if (h) {
+                mo[0][i] = B.m_a[i]; mo[1][i] = B.m_b[i]; mo[2][i] = B.m_c[i]; mo[3][i] = B.m_p00[i];
+                mo[4][i] = B.m_p01[i]; mo[6][i] = B.m_p22[i]; mo[7][i] = B.m_prior[i];
+                mo[5][i] = has_E ? B.node_p11tot[i] : B.m_p11[i];
+            }
+        }
+    }
+    uint8_t *act_out = (wb & WB_MERGED_NX) ? B.active_nx : B.active;
     unsigned n_act = 0, n_chg = 0;
     for (int ls = tid; ls < ns; ls += GTF_TILE_THREADS) {
         int s = s0 + ls;
@@ -494,36 +694,35 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, 2) k_tile(DevBatch B, Prog P
             n_act += a;
             n_chg += a != a0;
         }
-        if (P.wb & WB_ACTIVE) {
-            if (P.wb & WB_MERGED_NX) act_out[s] = a ? 1 : (a0 ? 0 : B.active[s]);
+        if (wb & WB_ACTIVE) {
+            if (wb & WB_MERGED_NX) act_out[s] = a ? 1 : (a0 ? 0 : B.active[s]);
             else if (a != a0) act_out[s] = a ? 1 : 0;
         }
         if (uts) {
-            if (P.wb & WB_PRESENT) {
+            if (wb & WB_PRESENT) {
                 if (f & F_NEW) B.uts_present[s] = 1;
                 else if (!(f & F_PRES) && present_in[s]) B.uts_present[s] = 0;
             }
-            if ((P.wb & WB_STATE) && (f & F_FRESH)) {
+            if ((wb & WB_STATE) && (f & F_FRESH)) {
                 B.uts_a[s] = sm.st[0][ls]; B.uts_b[s] = sm.st[1][ls]; B.uts_c[s] = sm.st[2][ls]; B.uts_tau[s] = sm.st[3][ls];
                 B.uts_p00[s] = sm.st[4][ls]; B.uts_p01[s] = sm.st[5][ls]; B.uts_p11[s] = sm.st[6][ls]; B.uts_p22[s] = sm.st[7][ls];
                 B.uts_lik[s] = sm.lik[ls];
                 if (f & F_NEW) B.uts_rank[s] = sm.rank[ls];
             }
             if (f & F_PRES) {
-                if (P.wb & WB_PRIOR) B.uts_prior[s] = sm.prior[ls];
-                if (P.wb & WB_W) B.uts_w[s] = sm.w[ls];
-                if ((P.wb & WB_UTSX) && (f & (F_RW | F_FRESH))) { B.uts_lrn[s] = sm.lrn[ls]; B.uts_side[s] = (int8_t)sm.side[ls]; }
-                if ((P.wb & WB_EDGEW) && (f & F_RW)) B.edge_w[s] = sm.w[ls];
+                if (wb & WB_PRIOR) B.uts_prior[s] = sm.prior[ls];
+                if (wb & WB_W) B.uts_w[s] = sm.w[ls];
+                if ((wb & WB_UTSX) && (f & (F_RW | F_FRESH))) { B.uts_lrn[s] = sm.lrn[ls]; B.uts_side[s] = (int8_t)sm.side[ls]; }
             }
         } else {
-            if ((P.wb & WB_PRESENT) && !(f & F_PRES) && present_in[s]) B.tse_present[s] = 0;
+            if ((wb & WB_PRESENT) && !(f & F_PRES) && present_in[s]) B.tse_present[s] = 0;
             if (f & F_PRES) {
-                if (P.wb & WB_PRIOR) B.tse_prior[s] = sm.prior[ls];
-                if (P.wb & WB_W) B.tse_w[s] = sm.w[ls];
+                if (wb & WB_PRIOR) B.tse_prior[s] = sm.prior[ls];
+                if (wb & WB_W) B.tse_w[s] = sm.w[ls];
             }
         }
     }
-    if (P.wb & WB_COUNT_ACTIVE) {
+    if (wb & WB_COUNT_ACTIVE) {
         if (n_act) atomicAdd(&sm.cnt[CNT_ACTIVE], n_act);
         if (n_chg) atomicAdd(&sm.cnt[CNT_CHANGED], n_chg);
     }

@@ -117,6 +117,11 @@ int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, int m
  * batch's shadow buffers WITHOUT committing it (idempotent: benchmark / profiling entry point) */
 int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st);
 
+/* per-kernel timing of the fused iteration (CUDA events recorded on the batch stream around k_prefix and
+ * k_tile): enable != 0 resets the accumulators; gtf_batch_timing returns averages over the calls since */
+int gtf_batch_set_timing(gtf_batch *b, int enable);
+int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms, int *count);
+
 /* ---- candidate extraction ------------------------------------------------------------------- */
 /* extract/extract_track_candidates.py:332-346 CCA: weakly connected components over active edges ->
  * `label` (smallest node index of the component; -1 for removed nodes) */

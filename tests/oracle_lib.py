@@ -78,7 +78,7 @@ class OracleBatch(object):
     """A host batch (dict of numpy arrays, every GTF_FIELDS array present) bound to the oracle."""
 
     def __init__(self, hb, geom=(0.3, 0.4, 0.6, 550.0)):
-        self.hb = F.complete_host_batch(hb)
+        self.hb = {k: np.array(v, copy=True) for k, v in F.complete_host_batch(hb).items()}   # never alias the caller's arrays
         self.N, self.E, self.S = len(self.hb["x"]), len(self.hb["in_src"]), len(self.hb["sub_off"]) - 1
         self.A = Arrays()
         self.A.N, self.A.E, self.A.S = self.N, self.E, self.S
