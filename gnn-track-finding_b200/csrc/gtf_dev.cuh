@@ -58,6 +58,9 @@ struct Prog {
 #define GTF_TILE_NODES 192
 #define GTF_TILE_THREADS 256
 #define GTF_MAXD 15
+#ifndef GTF_TILE_MINB
+#define GTF_TILE_MINB 3
+#endif
 
 struct gtf_batch {
     int N, E, S, device;

@@ -41,7 +41,8 @@ struct TileSmem {
     uint8_t nflags[GTF_TILE_NODES];
     double D[GTF_TILE_THREADS / 32][GTF_MAXD * (GTF_MAXD - 1) / 2 + 1];
     unsigned int cnt[GTF_NCOUNTERS];
-    int next_node, elist_n;
+    int next_node, elist_n, heavy_n;
+    uint8_t heavy[GTF_TILE_NODES];
 };
 
 __device__ __forceinline__ GtfState tile_state(const TileSmem &sm, int ls)
@@ -267,7 +268,7 @@ __device__ __forceinline__ bool node_cluster(TileSmem &sm, double *Dw, int b0, i
 // ------------------------------------------------------------------------------------------------
 // generic per-node program (any in-degree; state in shared memory).  Only used for nodes with more than 32
 // in-slots -- everything else runs the register-resident fast path below.
-__device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch &B, const Prog &P, const GtfGeom &g, int i,
+__device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch B, const Prog P, const GtfGeom g, int i,
                                                   int ln, int s0, int warp, int lane, bool uts, uint8_t *hm_out,
                                                   double *const *mo)
 {
@@ -528,8 +529,145 @@ __device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &
     }
 }
 
+
+// thread-per-node program of the fused iteration for nodes whose dict holds at most two entries (~87 % of
+// the nodes of a cfg2 event): no clustering can happen (clustering.py:207 needs >= 3), priors / side norms /
+// reweighting reduce to closed forms over two entries, so one thread does the whole node and a warp does
+// 32 nodes at once.  Same op order as fused_op(): E-rank, PRIOR, RW, PRIOR, RW, (CLUSTER: skip), DEGREE,
+// WEIGHTS, PRIOR.
+struct LightEntry {
+    int ls;
+    unsigned f;
+    int lay;
+    double sx, w, lik, prior, lrn;
+    int side;
+};
+__device__ __forceinline__ void light_load(const TileSmem &sm, int ls, LightEntry &e)
+{
+    e.ls = ls;
+    e.f = sm.flags[ls];
+    e.lay = sm.layer[ls];
+    e.sx = sm.srcx[ls] + 0.0;
+    e.w = sm.w[ls]; e.lik = sm.lik[ls]; e.prior = sm.prior[ls];
+    e.lrn = 0.0; e.side = 0;
+}
+__device__ __forceinline__ void light_prior(LightEntry &a, LightEntry &b, int n)
+{
+    const unsigned m3 = F_PRES | F_EX | F_ACT;
+    bool ea = (a.f & m3) == m3, eb = n == 2 && (b.f & m3) == m3;
+    bool same = ea && eb && a.lay == b.lay;
+    if (ea) a.prior = same ? 0.5 : 1.0; // helper.py:61: 1/len(group)
+    if (eb) b.prior = same ? 0.5 : 1.0;
+}
+__device__ __forceinline__ void light_reweight(TileSmem &sm, LightEntry &a, LightEntry &b, int n, double nodex, double thr,
+                                               double *edge_w_tile)
+{
+    const unsigned m3 = F_PRES | F_EX | F_ACT;
+    bool ea = (a.f & m3) == m3, eb = n == 2 && (b.f & m3) == m3;
+    if (!ea && !eb) return;
+    bool la = a.sx < nodex, lb = b.sx < nodex;
+    // len(set(x)) per side (helper.py:127,134)
+    double norm_a = 1.0, norm_b = 1.0;
+    if (ea && eb && la == lb && a.sx != b.sx) { norm_a = 2.0; norm_b = 2.0; }
+    // stale `neighbour_num`: the last dict key gates the norms (helper.py:131,138)
+    unsigned lf = n == 2 ? b.f : a.f;
+    if (!(lf & F_EX)) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_KEY);
+    bool last_active = (lf & (F_EX | F_ACT)) == (F_EX | F_ACT);
+    double denom = 0.0; // dict order (helper.py:165-169)
+    if (ea) denom += a.w * a.lik;
+    if (eb) denom += b.w * b.lik;
+    unsigned off = 0;
+    if (ea) {
+        double norm = last_active ? norm_a : 1.0;
+        double rw = (a.w * a.lik * a.prior) / denom;
+        rw = rw / norm;
+        a.lrn = norm; a.side = la ? 1 : 2; a.w = rw;
+        edge_w_tile[a.ls] = rw;
+        a.f |= F_RW;
+        if (rw < thr) { a.f &= ~F_ACT; off++; } else a.f |= F_ACT;
+    }
+    if (eb) {
+        double norm = last_active ? norm_b : 1.0;
+        double rw = (b.w * b.lik * b.prior) / denom;
+        rw = rw / norm;
+        b.lrn = norm; b.side = lb ? 1 : 2; b.w = rw;
+        edge_w_tile[b.ls] = rw;
+        b.f |= F_RW;
+        if (rw < thr) { b.f &= ~F_ACT; off++; } else b.f |= F_ACT;
+    }
+    if (off) atomicAdd(&sm.cnt[CNT_RWOFF], off);
+}
+__device__ __forceinline__ void light_store(TileSmem &sm, const LightEntry &e, int rank)
+{
+    sm.flags[e.ls] = (uint8_t)e.f;
+    sm.rank[e.ls] = rank;
+    sm.w[e.ls] = e.w;
+    sm.prior[e.ls] = e.prior;
+    if (e.f & F_RW) { sm.lrn[e.ls] = e.lrn; sm.side[e.ls] = (uint8_t)e.side; }
+}
+// returns false if the node needs the cooperative (warp) path
+__device__ __forceinline__ bool node_program_light(TileSmem &sm, const DevBatch &B, const Prog &P, int i, int ln, int s0)
+{
+    const int b0 = sm.nbeg[ln], b1 = sm.nbeg[ln + 1];
+    unsigned nf = sm.nflags[ln];
+    int e0 = -1, e1 = -1, n = 0;
+    for (int t = b0; t < b1; t++)
+        if (sm.flags[t] & F_PRES) {
+            if (n == 0) e0 = t; else if (n == 1) e1 = t;
+            n++;
+        }
+    if (n > 2) return false;
+    if (!(nf & NF_OK)) return true; // every op is guarded by NF_OK
+    LightEntry a, b;
+    a.f = 0; b.f = 0; a.ls = b.ls = b0; a.lay = b.lay = -1; a.sx = b.sx = 0; a.w = b.w = a.lik = b.lik = 0;
+    a.prior = b.prior = a.lrn = b.lrn = 0; a.side = b.side = 0;
+    int ra = 0, rb = 0;
+    if (n >= 1) { light_load(sm, e0, a); ra = sm.rank[e0]; }
+    if (n == 2) { light_load(sm, e1, b); rb = sm.rank[e1]; }
+    // OP_E: new entries enter the dict in ascending source order (extrapolate...py:419-447)
+    int nnew = ((a.f & F_NEW) != 0) + ((b.f & F_NEW) != 0);
+    if (nnew) {
+        int nxt = B.uts_next[i];
+        if (nnew == 2) {
+            bool a_first = sm.src[e0] < sm.src[e1];
+            ra = nxt + (a_first ? 0 : 1);
+            rb = nxt + (a_first ? 1 : 0);
+        } else if (a.f & F_NEW) ra = nxt; else rb = nxt;
+        B.uts_next[i] = nxt + nnew;
+        B.has_uts[i] = 1;
+        nf |= NF_DICT | NF_HASUTS;
+    }
+    if (n == 2 && rb < ra) { LightEntry t = a; a = b; b = t; int r = ra; ra = rb; rb = r; } // dict order
+    const bool rdict = (nf & (NF_MULTI | NF_DICT)) == (NF_MULTI | NF_DICT);
+    const bool ruts = (nf & (NF_MULTI | NF_HASUTS)) == (NF_MULTI | NF_HASUTS);
+    const double nodex = B.x[i];
+    if (n) {
+        if (rdict) light_prior(a, b, n);
+        if (ruts) light_reweight(sm, a, b, n, nodex, P.rw_thr, B.edge_w + s0);
+        if (rdict) light_prior(a, b, n);
+        if (ruts) light_reweight(sm, a, b, n, nodex, P.rw_thr, B.edge_w + s0);
+    }
+    // OP_WEIGHTS, final OP_PRIOR
+    if (rdict) {
+        if (n == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_ZERO_DIV);
+        else {
+            double mw = n == 2 ? 0.5 : 1.0;
+            a.w = mw;
+            b.w = mw;
+            light_prior(a, b, n);
+        }
+    }
+    if (n >= 1) light_store(sm, a, ra);
+    if (n == 2) light_store(sm, b, rb);
+    // OP_DEGREE (after all pruning)
+    int deg = 0;
+    for (int t = b0; t < b1; t++) deg += (sm.flags[t] & (F_EX | F_ACT)) == (F_EX | F_ACT);
+    B.degree[i] = deg;
+    return true;
+}
+
 template <bool FUSED>
-__global__ void __launch_bounds__(GTF_TILE_THREADS, 2) k_tile(DevBatch B, Prog P, GtfGeom g)
+__global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBatch B, Prog P, GtfGeom g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
@@ -658,13 +796,31 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, 2) k_tile(DevBatch B, Prog P
                            (wb & WB_MERGED_NX) ? B.m_c_nx : B.m_c,     (wb & WB_MERGED_NX) ? B.m_p00_nx : B.m_p00,
                            (wb & WB_MERGED_NX) ? B.m_p01_nx : B.m_p01, (wb & WB_MERGED_NX) ? B.m_p11_nx : B.m_p11,
                            (wb & WB_MERGED_NX) ? B.m_p22_nx : B.m_p22, (wb & WB_MERGED_NX) ? B.m_prior_nx : B.m_prior};
-    for (int ln = warp; ln < nn;) {
-        const int i = n0 + ln;
-        if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
-        else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
-        int nxt = 0;
-        if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
-        ln = __shfl_sync(0xffffffffu, nxt, 0);
+    if (FUSED) {
+        // light nodes (<= 2 dict entries): one thread each; the rest go to a list for the cooperative path
+        if (tid == 0) sm.heavy_n = 0;
+        __syncthreads();
+        for (int ln = tid; ln < nn; ln += GTF_TILE_THREADS)
+            if (!node_program_light(sm, B, P, n0 + ln, ln, s0)) sm.heavy[atomicAdd(&sm.heavy_n, 1)] = (uint8_t)ln;
+        __syncthreads();
+        const int nh = sm.heavy_n;
+        for (int q = warp; q < nh;) {
+            const int ln = sm.heavy[q], i = n0 + ln;
+            if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+            else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+            int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
+            q = __shfl_sync(0xffffffffu, nxt, 0);
+        }
+    } else {
+        for (int ln = warp; ln < nn;) {
+            const int i = n0 + ln;
+            if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+            else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+            int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
+            ln = __shfl_sync(0xffffffffu, nxt, 0);
+        }
     }
     __syncthreads();
 

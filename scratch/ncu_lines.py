@@ -42,3 +42,19 @@ def srcline(f, n):
 for key, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[4]) if len(sys.argv) > 4 else 40]:
     print("%5.1f%% smp %5.1f%% inst  %s:%d  [%s]  %s" % (100 * v[0] / tot, 100 * v[1] / toti, key[0], key[1],
           ' '.join('%s:%d' % kv for kv in v[2].most_common(3)), srcline(*key)))
+
+if len(sys.argv) > 5:
+    # phase summary: "name:file:lo-hi,..."
+    import collections as C
+    ph = C.OrderedDict()
+    for spec in sys.argv[5].split(','):
+        nm, fl, rng = spec.split(':'); lo, hi = map(int, rng.split('-')); ph[nm] = (fl, lo, hi)
+    res = C.defaultdict(lambda: [0, 0, C.Counter()])
+    for key, v in agg.items():
+        nm = 'other'
+        for k2, (fl, lo, hi) in ph.items():
+            if key[0] == fl and lo <= key[1] <= hi: nm = k2; break
+        res[nm][0] += v[0]; res[nm][1] += v[1]; res[nm][2].update(v[2])
+    print("---- phases")
+    for nm, v in sorted(res.items(), key=lambda kv: -kv[1][0]):
+        print("%-10s %5.1f%% smp %5.1f%% inst  %s" % (nm, 100 * v[0] / tot, 100 * v[1] / toti, ' '.join('%s:%d' % kv for kv in v[2].most_common(5))))
