@@ -54,12 +54,18 @@ struct Prog {
     double lut[28];
 };
 
+#ifndef GTF_TILE_SLOTS
 #define GTF_TILE_SLOTS 384
+#endif
+#ifndef GTF_TILE_NODES
 #define GTF_TILE_NODES 192
-#define GTF_TILE_THREADS 256
+#endif
+#ifndef GTF_TILE_THREADS
+#define GTF_TILE_THREADS 128
+#endif
 #define GTF_MAXD 15
 #ifndef GTF_TILE_MINB
-#define GTF_TILE_MINB 3
+#define GTF_TILE_MINB 4
 #endif
 
 struct gtf_batch {

@@ -53,11 +53,12 @@ def canonicalize(canon, snap, prev, graphs_alive_subs):
     smap = np.array([slot_of[(int(snap["in_key"][s]), int(snap["orig_id"][snap["slot_dst"][s]]))]
                      for s in range(len(snap["in_src"]))], np.int64)
     N, E, S = len(canon["x"]), len(canon["in_src"]), len(canon["sub_off"]) - 1
+    real = snap["alive"] > 0          # ghost rows (stale dict keys of removed nodes) are not graph nodes
     alive = np.zeros(N, np.uint8)
-    alive[nmap] = 1
+    alive[nmap[real]] = 1
     # nodes of sub-graphs that left the list as fragments stay alive (graph dropped, nodes not removed)
     sub_state = np.full(S, 2, np.uint8)
-    subs_present = set(int(canon["sub"][i]) for i in nmap)
+    subs_present = set(int(canon["sub"][i]) for i in nmap[real])
     for g in range(S):
         if g in subs_present:
             sub_state[g] = 0
@@ -75,7 +76,7 @@ def canonicalize(canon, snap, prev, graphs_alive_subs):
             continue
         ext = fields.FIELD_EXTENT[f]
         if ext == "N":
-            out[f][nmap] = snap[f]
+            out[f][nmap[real]] = snap[f][real]
         elif ext == "E":
             if f in ("tse_present", "uts_present"):
                 # entries of live nodes that are no longer in the dict were popped

@@ -1,0 +1,126 @@
+"""CPU: the oracle (oracle/gtf_oracle.c) against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  This is what pins the oracle; the GPU tests then compare against the
+oracle and the same fixtures."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import oracle_lib as ol
+
+ALL = ("alive", "active", "merged", "tse", "uts", "degree", "edge_w")
+FIX = ["barrel25_deg6", "barrel40_eta1"]
+
+
+def blank_seed(hb):
+    hb = dict(hb)
+    for f in list(hb):
+        if f.startswith("tse_") and f != "tse_present":
+            hb[f] = np.full_like(hb[f], np.nan)
+    hb["tse_present"] = np.zeros_like(hb["tse_present"])
+    hb["active"] = np.zeros_like(hb["active"])
+    return hb
+
+
+@pytest.mark.parametrize("name", FIX)
+def test_seed(name):
+    fx = gu.load(name)
+    ob = ol.OracleBatch(blank_seed(gu.stage_batch(fx, "seed")))
+    ob.seed()
+    assert ob.err == 0
+    assert gu.compare_states(ob.hb, gu.stage_batch(fx, "seed"), ("active", "tse", "degree")) == []
+
+
+STEPS = [
+    ("seed", "c1", lambda o: o.cluster(0, 1.0, 2.0)),
+    ("x1", "e2", lambda o: o.extrapolate_stage(2.0)),
+    ("x2", "m2", lambda o: o.remove_state_metadata()),
+    ("m2", "c3", lambda o: o.cluster(1, 1000.0, 100.0)),
+]
+
+
+@pytest.mark.parametrize("name", FIX)
+@pytest.mark.parametrize("step", range(len(STEPS)))
+def test_stage(name, step):
+    prev, stage, fn = STEPS[step]
+    fx = gu.load(name)
+    ob = ol.OracleBatch(gu.stage_batch(fx, prev))
+    fn(ob)
+    assert ob.err == 0
+    assert gu.compare_states(ob.hb, gu.stage_batch(fx, stage), ALL) == []
+
+
+@pytest.mark.parametrize("name", FIX)
+@pytest.mark.parametrize("prev,stage", [("c1", "x1"), ("e2", "x2"), ("c3", "x3")])
+def test_extract(name, prev, stage):
+    fx = gu.load(name)
+    ob = ol.OracleBatch(gu.stage_batch(fx, prev))
+    n, acc, pxy, pzr = ob.extract()
+    assert np.array_equal(acc, fx[stage + "/accepted"])
+    assert gu.compare_states(ob.hb, gu.stage_batch(fx, stage), ("alive",)) == []
+    lab = fx[stage + "/cand_label"]
+    roots = sorted(set(lab[lab >= 0].tolist()))
+    want = fx[stage + "/pvals"]
+    assert n == len(roots) == len(want)
+    if roots:
+        got = np.array([[pxy[r], pzr[r]] for r in roots])
+        assert gu.rel_err(np.sort(got[:, 0]), np.sort(want[:, 0])) <= 1e-8   # p = Q(k/2, chi2/2) amplifies chi2's 1e-10
+        assert gu.rel_err(np.sort(got[:, 1]), np.sort(want[:, 1])) <= 1e-8
+
+
+@pytest.mark.parametrize("name", FIX + ["barrel100_cfg1"])
+def test_full_schedule_chained(name):
+    """run_gnn_trackml_mod.sh:71-148 schedule, chained from the seeds: every decision bit-exact"""
+    fx = gu.load(name)
+    ob = ol.OracleBatch(blank_seed(gu.stage_batch(fx, "seed")))
+    ob.seed()
+    W = ("alive", "active", "merged", "degree")
+
+    def chk(stage):
+        assert gu.compare_states(ob.hb, gu.stage_batch(fx, stage), W, rtol=1e-7) == [], stage
+
+    chk("seed")
+    ob.cluster(0, 1.0, 2.0)
+    chk("c1")
+    assert np.array_equal(ob.extract()[1], fx["x1/accepted"])
+    chk("x1")
+    ob.extrapolate_stage(2.0)
+    chk("e2")
+    assert np.array_equal(ob.extract()[1], fx["x2/accepted"])
+    chk("x2")
+    ob.remove_state_metadata()
+    chk("m2")
+    ob.cluster(1, 1000.0, 100.0)
+    chk("c3")
+    assert np.array_equal(ob.extract()[1], fx["x3/accepted"])
+    chk("x3")
+    assert ob.err == 0
+
+
+def test_chi2_sf_matches_scipy():
+    from scipy.stats import chi2
+    L = ol.lib()
+    rng = np.random.default_rng(1)
+    for k in range(1, 20):
+        for x in np.concatenate([rng.uniform(0, 60, 20), [0.0, 1e-9, 200.0]]):
+            want = chi2.sf(x, k)
+            got = L.gtfo_chi2_sf(float(x), float(k))
+            assert abs(got - want) <= 1e-12 * max(want, 1e-300) + 1e-300 or abs(got - want) / want < 1e-10
+
+
+def test_cca_matches_scipy():
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    fx = gu.load("barrel40_eta1")
+    for stage in ("c1", "e2", "c3"):
+        ob = ol.OracleBatch(gu.stage_batch(fx, stage))
+        lab = ob.cca()
+        h = ob.hb
+        ex = gu.edge_exists(h) & (h["active"] != 0)
+        N = ob.N
+        nc, comp = connected_components(coo_matrix((np.ones(int(ex.sum())), (h["in_src"][ex], h["slot_dst"][ex])), shape=(N, N)),
+                                        directed=True, connection="weak")
+        mn = np.full(nc, N)
+        np.minimum.at(mn, comp, np.arange(N))
+        want = np.where(h["alive"] > 0, mn[comp], -1)
+        inplay = gu.inplay_nodes(h)
+        assert np.array_equal(lab[inplay], want[inplay])
