@@ -53,3 +53,51 @@ extern "C" void gtfh_track_fit(double *co4, int n, double sigma0xy, double sigma
 {
     gtf_track_fit((double (*)[4])co4, n, sigma0xy, sigma0rz, endcap, sep3d, pv2[0], pv2[1]);
 }
+
+// greedy clustering of one node in information form (mirrors node_cluster's loop in gtf_tile.cuh):
+// states8[n][8], prior[n], coords of node and neighbours; returns merged8, merged prior, remaining mask, or -1
+extern "C" int gtfh_cluster_node(const double *states8, const double *prior, int n, const double *node,
+                                 const double *nbc4, double chi2_thr, double kl_thr, const double *geom,
+                                 double *merged8, double *mprior, unsigned *rem_out)
+{
+    GtfGeom g{geom[0], geom[1], geom[2], geom[3]};
+    double best = INFINITY;
+    int bi = -1, bj = -1;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < i; j++) {
+            double v = gtf_pair_chi2(st(states8 + 8 * i), st(states8 + 8 * j), node[0], node[2], node[3], nbc4[4 * i],
+                                     nbc4[4 * i + 2], nbc4[4 * i + 3], nbc4[4 * j], nbc4[4 * j + 2], nbc4[4 * j + 3], g);
+            if (v != 0.0 && v < best) { best = v; bi = i; bj = j; }
+        }
+    if (bi < 0 || !(best < chi2_thr)) return 0;
+    GtfInfo M, t;
+    gtf_to_info(st(states8 + 8 * bi), M);
+    gtf_to_info(st(states8 + 8 * bj), t);
+    gtf_info_add(M, t);
+    GtfState m;
+    gtf_from_info(M, m);
+    double mp = prior[bi] + prior[bj];
+    unsigned rem = ((1u << n) - 1u) & ~((1u << bi) | (1u << bj));
+    while (rem) {
+        double bv = INFINITY;
+        int bk = -1;
+        for (int k = 0; k < n; k++)
+            if ((rem >> k) & 1u) {
+                GtfInfo ei;
+                gtf_to_info(st(states8 + 8 * k), ei);
+                double kl = gtf_kl_info(st(states8 + 8 * k), ei, m, M);
+                if (kl < bv) { bv = kl; bk = k; }
+            }
+        if (bk < 0 || !(bv < kl_thr)) break;
+        gtf_to_info(st(states8 + 8 * bk), t);
+        gtf_info_add(M, t);
+        gtf_from_info(M, m);
+        mp = prior[bk] + mp;
+        rem &= ~(1u << bk);
+    }
+    merged8[0] = m.a; merged8[1] = m.b; merged8[2] = m.c; merged8[3] = m.tau;
+    merged8[4] = m.p00; merged8[5] = m.p01; merged8[6] = m.p11; merged8[7] = m.p22;
+    *mprior = mp;
+    *rem_out = rem;
+    return 1;
+}

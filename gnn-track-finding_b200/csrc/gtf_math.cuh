@@ -388,3 +388,43 @@ GTF_HD void gtf_track_fit(double (*co)[4], int n, double sigma0xy, double sigma0
     pval_xy = gtf_gammq(0.5 * dof, 0.5 * chi_xy);
     pval_zr = gtf_gammq(0.5 * dof, 0.5 * chi_zr);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Information form of a block Gaussian, used by the greedy merge loop of the clustering kernel:
+// S = Sigma^-1 (2x2 block + scalar), v = S mu.  Merging is then a plain sum (clustering.py:97-105 computes
+// Sigma_m = (S1 + S2)^-1, mu_m = Sigma_m (S1 mu1 + S2 mu2)), and KL-to-merged needs no further inverse because
+// inv(Sigma_m) is the running sum itself.  One 2x2 inverse + one reciprocal per round instead of five.
+struct GtfInfo {
+    double s00, s01, s11, sq, v0, v1, vc, vt;
+};
+GTF_HD void gtf_to_info(const GtfState &s, GtfInfo &I)
+{
+    gtf_inv2(s.p00, s.p01, s.p11, I.s00, I.s01, I.s11);
+    I.sq = 1.0 / s.p22;
+    I.v0 = I.s00 * s.a + I.s01 * s.b;
+    I.v1 = I.s01 * s.a + I.s11 * s.b;
+    I.vc = I.sq * s.c;
+    I.vt = I.sq * s.tau;
+}
+GTF_HD void gtf_info_add(GtfInfo &m, const GtfInfo &e)
+{
+    m.s00 += e.s00; m.s01 += e.s01; m.s11 += e.s11; m.sq += e.sq;
+    m.v0 += e.v0; m.v1 += e.v1; m.vc += e.vc; m.vt += e.vt;
+}
+GTF_HD void gtf_from_info(const GtfInfo &I, GtfState &s)
+{
+    gtf_inv2(I.s00, I.s01, I.s11, s.p00, s.p01, s.p11);
+    s.p22 = 1.0 / I.sq;
+    s.a = s.p00 * I.v0 + s.p01 * I.v1;
+    s.b = s.p01 * I.v0 + s.p11 * I.v1;
+    s.c = s.p22 * I.vc;
+    s.tau = s.p22 * I.vt;
+}
+// KLDistance(entry, merged) with both inverses already at hand (element-wise trace, clustering.py:90-94)
+GTF_HD double gtf_kl_info(const GtfState &e, const GtfInfo &ei, const GtfState &m, const GtfInfo &mi)
+{
+    double tr = (e.p00 - m.p00) * (mi.s00 - ei.s00) + (e.p11 - m.p11) * (mi.s11 - ei.s11) + (e.p22 - m.p22) * (mi.sq - ei.sq);
+    double d0 = e.a - m.a, d1 = e.b - m.b, d2 = e.tau - m.tau;
+    return tr + (d0 * d0 * (ei.s00 + mi.s00) + 2.0 * d0 * d1 * (ei.s01 + mi.s01) + d1 * d1 * (ei.s11 + mi.s11) +
+                 d2 * d2 * (ei.sq + mi.sq));
+}

@@ -24,6 +24,8 @@
 #define F_ORIG 64u   // activated flag as loaded
 #define F_TMP 128u   // scratch (reweight eligibility)
 
+#define SD_ORIGPRES 0x80u // (side array) entry was in the dict when the tile was loaded
+
 #define NF_OK 1u     // node alive and its sub-graph still in play
 #define NF_MULTI 2u  // sub-graph has != 1 nodes
 #define NF_DICT 4u   // node has the working dict
@@ -32,8 +34,8 @@
 
 struct TileSmem {
     double st[8][GTF_TILE_SLOTS]; // a b c tau p00 p01 p11 p22 of the working dict entry
-    double prior[GTF_TILE_SLOTS], w[GTF_TILE_SLOTS], lik[GTF_TILE_SLOTS], lrn[GTF_TILE_SLOTS];
-    double srcx[GTF_TILE_SLOTS], srcz[GTF_TILE_SLOTS], srcr[GTF_TILE_SLOTS];
+    double prior[GTF_TILE_SLOTS], w[GTF_TILE_SLOTS], lik[GTF_TILE_SLOTS];
+    double srcx[GTF_TILE_SLOTS];
     int32_t src[GTF_TILE_SLOTS], rank[GTF_TILE_SLOTS], layer[GTF_TILE_SLOTS];
     uint16_t ordl[GTF_TILE_SLOTS], dstl[GTF_TILE_SLOTS];
     uint8_t flags[GTF_TILE_SLOTS], side[GTF_TILE_SLOTS];
@@ -41,8 +43,9 @@ struct TileSmem {
     uint8_t nflags[GTF_TILE_NODES];
     double D[GTF_TILE_THREADS / 32][GTF_MAXD * (GTF_MAXD - 1) / 2 + 1];
     unsigned int cnt[GTF_NCOUNTERS];
-    int next_node, elist_n, heavy_n;
-    uint8_t heavy[GTF_TILE_NODES];
+    int next_node, elist_n, heavy_n, light_n;
+    uint8_t heavy[GTF_TILE_NODES], light[GTF_TILE_NODES];
+    uint16_t ne0[GTF_TILE_NODES], ne1[GTF_TILE_NODES], ndeg[GTF_TILE_NODES]; // light nodes: their (<= 2) entries, active degree
 };
 
 __device__ __forceinline__ GtfState tile_state(const TileSmem &sm, int ls)
@@ -116,7 +119,7 @@ __device__ __forceinline__ void node_prior(TileSmem &sm, int b0, int b1, int lan
 
 // helper.py:99-200 calculate_side_norm_factor + reweight for one node
 __device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int n, double nodex, double thr, int lane,
-                                              double *edge_w_tile)
+                                              double *edge_w_tile, double *lrn_tile)
 {
     const unsigned m = F_PRES | F_EX | F_ACT;
     int nl = 0, nr = 0, normL = 0, normR = 0;
@@ -130,7 +133,7 @@ __device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int 
             for (int t = b0; t < ls; t++)
                 if ((sm.flags[t] & m) == m && (sm.srcx[t] < nodex) == left && sm.srcx[t] == xs) { first = false; break; }
             sm.flags[ls] |= F_TMP;
-            sm.side[ls] = left ? 1 : 2;
+            sm.side[ls] = (uint8_t)((sm.side[ls] & SD_ORIGPRES) | (left ? 1 : 2));
         } else if (ls < b1)
             sm.flags[ls] &= ~F_TMP;
         nl += __popc(__ballot_sync(0xffffffffu, left));
@@ -153,10 +156,10 @@ __device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int 
     for (int base = b0; base < b1; base += 32) {
         int ls = base + lane;
         if (ls < b1 && (sm.flags[ls] & F_TMP)) {
-            double norm = last_active ? (double)(sm.side[ls] == 1 ? normL : normR) : 1.0;
+            double norm = last_active ? (double)((sm.side[ls] & 3) == 1 ? normL : normR) : 1.0;
             double rw = (sm.w[ls] * sm.lik[ls] * sm.prior[ls]) / denom;
             rw = rw / norm;
-            sm.lrn[ls] = norm;
+            lrn_tile[ls] = norm;
             sm.w[ls] = rw;
             edge_w_tile[ls] = rw; // helper.py:180 edge attribute (coalesced: consecutive lanes, consecutive slots)
             unsigned f = sm.flags[ls] | F_RW;
@@ -168,26 +171,60 @@ __device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int 
     __syncwarp();
 }
 
+// order-preserving map double -> uint64 (no NaNs): lets REDUX (32-bit integer warp reductions) do fp64 arg-mins
+__device__ __forceinline__ unsigned long long dbl_key(double v)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_dbl(unsigned long long k)
+{
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+// warp minimum of v over lanes with `have` (three REDUX instead of ten 64-bit shuffle steps); first lane on ties
+__device__ __forceinline__ int warp_argmin(double v, bool have, double &vmin)
+{
+    const unsigned FULL = 0xffffffffu;
+    unsigned long long k = have ? dbl_key(v) : ~0ull;
+    unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    unsigned mh = __reduce_min_sync(FULL, hi);
+    bool c1 = have && hi == mh;
+    unsigned ml = __reduce_min_sync(FULL, c1 ? lo : 0xffffffffu);
+    unsigned m = __ballot_sync(FULL, c1 && lo == ml);
+    vmin = key_dbl(((unsigned long long)mh << 32) | ml);
+    return m ? __ffs(m) - 1 : -1;
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ void shfl_info(const GtfInfo &in, int src, GtfInfo &out)
+{
+    out.s00 = shfl_d(in.s00, src); out.s01 = shfl_d(in.s01, src); out.s11 = shfl_d(in.s11, src); out.sq = shfl_d(in.sq, src);
+    out.v0 = shfl_d(in.v0, src); out.v1 = shfl_d(in.v1, src); out.vc = shfl_d(in.vc, src); out.vt = shfl_d(in.vt, src);
+}
+
 // clustering.py:193-307 for one node.  Returns true and the merged state when a cluster was formed.
+// Lane k < n owns dict entry k.  Pairwise chi2: lane-per-pair into Dw.  Greedy loop in information form
+// (gtf_math.cuh): per round one KL per lane without any inverse, a REDUX arg-min, and one 2x2 inverse.
 __device__ __forceinline__ bool node_cluster(TileSmem &sm, double *Dw, int b0, int n, double nx, double nz, double nr_,
                                              double chi2_thr, double kl_thr, const GtfGeom &g, int lane,
-                                             GtfState &merged, double &mprior)
+                                             GtfState &merged, double &mprior, const double *gz, const double *gr)
 {
     if (n < 3 || n > GTF_MAXD) return false; // clustering.py:207
     const unsigned FULL = 0xffffffffu;
     int npairs = n * (n - 1) / 2;
-    double best = INFINITY;
+    double lbest = INFINITY;
     bool nz_any = false, nan_any = false;
     for (int p = lane; p < npairs; p += 32) {
         int i, j;
         pair_decode(p, i, j);
         int ei = sm.ordl[b0 + i], ej = sm.ordl[b0 + j];
-        double v = gtf_pair_chi2(tile_state(sm, ei), tile_state(sm, ej), nx, nz, nr_, sm.srcx[ei], sm.srcz[ei],
-                                 sm.srcr[ei], sm.srcx[ej], sm.srcz[ej], sm.srcr[ej], g);
+        int ui = sm.src[ei], uj = sm.src[ej];
+        double v = gtf_pair_chi2(tile_state(sm, ei), tile_state(sm, ej), nx, nz, nr_, sm.srcx[ei], gz[ui], gr[ui],
+                                 sm.srcx[ej], gz[uj], gr[uj], g);
         Dw[p] = v;
         if (v != 0.0) {          // np.nonzero keeps NaN, drops +-0 (clustering.py:119)
             nz_any = true;
-            if (v != v) nan_any = true; else best = fmin(best, v);
+            if (v != v) nan_any = true; else lbest = fmin(lbest, v);
         }
     }
     __syncwarp();
@@ -198,7 +235,8 @@ __device__ __forceinline__ bool node_cluster(TileSmem &sm, double *Dw, int b0, i
         return false;
     }
     if (nan_any) return false; // np.min -> nan, `nan < thr` False
-    best = warp_min(best);
+    double best;
+    warp_argmin(lbest, true, best);
     if (!(best < chi2_thr)) return false; // clustering.py:228
     // np.where(distances == smallest): all tied positions in row-major order (clustering.py:122-123)
     int p1 = 1 << 30, nm = 0;
@@ -211,44 +249,52 @@ __device__ __forceinline__ bool node_cluster(TileSmem &sm, double *Dw, int b0, i
             nm++;
             gone |= (1u << i) | (1u << j);
         }
-    int pfirst = warp_min_i(p1);
-    for (int o = 16; o > 0; o >>= 1) nm += __shfl_xor_sync(FULL, nm, o);
-    gone = warp_or(gone);
+    int pfirst = (int)__reduce_min_sync(FULL, (unsigned)p1);
+    nm = (int)__reduce_add_sync(FULL, (unsigned)nm);
+    gone = __reduce_or_sync(FULL, gone);
     int idx0, idx1;
     pair_decode(pfirst, idx0, idx1); // unique minimum: idx = [row, col]
     if (nm > 1) {                    // ties: idx = [rows..., cols...] -> idx[1] is the SECOND ROW
         int p2 = 1 << 30;
         for (int p = lane; p < npairs; p += 32)
             if (Dw[p] == best && p > pfirst) p2 = min(p2, p);
-        p2 = warp_min_i(p2);
+        p2 = (int)__reduce_min_sync(FULL, (unsigned)p2);
         int jj;
         pair_decode(p2, idx1, jj);
     }
-    int e0 = sm.ordl[b0 + idx0], e1 = sm.ordl[b0 + idx1];
-    gtf_merge(tile_state(sm, e0), tile_state(sm, e1), merged); // clustering.py:231-233
-    mprior = sm.prior[e0] + sm.prior[e1];                      // :234
     unsigned rem = ((1u << n) - 1u) & ~gone;
     if (rem == 0) { // np.min([]) at :252
         if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_EMPTY_MIN);
         return false;
     }
-    GtfState mine = merged;
-    if (lane < n) mine = tile_state(sm, sm.ordl[b0 + lane]);
+    GtfState mine;
+    GtfInfo mine_i, M, t;
+    double myprior = 0.0;
+    {
+        int e = sm.ordl[b0 + min(lane, n - 1)];
+        mine = tile_state(sm, e);
+        myprior = sm.prior[e];
+        gtf_to_info(mine, mine_i);
+    }
+    shfl_info(mine_i, idx0, M);                                // clustering.py:231-233: Sigma^-1 = S_i + S_j
+    shfl_info(mine_i, idx1, t);
+    gtf_info_add(M, t);
+    gtf_from_info(M, merged);
+    mprior = shfl_d(myprior, idx0) + shfl_d(myprior, idx1);    // :234
     for (;;) {
         bool have = lane < n && ((rem >> lane) & 1u);
-        double kl = have ? gtf_kl(mine, merged) : INFINITY; // clustering.py:107-112
-        if (__any_sync(FULL, have && kl != kl)) {           // list.index(nan) -> ValueError
+        double kl = have ? gtf_kl_info(mine, mine_i, merged, M) : INFINITY; // clustering.py:107-112
+        if (__any_sync(FULL, have && kl != kl)) {                           // list.index(nan) -> ValueError
             if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_NAN_INDEX);
             return false;
         }
-        double bv = warp_min(kl);
-        int bk = warp_min_i((have && kl == bv) ? lane : 64); // list.index: first occurrence
-        if (bk >= 64 || !(bv < kl_thr)) break;               // clustering.py:261
-        int eb = sm.ordl[b0 + bk];
-        GtfState nm_;
-        gtf_merge(tile_state(sm, eb), merged, nm_);          // :263-265 (entry first, merged second)
-        merged = nm_;
-        mprior = sm.prior[eb] + mprior;                      // :266
+        double bv;
+        int bk = warp_argmin(kl, have, bv);                  // list.index: first occurrence
+        if (bk < 0 || !(bv < kl_thr)) break;                 // clustering.py:261
+        shfl_info(mine_i, bk, t);                            // :263-265 merge_states(entry, merged)
+        gtf_info_add(M, t);
+        gtf_from_info(M, merged);
+        mprior = shfl_d(myprior, bk) + mprior;               // :266
         rem &= ~(1u << bk);
         if (rem == 0) break;                                 // :283
     }
@@ -263,7 +309,6 @@ __device__ __forceinline__ bool node_cluster(TileSmem &sm, double *Dw, int b0, i
     __syncwarp();
     return true;
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // generic per-node program (any in-degree; state in shared memory).  Only used for nodes with more than 32
@@ -321,7 +366,7 @@ __device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch B
         } else if (op == OP_RW) {
             if (uts && (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS)) {
                 if (n < 0) n = node_build_order(sm, b0, b1, lane);
-                node_reweight(sm, b0, b1, n, B.x[i], P.rw_thr, lane, B.edge_w + s0);
+                node_reweight(sm, b0, b1, n, B.x[i], P.rw_thr, lane, B.edge_w + s0, B.uts_lrn + s0);
             }
         } else if (op == OP_CLUSTER) {
             if ((nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT)) {
@@ -332,7 +377,7 @@ __device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch B
                     int bin = (ev == ev) ? (int)floor(ev / 0.05) : 27;
                     thr = P.lut[max(0, min(27, bin))];
                 }
-                clustered = node_cluster(sm, sm.D[warp], b0, n, B.x[i], B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior);
+                clustered = node_cluster(sm, sm.D[warp], b0, n, B.x[i], B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior, B.z, B.r);
             }
         } else if (op == OP_DEGREE) {
             int deg = 0;
@@ -390,7 +435,7 @@ __device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &
     int lay = valid ? sm.layer[ls] : (-100 - lane);
     int src = valid ? sm.src[ls] : 0, rank = valid ? sm.rank[ls] : 0x7fffffff;
     double sx = valid ? sm.srcx[ls] + 0.0 : 0.0;
-    double w = 0.0, lik = 0.0, prior = 0.0, lrnv = 0.0;
+    double w = 0.0, lik = 0.0, prior = 0.0;
     int sidev = 0;
     if (f & F_PRES) { w = sm.w[ls]; lik = sm.lik[ls]; prior = sm.prior[ls]; }
     const double nodex = B.x[i];
@@ -477,7 +522,7 @@ __device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &
                         double norm = last_active ? (double)(left ? normL : normR) : 1.0;
                         double rw = (w * lik * prior) / denom;
                         rw = rw / norm;
-                        lrnv = norm;
+                        B.uts_lrn[s0 + ls] = norm;
                         sidev = left ? 1 : 2;
                         w = rw;
                         B.edge_w[s0 + ls] = rw; // helper.py:180
@@ -499,7 +544,7 @@ __device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &
                     int bin = (ev == ev) ? (int)floor(ev / 0.05) : 27;
                     thr = P.lut[max(0, min(27, bin))];
                 }
-                clustered = node_cluster(sm, scratch, b0, n, nodex, B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior);
+                clustered = node_cluster(sm, scratch, b0, n, nodex, B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior, B.z, B.r);
                 if (valid) f = sm.flags[ls];
             }
         } else if (op == OP_DEGREE) {
@@ -518,7 +563,7 @@ __device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &
         sm.flags[ls] = (uint8_t)f;
         sm.rank[ls] = rank;
         if (f & F_PRES) { sm.w[ls] = w; sm.prior[ls] = prior; }
-        if (f & F_RW) { sm.lrn[ls] = lrnv; sm.side[ls] = (uint8_t)sidev; }
+        if (f & F_RW) sm.side[ls] = (uint8_t)((sm.side[ls] & SD_ORIGPRES) | sidev);
     }
     if (clustered && lane == 0) {
         hm_out[i] = 1;
@@ -539,7 +584,7 @@ struct LightEntry {
     int ls;
     unsigned f;
     int lay;
-    double sx, w, lik, prior, lrn;
+    double sx, w, lik, prior;
     int side;
 };
 __device__ __forceinline__ void light_load(const TileSmem &sm, int ls, LightEntry &e)
@@ -549,7 +594,7 @@ __device__ __forceinline__ void light_load(const TileSmem &sm, int ls, LightEntr
     e.lay = sm.layer[ls];
     e.sx = sm.srcx[ls] + 0.0;
     e.w = sm.w[ls]; e.lik = sm.lik[ls]; e.prior = sm.prior[ls];
-    e.lrn = 0.0; e.side = 0;
+    e.side = 0;
 }
 __device__ __forceinline__ void light_prior(LightEntry &a, LightEntry &b, int n)
 {
@@ -560,7 +605,7 @@ __device__ __forceinline__ void light_prior(LightEntry &a, LightEntry &b, int n)
     if (eb) b.prior = same ? 0.5 : 1.0;
 }
 __device__ __forceinline__ void light_reweight(TileSmem &sm, LightEntry &a, LightEntry &b, int n, double nodex, double thr,
-                                               double *edge_w_tile)
+                                               double *edge_w_tile, double *lrn_tile)
 {
     const unsigned m3 = F_PRES | F_EX | F_ACT;
     bool ea = (a.f & m3) == m3, eb = n == 2 && (b.f & m3) == m3;
@@ -581,7 +626,7 @@ __device__ __forceinline__ void light_reweight(TileSmem &sm, LightEntry &a, Ligh
         double norm = last_active ? norm_a : 1.0;
         double rw = (a.w * a.lik * a.prior) / denom;
         rw = rw / norm;
-        a.lrn = norm; a.side = la ? 1 : 2; a.w = rw;
+        lrn_tile[a.ls] = norm; a.side = la ? 1 : 2; a.w = rw;
         edge_w_tile[a.ls] = rw;
         a.f |= F_RW;
         if (rw < thr) { a.f &= ~F_ACT; off++; } else a.f |= F_ACT;
@@ -590,7 +635,7 @@ __device__ __forceinline__ void light_reweight(TileSmem &sm, LightEntry &a, Ligh
         double norm = last_active ? norm_b : 1.0;
         double rw = (b.w * b.lik * b.prior) / denom;
         rw = rw / norm;
-        b.lrn = norm; b.side = lb ? 1 : 2; b.w = rw;
+        lrn_tile[b.ls] = norm; b.side = lb ? 1 : 2; b.w = rw;
         edge_w_tile[b.ls] = rw;
         b.f |= F_RW;
         if (rw < thr) { b.f &= ~F_ACT; off++; } else b.f |= F_ACT;
@@ -603,24 +648,20 @@ __device__ __forceinline__ void light_store(TileSmem &sm, const LightEntry &e, i
     sm.rank[e.ls] = rank;
     sm.w[e.ls] = e.w;
     sm.prior[e.ls] = e.prior;
-    if (e.f & F_RW) { sm.lrn[e.ls] = e.lrn; sm.side[e.ls] = (uint8_t)e.side; }
+    if (e.f & F_RW) sm.side[e.ls] = (uint8_t)((sm.side[e.ls] & SD_ORIGPRES) | e.side);
 }
-// returns false if the node needs the cooperative (warp) path
-__device__ __forceinline__ bool node_program_light(TileSmem &sm, const DevBatch &B, const Prog &P, int i, int ln, int s0)
+// one light node (classified by the caller: n <= 2 dict entries at local slots e0, e1; deg0 = active in-degree
+// before the reweight passes)
+__device__ __forceinline__ void node_program_light(TileSmem &sm, const DevBatch &B, const Prog &P, int i, int ln, int s0)
 {
-    const int b0 = sm.nbeg[ln], b1 = sm.nbeg[ln + 1];
+    const int b0 = sm.nbeg[ln];
     unsigned nf = sm.nflags[ln];
-    int e0 = -1, e1 = -1, n = 0;
-    for (int t = b0; t < b1; t++)
-        if (sm.flags[t] & F_PRES) {
-            if (n == 0) e0 = t; else if (n == 1) e1 = t;
-            n++;
-        }
-    if (n > 2) return false;
-    if (!(nf & NF_OK)) return true; // every op is guarded by NF_OK
+    const int e0 = sm.ne0[ln], e1 = sm.ne1[ln];
+    const int n = (e0 != 0xffff) + (e1 != 0xffff);
+    if (!(nf & NF_OK)) return; // every op is guarded by NF_OK
     LightEntry a, b;
     a.f = 0; b.f = 0; a.ls = b.ls = b0; a.lay = b.lay = -1; a.sx = b.sx = 0; a.w = b.w = a.lik = b.lik = 0;
-    a.prior = b.prior = a.lrn = b.lrn = 0; a.side = b.side = 0;
+    a.prior = b.prior = 0; a.side = b.side = 0;
     int ra = 0, rb = 0;
     if (n >= 1) { light_load(sm, e0, a); ra = sm.rank[e0]; }
     if (n == 2) { light_load(sm, e1, b); rb = sm.rank[e1]; }
@@ -643,9 +684,9 @@ __device__ __forceinline__ bool node_program_light(TileSmem &sm, const DevBatch 
     const double nodex = B.x[i];
     if (n) {
         if (rdict) light_prior(a, b, n);
-        if (ruts) light_reweight(sm, a, b, n, nodex, P.rw_thr, B.edge_w + s0);
+        if (ruts) light_reweight(sm, a, b, n, nodex, P.rw_thr, B.edge_w + s0, B.uts_lrn + s0);
         if (rdict) light_prior(a, b, n);
-        if (ruts) light_reweight(sm, a, b, n, nodex, P.rw_thr, B.edge_w + s0);
+        if (ruts) light_reweight(sm, a, b, n, nodex, P.rw_thr, B.edge_w + s0, B.uts_lrn + s0);
     }
     // OP_WEIGHTS, final OP_PRIOR
     if (rdict) {
@@ -657,13 +698,18 @@ __device__ __forceinline__ bool node_program_light(TileSmem &sm, const DevBatch 
             light_prior(a, b, n);
         }
     }
-    if (n >= 1) light_store(sm, a, ra);
-    if (n == 2) light_store(sm, b, rb);
-    // OP_DEGREE (after all pruning)
-    int deg = 0;
-    for (int t = b0; t < b1; t++) deg += (sm.flags[t] & (F_EX | F_ACT)) == (F_EX | F_ACT);
-    B.degree[i] = deg;
-    return true;
+    // OP_DEGREE (after all pruning): entries that lost their activation in the reweight passes
+    int lost = 0;
+    if (n >= 1) {
+        lost += (sm.flags[a.ls] & (F_EX | F_ACT)) == (F_EX | F_ACT) && (a.f & (F_EX | F_ACT)) != (F_EX | F_ACT);
+        light_store(sm, a, ra);
+    }
+    if (n == 2) {
+        lost += (sm.flags[b.ls] & (F_EX | F_ACT)) == (F_EX | F_ACT) && (b.f & (F_EX | F_ACT)) != (F_EX | F_ACT);
+        light_store(sm, b, rb);
+    }
+    B.degree[i] = (int)sm.ndeg[ln] - lost;
+    (void)b0;
 }
 
 template <bool FUSED>
@@ -682,7 +728,8 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
         for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) has_E |= P.ops[k] == OP_E;
 
     if (tid < GTF_NCOUNTERS) sm.cnt[tid] = 0;
-    if (tid == 0) { sm.next_node = GTF_TILE_THREADS / 32; sm.elist_n = 0; }
+    if (tid == 0) { sm.next_node = GTF_TILE_THREADS / 32; sm.elist_n = 0; sm.heavy_n = 0; sm.light_n = 0; }
+    __syncthreads();
     // ---------------------------------------------------------------- node table
     for (int ln = tid; ln <= nn; ln += GTF_TILE_THREADS) {
         sm.nbeg[ln] = (uint16_t)(B.in_off[n0 + ln] - s0);
@@ -699,26 +746,49 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
     }
     // ---------------------------------------------------------------- load (thread per slot)
     const uint8_t *present_in = uts ? B.uts_present : B.tse_present;
-    for (int ls = tid; ls < ns; ls += GTF_TILE_THREADS) {
+    // stage 1: the coalesced per-slot arrays of all of this thread's slots (independent loads in flight together)
+    constexpr int NIT = (GTF_TILE_SLOTS + GTF_TILE_THREADS - 1) / GTF_TILE_THREADS;
+    int r_src[NIT], r_dst[NIT];
+    unsigned r_f[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int ls = it * GTF_TILE_THREADS + tid;
+        r_src[it] = -1; r_dst[it] = n0; r_f[it] = 0;
+        if (ls < ns) {
+            const int s = s0 + ls;
+            r_src[it] = B.in_src[s];
+            r_dst[it] = B.slot_dst[s];
+            unsigned f = 0;
+            if (B.active[s] == 1) f |= F_ACT | F_ORIG;
+            if (present_in[s]) f |= F_PRES;
+            r_f[it] = f;
+        }
+    }
+    // stage 2: gathers through the source index, shared-memory staging, message list
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int base = it * GTF_TILE_THREADS;
+        if (base >= ns) break;
+        const int ls = base + tid;
+        bool send = false;
+        if (ls < ns) {
         int s = s0 + ls;
-        int src = B.in_src[s], dst = B.slot_dst[s];
+        int src = r_src[it], dst = r_dst[it];
         sm.src[ls] = src;
         sm.dstl[ls] = (uint16_t)(dst - n0);
-        unsigned f = 0;
+        unsigned f = r_f[it];
         if (src >= 0 && B.alive[src] && B.alive[dst]) f |= F_EX;
-        if (B.active[s] == 1) f |= F_ACT | F_ORIG;
-        if (present_in[s]) f |= F_PRES;
-        double sx = 0, sz = 0, sr = 0;
+        double sx = 0;
         int lay = -1;
-        if (src >= 0) { sx = B.x[src]; sz = B.z[src]; sr = B.r[src]; lay = B.layer[src]; }
-        sm.srcx[ls] = sx; sm.srcz[ls] = sz; sm.srcr[ls] = sr; sm.layer[ls] = lay;
-        sm.side[ls] = 0;
+        if (src >= 0) { sx = B.x[src]; lay = B.layer[src]; }
+        sm.srcx[ls] = sx; sm.layer[ls] = lay;
+        unsigned sd = (f & F_PRES) ? SD_ORIGPRES : 0u;
         if (f & F_PRES) {
             if (uts) {
                 sm.st[0][ls] = B.uts_a[s]; sm.st[1][ls] = B.uts_b[s]; sm.st[2][ls] = B.uts_c[s]; sm.st[3][ls] = B.uts_tau[s];
                 sm.st[4][ls] = B.uts_p00[s]; sm.st[5][ls] = B.uts_p01[s]; sm.st[6][ls] = B.uts_p11[s]; sm.st[7][ls] = B.uts_p22[s];
                 sm.prior[ls] = B.uts_prior[s]; sm.w[ls] = B.uts_w[s]; sm.lik[ls] = B.uts_lik[s];
-                sm.lrn[ls] = B.uts_lrn[s]; sm.side[ls] = (uint8_t)B.uts_side[s];
+                sd |= (unsigned)B.uts_side[s] & 3u;
                 sm.rank[ls] = B.uts_rank[s];
             } else {
                 sm.st[0][ls] = B.tse_a[s]; sm.st[1][ls] = B.tse_b[s]; sm.st[2][ls] = B.tse_c[s]; sm.st[3][ls] = B.tse_tau[s];
@@ -729,21 +799,14 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
         } else
             sm.rank[ls] = uts ? 0x7fffffff : ls;
         sm.flags[ls] = (uint8_t)f;
-    }
-    __syncthreads();
-
-    // ---------------------------------------------------------------- OP_E
-    if (has_E) {
-        // pass 1: which slots carry a message this iteration -> dense list (so pass 2 runs with full warps)
-        for (int base = 0; base < ns; base += GTF_TILE_THREADS) {
-            int ls = base + tid;
-            bool send = false;
-            if (ls < ns) {
-                unsigned f = sm.flags[ls];
-                unsigned nf = sm.nflags[sm.dstl[ls]];
-                send = (f & (F_EX | F_ACT)) == (F_EX | F_ACT) && (nf & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI) &&
-                       B.has_merged[sm.src[ls]] != 0; // extrapolate_merged_states.py:425,431
-            }
+        sm.side[ls] = (uint8_t)sd;
+        // E pass 1 folded in: does this slot carry a message this iteration? (extrapolate...py:416,425,431)
+        if (has_E && (f & (F_EX | F_ACT)) == (F_EX | F_ACT)) {
+            int sg = B.sub[dst];
+            send = B.sub_state[sg] == GTF_SUB_INPLAY && B.sub_nalive[sg] != 1 && B.has_merged[src] != 0;
+        }
+        }
+        if (has_E) { // dense list of message slots, so the extrapolation runs with full warps
             unsigned m = __ballot_sync(0xffffffffu, send);
             if (m) {
                 int basepos = 0;
@@ -752,7 +815,11 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
                 if (send) sm.ordl[basepos + __popc(m & ((1u << lane) - 1u))] = (uint16_t)ls;
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- OP_E
+    if (has_E) {
         const int nsend = sm.elist_n;
         unsigned gated = 0;
         // pass 2: thread per message: extrapolate, chi2 gate, Kalman update (extrapolate...py:26-402)
@@ -762,7 +829,7 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
             int u = sm.src[ls];
             int s = s0 + ls, v = n0 + sm.dstl[ls];
             GtfExtrapOut o;
-            gtf_extrapolate(sm.srcx[ls], B.y[u], sm.srcz[ls], sm.srcr[ls], B.x[v], B.y[v], B.z[v], B.r[v], B.m_a[u],
+            gtf_extrapolate(sm.srcx[ls], B.y[u], B.z[u], B.r[u], B.x[v], B.y[v], B.z[v], B.r[v], B.m_a[u],
                             B.m_b[u], B.m_c[u], B.m_p00[u], B.m_p01[u], B.slot_p11[s], B.m_p22[u], B.slot_vms[s],
                             P.chi2_cut, g, o);
             B.uts_chi2[s] = o.chi2;
@@ -775,8 +842,7 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
                 sm.lik[ls] = o.lik;
                 sm.w[ls] = wv;
                 sm.prior[ls] = NAN; // a fresh dict entry has no prior / lr_layer_norm / side yet
-                sm.lrn[ls] = NAN;
-                sm.side[ls] = 0;
+                sm.side[ls] &= SD_ORIGPRES;
                 f |= F_FRESH;
                 if (!(f & F_PRES)) f |= F_PRES | F_NEW;
             } else {
@@ -797,17 +863,38 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
                            (wb & WB_MERGED_NX) ? B.m_p01_nx : B.m_p01, (wb & WB_MERGED_NX) ? B.m_p11_nx : B.m_p11,
                            (wb & WB_MERGED_NX) ? B.m_p22_nx : B.m_p22, (wb & WB_MERGED_NX) ? B.m_prior_nx : B.m_prior};
     if (FUSED) {
-        // light nodes (<= 2 dict entries): one thread each; the rest go to a list for the cooperative path
-        if (tid == 0) sm.heavy_n = 0;
+        // classify (thread per node, one scan of its slots): dict entries, active in-degree
+        for (int ln = tid; ln < nn; ln += GTF_TILE_THREADS) {
+            const int b0 = sm.nbeg[ln], b1 = sm.nbeg[ln + 1];
+            int e0 = 0xffff, e1 = 0xffff, np = 0, deg = 0;
+            for (int t = b0; t < b1; t++) {
+                unsigned f = sm.flags[t];
+                deg += (f & (F_EX | F_ACT)) == (F_EX | F_ACT);
+                if (f & F_PRES) {
+                    if (np == 0) e0 = t; else if (np == 1) e1 = t;
+                    np++;
+                }
+            }
+            sm.ne0[ln] = (uint16_t)e0; sm.ne1[ln] = (uint16_t)e1; sm.ndeg[ln] = (uint16_t)deg;
+            if (np > 2) sm.heavy[atomicAdd(&sm.heavy_n, 1)] = (uint8_t)ln;
+            else sm.light[atomicAdd(&sm.light_n, 1)] = (uint8_t)ln;
+        }
         __syncthreads();
-        for (int ln = tid; ln < nn; ln += GTF_TILE_THREADS)
-            if (!node_program_light(sm, B, P, n0 + ln, ln, s0)) sm.heavy[atomicAdd(&sm.heavy_n, 1)] = (uint8_t)ln;
-        __syncthreads();
-        const int nh = sm.heavy_n;
-        for (int q = warp; q < nh;) {
-            const int ln = sm.heavy[q], i = n0 + ln;
-            if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
-            else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+        // one work queue: cooperative (warp-per-node) items first, then chunks of 32 light nodes (thread-per-node)
+        const int nh = sm.heavy_n, nl = sm.light_n, nitems = nh + (nl + 31) / 32;
+        for (int q = warp; q < nitems;) {
+            if (q < nh) {
+                const int ln = sm.heavy[q], i = n0 + ln;
+                if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+                else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+            } else {
+                const int idx = (q - nh) * 32 + lane;
+                if (idx < nl) {
+                    const int ln = sm.light[idx];
+                    node_program_light(sm, B, P, n0 + ln, ln, s0);
+                }
+                __syncwarp();
+            }
             int nxt = 0;
             if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
             q = __shfl_sync(0xffffffffu, nxt, 0);
@@ -851,13 +938,13 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
             n_chg += a != a0;
         }
         if (wb & WB_ACTIVE) {
-            if (wb & WB_MERGED_NX) act_out[s] = a ? 1 : (a0 ? 0 : B.active[s]);
+            if (wb & WB_MERGED_NX) act_out[s] = a ? 1 : 0;
             else if (a != a0) act_out[s] = a ? 1 : 0;
         }
         if (uts) {
             if (wb & WB_PRESENT) {
                 if (f & F_NEW) B.uts_present[s] = 1;
-                else if (!(f & F_PRES) && present_in[s]) B.uts_present[s] = 0;
+                else if (!(f & F_PRES) && (sm.side[ls] & SD_ORIGPRES)) B.uts_present[s] = 0;
             }
             if ((wb & WB_STATE) && (f & F_FRESH)) {
                 B.uts_a[s] = sm.st[0][ls]; B.uts_b[s] = sm.st[1][ls]; B.uts_c[s] = sm.st[2][ls]; B.uts_tau[s] = sm.st[3][ls];
@@ -868,10 +955,13 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
             if (f & F_PRES) {
                 if (wb & WB_PRIOR) B.uts_prior[s] = sm.prior[ls];
                 if (wb & WB_W) B.uts_w[s] = sm.w[ls];
-                if ((wb & WB_UTSX) && (f & (F_RW | F_FRESH))) { B.uts_lrn[s] = sm.lrn[ls]; B.uts_side[s] = (int8_t)sm.side[ls]; }
+                if ((wb & WB_UTSX) && (f & (F_RW | F_FRESH))) {
+                    B.uts_side[s] = (int8_t)(sm.side[ls] & 3);
+                    if (!(f & F_RW)) B.uts_lrn[s] = NAN; // fresh entry never reweighted: no lr_layer_norm yet
+                }
             }
         } else {
-            if ((wb & WB_PRESENT) && !(f & F_PRES) && present_in[s]) B.tse_present[s] = 0;
+            if ((wb & WB_PRESENT) && !(f & F_PRES) && (sm.side[ls] & SD_ORIGPRES)) B.tse_present[s] = 0;
             if (f & F_PRES) {
                 if (wb & WB_PRIOR) B.tse_prior[s] = sm.prior[ls];
                 if (wb & WB_W) B.tse_w[s] = sm.w[ls];

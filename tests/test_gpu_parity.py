@@ -236,7 +236,7 @@ def test_stage_wrappers_on_networkx_graphs():
 def test_lut_threshold_mode_vs_oracle():
     """per-node KL threshold from the emp_var bin (the hook the reference never wired in)"""
     hb = synth_batch(1, 300, 2400)
-    lut = np.linspace(0.02, 0.3, 28)
+    lut = np.where(np.arange(28) % 2 == 1, 1e9, 1e-9)       # alternately absorb everything / nothing
     ob = ol.OracleBatch(hb)
     ob.seed()
     ob.cluster(0, 1.0, 2.0, lut=lut)

@@ -149,3 +149,49 @@ def test_pair_merge_kl_match_oracle(hm):
         n += 1
     assert n > 100
     assert all(v <= gu.RTOL for v in worst.values()), worst
+
+
+@pytest.mark.parametrize("name,prev,stage,key,chi2,kl", [
+    ("barrel25_deg6", "seed", "c1", "tse", 1.0, 2.0), ("barrel40_eta1", "seed", "c1", "tse", 1.0, 2.0),
+    ("barrel25_deg6", "m2", "c3", "uts", 1000.0, 100.0), ("barrel40_eta1", "m2", "c3", "uts", 1000.0, 100.0)])
+def test_information_form_clustering_matches_reference(hm, name, prev, stage, key, chi2, kl):
+    """the kernels' greedy merge loop runs in information form (sum of inverse covariances); check the
+    merged states and the set of un-absorbed components against the unmodified reference's cluster()"""
+    hm.gtfh_cluster_node.argtypes = [dp, dp, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp,
+                                     ctypes.POINTER(ctypes.c_uint)]
+    fx = gu.load(name)
+    hb = gu.stage_batch(fx, prev)
+    want = gu.stage_batch(fx, stage)
+    order = gu.dict_order(hb, key)
+    ex = gu.edge_exists(hb)
+    n_checked = 0
+    worst = 0.0
+    for i in range(len(hb["x"])):
+        if not gu.inplay_nodes(hb)[i] or (key == "uts" and not hb["has_uts"][i]):
+            continue
+        sl = order[i]
+        n = len(sl)
+        if n < 3 or n > 15:
+            continue
+        S = np.array([[hb["%s_%s" % (key, f)][s] for f in ("a", "b", "c", "tau", "p00", "p01", "p11", "p22")] for s in sl])
+        pr = np.array([hb[key + "_prior"][s] for s in sl])
+        nb = np.array([xyzr(hb, hb["in_src"][s]) for s in sl])
+        m8, mp, rem = np.zeros(8), ctypes.c_double(0), ctypes.c_uint(0)
+        ok = hm.gtfh_cluster_node(P(np.ascontiguousarray(S)), P(pr), n, P(xyzr(hb, i)), P(np.ascontiguousarray(nb)), chi2, kl,
+                                  P(GEOM), P(m8), ctypes.byref(mp), ctypes.byref(rem))
+        newly = bool(ok)
+        if key == "tse":
+            assert newly == bool(want["has_merged"][i])
+        if not newly:
+            continue
+        w = np.array([want["m_a"][i], want["m_b"][i], want["m_c"][i], want["m_p00"][i], want["m_p01"][i], want["m_p11"][i],
+                      want["m_p22"][i], want["m_prior"][i]])
+        got = np.array([m8[0], m8[1], m8[2], m8[4], m8[5], m8[6], m8[7], mp.value])
+        worst = max(worst, gu.rel_err(got, w))
+        for k, s in enumerate(sl):      # un-absorbed components are switched off, absorbed ones keep their flag
+            if (rem.value >> k) & 1 and ex[s]:
+                assert want["active"][s] == 0
+        n_checked += 1
+    assert n_checked > (20 if key == "tse" else -1), n_checked
+    print(name, stage, "nodes", n_checked, "worst rel err %.3g" % worst)
+    assert worst <= gu.RTOL, worst
