@@ -158,6 +158,13 @@ extern "C" int gtf_batch_download(gtf_batch *b, int f, void *host)
     CK(cudaStreamSynchronize(b->stream));
     return 0;
 }
+extern "C" int gtf_batch_download_async(gtf_batch *b, int f, void *host)
+{
+    if (!b || f < 0 || f >= GTF_NFIELDS || !host) return fail(GTF_E_ARG, "gtf_batch_download_async: bad argument");
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpyAsync(host, b->f[f], (size_t)gtf_field_bytes(b, f), cudaMemcpyDeviceToHost, b->stream));
+    return 0;
+}
 extern "C" int gtf_batch_device_ptr(gtf_batch *b, int f, void **dptr)
 {
     if (!b || f < 0 || f >= GTF_NFIELDS || !dptr) return fail(GTF_E_ARG, "gtf_batch_device_ptr: bad argument");

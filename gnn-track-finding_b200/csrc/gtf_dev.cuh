@@ -55,17 +55,17 @@ struct Prog {
 };
 
 #ifndef GTF_TILE_SLOTS
-#define GTF_TILE_SLOTS 384
+#define GTF_TILE_SLOTS 768
 #endif
 #ifndef GTF_TILE_NODES
-#define GTF_TILE_NODES 192
+#define GTF_TILE_NODES 255
 #endif
 #ifndef GTF_TILE_THREADS
-#define GTF_TILE_THREADS 128
+#define GTF_TILE_THREADS 256
 #endif
 #define GTF_MAXD 15
 #ifndef GTF_TILE_MINB
-#define GTF_TILE_MINB 4
+#define GTF_TILE_MINB 2
 #endif
 
 struct gtf_batch {

@@ -75,6 +75,7 @@ def lib():
         "gtf_field_bytes": (i64, [vp, ctypes.c_int]),
         "gtf_batch_upload": (ctypes.c_int, [vp, ctypes.c_int, vp]),
         "gtf_batch_download": (ctypes.c_int, [vp, ctypes.c_int, vp]),
+        "gtf_batch_download_async": (ctypes.c_int, [vp, ctypes.c_int, vp]),
         "gtf_batch_device_ptr": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp)]),
         "gtf_batch_finalize": (ctypes.c_int, [vp]),
         "gtf_batch_sync": (ctypes.c_int, [vp]),

@@ -75,6 +75,8 @@ int64_t gtf_field_bytes(const gtf_batch *b, int field_id);
  * download synchronises before returning) */
 int gtf_batch_upload(gtf_batch *b, int field_id, const void *host);
 int gtf_batch_download(gtf_batch *b, int field_id, void *host);
+/* same without the synchronisation (host must be pinned; call gtf_batch_sync before reading it) */
+int gtf_batch_download_async(gtf_batch *b, int field_id, void *host);
 int gtf_batch_device_ptr(gtf_batch *b, int field_id, void **dptr);
 /* after the topology arrays (in_off, in_src, slot_dst, out_off, out_slot, rev_slot, sub, sub_off,
  * sub_state, alive) are uploaded: builds the node tiles and per-sub-graph counters */
