@@ -180,10 +180,10 @@ class EventBatch(object):
         L.check(self.lib.gtf_batch_set_timing(self.h, 1 if enable else 0))
 
     def timing(self):
-        """(prefix_ms, tile_ms, n): average CUDA-event durations of the two kernels of the fused iteration"""
-        a, b_, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
-        L.check(self.lib.gtf_batch_timing(self.h, ctypes.byref(a), ctypes.byref(b_), ctypes.byref(n)))
-        return a.value, b_.value, n.value
+        """(prefix_ms, tile_ms, heavy_ms, n): average CUDA-event durations of the kernels of the fused iteration"""
+        a, b_, c, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
+        L.check(self.lib.gtf_batch_timing(self.h, ctypes.byref(a), ctypes.byref(b_), ctypes.byref(c), ctypes.byref(n)))
+        return a.value, b_.value, c.value, n.value
 
     def CCA(self):
         """extract_track_candidates.py:332: component label per node (smallest node index; -1 = removed)."""

@@ -2,6 +2,7 @@
 // seeding / component / extraction / tag-propagation kernels.  Built for sm_100a only; no CPU fallback.
 #include <cub/device/device_radix_sort.cuh>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -114,6 +115,19 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
     DA(d.m_a_nx, N); DA(d.m_b_nx, N); DA(d.m_c_nx, N); DA(d.m_p00_nx, N); DA(d.m_p01_nx, N);
     DA(d.m_p11_nx, N); DA(d.m_p22_nx, N); DA(d.m_prior_nx, N);
     DA(d.counters, GTF_NCOUNTERS);
+    {
+        // optional: run the cooperative (>= 3 component) nodes in their own kernel (k_heavy).  Measured on B200 it is
+        // slower than keeping them inside k_tile (0.36 + 0.14 ms vs 0.44 ms per 32 cfg2 events), so it is opt-in.
+        const char *e = getenv("GTF_SPLIT_HEAVY");
+        b->split_heavy = (e && e[0] == '1');
+        DA(b->heavy_list, N);
+        DA(b->heavy_slot, N);
+        if ((int64_t)E >= (1LL << 25)) b->split_heavy = false;   // packed (slot << 6 | degree) must fit an int32
+        DA(b->heavy_count, 2);
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        b->n_sm = prop.multiProcessorCount;
+    }
     DA(b->accepted_total, N); DA(b->cand_root, N); DA(b->sub_has_inactive, S); DA(b->sub_first, S);
     DA(b->sort_keys, N); DA(b->sort_vals, N); DA(b->sort_keys2, N); DA(b->sort_vals2, N);
     DA(b->pv_xy, N); DA(b->pv_zr, N); DA(b->acc_now, N); DA(b->tags_a, N); DA(b->tags_b, N);
@@ -135,7 +149,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
                      d.m_b_nx, d.m_c_nx, d.m_p00_nx, d.m_p01_nx, d.m_p11_nx, d.m_p22_nx, d.m_prior_nx, d.counters,
                      b->accepted_total, b->cand_root, b->sub_has_inactive, b->sub_first, b->sort_keys, b->sort_vals,
                      b->sort_keys2, b->sort_vals2, b->pv_xy, b->pv_zr, b->acc_now, b->tags_a, b->tags_b,
-                     b->tile_begin, b->sort_tmp};
+                     b->tile_begin, b->sort_tmp, b->heavy_list, b->heavy_slot, b->heavy_count};
     for (void *p : extra) cudaFree(p);
     cudaFreeHost(b->h_counters);
     cudaStreamDestroy(b->stream);
@@ -485,14 +499,25 @@ extern "C" int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf
     if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
     TRY(launch_prefix(b, gg));
     if (b->timing) CK(cudaEventRecord(b->ev[1], b->stream));
-    TRY(launch_tile(b, fused_prog(p), gg, true));
+    Prog P = fused_prog(p);
+    b->d.heavy_list = b->split_heavy ? b->heavy_list : nullptr;
+    b->d.heavy_slot = b->heavy_slot;
+    b->d.heavy_count = b->heavy_count;
+    if (b->split_heavy) CK(cudaMemsetAsync(b->heavy_count, 0, 2 * sizeof(int), b->stream));
+    TRY(launch_tile(b, P, gg, true));
+    if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
+    if (b->split_heavy && b->n_tiles) {
+        k_heavy<<<b->n_sm * GTF_HEAVY_MINB, GTF_HEAVY_WARPS * 32, 0, b->stream>>>(b->d, P, gg);
+        CK(cudaGetLastError());
+    }
     if (b->timing) {
-        CK(cudaEventRecord(b->ev[2], b->stream));
-        CK(cudaEventSynchronize(b->ev[2]));
-        float t0 = 0, t1 = 0;
+        CK(cudaEventRecord(b->ev[3], b->stream));
+        CK(cudaEventSynchronize(b->ev[3]));
+        float t0 = 0, t1 = 0, t2 = 0;
         CK(cudaEventElapsedTime(&t0, b->ev[0], b->ev[1]));
         CK(cudaEventElapsedTime(&t1, b->ev[1], b->ev[2]));
-        b->t_prefix_ms += t0; b->t_tile_ms += t1; b->t_count++;
+        CK(cudaEventElapsedTime(&t2, b->ev[2], b->ev[3]));
+        b->t_prefix_ms += t0; b->t_tile_ms += t1; b->t_heavy_ms += t2; b->t_count++;
     }
     if (st) return counters_read(b, st);
     return 0;
@@ -504,18 +529,19 @@ extern "C" int gtf_batch_set_timing(gtf_batch *b, int enable)
     if (!b) return fail(GTF_E_ARG, "null batch");
     CK(cudaSetDevice(b->device));
     if (enable && !b->ev[0])
-        for (int k = 0; k < 3; k++) CK(cudaEventCreate(&b->ev[k]));
+        for (int k = 0; k < 4; k++) CK(cudaEventCreate(&b->ev[k]));
     b->timing = enable != 0;
-    b->t_prefix_ms = b->t_tile_ms = 0.0;
+    b->t_prefix_ms = b->t_tile_ms = b->t_heavy_ms = 0.0;
     b->t_count = 0;
     return 0;
 }
-extern "C" int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms, int *count)
+extern "C" int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms, double *heavy_ms, int *count)
 {
     if (!b) return fail(GTF_E_ARG, "null batch");
     int n = b->t_count ? b->t_count : 1;
     if (prefix_ms) *prefix_ms = b->t_prefix_ms / n;
     if (tile_ms) *tile_ms = b->t_tile_ms / n;
+    if (heavy_ms) *heavy_ms = b->t_heavy_ms / n;
     if (count) *count = b->t_count;
     return 0;
 }

@@ -29,6 +29,10 @@ struct DevBatch {
     uint8_t *active_nx, *has_merged_nx;
     double *m_a_nx, *m_b_nx, *m_c_nx, *m_p00_nx, *m_p01_nx, *m_p11_nx, *m_p22_nx, *m_prior_nx;
     unsigned long long *counters; // [GTF_NCOUNTERS]
+    // cooperative (>= 3 components) nodes of the fused iteration, filled by k_tile, consumed by k_heavy
+    int32_t *heavy_list; // [N] (nullptr: process them inside k_tile)
+    int32_t *heavy_slot; // [N] first slot << 6 | degree  (E < 2^25 slots per batch when the split is on)
+    int *heavy_count;    // [2]: count, next
 };
 
 enum {
@@ -89,9 +93,14 @@ struct gtf_batch {
     double *pv_xy, *pv_zr;     // [N]
     uint8_t *acc_now;          // [N]
     int32_t *tags_a, *tags_b;  // [N]
+    // cooperative nodes of the fused iteration run in their own kernel (k_heavy) unless GTF_SPLIT_HEAVY=0
+    bool split_heavy;
+    int32_t *heavy_list, *heavy_slot;
+    int *heavy_count;
+    int n_sm;
     // optional per-kernel timing of the fused iteration
     bool timing;
-    cudaEvent_t ev[3];
-    double t_prefix_ms, t_tile_ms;
+    cudaEvent_t ev[4];
+    double t_prefix_ms, t_tile_ms, t_heavy_ms;
     int t_count;
 };

@@ -31,6 +31,8 @@
 #define NF_DICT 4u   // node has the working dict
 #define NF_HASUTS 8u
 #define NF_CLUSTERED 16u
+#define NF_DEFER 32u   // cooperative node handed to k_heavy (fused iteration)
+#define GTF_NEWMARK 0x7ffffffe // uts_rank of an entry inserted by k_tile whose dict position k_heavy still has to assign
 
 struct TileSmem {
     double st[8][GTF_TILE_SLOTS]; // a b c tau p00 p01 p11 p22 of the working dict entry
@@ -43,19 +45,21 @@ struct TileSmem {
     uint8_t nflags[GTF_TILE_NODES];
     double D[GTF_TILE_THREADS / 32][GTF_MAXD * (GTF_MAXD - 1) / 2 + 1];
     unsigned int cnt[GTF_NCOUNTERS];
-    int next_node, elist_n, heavy_n, light_n;
+    int next_node, elist_n, heavy_n, light_n, defer_n, defer_base;
     uint8_t heavy[GTF_TILE_NODES], light[GTF_TILE_NODES];
     uint16_t ne0[GTF_TILE_NODES], ne1[GTF_TILE_NODES], ndeg[GTF_TILE_NODES]; // light nodes: their (<= 2) entries, active degree
 };
 
-__device__ __forceinline__ GtfState tile_state(const TileSmem &sm, int ls)
+template <class SM>
+__device__ __forceinline__ GtfState tile_state(const SM &sm, int ls)
 {
     GtfState s;
     s.a = sm.st[0][ls]; s.b = sm.st[1][ls]; s.c = sm.st[2][ls]; s.tau = sm.st[3][ls];
     s.p00 = sm.st[4][ls]; s.p01 = sm.st[5][ls]; s.p11 = sm.st[6][ls]; s.p22 = sm.st[7][ls];
     return s;
 }
-__device__ __forceinline__ void tile_put_state(TileSmem &sm, int ls, const GtfState &s)
+template <class SM>
+__device__ __forceinline__ void tile_put_state(SM &sm, int ls, const GtfState &s)
 {
     sm.st[0][ls] = s.a; sm.st[1][ls] = s.b; sm.st[2][ls] = s.c; sm.st[3][ls] = s.tau;
     sm.st[4][ls] = s.p00; sm.st[5][ls] = s.p01; sm.st[6][ls] = s.p11; sm.st[7][ls] = s.p22;
@@ -75,11 +79,21 @@ __device__ __forceinline__ unsigned warp_or(unsigned v)
     for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// pair p of the strictly lower triangle in row-major order: p = i (i - 1) / 2 + j, j < i <= 14
+__constant__ uint8_t c_pair_i[GTF_MAXD * (GTF_MAXD - 1) / 2] = {
+    1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8,
+    9, 9, 9, 9, 9, 9, 9, 9, 9, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10, 11, 11, 11, 11, 11, 11, 11, 11, 11, 11, 11,
+    12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 12, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13,
+    14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14, 14};
 __device__ __forceinline__ void pair_decode(int p, int &i, int &j)
 {
-    i = 1;
-    while (i * (i + 1) / 2 <= p) i++;
+    i = c_pair_i[p];
     j = p - i * (i - 1) / 2;
+}
+// 1/k for small positive integer k, exactly the correctly rounded quotient (helper.py:61,90)
+__device__ __forceinline__ double recip_small(int k)
+{
+    return k == 1 ? 1.0 : k == 2 ? 0.5 : k == 4 ? 0.25 : 1.0 / (double)k;
 }
 
 // dict order: ordl[b0 + k] = local slot of the k-th entry (ascending rank); returns the entry count
@@ -205,7 +219,8 @@ __device__ __forceinline__ void shfl_info(const GtfInfo &in, int src, GtfInfo &o
 // clustering.py:193-307 for one node.  Returns true and the merged state when a cluster was formed.
 // Lane k < n owns dict entry k.  Pairwise chi2: lane-per-pair into Dw.  Greedy loop in information form
 // (gtf_math.cuh): per round one KL per lane without any inverse, a REDUX arg-min, and one 2x2 inverse.
-__device__ __forceinline__ bool node_cluster(TileSmem &sm, double *Dw, int b0, int n, double nx, double nz, double nr_,
+template <class SM>
+__device__ __forceinline__ bool node_cluster(SM &sm, double *Dw, int b0, int n, double nx, double nz, double nr_,
                                              double chi2_thr, double kl_thr, const GtfGeom &g, int lane,
                                              GtfState &merged, double &mprior, const double *gz, const double *gr)
 {
@@ -421,8 +436,8 @@ __device__ __forceinline__ constexpr int fused_op(int k)
 // register-resident per-node program for nodes with <= 32 in-slots: lane l owns slot b0 + l; counts,
 // same-layer / same-x groupings and dict positions come from ballots, MATCH.ANY and shuffles instead of
 // O(d^2) shared-memory loops.
-template <bool FUSED>
-__device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &B, const Prog &P, const GtfGeom &g, int i,
+template <bool FUSED, class SM>
+__device__ __forceinline__ void node_program_fast(SM &sm, const DevBatch &B, const Prog &P, const GtfGeom &g, int i,
                                                   int ln, int s0, int warp, int lane, bool uts, uint8_t *hm_out,
                                                   double *const *mo)
 {
@@ -493,7 +508,7 @@ __device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &
                 bool el = (f & m3) == m3;
                 unsigned elmask = __ballot_sync(FULL, el);
                 unsigned same = __match_any_sync(FULL, lay);
-                if (el) prior = 1.0 / (double)__popc(same & elmask); // helper.py:61
+                if (el) prior = recip_small(__popc(same & elmask)); // helper.py:61
             }
         } else if (op == OP_RW) {
             if (uts && (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS)) {
@@ -521,7 +536,7 @@ __device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &
                     if (el) {
                         double norm = last_active ? (double)(left ? normL : normR) : 1.0;
                         double rw = (w * lik * prior) / denom;
-                        rw = rw / norm;
+                        if (norm != 1.0) rw = rw / norm;
                         B.uts_lrn[s0 + ls] = norm;
                         sidev = left ? 1 : 2;
                         w = rw;
@@ -555,7 +570,7 @@ __device__ __forceinline__ void node_program_fast(TileSmem &sm, const DevBatch &
                 if (n == 0) {
                     if (lane == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_ZERO_DIV);
                 } else if (f & F_PRES)
-                    w = 1.0 / (double)n;
+                    w = recip_small(n);
             }
         }
     }
@@ -625,7 +640,7 @@ __device__ __forceinline__ void light_reweight(TileSmem &sm, LightEntry &a, Ligh
     if (ea) {
         double norm = last_active ? norm_a : 1.0;
         double rw = (a.w * a.lik * a.prior) / denom;
-        rw = rw / norm;
+        if (norm != 1.0) rw = rw / norm;
         lrn_tile[a.ls] = norm; a.side = la ? 1 : 2; a.w = rw;
         edge_w_tile[a.ls] = rw;
         a.f |= F_RW;
@@ -634,7 +649,7 @@ __device__ __forceinline__ void light_reweight(TileSmem &sm, LightEntry &a, Ligh
     if (eb) {
         double norm = last_active ? norm_b : 1.0;
         double rw = (b.w * b.lik * b.prior) / denom;
-        rw = rw / norm;
+        if (norm != 1.0) rw = rw / norm;
         lrn_tile[b.ls] = norm; b.side = lb ? 1 : 2; b.w = rw;
         edge_w_tile[b.ls] = rw;
         b.f |= F_RW;
@@ -728,7 +743,7 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
         for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) has_E |= P.ops[k] == OP_E;
 
     if (tid < GTF_NCOUNTERS) sm.cnt[tid] = 0;
-    if (tid == 0) { sm.next_node = GTF_TILE_THREADS / 32; sm.elist_n = 0; sm.heavy_n = 0; sm.light_n = 0; }
+    if (tid == 0) { sm.next_node = GTF_TILE_THREADS / 32; sm.elist_n = 0; sm.heavy_n = 0; sm.light_n = 0; sm.defer_n = 0; sm.defer_base = 0; }
     __syncthreads();
     // ---------------------------------------------------------------- node table
     for (int ln = tid; ln <= nn; ln += GTF_TILE_THREADS) {
@@ -876,16 +891,32 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
                 }
             }
             sm.ne0[ln] = (uint16_t)e0; sm.ne1[ln] = (uint16_t)e1; sm.ndeg[ln] = (uint16_t)deg;
-            if (np > 2) sm.heavy[atomicAdd(&sm.heavy_n, 1)] = (uint8_t)ln;
-            else sm.light[atomicAdd(&sm.light_n, 1)] = (uint8_t)ln;
+            if (np > 2) {
+                if (B.heavy_list && b1 - b0 <= 32) { // cooperative node: its own kernel (k_heavy), off this CTA's critical path
+                    sm.light[GTF_TILE_NODES - 1 - atomicAdd(&sm.defer_n, 1)] = (uint8_t)ln; // deferred list grows from the top
+                    sm.nflags[ln] |= NF_DEFER;
+                } else
+                    sm.heavy[atomicAdd(&sm.heavy_n, 1)] = (uint8_t)ln;
+            } else
+                sm.light[atomicAdd(&sm.light_n, 1)] = (uint8_t)ln;
         }
         __syncthreads();
+        // hand the deferred nodes to k_heavy: ONE global atomic per tile reserves the range
+        if (sm.defer_n) {
+            if (tid == 0) sm.defer_base = atomicAdd(B.heavy_count, sm.defer_n);
+            __syncthreads();
+            for (int q = tid; q < sm.defer_n; q += GTF_TILE_THREADS) {
+                const int ln = sm.light[GTF_TILE_NODES - 1 - q];
+                B.heavy_list[sm.defer_base + q] = n0 + ln;
+                B.heavy_slot[sm.defer_base + q] = ((s0 + sm.nbeg[ln]) << 6) | (sm.nbeg[ln + 1] - sm.nbeg[ln]);
+            }
+        }
         // one work queue: cooperative (warp-per-node) items first, then chunks of 32 light nodes (thread-per-node)
         const int nh = sm.heavy_n, nl = sm.light_n, nitems = nh + (nl + 31) / 32;
         for (int q = warp; q < nitems;) {
             if (q < nh) {
                 const int ln = sm.heavy[q], i = n0 + ln;
-                if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+                if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED, TileSmem>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
                 else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
             } else {
                 const int idx = (q - nh) * 32 + lane;
@@ -902,7 +933,7 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
     } else {
         for (int ln = warp; ln < nn;) {
             const int i = n0 + ln;
-            if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+            if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED, TileSmem>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
             else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
             int nxt = 0;
             if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
@@ -933,7 +964,8 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
         int s = s0 + ls;
         unsigned f = sm.flags[ls];
         bool a = f & F_ACT, a0 = f & F_ORIG;
-        if (f & F_EX) {
+        const bool deferred = FUSED && (sm.nflags[sm.dstl[ls]] & NF_DEFER);
+        if ((f & F_EX) && !deferred) {
             n_act += a;
             n_chg += a != a0;
         }
@@ -950,7 +982,7 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
                 B.uts_a[s] = sm.st[0][ls]; B.uts_b[s] = sm.st[1][ls]; B.uts_c[s] = sm.st[2][ls]; B.uts_tau[s] = sm.st[3][ls];
                 B.uts_p00[s] = sm.st[4][ls]; B.uts_p01[s] = sm.st[5][ls]; B.uts_p11[s] = sm.st[6][ls]; B.uts_p22[s] = sm.st[7][ls];
                 B.uts_lik[s] = sm.lik[ls];
-                if (f & F_NEW) B.uts_rank[s] = sm.rank[ls];
+                if (f & F_NEW) B.uts_rank[s] = deferred ? GTF_NEWMARK : sm.rank[ls];
             }
             if (f & F_PRES) {
                 if (wb & WB_PRIOR) B.uts_prior[s] = sm.prior[ls];
@@ -969,6 +1001,108 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
         }
     }
     if (wb & WB_COUNT_ACTIVE) {
+        if (n_act) atomicAdd(&sm.cnt[CNT_ACTIVE], n_act);
+        if (n_chg) atomicAdd(&sm.cnt[CNT_CHANGED], n_chg);
+    }
+    __syncthreads();
+    if (tid < GTF_NCOUNTERS && sm.cnt[tid]) {
+        if (tid == CNT_REFERR) atomicOr(&B.counters[tid], (unsigned long long)sm.cnt[tid]);
+        else atomicAdd(&B.counters[tid], (unsigned long long)sm.cnt[tid]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_heavy: the cooperative nodes (>= 3 mixture components, <= 32 in-slots) of the fused iteration, one warp per
+// node, pulled from the list k_tile filled.  Same register-resident node program (node_program_fast) on a
+// per-warp 32-slot mini tile; no CTA-wide barriers, so a 15-component node no longer stalls a whole tile.
+#define GTF_HEAVY_WARPS 4
+#ifndef GTF_HEAVY_MINB
+#define GTF_HEAVY_MINB 6
+#endif
+struct HeavySmem {
+    double st[8][GTF_HEAVY_WARPS * 32];
+    double prior[GTF_HEAVY_WARPS * 32], w[GTF_HEAVY_WARPS * 32], lik[GTF_HEAVY_WARPS * 32], srcx[GTF_HEAVY_WARPS * 32];
+    int32_t src[GTF_HEAVY_WARPS * 32], rank[GTF_HEAVY_WARPS * 32], layer[GTF_HEAVY_WARPS * 32];
+    uint16_t ordl[GTF_HEAVY_WARPS * 32];
+    uint8_t flags[GTF_HEAVY_WARPS * 32], side[GTF_HEAVY_WARPS * 32];
+    uint16_t nbeg[2 * GTF_HEAVY_WARPS];
+    uint8_t nflags[2 * GTF_HEAVY_WARPS];
+    double D[GTF_HEAVY_WARPS][GTF_MAXD * (GTF_MAXD - 1) / 2 + 1];
+    unsigned int cnt[GTF_NCOUNTERS];
+};
+
+__global__ void __launch_bounds__(GTF_HEAVY_WARPS * 32, GTF_HEAVY_MINB) k_heavy(DevBatch B, Prog P, GtfGeom g)
+{
+    __shared__ HeavySmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < GTF_NCOUNTERS) sm.cnt[tid] = 0;
+    __syncthreads();
+    uint8_t *hm_out = B.has_merged_nx;
+    double *const mo[8] = {B.m_a_nx, B.m_b_nx, B.m_c_nx, B.m_p00_nx, B.m_p01_nx, B.m_p11_nx, B.m_p22_nx, B.m_prior_nx};
+    const int count = B.heavy_count[0];
+    const int b0 = warp * 32, ls = b0 + lane;
+    unsigned n_act = 0, n_chg = 0;
+    const int nwarps = gridDim.x * GTF_HEAVY_WARPS;
+    for (int idx = blockIdx.x * GTF_HEAVY_WARPS + warp; idx < count; idx += nwarps) { // static striding: no contended atomic
+        const int i = B.heavy_list[idx];
+        const int packed = B.heavy_slot[idx];
+        const int gs0 = packed >> 6, d = packed & 63;
+        const bool valid = lane < d;
+        const int s = gs0 + lane;
+        if (lane == 0) {
+            sm.nbeg[2 * warp] = (uint16_t)b0;
+            sm.nbeg[2 * warp + 1] = (uint16_t)(b0 + d);
+            int sg = B.sub[i];
+            unsigned nf = NF_DICT;
+            if (B.alive[i] && B.sub_state[sg] == GTF_SUB_INPLAY) nf |= NF_OK;
+            if (B.sub_nalive[sg] != 1) nf |= NF_MULTI;
+            if (B.has_uts[i]) nf |= NF_HASUTS;
+            sm.nflags[2 * warp] = (uint8_t)nf;
+        }
+        if (valid) {
+            int src = B.in_src[s];
+            unsigned f = 0;
+            if (src >= 0 && B.alive[src] && B.alive[i]) f |= F_EX;
+            if (B.active_nx[s] == 1) f |= F_ACT;      // after the extrapolation gate of k_tile
+            if (B.active[s] == 1) f |= F_ORIG;
+            unsigned sd = 0;
+            int rk = 0x7fffffff;
+            if (B.uts_present[s]) {
+                f |= F_PRES;
+                sd = SD_ORIGPRES | ((unsigned)B.uts_side[s] & 3u);
+                sm.st[0][ls] = B.uts_a[s]; sm.st[1][ls] = B.uts_b[s]; sm.st[2][ls] = B.uts_c[s]; sm.st[3][ls] = B.uts_tau[s];
+                sm.st[4][ls] = B.uts_p00[s]; sm.st[5][ls] = B.uts_p01[s]; sm.st[6][ls] = B.uts_p11[s]; sm.st[7][ls] = B.uts_p22[s];
+                sm.prior[ls] = B.uts_prior[s]; sm.w[ls] = B.uts_w[s]; sm.lik[ls] = B.uts_lik[s];
+                rk = B.uts_rank[s];
+                if (rk == GTF_NEWMARK) f |= F_NEW;
+            }
+            sm.src[ls] = src;
+            sm.srcx[ls] = src >= 0 ? B.x[src] : 0.0;
+            sm.layer[ls] = src >= 0 ? B.layer[src] : -1;
+            sm.rank[ls] = rk;
+            sm.side[ls] = (uint8_t)sd;
+            sm.flags[ls] = (uint8_t)f;
+        }
+        __syncwarp();
+        node_program_fast<true, HeavySmem>(sm, B, P, g, i, 2 * warp, gs0 - b0, warp, lane, true, hm_out, mo);
+        __syncwarp();
+        if (valid) {
+            unsigned f = sm.flags[ls];
+            bool a = f & F_ACT, a0 = f & F_ORIG;
+            if (f & F_EX) { n_act += a; n_chg += a != a0; }
+            B.active_nx[s] = a ? 1 : 0;
+            if (f & F_PRES) {
+                B.uts_prior[s] = sm.prior[ls];
+                B.uts_w[s] = sm.w[ls];
+                if (f & F_RW) B.uts_side[s] = (int8_t)(sm.side[ls] & 3);
+                if (f & F_NEW) B.uts_rank[s] = sm.rank[ls];
+            }
+        }
+        __syncwarp();
+    }
+    n_act = __reduce_add_sync(0xffffffffu, n_act);
+    n_chg = __reduce_add_sync(0xffffffffu, n_chg);
+    if (lane == 0) {
         if (n_act) atomicAdd(&sm.cnt[CNT_ACTIVE], n_act);
         if (n_chg) atomicAdd(&sm.cnt[CNT_CHANGED], n_chg);
     }

@@ -95,7 +95,7 @@ def lib():
                                        ctypes.POINTER(ctypes.c_int)]),
         "gtf_iterate_dry": (ctypes.c_int, [vp, ctypes.POINTER(IterParams), pg, ps]),
         "gtf_batch_set_timing": (ctypes.c_int, [vp, ctypes.c_int]),
-        "gtf_batch_timing": (ctypes.c_int, [vp, dp, dp, ctypes.POINTER(ctypes.c_int)]),
+        "gtf_batch_timing": (ctypes.c_int, [vp, dp, dp, dp, ctypes.POINTER(ctypes.c_int)]),
         "gtf_components": (ctypes.c_int, [vp]),
         "gtf_extract": (ctypes.c_int, [vp, pg, dbl, ctypes.c_int, dbl, dbl, ctypes.POINTER(i32),
                                        ctypes.POINTER(ctypes.c_uint8), dp, dp]),

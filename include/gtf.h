@@ -110,7 +110,8 @@ int gtf_extrapolate_stage(gtf_batch *b, double chi2_cut, const gtf_geom *g, gtf_
 int gtf_remove_state_metadata(gtf_batch *b, gtf_stats *st);
 
 /* ---- fused iteration: [message_passing, prior, reweight, prior, reweight, cluster(updated states)] --- */
-/* One launch pair per iteration (per-source prefix + fused per-node kernel).  Runs `max_iter` iterations or
+/* Per iteration: k_prefix (per-source multiple-scattering prefix), k_tile (fused load + extrapolate/update + per-node
+ * reweight/prune), k_heavy (nodes holding >= 3 components: reweight + clustering, one warp per node).  Runs `max_iter` iterations or
  * stops early when an iteration leaves the active-edge bitmap unchanged (SURVEY.md §8d "converged").
  * stats[i] receives iteration i's counters (may be NULL); *n_done the number of iterations run. */
 int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, int max_iter, int stop_when_converged,
@@ -119,10 +120,10 @@ int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, int m
  * batch's shadow buffers WITHOUT committing it (idempotent: benchmark / profiling entry point) */
 int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st);
 
-/* per-kernel timing of the fused iteration (CUDA events recorded on the batch stream around k_prefix and
- * k_tile): enable != 0 resets the accumulators; gtf_batch_timing returns averages over the calls since */
+/* per-kernel timing of the fused iteration (CUDA events recorded on the batch stream around k_prefix, k_tile
+ * and k_heavy): enable != 0 resets the accumulators; gtf_batch_timing returns averages over the calls since */
 int gtf_batch_set_timing(gtf_batch *b, int enable);
-int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms, int *count);
+int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms, double *heavy_ms, int *count);
 
 /* ---- candidate extraction ------------------------------------------------------------------- */
 /* extract/extract_track_candidates.py:332-346 CCA: weakly connected components over active edges ->

@@ -11,4 +11,4 @@ b.sync()
 # timing of sub-programs through the stage entry points on copies of state is destructive; just time the fused one
 b.set_timing(True)
 for _ in range(5): b.iterate_dry()
-print("prefix_ms, tile_ms, n:", b.timing())
+print("prefix_ms, tile_ms, heavy_ms, n:", b.timing())

@@ -269,3 +269,19 @@ def test_driver_schedules_run_and_agree_with_oracle():
     rows = b.candidates()
     assert len(rows) == int((a1 | a2 | a3).sum())
     assert set(rows[:, 0].tolist()) <= {0, 1}
+
+
+def test_split_heavy_kernel_matches(monkeypatch):
+    """opt-in k_heavy path (GTF_SPLIT_HEAVY=1): same results as the single fused kernel"""
+    hb = synth_batch(2, 300, 2600)
+    res = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("GTF_SPLIT_HEAVY", flag)
+        b = gpu_batch(hb)
+        b.seed()
+        b.cluster(0, 1.0, 2.0)
+        st = b.iterate(max_iter=3, stop_when_converged=False)
+        res.append((st, state_of(b)))
+        b.close()
+    assert res[0][0] == res[1][0]
+    assert gu.compare_states(res[1][1], res[0][1], ALL) == []
