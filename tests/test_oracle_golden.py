@@ -124,3 +124,45 @@ def test_cca_matches_scipy():
         want = np.where(h["alive"] > 0, mn[comp], -1)
         inplay = gu.inplay_nodes(h)
         assert np.array_equal(lab[inplay], want[inplay])
+
+
+def test_kl_distance_known_answer_from_reference_csv():
+    """The reference's one shipped golden vector (1_events_training_data.csv, 7,574 KL values):
+    the oracle's KLDistance on the reference-seeded components reproduces it as a sorted multiset.  With a true
+    matrix product inside the trace the values are off by orders of magnitude, so this pins the element-wise
+    trace (clustering.py:93)."""
+    import ctypes
+    fx = np.load(gu.GOLDEN + "/kl_parabolic_known_answer.npz")
+    L = ol.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    mean, cov, off = fx["mean"], fx["cov"], fx["off"]
+    out = []
+    for a, b in zip(off[:-1], off[1:]):
+        for i in range(a, b):
+            for j in range(a, i):
+                mi, ci, mj, cj = (np.ascontiguousarray(x) for x in (mean[i], cov[i], mean[j], cov[j]))
+                out.append(L.gtfo_kl_distance(mi.ctypes.data_as(dp), ci.ctypes.data_as(dp), mj.ctypes.data_as(dp),
+                                              cj.ctypes.data_as(dp)))
+    got = np.sort(np.array(out))
+    want = fx["kl_sorted"]
+    assert len(got) == len(want) == 7574
+    assert gu.rel_err(got, want) <= 1e-9
+    # the discriminating power of the fixture: a proper matrix product in the trace does NOT reproduce it
+    alt = []
+    for a, b in zip(off[:-1], off[1:]):
+        if b - a < 3:
+            continue
+        c = cov[a:b].reshape(-1, 3, 3)
+        inv = np.linalg.inv(c)
+        for i in range(b - a):
+            for j in range(i):
+                d = mean[a + i] - mean[a + j]
+                alt.append(np.trace((c[i] - c[j]) @ (inv[j] - inv[i])) + d @ (inv[i] + inv[j]) @ d)
+        if len(alt) > 500:
+            break
+    alt = np.array(alt)
+    # every element-wise value is in the CSV; the matrix-product values are not
+    idx = np.searchsorted(want, alt)
+    idx = np.clip(idx, 1, len(want) - 1)
+    nearest = np.minimum(np.abs(want[idx] - alt), np.abs(want[idx - 1] - alt))
+    assert (nearest > 1e-6 * np.abs(alt)).mean() > 0.5
