@@ -47,7 +47,7 @@ E2E_DOWN = ("active", "has_merged", "m_a", "m_b", "m_c", "m_p00", "m_p01", "m_p1
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=128, help="events per GPU")
@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches of the end-to-end pipeline (copy/compute overlap)")
     return ap.parse_args()
 
 
@@ -193,24 +194,50 @@ def count_active(b):
     return int(((hb["active"] == 1) & ex).sum())
 
 
-def e2e_loop(b, steps, torch):
-    from gtf_b200 import fields as F
-    from gtf_b200 import lib as L
-    state = b.download(list(E2E_UP))
-    up = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in state.items()}
-    dn = {k: torch.from_numpy(np.empty(F.extent_len(F.FIELD_EXTENT[k], b.N, b.E, b.S), F.FIELD_DTYPE[k])).pin_memory()
-          for k in E2E_DOWN}
-    h2d = sum(t.numel() * t.element_size() for t in up.values())
-    d2h = sum(t.numel() * t.element_size() for t in dn.values())
-    lib = b.lib
+class E2EChunk(object):
+    """one sub-batch of the end-to-end pipeline: its own EventBatch (own CUDA stream) + pinned host buffers"""
 
+    def __init__(self, hb, device, torch):
+        import gtf_b200
+        from gtf_b200 import fields as F
+        self.F = F
+        self.b = gtf_b200.EventBatch(hb, device=device)
+        self.b.seed()
+        self.b.cluster("track_state_estimates", 1.0, 2.0)
+        state = self.b.download(list(E2E_UP))
+        self.up = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in state.items()}
+        b = self.b
+        self.dn = {k: torch.from_numpy(np.empty(F.extent_len(F.FIELD_EXTENT[k], b.N, b.E, b.S), F.FIELD_DTYPE[k])).pin_memory()
+                   for k in E2E_DOWN}
+        self.h2d = sum(t.numel() * t.element_size() for t in self.up.values())
+        self.d2h = sum(t.numel() * t.element_size() for t in self.dn.values())
+
+    def upload(self):
+        from gtf_b200 import lib as L
+        for k, t in self.up.items():
+            L.check(self.b.lib.gtf_batch_upload(self.b.h, self.F.FIELD_ID[k], ctypes.c_void_p(t.data_ptr())))
+
+    def compute(self):
+        self.b.iterate(max_iter=1, stop_when_converged=False)
+
+    def download(self):
+        from gtf_b200 import lib as L
+        for k, t in self.dn.items():
+            L.check(self.b.lib.gtf_batch_download_async(self.b.h, self.F.FIELD_ID[k], ctypes.c_void_p(t.data_ptr())))
+
+
+def e2e_loop(chunks, steps, torch):
+    """per step, through the C-ABI from HOST buffers: pinned H2D of every chunk's per-iteration inputs, one committed
+    fused iteration per chunk, D2H of the results.  Chunks own separate streams, so chunk i+1's upload and chunk i-1's
+    download overlap chunk i's kernels (events are independent)."""
     def one():
-        for k, t in up.items():
-            L.check(lib.gtf_batch_upload(b.h, F.FIELD_ID[k], ctypes.c_void_p(t.data_ptr())))
-        b.iterate(max_iter=1, stop_when_converged=False)
-        for k, t in dn.items():
-            L.check(lib.gtf_batch_download_async(b.h, F.FIELD_ID[k], ctypes.c_void_p(t.data_ptr())))
-        b.sync()
+        for c in chunks:
+            c.upload()
+        for c in chunks:
+            c.compute()
+            c.download()
+        for c in chunks:
+            c.b.sync()
 
     one()
     torch.cuda.synchronize()
@@ -219,10 +246,7 @@ def e2e_loop(b, steps, torch):
         one()
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 1e3
-    for k, t in up.items():     # restore the pristine post-iteration-1 state
-        L.check(lib.gtf_batch_upload(b.h, F.FIELD_ID[k], ctypes.c_void_p(t.data_ptr())))
-    b.sync()
-    return ms, h2d, d2h
+    return ms, sum(c.h2d for c in chunks), sum(c.d2h for c in chunks)
 
 
 def main():
@@ -270,6 +294,14 @@ def main():
         e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    if len(sampler.rows) < 3:
+        # the timed region is shorter than nvidia-smi's latency: keep the SAME step running (untimed) until the
+        # sampler has seen the load
+        t_end = time.perf_counter() + 1.5
+        while time.perf_counter() < t_end and len(sampler.rows) < 4:
+            for _ in range(10):
+                b.iterate_dry()
+            b.sync()
     clocks = sampler.stop()
     # per-kernel durations (CUDA events recorded by the library on its stream around each kernel)
     b.set_timing(True)
@@ -279,8 +311,14 @@ def main():
     b.set_timing(False)
     e2e_ms, h2d, d2h = (None, 0, 0)
     if not a.no_e2e:
+        nch = max(1, min(a.e2e_chunks, a.events))
+        per = [a.events // nch + (1 if k < a.events % nch else 0) for k in range(nch)]
+        chunks = [E2EChunk(build_batch(n, a.tracks, 3000 + 100000 * rank + 1000 * k, a.distinct), local, torch)
+                  for k, n in enumerate(per)]
         barrier()
-        e2e_ms, h2d, d2h = e2e_loop(b, a.steps, torch)
+        e2e_ms, h2d, d2h = e2e_loop(chunks, a.steps, torch)
+        for c in chunks:
+            c.b.close()
     red = torch.tensor([ms, e2e_ms or 0.0], device="cuda", dtype=torch.float64)
     tot = torch.tensor([float(n_active), float(b.E), float(a.events)], device="cuda", dtype=torch.float64)
     if dist is not None:
@@ -316,7 +354,8 @@ def main():
         }
         if e2e_ms:
             out["e2e"] = {"value": n_act_all / (e2e_ms / 1e3 / a.steps), "unit": "edges/s", "h2d_bytes_per_step": h2d,
-                          "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps}
+                          "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps,
+                          "chunks": min(a.e2e_chunks, a.events)}
         if not a.no_cpu and world == 1:
             act, evs, eff, done, wall = cpu_iteration_rate(a.tracks, 1, a.cpu_seconds)
             out["cpu_baseline"] = {"value": act, "unit": "edges/s", "cores": 1, "kind": "port", "events_per_s": evs,
