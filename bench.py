@@ -332,6 +332,9 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         step_s = ms / a.steps / 1e3
         ach = B_ALG * n_active / ((tile_ms + heavy_ms) / 1e3) / 1e9      # both kernels that touch the per-edge state
+        traffic, tr_path = None, os.path.join(REPO, "profiles", "r01_k_tile_traffic.json")
+        if os.path.exists(tr_path):   # dram__bytes_read+write of k_tile from the committed `ncu --set full` capture, per active edge
+            traffic = json.load(open(tr_path))["dram_bytes_per_active_edge"] * n_active
         out = {
             "metric": METRIC, "value": n_act_all / step_s, "unit": "edges/s", "n_gpus": world, "steps": a.steps,
             "warmup": warm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -345,7 +348,8 @@ def main():
                        "step": "gtf_iterate_dry = k_prefix + k_tile (fused load/E/R) + k_heavy (R+C of >=3-component nodes), idempotent"},
             "gpu_launches": 3 * a.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "traffic_source": "profiles/r01_k_tile_traffic.json (ncu capture at 16 events) x active edges of this launch",
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
                          "kernel": "k_tile + k_heavy", "kernel_ms": tile_ms + heavy_ms, "k_tile_ms": tile_ms,
                          "k_heavy_ms": heavy_ms, "k_prefix_ms": prefix_ms,
