@@ -173,7 +173,7 @@ def reference_arm(a):
     for _ in range(min(a.warmup, 1) + steps):
         rate = cpu_iteration_rate(a.tracks, cores, max(2.0, a.cpu_seconds / steps))
     act, evs, eff, done, wall = rate
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": act, "unit": "edges/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": eff * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "events_per_s": evs,
@@ -184,7 +184,7 @@ def reference_arm(a):
         "cpu_baseline": {"value": act, "unit": "edges/s", "cores": cores, "kind": "port",
                          "sample": "%d event-iterations (8 distinct cfg2 events) on %d threads, %.1f s" % (done, cores, wall)},
         "e2e": {"value": act, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -249,7 +249,25 @@ def e2e_loop(chunks, steps, torch):
     return ms, sum(c.h2d for c in chunks), sum(c.d2h for c in chunks)
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line, on the process's original stdout"""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # libraries (NCCL version banner, ...) print to fd 1: keep stdout clean for the single JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -365,7 +383,7 @@ def main():
             out["cpu_baseline"] = {"value": act, "unit": "edges/s", "cores": 1, "kind": "port", "events_per_s": evs,
                                    "sample": "%d event-iterations of cfg2 events (8 distinct), single-threaded C oracle, "
                                              "%.1f s of CPU work" % (done, eff)}
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
