@@ -110,6 +110,8 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
     }
     DevBatch &d = b->d;
     DA(d.sub_nalive, S);
+    DA(d.node_ok, N);
+    DA(b->n_dead, 1);
     DA(d.slot_p11, E); DA(d.slot_vms, E); DA(d.node_p11tot, N);
     DA(d.active_nx, E); DA(d.has_merged_nx, N);
     DA(d.m_a_nx, N); DA(d.m_b_nx, N); DA(d.m_c_nx, N); DA(d.m_p00_nx, N); DA(d.m_p01_nx, N);
@@ -145,7 +147,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     cudaStreamSynchronize(b->stream);
     for (int f = 0; f < GTF_NFIELDS; f++) cudaFree(b->f[f]);
     DevBatch &d = b->d;
-    void *extra[] = {d.sub_nalive, d.slot_p11, d.slot_vms, d.node_p11tot, d.active_nx, d.has_merged_nx, d.m_a_nx,
+    void *extra[] = {d.sub_nalive, d.node_ok, b->n_dead, d.slot_p11, d.slot_vms, d.node_p11tot, d.active_nx, d.has_merged_nx, d.m_a_nx,
                      d.m_b_nx, d.m_c_nx, d.m_p00_nx, d.m_p01_nx, d.m_p11_nx, d.m_p22_nx, d.m_prior_nx, d.counters,
                      b->accepted_total, b->cand_root, b->sub_has_inactive, b->sub_first, b->sort_keys, b->sort_vals,
                      b->sort_keys2, b->sort_vals2, b->pv_xy, b->pv_zr, b->acc_now, b->tags_a, b->tags_b,
@@ -162,6 +164,7 @@ extern "C" int gtf_batch_upload(gtf_batch *b, int f, const void *host)
     if (!b || f < 0 || f >= GTF_NFIELDS || !host) return fail(GTF_E_ARG, "gtf_batch_upload: bad argument");
     CK(cudaSetDevice(b->device));
     CK(cudaMemcpyAsync(b->f[f], host, (size_t)gtf_field_bytes(b, f), cudaMemcpyHostToDevice, b->stream));
+    if (f == GTF_F_alive || f == GTF_F_sub_state || f == GTF_F_sub) b->derived_dirty = true;
     return 0;
 }
 extern "C" int gtf_batch_download(gtf_batch *b, int f, void *host)
@@ -205,11 +208,32 @@ __global__ void k_sub_count(DevBatch B)
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B.N && B.alive[i]) atomicAdd(&B.sub_nalive[B.sub[i]], 1);
 }
+__global__ void k_node_ok(DevBatch B, unsigned long long *n_dead)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N) return;
+    int sg = B.sub[i];
+    unsigned f = 0;
+    if (B.alive[i] && B.sub_state[sg] == GTF_SUB_INPLAY) f |= NF_OK;
+    if (B.sub_nalive[sg] != 1) f |= NF_MULTI;
+    B.node_ok[i] = (uint8_t)f;
+    if (!B.alive[i]) atomicAdd(n_dead, 1ull);
+}
+// derived per-sub-graph / per-node flags; call after alive / sub_state changed
 static int recount_subs(gtf_batch *b)
 {
     CK(cudaMemsetAsync(b->d.sub_nalive, 0, sizeof(int32_t) * (b->S ? b->S : 1), b->stream));
-    if (b->N) k_sub_count<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d);
+    CK(cudaMemsetAsync(b->n_dead, 0, sizeof(unsigned long long), b->stream));
+    if (b->N) {
+        k_sub_count<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d);
+        k_node_ok<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, b->n_dead);
+    }
     CK(cudaGetLastError());
+    unsigned long long nd = 0;
+    CK(cudaMemcpyAsync(&nd, b->n_dead, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    b->d.all_alive = nd == 0;
+    b->derived_dirty = false;
     return 0;
 }
 
@@ -293,6 +317,10 @@ static int launch_tile(gtf_batch *b, const Prog &P, const GtfGeom &g, bool fused
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized (call gtf_batch_finalize after uploading the topology)");
     CK(cudaSetDevice(b->device));
     if (b->n_tiles == 0) return 0;
+    if (b->derived_dirty) {
+        int r_ = recount_subs(b);
+        if (r_) return r_;
+    }
     if (fused) k_tile<true><<<b->n_tiles, GTF_TILE_THREADS, sizeof(TileSmem), b->stream>>>(b->d, P, g);
     else k_tile<false><<<b->n_tiles, GTF_TILE_THREADS, sizeof(TileSmem), b->stream>>>(b->d, P, g);
     CK(cudaGetLastError());
@@ -311,6 +339,10 @@ static Prog make_prog(int key, int wb, std::initializer_list<int> ops)
 }
 static int launch_prefix(gtf_batch *b, const GtfGeom &g)
 {
+    if (b->derived_dirty) {
+        int r_ = recount_subs(b);
+        if (r_) return r_;
+    }
     if (b->N) k_prefix<<<(b->N + 127) / 128, 128, 0, b->stream>>>(b->d, g);
     CK(cudaGetLastError());
     return 0;

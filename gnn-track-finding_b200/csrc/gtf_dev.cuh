@@ -21,6 +21,8 @@ struct DevBatch {
     // derived topology
     const int32_t *tile_begin;   // [n_tiles + 1] node ranges, <= TILE_SLOTS slots and <= TILE_NODES nodes each
     int32_t *sub_nalive;         // [S] alive nodes per sub-graph ("len(subGraph.nodes()) == 1: continue")
+    uint8_t *node_ok;            // [N] bit0: alive and sub-graph in play, bit1: sub-graph has != 1 nodes (derived)
+    int all_alive;               // no node removed yet: every edge exists, the alive[] gathers can be skipped
     // per-source multiple-scattering prefix (extrapolate_merged_states.py:127-128, quirk 2)
     double *slot_p11;            // [E] merged_cov[1,1] as seen by this edge
     double *slot_vms;            // [E] var_ms of this edge
@@ -77,7 +79,8 @@ struct gtf_batch {
     cudaStream_t stream;
     void *f[GTF_NFIELDS];
     DevBatch d;
-    bool finalized;
+    bool finalized, derived_dirty;
+    unsigned long long *n_dead;
     int n_tiles, n_big;
     int32_t *tile_begin;
     unsigned long long *h_counters; // pinned

@@ -749,10 +749,8 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
     for (int ln = tid; ln <= nn; ln += GTF_TILE_THREADS) {
         sm.nbeg[ln] = (uint16_t)(B.in_off[n0 + ln] - s0);
         if (ln < nn) {
-            int i = n0 + ln, sg = B.sub[i];
-            unsigned f = 0;
-            if (B.alive[i] && B.sub_state[sg] == GTF_SUB_INPLAY) f |= NF_OK;
-            if (B.sub_nalive[sg] != 1) f |= NF_MULTI;
+            int i = n0 + ln;
+            unsigned f = B.node_ok[i]; // NF_OK | NF_MULTI, derived per node
             bool hu = B.has_uts[i] != 0;
             if (hu) f |= NF_HASUTS;
             if (!uts || hu) f |= NF_DICT;
@@ -792,10 +790,14 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
         sm.src[ls] = src;
         sm.dstl[ls] = (uint16_t)(dst - n0);
         unsigned f = r_f[it];
-        if (src >= 0 && B.alive[src] && B.alive[dst]) f |= F_EX;
+        if (src >= 0 && (B.all_alive || (B.alive[src] && B.alive[dst]))) f |= F_EX;
+        // E pass 1 folded in: does this slot carry a message this iteration? (extrapolate...py:416,425,431)
+        if (has_E && (f & (F_EX | F_ACT)) == (F_EX | F_ACT))
+            send = (B.node_ok[dst] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI) && B.has_merged[src] != 0;
+        // source x / layer are only ever used for dict entries (priors, side norm, pairwise chi2) and messages
         double sx = 0;
         int lay = -1;
-        if (src >= 0) { sx = B.x[src]; lay = B.layer[src]; }
+        if (src >= 0 && ((f & F_PRES) || send)) { sx = B.x[src]; lay = B.layer[src]; }
         sm.srcx[ls] = sx; sm.layer[ls] = lay;
         unsigned sd = (f & F_PRES) ? SD_ORIGPRES : 0u;
         if (f & F_PRES) {
@@ -815,11 +817,6 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
             sm.rank[ls] = uts ? 0x7fffffff : ls;
         sm.flags[ls] = (uint8_t)f;
         sm.side[ls] = (uint8_t)sd;
-        // E pass 1 folded in: does this slot carry a message this iteration? (extrapolate...py:416,425,431)
-        if (has_E && (f & (F_EX | F_ACT)) == (F_EX | F_ACT)) {
-            int sg = B.sub[dst];
-            send = B.sub_state[sg] == GTF_SUB_INPLAY && B.sub_nalive[sg] != 1 && B.has_merged[src] != 0;
-        }
         }
         if (has_E) { // dense list of message slots, so the extrapolation runs with full warps
             unsigned m = __ballot_sync(0xffffffffu, send);
@@ -1052,17 +1049,14 @@ __global__ void __launch_bounds__(GTF_HEAVY_WARPS * 32, GTF_HEAVY_MINB) k_heavy(
         if (lane == 0) {
             sm.nbeg[2 * warp] = (uint16_t)b0;
             sm.nbeg[2 * warp + 1] = (uint16_t)(b0 + d);
-            int sg = B.sub[i];
-            unsigned nf = NF_DICT;
-            if (B.alive[i] && B.sub_state[sg] == GTF_SUB_INPLAY) nf |= NF_OK;
-            if (B.sub_nalive[sg] != 1) nf |= NF_MULTI;
+            unsigned nf = NF_DICT | B.node_ok[i];
             if (B.has_uts[i]) nf |= NF_HASUTS;
             sm.nflags[2 * warp] = (uint8_t)nf;
         }
         if (valid) {
             int src = B.in_src[s];
             unsigned f = 0;
-            if (src >= 0 && B.alive[src] && B.alive[i]) f |= F_EX;
+            if (src >= 0 && (B.all_alive || (B.alive[src] && B.alive[i]))) f |= F_EX;
             if (B.active_nx[s] == 1) f |= F_ACT;      // after the extrapolation gate of k_tile
             if (B.active[s] == 1) f |= F_ORIG;
             unsigned sd = 0;
@@ -1121,13 +1115,12 @@ __global__ void k_prefix(DevBatch B, GtfGeom g)
     int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= B.N) return;
     double p = B.m_p11[u];
-    int sg = B.sub[u];
-    bool ok = B.alive[u] && B.has_merged[u] && B.sub_state[sg] == GTF_SUB_INPLAY && B.sub_nalive[sg] != 1;
+    bool ok = B.has_merged[u] && (B.node_ok[u] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI);
     if (ok) {
         double a = B.m_a[u], b = B.m_b[u], ur = B.r[u], uz = B.z[u];
         for (int o = B.out_off[u]; o < B.out_off[u + 1]; o++) {
             int s = B.out_slot[o], v = B.slot_dst[s];
-            if (!B.alive[v] || B.active[s] != 1) continue;
+            if (B.active[s] != 1 || !(B.all_alive || B.alive[v])) continue;
             double vms = gtf_var_ms(a, b, B.x[v], B.r[v] - ur, B.z[v] - uz, uz, g.endcap);
             p += vms;
             B.slot_p11[s] = p;

@@ -1,5 +1,7 @@
-"""Join an ncu SASS source page (csv) with nvdisasm -g line info -> samples / instructions per source line."""
-import csv, re, sys, subprocess, collections
+"""Join an ncu SASS source page (csv) with nvdisasm -g line info -> warp-stall samples / executed instructions per CUDA
+source line (and per named line range).  Usage:
+  python tools/ncu_lines.py <report.ncu-rep> <libgtf_b200.so> <mangled-kernel-substring> [top_n] [name:file:lo-hi,...]"""
+import csv, os, re, sys, subprocess, collections
 rep, so, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 subprocess.run("cd /tmp && rm -rf cubx && mkdir cubx && cd cubx && cuobjdump -xelf all %s >/dev/null 2>&1 && nvdisasm -g -c *.cubin > all.sass 2>/dev/null" % so, shell=True, check=True)
 lines = open('/tmp/cubx/all.sass').read().split('\n')
@@ -36,7 +38,7 @@ print("total samples %d, warp instructions %d" % (tot, toti))
 src = {}
 def srcline(f, n):
     try:
-        if f not in src: src[f] = open('/root/repo/gnn-track-finding_b200/csrc/' + f).read().split('\n')
+        if f not in src: src[f] = open('' + os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'gnn-track-finding_b200', 'csrc') + '/' + f).read().split('\n')
         return src[f][n - 1].strip()[:90]
     except Exception: return ''
 for key, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[4]) if len(sys.argv) > 4 else 40]:
