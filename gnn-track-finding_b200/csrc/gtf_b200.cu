@@ -122,6 +122,11 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         // slower than keeping them inside k_tile (0.36 + 0.14 ms vs 0.44 ms per 32 cfg2 events), so it is opt-in.
         const char *e = getenv("GTF_SPLIT_HEAVY");
         b->split_heavy = (e && e[0] == '1');
+        const char *pe = getenv("GTF_PIPELINE");
+        b->pipeline = (pe && pe[0] == '1');
+        DA(b->msg_list, E);
+        DA(b->big_list, N);
+        DA(b->pipe_counts, 2);
         DA(b->heavy_list, N);
         DA(b->heavy_slot, N);
         if ((int64_t)E >= (1LL << 25)) b->split_heavy = false;   // packed (slot << 6 | degree) must fit an int32
@@ -151,7 +156,8 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
                      d.m_b_nx, d.m_c_nx, d.m_p00_nx, d.m_p01_nx, d.m_p11_nx, d.m_p22_nx, d.m_prior_nx, d.counters,
                      b->accepted_total, b->cand_root, b->sub_has_inactive, b->sub_first, b->sort_keys, b->sort_vals,
                      b->sort_keys2, b->sort_vals2, b->pv_xy, b->pv_zr, b->acc_now, b->tags_a, b->tags_b,
-                     b->tile_begin, b->sort_tmp, b->heavy_list, b->heavy_slot, b->heavy_count};
+                     b->tile_begin, b->sort_tmp, b->heavy_list, b->heavy_slot, b->heavy_count, b->msg_list, b->big_list,
+                     b->pipe_counts};
     for (void *p : extra) cudaFree(p);
     cudaFreeHost(b->h_counters);
     cudaStreamDestroy(b->stream);
@@ -270,6 +276,7 @@ extern "C" int gtf_batch_finalize(gtf_batch *b)
     if (r) return r;
     CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     CK(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CK(cudaFuncSetAttribute(k_bignode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     CK(cudaStreamSynchronize(b->stream));
     b->finalized = true;
     return 0;
@@ -532,15 +539,38 @@ extern "C" int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf
     TRY(launch_prefix(b, gg));
     if (b->timing) CK(cudaEventRecord(b->ev[1], b->stream));
     Prog P = fused_prog(p);
-    b->d.heavy_list = b->split_heavy ? b->heavy_list : nullptr;
     b->d.heavy_slot = b->heavy_slot;
     b->d.heavy_count = b->heavy_count;
-    if (b->split_heavy) CK(cudaMemsetAsync(b->heavy_count, 0, 2 * sizeof(int), b->stream));
-    TRY(launch_tile(b, P, gg, true));
-    if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
-    if (b->split_heavy && b->n_tiles) {
-        k_heavy<<<b->n_sm * GTF_HEAVY_MINB, GTF_HEAVY_WARPS * 32, 0, b->stream>>>(b->d, P, gg);
+    b->d.msg_list = b->msg_list;
+    b->d.big_list = b->big_list;
+    b->d.msg_count = b->pipe_counts;
+    b->d.big_count = b->pipe_counts + 1;
+    if (b->pipeline && (int64_t)b->E < (1LL << 25)) {
+        // multi-kernel form: message list -> message execution -> thread-per-node -> cooperative nodes
+        b->d.heavy_list = b->heavy_list;
+        CK(cudaMemsetAsync(b->heavy_count, 0, 2 * sizeof(int), b->stream));
+        CK(cudaMemsetAsync(b->pipe_counts, 0, 2 * sizeof(int), b->stream));
+        if (b->E) {
+            k_msg_list<<<(b->E + GTF_PIPE_THREADS - 1) / GTF_PIPE_THREADS, GTF_PIPE_THREADS, 0, b->stream>>>(b->d);
+            k_msg_exec<<<b->n_sm * 8, GTF_PIPE_THREADS, 0, b->stream>>>(b->d, P.chi2_cut, gg);
+        }
+        if (b->N) k_node<<<(b->N + GTF_NODE_THREADS - 1) / GTF_NODE_THREADS, GTF_NODE_THREADS, 0, b->stream>>>(b->d, P);
         CK(cudaGetLastError());
+        if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
+        if (b->N) {
+            k_heavy<<<b->n_sm * GTF_HEAVY_MINB, GTF_HEAVY_WARPS * 32, 0, b->stream>>>(b->d, P, gg);
+            k_bignode<<<b->n_sm * 2, 32, sizeof(TileSmem), b->stream>>>(b->d, P, gg);
+        }
+        CK(cudaGetLastError());
+    } else {
+        b->d.heavy_list = b->split_heavy ? b->heavy_list : nullptr;
+        if (b->split_heavy) CK(cudaMemsetAsync(b->heavy_count, 0, 2 * sizeof(int), b->stream));
+        TRY(launch_tile(b, P, gg, true));
+        if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
+        if (b->split_heavy && b->n_tiles) {
+            k_heavy<<<b->n_sm * GTF_HEAVY_MINB, GTF_HEAVY_WARPS * 32, 0, b->stream>>>(b->d, P, gg);
+            CK(cudaGetLastError());
+        }
     }
     if (b->timing) {
         CK(cudaEventRecord(b->ev[3], b->stream));

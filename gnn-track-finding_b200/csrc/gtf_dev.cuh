@@ -35,6 +35,10 @@ struct DevBatch {
     int32_t *heavy_list; // [N] (nullptr: process them inside k_tile)
     int32_t *heavy_slot; // [N] first slot << 6 | degree  (E < 2^25 slots per batch when the split is on)
     int *heavy_count;    // [2]: count, next
+    // pipeline mode (gtf_pipe.cuh)
+    int32_t *msg_list;   // [E] slots that carry a message this iteration
+    int32_t *big_list;   // [N] cooperative nodes with more than 32 in-slots
+    int *msg_count, *big_count;
 };
 
 enum {
@@ -101,6 +105,9 @@ struct gtf_batch {
     int32_t *heavy_list, *heavy_slot;
     int *heavy_count;
     int n_sm;
+    bool pipeline;             // GTF_PIPELINE=1: multi-kernel form of the fused iteration (gtf_pipe.cuh)
+    int32_t *msg_list, *big_list;
+    int *pipe_counts;          // [2]: messages, big nodes
     // optional per-kernel timing of the fused iteration
     bool timing;
     cudaEvent_t ev[4];

@@ -619,7 +619,7 @@ __device__ __forceinline__ void light_prior(LightEntry &a, LightEntry &b, int n)
     if (ea) a.prior = same ? 0.5 : 1.0; // helper.py:61: 1/len(group)
     if (eb) b.prior = same ? 0.5 : 1.0;
 }
-__device__ __forceinline__ void light_reweight(TileSmem &sm, LightEntry &a, LightEntry &b, int n, double nodex, double thr,
+__device__ __forceinline__ void light_reweight(unsigned int *cnt, LightEntry &a, LightEntry &b, int n, double nodex, double thr,
                                                double *edge_w_tile, double *lrn_tile)
 {
     const unsigned m3 = F_PRES | F_EX | F_ACT;
@@ -631,7 +631,7 @@ __device__ __forceinline__ void light_reweight(TileSmem &sm, LightEntry &a, Ligh
     if (ea && eb && la == lb && a.sx != b.sx) { norm_a = 2.0; norm_b = 2.0; }
     // stale `neighbour_num`: the last dict key gates the norms (helper.py:131,138)
     unsigned lf = n == 2 ? b.f : a.f;
-    if (!(lf & F_EX)) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_KEY);
+    if (!(lf & F_EX)) atomicOr(&cnt[CNT_REFERR], (unsigned)GTF_REF_KEY);
     bool last_active = (lf & (F_EX | F_ACT)) == (F_EX | F_ACT);
     double denom = 0.0; // dict order (helper.py:165-169)
     if (ea) denom += a.w * a.lik;
@@ -655,7 +655,7 @@ __device__ __forceinline__ void light_reweight(TileSmem &sm, LightEntry &a, Ligh
         b.f |= F_RW;
         if (rw < thr) { b.f &= ~F_ACT; off++; } else b.f |= F_ACT;
     }
-    if (off) atomicAdd(&sm.cnt[CNT_RWOFF], off);
+    if (off) atomicAdd(&cnt[CNT_RWOFF], off);
 }
 __device__ __forceinline__ void light_store(TileSmem &sm, const LightEntry &e, int rank)
 {
@@ -699,9 +699,9 @@ __device__ __forceinline__ void node_program_light(TileSmem &sm, const DevBatch 
     const double nodex = B.x[i];
     if (n) {
         if (rdict) light_prior(a, b, n);
-        if (ruts) light_reweight(sm, a, b, n, nodex, P.rw_thr, B.edge_w + s0, B.uts_lrn + s0);
+        if (ruts) light_reweight(sm.cnt, a, b, n, nodex, P.rw_thr, B.edge_w + s0, B.uts_lrn + s0);
         if (rdict) light_prior(a, b, n);
-        if (ruts) light_reweight(sm, a, b, n, nodex, P.rw_thr, B.edge_w + s0, B.uts_lrn + s0);
+        if (ruts) light_reweight(sm.cnt, a, b, n, nodex, P.rw_thr, B.edge_w + s0, B.uts_lrn + s0);
     }
     // OP_WEIGHTS, final OP_PRIOR
     if (rdict) {
@@ -1129,3 +1129,5 @@ __global__ void k_prefix(DevBatch B, GtfGeom g)
     }
     B.node_p11tot[u] = p;
 }
+
+#include "gtf_pipe.cuh"

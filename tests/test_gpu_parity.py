@@ -323,3 +323,25 @@ def test_cfg5_degree_sweep_vs_oracle(deg):
     b.cluster(0, 1.0, 2.0)
     b.iterate(max_iter=1, stop_when_converged=False)
     assert gu.compare_states(state_of(b), ob.hb, ALL, rtol=1e-7) == []
+
+
+@pytest.mark.parametrize("n_events,n_tracks,eta", [(2, 300, 0.5), (1, 1000, 1.0)])
+def test_pipeline_mode_matches_fused_and_oracle(monkeypatch, n_events, n_tracks, eta):
+    """GTF_PIPELINE=1 (multi-kernel form of the iteration, gtf_pipe.cuh): same results as the single fused kernel"""
+    hb = synth_batch(n_events, n_tracks, 2700, eta_max=eta)
+    res = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("GTF_PIPELINE", flag)
+        b = gpu_batch(hb)
+        b.seed()
+        b.cluster(0, 1.0, 2.0)
+        st = b.iterate(max_iter=3, stop_when_converged=False)
+        res.append((st, state_of(b)))
+        b.close()
+    assert res[0][0] == res[1][0]
+    assert gu.compare_states(res[1][1], res[0][1], ALL) == []
+    assert dict_orders_equal(res[1][1], res[0][1])
+
+
+def dict_orders_equal(a, b):
+    return gu.dict_order(a) == gu.dict_order(b)
