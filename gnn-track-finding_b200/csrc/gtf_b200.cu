@@ -101,6 +101,9 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
     memset((void *)b, 0, sizeof(*b));
     b->N = N; b->E = E; b->S = S; b->device = device;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
     for (int f = 0; f < GTF_NFIELDS; f++) {
         size_t bytes = (size_t)field_count(b, f) * g_fields[f].elem;
         if (!bytes) bytes = 8;
@@ -122,8 +125,10 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         // slower than keeping them inside k_tile (0.36 + 0.14 ms vs 0.44 ms per 32 cfg2 events), so it is opt-in.
         const char *e = getenv("GTF_SPLIT_HEAVY");
         b->split_heavy = (e && e[0] == '1');
+        // default: the multi-kernel pipeline (faster on B200); GTF_PIPELINE=0 selects the single
+        // fused tile kernel (k_tile<true>)
         const char *pe = getenv("GTF_PIPELINE");
-        b->pipeline = (pe && pe[0] == '1');
+        b->pipeline = !(pe && pe[0] == '0');
         DA(b->msg_list, E);
         DA(b->big_list, N);
         DA(b->pipe_counts, 2);
@@ -161,6 +166,9 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     cudaFreeHost(b->h_counters);
     cudaStreamDestroy(b->stream);
+    cudaStreamDestroy(b->stream2);
+    cudaEventDestroy(b->ev_fork);
+    cudaEventDestroy(b->ev_join);
     delete b;
     return 0;
 }
@@ -535,31 +543,43 @@ extern "C" int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf
     CK(cudaSetDevice(b->device));
     TRY(counters_reset(b));
     GtfGeom gg = geom_of(g);
+    const bool pipe = b->pipeline && (int64_t)b->E < (1LL << 25);
+    b->d.msg_list = b->msg_list;
+    b->d.msg_count = b->pipe_counts;
+    b->d.big_count = b->pipe_counts + 1;
     if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
+    if (pipe && b->E) {
+        // the message list only reads the committed state: build it beside the prefix on the second stream
+        if (b->derived_dirty) TRY(recount_subs(b));
+        CK(cudaMemsetAsync(b->pipe_counts, 0, 2 * sizeof(int), b->stream));
+        CK(cudaEventRecord(b->ev_fork, b->stream));
+        CK(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
+        k_msg_list<<<(b->E + GTF_PIPE_THREADS - 1) / GTF_PIPE_THREADS, GTF_PIPE_THREADS, 0, b->stream2>>>(b->d);
+        CK(cudaEventRecord(b->ev_join, b->stream2));
+    }
     TRY(launch_prefix(b, gg));
+    if (pipe && b->E) CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
     if (b->timing) CK(cudaEventRecord(b->ev[1], b->stream));
     Prog P = fused_prog(p);
     b->d.heavy_slot = b->heavy_slot;
     b->d.heavy_count = b->heavy_count;
-    b->d.msg_list = b->msg_list;
     b->d.big_list = b->big_list;
-    b->d.msg_count = b->pipe_counts;
-    b->d.big_count = b->pipe_counts + 1;
-    if (b->pipeline && (int64_t)b->E < (1LL << 25)) {
+    if (pipe) {
         // multi-kernel form: message list -> message execution -> thread-per-node -> cooperative nodes
         b->d.heavy_list = b->heavy_list;
         CK(cudaMemsetAsync(b->heavy_count, 0, 2 * sizeof(int), b->stream));
-        CK(cudaMemsetAsync(b->pipe_counts, 0, 2 * sizeof(int), b->stream));
-        if (b->E) {
-            k_msg_list<<<(b->E + GTF_PIPE_THREADS - 1) / GTF_PIPE_THREADS, GTF_PIPE_THREADS, 0, b->stream>>>(b->d);
-            k_msg_exec<<<b->n_sm * 8, GTF_PIPE_THREADS, 0, b->stream>>>(b->d, P.chi2_cut, gg);
-        }
+        if (b->E) k_msg_exec<<<b->n_sm * 8, GTF_PIPE_THREADS, 0, b->stream>>>(b->d, P.chi2_cut, gg);
         if (b->N) k_node<<<(b->N + GTF_NODE_THREADS - 1) / GTF_NODE_THREADS, GTF_NODE_THREADS, 0, b->stream>>>(b->d, P);
         CK(cudaGetLastError());
         if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
         if (b->N) {
+            // the (few, long) > 32-slot cooperative nodes run beside k_heavy on the second stream
+            CK(cudaEventRecord(b->ev_fork, b->stream));
+            CK(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
+            k_bignode<<<b->n_sm * 2, 32, sizeof(TileSmem), b->stream2>>>(b->d, P, gg);
+            CK(cudaEventRecord(b->ev_join, b->stream2));
             k_heavy<<<b->n_sm * GTF_HEAVY_MINB, GTF_HEAVY_WARPS * 32, 0, b->stream>>>(b->d, P, gg);
-            k_bignode<<<b->n_sm * 2, 32, sizeof(TileSmem), b->stream>>>(b->d, P, gg);
+            CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
         }
         CK(cudaGetLastError());
     } else {

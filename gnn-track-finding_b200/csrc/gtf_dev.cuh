@@ -80,7 +80,8 @@ struct Prog {
 
 struct gtf_batch {
     int N, E, S, device;
-    cudaStream_t stream;
+    cudaStream_t stream, stream2;
+    cudaEvent_t ev_fork, ev_join;
     void *f[GTF_NFIELDS];
     DevBatch d;
     bool finalized, derived_dirty;

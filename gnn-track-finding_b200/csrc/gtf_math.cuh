@@ -95,12 +95,14 @@ GTF_HD void gtf_extrapolate(double ux, double uy, double uz, double ur, double v
 {
     // rotation into the source frame (:41,52) -- only x_A is live
     double rho = sqrt(ux * ux + uy * uy);
-    double ca = rho > 0.0 ? ux / rho : 1.0, sa = rho > 0.0 ? uy / rho : 0.0;
+    double irho = 1.0 / rho;                                                    // one reciprocal instead of two quotients
+    double ca = rho > 0.0 ? ux * irho : 1.0, sa = rho > 0.0 ? uy * irho : 0.0;
     double xA = (vx - ux) * ca + (vy - uy) * sa;
     // phi between the two radius vectors (:59): sin/cos taken algebraically
     double cr = ux * vy - uy * vx, dt = ux * vx + uy * vy;
     double h = sqrt(cr * cr + dt * dt);
-    double sp = h > 0.0 ? cr / h : 0.0, cp = h > 0.0 ? dt / h : 1.0;
+    double ih = 1.0 / h;
+    double sp = h > 0.0 ? cr * ih : 0.0, cp = h > 0.0 ? dt * ih : 1.0;
     double xp = xA + c * sp, Vx = cp + b * sp, Ax = a * sp;                     // :63-65
     double Vx2 = Vx * Vx;
     double s_star = (-xp * (2.0 * Vx2 + Ax * xp)) / (2.0 * Vx2 * Vx);           // :68
