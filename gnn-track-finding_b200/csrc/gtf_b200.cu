@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include "gtf_tile.cuh"
+#include "gtf_iter.cuh"
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -20,6 +21,12 @@ static int fail(int code, const std::string &msg)
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess)                                                                     \
             return fail(GTF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+#define TRY_(x)             \
+    do {                    \
+        int r__ = (x);      \
+        if (r__) return r__; \
     } while (0)
 
 struct FieldInfo { const char *name; int elem; char ext; };
@@ -140,6 +147,26 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         CK(cudaGetDeviceProperties(&prop, device));
         b->n_sm = prop.multiProcessorCount;
     }
+    {
+        // packed iteration layout (gtf_iter.cuh)
+        DevPack &k = b->k;
+        const int64_t words = ((int64_t)E + 31) / 32 + 2;
+        DA(k.out_dst, E); DA(k.out_rev, E); DA(k.geo, E); DA(k.xyzr, N);
+        DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words);
+        DA(k.state, (int64_t)E * 8); DA(k.meta, E);
+        DA(k.msg_slot, E); DA(k.msg_src, E); DA(k.msg_dst, E); DA(k.msg_w, E);
+        DA(k.src_first, N); DA(k.src_cnt, N);
+        DA(k.hv_list, (int64_t)(HV_BINS + 1) * N);
+        DA(k.counts, PK_NCOUNTS);
+        b->pack_static_stale = true;
+        for (int q = 0; q < 3; q++) { b->pack_stale[q] = true; b->soa_stale[q] = false; }
+        const char *ie = getenv("GTF_ITER");   // experiments: 0 fused tile kernel, 1 SoA pipeline, default packed pipeline
+        b->iter_mode = ie ? atoi(ie) : 2;
+        CK(cudaStreamCreateWithFlags(&b->stream3, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&b->ev_fork2, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b->ev_join3, cudaEventDisableTiming));
+    }
     DA(b->accepted_total, N); DA(b->cand_root, N); DA(b->sub_has_inactive, S); DA(b->sub_first, S);
     DA(b->sort_keys, N); DA(b->sort_vals, N); DA(b->sort_keys2, N); DA(b->sort_vals2, N);
     DA(b->pv_xy, N); DA(b->pv_zr, N); DA(b->acc_now, N); DA(b->tags_a, N); DA(b->tags_b, N);
@@ -164,6 +191,15 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
                      b->tile_begin, b->sort_tmp, b->heavy_list, b->heavy_slot, b->heavy_count, b->msg_list, b->big_list,
                      b->pipe_counts};
     for (void *p : extra) cudaFree(p);
+    {
+        DevPack &k = b->k;
+        void *pk[] = {k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.state, k.meta, k.msg_slot,
+                      k.msg_src, k.msg_dst, k.msg_w, k.src_first, k.src_cnt, k.hv_list, k.counts};
+        for (void *p : pk) cudaFree(p);
+        cudaStreamDestroy(b->stream3);
+        cudaEventDestroy(b->ev_fork2); cudaEventDestroy(b->ev_join2); cudaEventDestroy(b->ev_join3);
+        for (int q = 0; q < 6; q++) if (b->evk[q]) cudaEventDestroy(b->evk[q]);
+    }
     cudaFreeHost(b->h_counters);
     cudaStreamDestroy(b->stream);
     cudaStreamDestroy(b->stream2);
@@ -173,32 +209,84 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     return 0;
 }
 
+// ---- SoA fields <-> packed iteration layout: which side holds the newer copy, per group of fields
+static int field_group(int f)
+{
+    switch (f) {
+    case GTF_F_active: return PG_ACT;
+    case GTF_F_uts_present: return PG_PRES;
+    case GTF_F_uts_rank: case GTF_F_uts_a: case GTF_F_uts_b: case GTF_F_uts_c: case GTF_F_uts_tau: case GTF_F_uts_p00:
+    case GTF_F_uts_p01: case GTF_F_uts_p11: case GTF_F_uts_p22: case GTF_F_uts_lik: case GTF_F_uts_prior: case GTF_F_uts_w:
+    case GTF_F_uts_lrn: case GTF_F_uts_side: return PG_REC;
+    default: return -1;
+    }
+}
+static bool field_is_pack_static(int f)
+{
+    return f == GTF_F_x || f == GTF_F_y || f == GTF_F_z || f == GTF_F_r || f == GTF_F_layer || f == GTF_F_in_src ||
+           f == GTF_F_slot_dst || f == GTF_F_out_slot || f == GTF_F_rev_slot || f == GTF_F_in_off || f == GTF_F_out_off;
+}
+// bring the SoA arrays of the groups in `mask` up to date (after packed iterations)
+static int soa_sync(gtf_batch *b, unsigned mask)
+{
+    int d[3];
+    bool any = false;
+    for (int q = 0; q < 3; q++) { d[q] = ((mask >> q) & 1u) && b->soa_stale[q]; any |= d[q] != 0; }
+    if (!any || !b->E) { for (int q = 0; q < 3; q++) if ((mask >> q) & 1u) b->soa_stale[q] = false; return 0; }
+    k_unpack_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, b->k, d[PG_ACT], d[PG_PRES], d[PG_REC]);
+    CK(cudaGetLastError());
+    for (int q = 0; q < 3; q++) if (d[q]) b->soa_stale[q] = false;
+    return 0;
+}
+// a stage that works on the SoA arrays is about to run: SoA current, packed copy invalid afterwards
+static int soa_for_stage(gtf_batch *b, bool writes)
+{
+    int r = soa_sync(b, 7u);
+    if (r) return r;
+    if (writes) for (int q = 0; q < 3; q++) b->pack_stale[q] = true;
+    return 0;
+}
+
 extern "C" int gtf_batch_upload(gtf_batch *b, int f, const void *host)
 {
     if (!b || f < 0 || f >= GTF_NFIELDS || !host) return fail(GTF_E_ARG, "gtf_batch_upload: bad argument");
     CK(cudaSetDevice(b->device));
+    const int grp = field_group(f);
+    if (grp == PG_REC) { int r = soa_sync(b, 1u << PG_REC); if (r) return r; }   // the other record fields must be current
+    if (f == GTF_F_alive) { int r = soa_sync(b, 1u << PG_ACT); if (r) return r; b->pack_stale[PG_ACT] = true; }
     CK(cudaMemcpyAsync(b->f[f], host, (size_t)gtf_field_bytes(b, f), cudaMemcpyHostToDevice, b->stream));
+    if (grp >= 0) { b->soa_stale[grp] = false; b->pack_stale[grp] = true; }
+    if (field_is_pack_static(f)) b->pack_static_stale = true;
     if (f == GTF_F_alive || f == GTF_F_sub_state || f == GTF_F_sub) b->derived_dirty = true;
-    return 0;
-}
-extern "C" int gtf_batch_download(gtf_batch *b, int f, void *host)
-{
-    if (!b || f < 0 || f >= GTF_NFIELDS || !host) return fail(GTF_E_ARG, "gtf_batch_download: bad argument");
-    CK(cudaSetDevice(b->device));
-    CK(cudaMemcpyAsync(host, b->f[f], (size_t)gtf_field_bytes(b, f), cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
     return 0;
 }
 extern "C" int gtf_batch_download_async(gtf_batch *b, int f, void *host)
 {
     if (!b || f < 0 || f >= GTF_NFIELDS || !host) return fail(GTF_E_ARG, "gtf_batch_download_async: bad argument");
     CK(cudaSetDevice(b->device));
+    const int grp = field_group(f);
+    if (grp >= 0) { int r = soa_sync(b, 1u << grp); if (r) return r; }
     CK(cudaMemcpyAsync(host, b->f[f], (size_t)gtf_field_bytes(b, f), cudaMemcpyDeviceToHost, b->stream));
+    return 0;
+}
+extern "C" int gtf_batch_download(gtf_batch *b, int f, void *host)
+{
+    int r = gtf_batch_download_async(b, f, host);
+    if (r) return r;
+    CK(cudaStreamSynchronize(b->stream));
     return 0;
 }
 extern "C" int gtf_batch_device_ptr(gtf_batch *b, int f, void **dptr)
 {
     if (!b || f < 0 || f >= GTF_NFIELDS || !dptr) return fail(GTF_E_ARG, "gtf_batch_device_ptr: bad argument");
+    const int grp = field_group(f);
+    if (grp >= 0) { // the caller may write through the pointer: the SoA array becomes the authority for this group
+        CK(cudaSetDevice(b->device));
+        int r = soa_sync(b, 1u << grp);
+        if (r) return r;
+        b->pack_stale[grp] = true;
+    }
+    if (field_is_pack_static(f)) b->pack_static_stale = true;
     *dptr = b->f[f];
     return 0;
 }
@@ -285,6 +373,7 @@ extern "C" int gtf_batch_finalize(gtf_batch *b)
     CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     CK(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     CK(cudaFuncSetAttribute(k_bignode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CK(cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GTF_BIG_SMEM));
     CK(cudaStreamSynchronize(b->stream));
     b->finalized = true;
     return 0;
@@ -331,6 +420,7 @@ static int launch_tile(gtf_batch *b, const Prog &P, const GtfGeom &g, bool fused
 {
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized (call gtf_batch_finalize after uploading the topology)");
     CK(cudaSetDevice(b->device));
+    if (!fused) TRY_(soa_for_stage(b, true));
     if (b->n_tiles == 0) return 0;
     if (b->derived_dirty) {
         int r_ = recount_subs(b);
@@ -354,6 +444,7 @@ static Prog make_prog(int key, int wb, std::initializer_list<int> ops)
 }
 static int launch_prefix(gtf_batch *b, const GtfGeom &g)
 {
+    TRY_(soa_for_stage(b, true));
     if (b->derived_dirty) {
         int r_ = recount_subs(b);
         if (r_) return r_;
@@ -406,6 +497,7 @@ extern "C" int gtf_seed(gtf_batch *b, const gtf_geom *g)
     if (!b || !g) return fail(GTF_E_ARG, "gtf_seed: null argument");
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
     CK(cudaSetDevice(b->device));
+    TRY_(soa_for_stage(b, true));
     GtfGeom gg = geom_of(g);
     if (b->E) k_seed_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, gg);
     if (b->N) k_seed_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d);
@@ -417,6 +509,7 @@ extern "C" int gtf_initialize_edge_activation(gtf_batch *b)
 {
     if (!b) return fail(GTF_E_ARG, "null batch");
     CK(cudaSetDevice(b->device));
+    TRY_(soa_for_stage(b, true));
     CK(cudaMemsetAsync(b->f[GTF_F_active], 1, (size_t)(b->E ? b->E : 0), b->stream));
     return 0;
 }
@@ -536,8 +629,113 @@ static void commit_next(gtf_batch *b)
     std::swap(b->f[GTF_F_m_prior], *(void **)&d.m_prior_nx);
     sync_dev_view(b);
 }
+// ---- packed pipeline (gtf_iter.cuh) --------------------------------------------------------------------------------
+static int ensure_packed(gtf_batch *b)
+{
+    if (b->derived_dirty) TRY(recount_subs(b));
+    const bool st = b->pack_static_stale;
+    const bool any = st || b->pack_stale[0] || b->pack_stale[1] || b->pack_stale[2];
+    if (!any) return 0;
+    DevPack &k = b->k;
+    if (st) {
+        if (b->E) k_pack_out<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k);
+        if (b->N) k_pack_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, k);
+    }
+    if (b->pack_stale[PG_ACT]) CK(cudaMemsetAsync(k.counts + PK_MISSING, 0, sizeof(int), b->stream));
+    if (b->E)
+        k_pack_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k, st, b->pack_stale[PG_ACT], b->pack_stale[PG_PRES],
+                                                                b->pack_stale[PG_REC]);
+    CK(cudaGetLastError());
+    if (b->pack_stale[PG_ACT]) {
+        int missing = 0;
+        CK(cudaMemcpyAsync(&missing, k.counts + PK_MISSING, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        k.all_exist = missing == 0;
+    }
+    b->pack_static_stale = false;
+    for (int q = 0; q < 3; q++) b->pack_stale[q] = false;
+    return 0;
+}
+template <int G> static void launch_hv(gtf_batch *b, cudaStream_t s, const Prog &P, const GtfGeom &gg, int bin, const MergedOut &mo)
+{
+    k_hv<G><<<b->n_sm * GTF_HV_MINB, GTF_HV_WARPS * 32, 0, s>>>(b->d, b->k, P, gg, bin, mo);
+}
+// one iteration on the packed layout.  commit: the next state becomes the current one (merged states are written in
+// place, the activation bitmap and the accumulated p11 swap); otherwise the merged states of this pass go to the shadow
+// buffers and nothing the next pass reads is changed (profiling / benchmark entry point).
+static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom &gg, gtf_stats *st, bool commit)
+{
+    TRY(ensure_packed(b));
+    TRY(counters_reset(b));
+    DevPack &k = b->k;
+    DevBatch &d = b->d;
+    const Prog P = fused_prog(p);
+    const size_t words = ((size_t)b->E + 31) / 32 + 2;
+    cudaStream_t s0 = b->stream;
+    if (b->timing) CK(cudaEventRecord(b->evk[0], s0));
+    CK(cudaMemsetAsync(k.counts, 0, sizeof(int) * (PK_BIG + 1), s0));
+    CK(cudaMemcpyAsync(k.act_nx, k.act, sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, s0));
+    if (b->N) k_send<<<(b->N + GTF_SEND_THREADS - 1) / GTF_SEND_THREADS, GTF_SEND_THREADS, 0, s0>>>(d, k);
+    if (b->timing) CK(cudaEventRecord(b->evk[1], s0));
+    if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * 2, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg);
+    if (b->timing) CK(cudaEventRecord(b->evk[2], s0));
+    if (b->N) k_node2<<<(b->N + GTF_NODE2_THREADS - 1) / GTF_NODE2_THREADS, GTF_NODE2_THREADS, 0, s0>>>(d, k, P);
+    if (b->timing) CK(cudaEventRecord(b->evk[3], s0));
+    CK(cudaGetLastError());
+    if (b->N) {
+        MergedOut mo;
+        if (commit) {
+            mo.hm = d.has_merged;
+            mo.m[0] = d.m_a; mo.m[1] = d.m_b; mo.m[2] = d.m_c; mo.m[3] = d.m_p00; mo.m[4] = d.m_p01; mo.m[6] = d.m_p22;
+            mo.m[7] = d.m_prior;
+        } else {
+            mo.hm = d.has_merged_nx;
+            mo.m[0] = d.m_a_nx; mo.m[1] = d.m_b_nx; mo.m[2] = d.m_c_nx; mo.m[3] = d.m_p00_nx; mo.m[4] = d.m_p01_nx;
+            mo.m[6] = d.m_p22_nx; mo.m[7] = d.m_prior_nx;
+        }
+        mo.m[5] = d.m_p11_nx; // k_send / k_exec wrote every node's accumulated value there; a new cluster replaces it
+        // the bins are independent (disjoint nodes): run them side by side
+        CK(cudaEventRecord(b->ev_fork2, s0));
+        CK(cudaStreamWaitEvent(b->stream2, b->ev_fork2, 0));
+        CK(cudaStreamWaitEvent(b->stream3, b->ev_fork2, 0));
+        launch_hv<8>(b, s0, P, gg, 1, mo);
+        launch_hv<16>(b, b->stream2, P, gg, 2, mo);
+        launch_hv<4>(b, b->stream3, P, gg, 0, mo);
+        launch_hv<32>(b, b->stream3, P, gg, 3, mo);
+        k_big<<<b->n_sm * 2, 32, GTF_BIG_SMEM, b->stream2>>>(d, k, P, gg, mo);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(b->ev_join2, b->stream2));
+        CK(cudaEventRecord(b->ev_join3, b->stream3));
+        CK(cudaStreamWaitEvent(s0, b->ev_join2, 0));
+        CK(cudaStreamWaitEvent(s0, b->ev_join3, 0));
+    }
+    if (b->timing) {
+        CK(cudaEventRecord(b->evk[4], s0));
+        CK(cudaEventSynchronize(b->evk[4]));
+        for (int q = 0; q < 4; q++) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, b->evk[q], b->evk[q + 1]));
+            b->t_k[q] += t;
+        }
+        b->t_prefix_ms += 0; b->t_count++;
+    }
+    for (int q = 0; q < 3; q++) b->soa_stale[q] = true; // (a dry pass also rewrites dict entries in place)
+    if (commit) {
+        std::swap(k.act, k.act_nx);
+        std::swap(b->f[GTF_F_m_p11], *(void **)&d.m_p11_nx);
+        sync_dev_view(b);
+    }
+    if (st) return counters_read(b, st);
+    return 0;
+}
+
 extern "C" int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st)
 {
+    if (b && p && g && b->finalized && b->iter_mode == 2) {
+        CK(cudaSetDevice(b->device));
+        return iterate_packed(b, p, geom_of(g), st, false);
+    }
+    if (b && b->finalized) TRY(soa_for_stage(b, true));
     if (!b || !p || !g) return fail(GTF_E_ARG, "gtf_iterate_dry: null argument");
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
     CK(cudaSetDevice(b->device));
@@ -610,8 +808,11 @@ extern "C" int gtf_batch_set_timing(gtf_batch *b, int enable)
 {
     if (!b) return fail(GTF_E_ARG, "null batch");
     CK(cudaSetDevice(b->device));
-    if (enable && !b->ev[0])
+    if (enable && !b->ev[0]) {
         for (int k = 0; k < 4; k++) CK(cudaEventCreate(&b->ev[k]));
+        for (int k = 0; k < 6; k++) CK(cudaEventCreate(&b->evk[k]));
+    }
+    for (int k = 0; k < 5; k++) b->t_k[k] = 0.0;
     b->timing = enable != 0;
     b->t_prefix_ms = b->t_tile_ms = b->t_heavy_ms = 0.0;
     b->t_count = 0;
@@ -621,9 +822,25 @@ extern "C" int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms
 {
     if (!b) return fail(GTF_E_ARG, "null batch");
     int n = b->t_count ? b->t_count : 1;
+    if (b->iter_mode == 2) { // packed pipeline: k_send | k_exec + k_node2 | k_hv<*> + k_big
+        if (prefix_ms) *prefix_ms = b->t_k[0] / n;
+        if (tile_ms) *tile_ms = (b->t_k[1] + b->t_k[2]) / n;
+        if (heavy_ms) *heavy_ms = b->t_k[3] / n;
+        if (count) *count = b->t_count;
+        return 0;
+    }
     if (prefix_ms) *prefix_ms = b->t_prefix_ms / n;
     if (tile_ms) *tile_ms = b->t_tile_ms / n;
     if (heavy_ms) *heavy_ms = b->t_heavy_ms / n;
+    if (count) *count = b->t_count;
+    return 0;
+}
+/* per-kernel averages of the packed pipeline: ms[0..3] = k_send, k_exec, k_node2, cooperative kernels */
+extern "C" int gtf_batch_timing_kernels(gtf_batch *b, double *ms, int n_ms, int *count)
+{
+    if (!b || !ms) return fail(GTF_E_ARG, "null argument");
+    int n = b->t_count ? b->t_count : 1;
+    for (int q = 0; q < n_ms && q < 5; q++) ms[q] = b->t_k[q] / n;
     if (count) *count = b->t_count;
     return 0;
 }
@@ -634,8 +851,13 @@ extern "C" int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geo
     int it = 0;
     for (; it < max_iter; it++) {
         gtf_stats st;
-        TRY(gtf_iterate_dry(b, p, g, &st));
-        commit_next(b);
+        if (b->finalized && b->iter_mode == 2) {
+            CK(cudaSetDevice(b->device));
+            TRY(iterate_packed(b, p, geom_of(g), &st, true));
+        } else {
+            TRY(gtf_iterate_dry(b, p, g, &st));
+            commit_next(b);
+        }
         if (stats) stats[it] = st;
         if (stop_when_converged && st.active_changed == 0) { it++; break; }
     }
@@ -713,6 +935,7 @@ extern "C" int gtf_components(gtf_batch *b)
     if (!b) return fail(GTF_E_ARG, "null batch");
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
     CK(cudaSetDevice(b->device));
+    TRY_(soa_sync(b, 1u << PG_ACT));
     int n = b->N > b->S ? b->N : b->S;
     if (n == 0) return 0;
     k_cca_init<<<(n + 255) / 256, 256, 0, b->stream>>>(b->d, b->sub_has_inactive, b->sub_first);
@@ -829,6 +1052,8 @@ extern "C" int gtf_extract(gtf_batch *b, const gtf_geom *g, double pval_cut, int
                            int32_t *n_accepted, uint8_t *accepted, double *pval_xy, double *pval_zr)
 {
     if (!b || !g) return fail(GTF_E_ARG, "gtf_extract: null argument");
+    CK(cudaSetDevice(b->device));
+    TRY_(soa_for_stage(b, true));   // removes nodes: the packed copy (existing-edge bitmap) is rebuilt afterwards
     TRY(gtf_components(b));
     if (n_accepted) *n_accepted = 0;
     if (b->N == 0) return 0;

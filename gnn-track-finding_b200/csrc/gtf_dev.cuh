@@ -41,11 +41,46 @@ struct DevBatch {
     int *msg_count, *big_count;
 };
 
+// ---- packed iteration layout (gtf_iter.cuh): per-slot records + bitmaps, built from / written back to the SoA
+// fields by k_pack_* / k_unpack_slots.  The SoA arrays stay the exchange format of the C-ABI.
+struct __align__(32) MetaRec {   // the part of an updated_track_states entry the re-weighting touches
+    double w, lik, prior;        // mixture_weight, likelihood, prior
+    int32_t rank;                // dict insertion stamp (GTF_NEWMARK: inserted by k_exec, stamp assigned by the node kernels)
+    int8_t side, pad;            // helper.py:129-139 'side' (0 none, 1 left, 2 right)
+    int16_t lrn;                 // lr_layer_norm: -1 untouched since packing (SoA value stands), 0 NaN, k > 0 the integer norm
+};
+struct __align__(16) GeoRec {    // static per-slot view of the source hit
+    double sx;                   // x of the source hit
+    int32_t lay, src;            // its layer id; its node index (-1: ghost slot)
+};
+struct __align__(32) NodeXYZR { double x, y, z, r; };
+
+enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_NCOUNTS = 8 };
+
+struct DevPack {
+    // static, derived from the topology and the hit coordinates
+    int32_t *out_dst, *out_rev;  // [E] out-CSR order: destination node / slot of the reverse edge (-1 none)
+    GeoRec *geo;                 // [E]
+    NodeXYZR *xyzr;              // [N]
+    int all_exist;               // every slot is an existing edge (no ghost slot, no removed node)
+    // mutable slot state
+    uint32_t *act, *act_nx, *pres, *exists; // bitmaps over slots, 2 zero words of padding
+    double *state;               // [E][8] a b c tau p00 p01 p11 p22
+    MetaRec *meta;               // [E]
+    // message list of one iteration, source-major (a source's messages are contiguous, in successor order)
+    int32_t *msg_slot, *msg_src, *msg_dst; // [E]  (msg_slot bit 31: the source has no seed entry for this neighbour)
+    double *msg_w;               // [E] mixture weight carried by the message (extrapolate...py:384)
+    int32_t *src_first, *src_cnt; // [N] a source's range in the list
+    int32_t *hv_list;            // [(HV_BINS + 1) * N] cooperative nodes binned by dict size: <=4, <=8, <=16, <=32, more
+    int *counts;                 // [PK_NCOUNTS] messages, 4 bins, big, missing slots
+};
+
 enum {
     CNT_MERGED = 0, CNT_DEACT, CNT_SENT, CNT_GATED, CNT_RWOFF, CNT_ACTIVE, CNT_CHANGED, CNT_REFERR, GTF_NCOUNTERS
 };
 
 // per-node program executed by the tile kernel
+enum { PG_ACT = 0, PG_PRES = 1, PG_REC = 2 };
 enum { OP_END = 0, OP_E, OP_PRIOR, OP_RW, OP_CLUSTER, OP_DEGREE, OP_WEIGHTS, OP_POP };
 
 // write-back masks
@@ -106,6 +141,15 @@ struct gtf_batch {
     int32_t *heavy_list, *heavy_slot;
     int *heavy_count;
     int n_sm;
+    // packed iteration layout
+    DevPack k;
+    int iter_mode;             // 2 packed pipeline (default), 1 SoA multi-kernel pipeline, 0 single fused tile kernel
+    bool pack_static_stale;    // topology / coordinates changed since the static part was built
+    bool pack_stale[3], soa_stale[3]; // per group (PG_ACT, PG_PRES, PG_REC): which side holds the newer state
+    cudaStream_t stream3;
+    cudaEvent_t ev_fork2, ev_join2, ev_join3;
+    cudaEvent_t evk[6];
+    double t_k[5];             // send, exec, node, heavy, (spare)
     bool pipeline;             // GTF_PIPELINE=1: multi-kernel form of the fused iteration (gtf_pipe.cuh)
     int32_t *msg_list, *big_list;
     int *pipe_counts;          // [2]: messages, big nodes

@@ -1,0 +1,901 @@
+// gtf_iter.cuh -- one message-passing iteration on the packed layout (DevPack, gtf_dev.cuh):
+//   k_send     thread per source  : which out-edges carry a message (extrapolate...py:416,425,431) -> compact
+//                                   source-major message list (a source's messages contiguous, successor order)
+//   k_exec     thread per message : multiple-scattering term + its per-source running sum (quirk 2, sequential order
+//                                   kept with warp shuffles), extrapolate, chi2 gate, Kalman update
+//                                   (extrapolate_merged_states.py:26-402); writes the 64 B state record and the
+//                                   32 B weight record of the receiving dict entry
+//   k_node     thread per node    : scans the node's bits; <= 2 dict entries -> closed-form priors / side norms /
+//                                   re-weighting / pruning right here (helper.py:30-200); >= 3 -> binned lists
+//   k_hv<G>    G lanes per node   : cooperative nodes (3..32 entries), G = 4, 8, 16, 32 lanes per node, entries in
+//                                   registers in dict order: priors, re-weighting, pairwise chi2 + greedy KL merge
+//                                   (clustering.py:193-307), degree, mixture weights, priors
+//   k_big      CTA per node       : more than 32 entries (generic shared-memory program of gtf_tile.cuh)
+//   k_pack_* / k_unpack_slots     : SoA fields <-> packed records and bitmaps
+// Activation / presence flags are bitmaps (1.6 MB per 12.8 M slots: L2 resident, so the scattered tests of k_send
+// and the per-node scans cost no DRAM traffic); state and weights are array-of-records so a dict entry is read
+// and written as whole 32 B sectors.
+#pragma once
+
+#define H_EX 1u
+#define H_ACT 2u
+#define H_PRES 4u
+#define H_NEW 8u
+#define H_RW 32u
+#define H_ORIG 64u   // activated flag of the committed state
+#define H_ACT0 128u  // activated flag as loaded (after the extrapolation gate)
+
+__device__ __forceinline__ bool bm_get(const uint32_t *bm, int s) { return (bm[s >> 5] >> (s & 31)) & 1u; }
+// 32 bits starting at bit p
+__device__ __forceinline__ uint32_t bm_win(const uint32_t *bm, int p)
+{
+    const uint32_t lo = bm[p >> 5], hi = bm[(p >> 5) + 1];
+    return __funnelshift_r(lo, hi, p & 31);
+}
+__device__ __forceinline__ void bm_clear(uint32_t *bm, int s) { atomicAnd(&bm[s >> 5], ~(1u << (s & 31))); }
+__device__ __forceinline__ void bm_set(uint32_t *bm, int s) { atomicOr(&bm[s >> 5], 1u << (s & 31)); }
+
+__device__ __forceinline__ void flush_counters(unsigned int *s_cnt, unsigned long long *counters, int tid)
+{
+    if (tid < GTF_NCOUNTERS && s_cnt[tid]) {
+        if (tid == CNT_REFERR) atomicOr(&counters[tid], (unsigned long long)s_cnt[tid]);
+        else atomicAdd(&counters[tid], (unsigned long long)s_cnt[tid]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pack / unpack
+__global__ void k_pack_slots(DevBatch B, DevPack K, int do_static, int do_act, int do_pres, int do_rec)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool in = s < B.E;
+    int src = -1, dst = 0;
+    if (in) { src = B.in_src[s]; dst = B.slot_dst[s]; }
+    const bool ex = in && src >= 0 && B.alive[src] && B.alive[dst];
+    const unsigned mex = __ballot_sync(0xffffffffu, ex);
+    const unsigned mact = __ballot_sync(0xffffffffu, in && B.active[s] == 1);
+    const unsigned mpres = __ballot_sync(0xffffffffu, in && B.uts_present[s] != 0);
+    const unsigned min_ = __ballot_sync(0xffffffffu, in);
+    if (lane == 0 && min_) {
+        if (do_act) { K.act[s >> 5] = mact; K.exists[s >> 5] = mex; }
+        if (do_pres) K.pres[s >> 5] = mpres;
+        if (do_act && mex != min_) atomicAdd(&K.counts[PK_MISSING], __popc(min_ & ~mex));
+    }
+    if (!in) return;
+    if (do_static) {
+        GeoRec gr;
+        gr.sx = src >= 0 ? B.x[src] : 0.0;
+        gr.lay = src >= 0 ? B.layer[src] : -1;
+        gr.src = src;
+        K.geo[s] = gr;
+    }
+    if (do_rec) {
+        double2 *st = reinterpret_cast<double2 *>(K.state + 8 * (size_t)s);
+        st[0] = make_double2(B.uts_a[s], B.uts_b[s]);
+        st[1] = make_double2(B.uts_c[s], B.uts_tau[s]);
+        st[2] = make_double2(B.uts_p00[s], B.uts_p01[s]);
+        st[3] = make_double2(B.uts_p11[s], B.uts_p22[s]);
+        MetaRec m;
+        m.w = B.uts_w[s]; m.lik = B.uts_lik[s]; m.prior = B.uts_prior[s];
+        m.rank = B.uts_rank[s]; m.side = B.uts_side[s]; m.pad = 0; m.lrn = -1;
+        K.meta[s] = m;
+    }
+}
+__global__ void k_pack_out(DevBatch B, DevPack K)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= B.E) return;
+    const int s = B.out_slot[o];
+    K.out_dst[o] = B.slot_dst[s];
+    K.out_rev[o] = B.rev_slot[s];
+}
+__global__ void k_pack_nodes(DevBatch B, DevPack K)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N) return;
+    NodeXYZR v;
+    v.x = B.x[i]; v.y = B.y[i]; v.z = B.z[i]; v.r = B.r[i];
+    K.xyzr[i] = v;
+}
+__global__ void k_unpack_slots(DevBatch B, DevPack K, int do_act, int do_pres, int do_rec)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B.E) return;
+    if (do_act) B.active[s] = bm_get(K.act, s) ? 1 : 0;
+    if (do_pres) B.uts_present[s] = bm_get(K.pres, s) ? 1 : 0;
+    if (do_rec) {
+        const double2 *st = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)s);
+        double2 v0 = st[0], v1 = st[1], v2 = st[2], v3 = st[3];
+        B.uts_a[s] = v0.x; B.uts_b[s] = v0.y; B.uts_c[s] = v1.x; B.uts_tau[s] = v1.y;
+        B.uts_p00[s] = v2.x; B.uts_p01[s] = v2.y; B.uts_p11[s] = v3.x; B.uts_p22[s] = v3.y;
+        const MetaRec m = K.meta[s];
+        B.uts_w[s] = m.w; B.uts_lik[s] = m.lik; B.uts_prior[s] = m.prior;
+        B.uts_rank[s] = m.rank; B.uts_side[s] = m.side;
+        if (m.lrn >= 0) B.uts_lrn[s] = m.lrn == 0 ? NAN : (double)m.lrn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_send
+#define GTF_SEND_THREADS 128
+__global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack K)
+{
+    __shared__ int s_warp[GTF_SEND_THREADS / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u = blockIdx.x * GTF_SEND_THREADS + tid;
+    int cnt = 0, o0 = 0, o1 = 0;
+    const bool ok = u < B.N && B.has_merged[u] && (B.node_ok[u] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI);
+    if (ok) {
+        o0 = B.out_off[u]; o1 = B.out_off[u + 1];
+        for (int o = o0; o < o1; o++) {
+            const int s = B.out_slot[o];
+            cnt += bm_get(K.act, s) && (K.all_exist || bm_get(K.exists, s));
+        }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < GTF_SEND_THREADS / 32; w++) {
+        if (w < warp) woff += s_warp[w];
+        total += s_warp[w];
+    }
+    if (tid == 0 && total) s_base = atomicAdd(&K.counts[PK_MSG], total); // one global atomic per CTA
+    __syncthreads();
+    if (u >= B.N) return;
+    const int first = (total ? s_base : 0) + woff + incl - cnt;
+    K.src_first[u] = first;
+    K.src_cnt[u] = cnt;
+    if (cnt == 0) { B.m_p11_nx[u] = B.m_p11[u]; return; } // nothing accumulates on this node (quirk 2)
+    int q = first;
+    for (int o = o0; o < o1; o++) {
+        const int s = B.out_slot[o];
+        if (!(bm_get(K.act, s) && (K.all_exist || bm_get(K.exists, s)))) continue;
+        const int rs = K.out_rev[o];
+        const bool has = rs >= 0 && B.tse_present[rs];      // extrapolate...py:384: u's seed entry for this neighbour
+        K.msg_slot[q] = has ? s : (s | (int)0x80000000);
+        K.msg_src[q] = u;
+        K.msg_dst[q] = K.out_dst[o];
+        K.msg_w[q] = has ? B.tse_w[rs] : NAN;
+        q++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_exec
+#ifndef GTF_EXEC_THREADS
+#define GTF_EXEC_THREADS 128
+#endif
+#ifndef GTF_EXEC_MINB
+#define GTF_EXEC_MINB 4
+#endif
+__device__ __noinline__ double var_ms_nb(double a, double b, double xk, double dr, double dz, double ez, double endcap)
+{
+    return gtf_var_ms(a, b, xk, dr, dz, ez, endcap);
+}
+__global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBatch B, DevPack K, double chi2_cut, GtfGeom g)
+{
+    __shared__ unsigned int s_cnt[GTF_NCOUNTERS];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < GTF_NCOUNTERS) s_cnt[tid] = 0;
+    __syncthreads();
+    const int count = K.counts[PK_MSG];
+    unsigned gated = 0, sent = 0;
+    for (int base = blockIdx.x * GTF_EXEC_THREADS + (tid & ~31); base < count; base += gridDim.x * GTF_EXEC_THREADS) {
+        const int q = base + lane;
+        const bool valid = q < count;
+        const int qq = valid ? q : count - 1;
+        const int sraw = K.msg_slot[qq], s = sraw & 0x7fffffff;
+        const int u = K.msg_src[qq], v = K.msg_dst[qq];
+        const int sf = K.src_first[u], sc = K.src_cnt[u];
+        const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
+        const double a = B.m_a[u], bb = B.m_b[u], p11b = B.m_p11[u];
+        const double vms = gtf_var_ms(a, bb, V.x, V.r - U.r, V.z - U.z, U.z, g.endcap);
+        // merged_cov[1,1] accumulates var_ms over the source's active successors, left to right (quirk 2).
+        // Messages of this source that sit before this warp's first message: recompute their terms.
+        const int k0 = __shfl_sync(FULL, qq - sf, 0);
+        double acc0 = __shfl_sync(FULL, p11b, 0);
+        if (k0 > 0) {
+            const double a0 = __shfl_sync(FULL, a, 0), b0 = __shfl_sync(FULL, bb, 0);
+            const double ur0 = __shfl_sync(FULL, U.r, 0), uz0 = __shfl_sync(FULL, U.z, 0);
+            for (int off = 0; off < k0; off += 32) {
+                const int j = off + lane;
+                const int dj = K.msg_dst[j < k0 ? base - k0 + j : base];
+                const NodeXYZR W = K.xyzr[dj];
+                const double vj = var_ms_nb(a0, b0, W.x, W.r - ur0, W.z - uz0, uz0, g.endcap);
+                const int m = min(32, k0 - off);
+                for (int t = 0; t < m; t++) acc0 += __shfl_sync(FULL, vj, t);
+            }
+        }
+        const int first_lane = max(sf - base, 0);
+        double p = sf < base ? acc0 : p11b;
+        const int maxlen = (int)__reduce_max_sync(FULL, (unsigned)(valid ? lane - first_lane + 1 : 0));
+        for (int d = 0; d < maxlen; d++) {
+            const int sl = first_lane + d;
+            const double vj = __shfl_sync(FULL, vms, sl & 31);
+            if (sl <= lane) p += vj;
+        }
+        if (!valid) continue;
+        if (qq - sf == sc - 1) B.m_p11_nx[u] = p; // the total stays on the node
+        GtfExtrapOut o;
+        gtf_extrapolate(U.x, U.y, U.z, U.r, V.x, V.y, V.z, V.r, a, bb, B.m_c[u], B.m_p00[u], B.m_p01[u], p, B.m_p22[u], vms,
+                        chi2_cut, g, o);
+        B.uts_chi2[s] = o.chi2;
+        sent++;
+        if (o.pass) {
+            if (sraw < 0) atomicOr(&s_cnt[CNT_REFERR], (unsigned)GTF_REF_NO_TSE);
+            double2 *st = reinterpret_cast<double2 *>(K.state + 8 * (size_t)s);
+            st[0] = make_double2(o.s.a, o.s.b);
+            st[1] = make_double2(o.s.c, o.s.tau);
+            st[2] = make_double2(o.s.p00, o.s.p01);
+            st[3] = make_double2(o.s.p11, o.s.p22);
+            MetaRec *m = K.meta + s;
+            *reinterpret_cast<double2 *>(m) = make_double2(K.msg_w[qq], o.lik);
+            m->prior = NAN;                                   // a fresh dict entry has no prior / lr_layer_norm / side yet
+            reinterpret_cast<int32_t *>(m)[7] = 0;            // side = 0, lrn = 0 (NaN)
+            if (!bm_get(K.pres, s)) { m->rank = GTF_NEWMARK; bm_set(K.pres, s); }
+        } else {
+            bm_clear(K.act_nx, s); // :393
+            gated++;
+        }
+    }
+    if (sent) atomicAdd(&s_cnt[CNT_SENT], sent);
+    if (gated) atomicAdd(&s_cnt[CNT_GATED], gated);
+    __syncthreads();
+    flush_counters(s_cnt, B.counters, tid);
+}
+
+// ------------------------------------------------------------------------------------------------ k_node
+struct LEnt {          // one dict entry of a light node
+    int s;             // slot
+    unsigned f;        // H_*
+    int lay, rank, side, lrn;
+    double sx, w, lik, prior, ew;
+};
+__device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, int s, LEnt &e)
+{
+    const double2 m0 = *reinterpret_cast<const double2 *>(K.meta + s);
+    const double2 m1 = *(reinterpret_cast<const double2 *>(K.meta + s) + 1);
+    const long long tag = __double_as_longlong(m1.y);
+    const GeoRec gr = K.geo[s];
+    e.s = s;
+    e.w = m0.x; e.lik = m0.y; e.prior = m1.x;
+    e.rank = (int)(tag & 0xffffffffll);
+    e.side = (int)(int8_t)((tag >> 32) & 0xff);
+    e.lrn = (int)(int16_t)((tag >> 48) & 0xffff);
+    e.sx = gr.sx + 0.0; e.lay = gr.lay;
+    unsigned f = H_PRES;
+    if (K.all_exist || bm_get(K.exists, s)) f |= H_EX;
+    if (bm_get(K.act_nx, s)) f |= H_ACT | H_ACT0;
+    if (bm_get(K.act, s)) f |= H_ORIG;
+    if (e.rank == GTF_NEWMARK) f |= H_NEW;
+    e.f = f;
+    e.ew = 0.0;
+}
+__device__ __forceinline__ long long meta_tag(int rank, int side, int lrn)
+{
+    return (long long)(unsigned)rank | ((long long)(side & 0xff) << 32) | ((long long)(lrn & 0xffff) << 48);
+}
+__device__ __forceinline__ void lent_store(const DevBatch &B, const DevPack &K, const LEnt &e)
+{
+    double2 *m = reinterpret_cast<double2 *>(K.meta + e.s);
+    m[0] = make_double2(e.w, e.lik);
+    m[1] = make_double2(e.prior, __longlong_as_double(meta_tag(e.rank, e.side, e.lrn)));
+    if (e.f & H_RW) B.edge_w[e.s] = e.ew; // helper.py:180
+    if ((e.f & H_ACT0) && !(e.f & H_ACT)) bm_clear(K.act_nx, e.s);
+}
+__device__ __forceinline__ void lent_prior(LEnt &a, LEnt &b, int n)
+{
+    const unsigned m3 = H_PRES | H_EX | H_ACT;
+    const bool ea = (a.f & m3) == m3, eb = n == 2 && (b.f & m3) == m3;
+    const bool same = ea && eb && a.lay == b.lay;
+    if (ea) a.prior = same ? 0.5 : 1.0; // helper.py:61: 1/len(group)
+    if (eb) b.prior = same ? 0.5 : 1.0;
+}
+__device__ __forceinline__ void lent_reweight(unsigned int *cnt, LEnt &a, LEnt &b, int n, double nodex, double thr)
+{
+    const unsigned m3 = H_PRES | H_EX | H_ACT;
+    const bool ea = (a.f & m3) == m3, eb = n == 2 && (b.f & m3) == m3;
+    if (!ea && !eb) return;
+    const bool la = a.sx < nodex, lb = b.sx < nodex;
+    int norm2 = 1;                                                    // len(set(x)) per side (helper.py:127,134)
+    if (ea && eb && la == lb && a.sx != b.sx) norm2 = 2;
+    const unsigned lf = n == 2 ? b.f : a.f;                           // stale `neighbour_num` (helper.py:131,138)
+    if (!(lf & H_EX)) atomicOr(&cnt[CNT_REFERR], (unsigned)GTF_REF_KEY);
+    const bool last_active = (lf & (H_EX | H_ACT)) == (H_EX | H_ACT);
+    const int norm = last_active ? norm2 : 1;
+    double denom = 0.0;                                               // dict order (helper.py:165-169)
+    if (ea) denom += a.w * a.lik;
+    if (eb) denom += b.w * b.lik;
+    unsigned off = 0;
+    if (ea) {
+        double rw = (a.w * a.lik * a.prior) / denom;
+        if (norm != 1) rw = rw / (double)norm;
+        a.lrn = norm; a.side = la ? 1 : 2; a.w = rw; a.ew = rw;
+        a.f |= H_RW;
+        if (rw < thr) { a.f &= ~H_ACT; off++; }
+    }
+    if (eb) {
+        double rw = (b.w * b.lik * b.prior) / denom;
+        if (norm != 1) rw = rw / (double)norm;
+        b.lrn = norm; b.side = lb ? 1 : 2; b.w = rw; b.ew = rw;
+        b.f |= H_RW;
+        if (rw < thr) { b.f &= ~H_ACT; off++; }
+    }
+    if (off) atomicAdd(&cnt[CNT_RWOFF], off);
+}
+
+#define GTF_NODE2_THREADS 256
+__global__ void __launch_bounds__(GTF_NODE2_THREADS) k_node2(DevBatch B, DevPack K, Prog P)
+{
+    __shared__ unsigned int s_cnt[GTF_NCOUNTERS];
+    __shared__ int s_n[HV_BINS + 1], s_base[HV_BINS + 1];
+    __shared__ int s_list[HV_BINS + 1][GTF_NODE2_THREADS];
+    const int tid = threadIdx.x;
+    if (tid < GTF_NCOUNTERS) s_cnt[tid] = 0;
+    if (tid <= HV_BINS) s_n[tid] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * GTF_NODE2_THREADS + tid;
+    unsigned n_act = 0, n_chg = 0;
+    if (i < B.N) {
+        unsigned nf = B.node_ok[i];
+        const int b0 = B.in_off[i], b1 = B.in_off[i + 1];
+        int np = 0, e0 = -1, e1 = -1, deg = 0, chg = 0;
+        for (int c = b0; c < b1; c += 32) {
+            const int nb = min(32, b1 - c);
+            const unsigned mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            const unsigned ex = K.all_exist ? mask : (bm_win(K.exists, c) & mask);
+            const unsigned pr = bm_win(K.pres, c) & mask;
+            const unsigned an = bm_win(K.act_nx, c) & ex, a0 = bm_win(K.act, c) & ex;
+            deg += __popc(an);
+            chg += __popc(an ^ a0);
+            if (pr) {
+                if (np == 0) {
+                    e0 = c + __ffs(pr) - 1;
+                    const unsigned r = pr & (pr - 1);
+                    if (r) e1 = c + __ffs(r) - 1;
+                } else if (np == 1)
+                    e1 = c + __ffs(pr) - 1;
+                np += __popc(pr);
+            }
+        }
+        if (np > 2 && (nf & NF_OK)) {
+            const int bin = np <= 4 ? 0 : np <= 8 ? 1 : np <= 16 ? 2 : np <= 32 ? 3 : 4;
+            s_list[bin][atomicAdd(&s_n[bin], 1)] = i;
+        } else {
+            if (nf & NF_OK) {
+                const int n = np;
+                LEnt a, b;
+                a.f = 0; b.f = 0; a.s = b.s = b0; a.lay = b.lay = -1; a.sx = b.sx = 0; a.w = b.w = a.lik = b.lik = 0;
+                a.prior = b.prior = a.ew = b.ew = 0; a.side = b.side = a.rank = b.rank = 0; a.lrn = b.lrn = -1;
+                if (n >= 1) lent_load(B, K, e0, a);
+                if (n == 2) lent_load(B, K, e1, b);
+                if (B.has_uts[i]) nf |= NF_HASUTS | NF_DICT;
+                const int nnew = ((a.f & H_NEW) != 0) + ((b.f & H_NEW) != 0);
+                if (nnew) { // new entries enter the dict in ascending source order (extrapolate...py:419-447)
+                    const int nxt = B.uts_next[i];
+                    if (nnew == 2) {
+                        const bool a_first = K.geo[e0].src < K.geo[e1].src;
+                        a.rank = nxt + (a_first ? 0 : 1);
+                        b.rank = nxt + (a_first ? 1 : 0);
+                    } else if (a.f & H_NEW) a.rank = nxt; else b.rank = nxt;
+                    B.uts_next[i] = nxt + nnew;
+                    B.has_uts[i] = 1;
+                    nf |= NF_DICT | NF_HASUTS;
+                }
+                if (n == 2 && b.rank < a.rank) { LEnt t = a; a = b; b = t; } // dict order
+                const bool rdict = (nf & (NF_MULTI | NF_DICT)) == (NF_MULTI | NF_DICT);
+                const bool ruts = (nf & (NF_MULTI | NF_HASUTS)) == (NF_MULTI | NF_HASUTS);
+                if (n) {
+                    const double nodex = K.xyzr[i].x;
+                    if (rdict) lent_prior(a, b, n);
+                    if (ruts) lent_reweight(s_cnt, a, b, n, nodex, P.rw_thr);
+                    if (rdict) lent_prior(a, b, n);
+                    if (ruts) lent_reweight(s_cnt, a, b, n, nodex, P.rw_thr);
+                }
+                if (rdict) {
+                    if (n == 0) atomicOr(&s_cnt[CNT_REFERR], (unsigned)GTF_REF_ZERO_DIV);
+                    else {
+                        const double mw = n == 2 ? 0.5 : 1.0; // helper.py:90
+                        a.w = mw;
+                        b.w = mw;
+                        lent_prior(a, b, n);
+                    }
+                }
+                if (n >= 1) {
+                    if ((a.f & (H_EX | H_ACT0)) == (H_EX | H_ACT0) && !(a.f & H_ACT)) { deg--; chg += (a.f & H_ORIG) ? 1 : -1; }
+                    lent_store(B, K, a);
+                }
+                if (n == 2) {
+                    if ((b.f & (H_EX | H_ACT0)) == (H_EX | H_ACT0) && !(b.f & H_ACT)) { deg--; chg += (b.f & H_ORIG) ? 1 : -1; }
+                    lent_store(B, K, b);
+                }
+                B.degree[i] = deg;
+            }
+            n_act = deg;
+            n_chg = chg;
+        }
+    }
+    n_act = __reduce_add_sync(0xffffffffu, n_act);
+    n_chg = __reduce_add_sync(0xffffffffu, n_chg);
+    if ((tid & 31) == 0) {
+        if (n_act) atomicAdd(&s_cnt[CNT_ACTIVE], n_act);
+        if (n_chg) atomicAdd(&s_cnt[CNT_CHANGED], n_chg);
+    }
+    __syncthreads();
+    if (tid <= HV_BINS && s_n[tid]) s_base[tid] = atomicAdd(&K.counts[PK_HV0 + tid], s_n[tid]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k <= HV_BINS; k++)
+        if (tid < s_n[k]) K.hv_list[(size_t)k * B.N + s_base[k] + tid] = s_list[k][tid];
+    flush_counters(s_cnt, B.counters, tid);
+}
+
+// ------------------------------------------------------------------------------------------------ k_hv<G>
+struct MergedOut {
+    uint8_t *hm;
+    double *m[8]; // a b c p00 p01 p11 p22 prior
+};
+
+template <int G> __device__ __forceinline__ unsigned grp_min_u32(unsigned v)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int G> __device__ __forceinline__ unsigned grp_add_u32(unsigned v)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int G> __device__ __forceinline__ unsigned grp_or_u32(unsigned v)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int G> __device__ __forceinline__ unsigned long long grp_min_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+// group arg-min over lanes with `have`: value and the first group lane holding it (-1: none)
+template <int G> __device__ __forceinline__ int grp_argmin(double v, bool have, unsigned gmask, int gbase, double &vmin)
+{
+    const unsigned long long k = have ? dbl_key(v) : ~0ull;
+    const unsigned long long mk = grp_min_u64<G>(k);
+    const unsigned m = __ballot_sync(0xffffffffu, have && k == mk) & gmask;
+    vmin = key_dbl(mk);
+    return m ? __ffs(m) - 1 - gbase : -1;
+}
+template <int G> __device__ __forceinline__ void grp_shfl_info(const GtfInfo &in, int src, GtfInfo &out)
+{
+    const unsigned FULL = 0xffffffffu;
+    out.s00 = __shfl_sync(FULL, in.s00, src, G); out.s01 = __shfl_sync(FULL, in.s01, src, G);
+    out.s11 = __shfl_sync(FULL, in.s11, src, G); out.sq = __shfl_sync(FULL, in.sq, src, G);
+    out.v0 = __shfl_sync(FULL, in.v0, src, G); out.v1 = __shfl_sync(FULL, in.v1, src, G);
+    out.vc = __shfl_sync(FULL, in.vc, src, G); out.vt = __shfl_sync(FULL, in.vt, src, G);
+}
+
+#define GTF_HV_WARPS 4
+#ifndef GTF_HV_MINB
+#define GTF_HV_MINB 4
+#endif
+struct HvStage { double v[11][32]; }; // a b c tau p00 p01 p11 p22 sx sz sr of the warp's 32 entries
+
+template <int G>
+__global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch B, DevPack K, Prog P, GtfGeom g, int bin,
+                                                                         MergedOut MO)
+{
+    constexpr int NG = 32 / G;                                   // nodes per warp
+    constexpr int MAXN = G == 4 ? 4 : G == 8 ? 8 : 15;           // largest dict that can cluster in this bin
+    constexpr int R = (MAXN * (MAXN - 1) / 2 + G - 1) / G;       // pair rounds
+    const unsigned FULL = 0xffffffffu;
+    __shared__ unsigned int s_cnt[GTF_NCOUNTERS];
+    __shared__ HvStage s_stage[GTF_HV_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gl = lane % G, gbase = lane - gl;
+    const unsigned gmask = G == 32 ? FULL : (((1u << G) - 1u) << gbase);
+    if (tid < GTF_NCOUNTERS) s_cnt[tid] = 0;
+    __syncthreads();
+    const int count = K.counts[PK_HV0 + bin];
+    const int32_t *list = K.hv_list + (size_t)bin * B.N;
+    HvStage &ss = s_stage[warp];
+    unsigned n_act = 0, n_chg = 0, n_off = 0, n_deact = 0, n_merged = 0, referr = 0;
+    const int nwarps = gridDim.x * GTF_HV_WARPS;
+    for (int base = (blockIdx.x * GTF_HV_WARPS + warp) * NG; base < count; base += nwarps * NG) {
+        const int idx = base + lane / G;
+        const bool gv = idx < count;
+        const int i = gv ? list[idx] : 0;
+        int b0 = 0, b1 = 0;
+        unsigned nf = 0;
+        if (gv) { b0 = B.in_off[i]; b1 = B.in_off[i + 1]; nf = B.node_ok[i] | (B.has_uts[i] ? (NF_HASUTS | NF_DICT) : 0u); }
+        // ---- the node's bits: my entry = the gl-th present slot; totals over the slots that hold no entry
+        int slot = -1, n = 0, deg_np = 0, chg_np = 0;
+        for (int c = b0; c < b1; c += 32) {
+            const int nb = min(32, b1 - c);
+            const unsigned mask = nb == 32 ? FULL : ((1u << nb) - 1u);
+            const unsigned ex = K.all_exist ? mask : (bm_win(K.exists, c) & mask);
+            const unsigned pr = bm_win(K.pres, c) & mask;
+            const unsigned an = bm_win(K.act_nx, c) & ex, a0 = bm_win(K.act, c) & ex;
+            deg_np += __popc(an & ~pr);
+            chg_np += __popc((an ^ a0) & ~pr);
+            const int cnt = __popc(pr);
+            if (slot < 0 && gl < n + cnt) slot = c + (int)__fns(pr, 0, gl - n + 1);
+            n += cnt;
+        }
+        const bool valid = gv && gl < n;
+        // ---- weight record, flags
+        double w = 0.0, lik = 0.0, prior = 0.0, sx = 0.0, ew = 0.0;
+        int rank = 0x7fffffff, side = 0, lrn = -1, lay = -1000 - lane, src = 0;
+        unsigned f = 0;
+        if (valid) {
+            const double2 m0 = *reinterpret_cast<const double2 *>(K.meta + slot);
+            const double2 m1 = *(reinterpret_cast<const double2 *>(K.meta + slot) + 1);
+            const long long tag = __double_as_longlong(m1.y);
+            w = m0.x; lik = m0.y; prior = m1.x;
+            rank = (int)(tag & 0xffffffffll);
+            side = (int)(int8_t)((tag >> 32) & 0xff);
+            lrn = (int)(int16_t)((tag >> 48) & 0xffff);
+            const GeoRec gr = K.geo[slot];
+            sx = gr.sx + 0.0; lay = gr.lay; src = gr.src;
+            f = H_PRES;
+            if (K.all_exist || bm_get(K.exists, slot)) f |= H_EX;
+            if (bm_get(K.act_nx, slot)) f |= H_ACT | H_ACT0;
+            if (bm_get(K.act, slot)) f |= H_ORIG;
+            if (rank == GTF_NEWMARK) f |= H_NEW;
+        }
+        // ---- new entries enter the dict in ascending source order (extrapolate...py:419-447)
+        const unsigned newm = __ballot_sync(FULL, (f & H_NEW) != 0);
+        if (newm) {
+            const int nxt = gv ? B.uts_next[i] : 0;
+            int before = 0;
+            for (int t = 0; t < G; t++) {
+                const int sk = __shfl_sync(FULL, src, t, G);
+                before += ((newm >> (gbase + t)) & 1u) && sk < src;
+            }
+            if (f & H_NEW) rank = nxt + before;
+            const int nnew = __popc(newm & gmask);
+            if (nnew) {
+                if (gl == 0) { B.uts_next[i] = nxt + nnew; B.has_uts[i] = 1; }
+                nf |= NF_DICT | NF_HASUTS;
+            }
+        }
+        // ---- bring the entries into dict order (ascending stamp): lane k of the group holds dict position k
+        const int nmax = (int)__reduce_max_sync(FULL, (unsigned)n);
+        {
+            int pos = 0;
+            for (int t = 0; t < nmax; t++) {
+                const int rt = __shfl_sync(FULL, rank, t, G);
+                pos += (t < n) && rt < rank;
+            }
+            if (!valid) pos = gl;
+            int inv = gl;
+            for (int t = 0; t < nmax; t++) {
+                const int pt = __shfl_sync(FULL, pos, t, G);
+                if (t < n && pt == gl) inv = t;
+            }
+            slot = __shfl_sync(FULL, slot, inv, G); f = __shfl_sync(FULL, f, inv, G);
+            rank = __shfl_sync(FULL, rank, inv, G); lay = __shfl_sync(FULL, lay, inv, G);
+            src = __shfl_sync(FULL, src, inv, G);
+            const int sl2 = __shfl_sync(FULL, side | (lrn << 8), inv, G);
+            side = (int)(int8_t)(sl2 & 0xff); lrn = sl2 >> 8;
+            w = __shfl_sync(FULL, w, inv, G); lik = __shfl_sync(FULL, lik, inv, G);
+            prior = __shfl_sync(FULL, prior, inv, G); sx = __shfl_sync(FULL, sx, inv, G);
+        }
+        // ---- state record of my entry, node coordinates
+        GtfState mine;
+        mine.a = mine.b = mine.c = mine.tau = mine.p00 = mine.p01 = mine.p11 = mine.p22 = 0.0;
+        double sz = 0.0, sr = 0.0;
+        NodeXYZR X;
+        X.x = X.y = X.z = X.r = 0.0;
+        if (gv) X = K.xyzr[i];
+        const bool cl_node = G < 32 && gv && (nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT) && n >= 3 && n <= GTF_MAXD; // clustering.py:207
+        if (valid && cl_node) {
+            const double2 *st = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)slot);
+            const double2 v0 = st[0], v1 = st[1], v2 = st[2], v3 = st[3];
+            mine.a = v0.x; mine.b = v0.y; mine.c = v1.x; mine.tau = v1.y;
+            mine.p00 = v2.x; mine.p01 = v2.y; mine.p11 = v3.x; mine.p22 = v3.y;
+            if (src >= 0) { const NodeXYZR S = K.xyzr[src]; sz = S.z; sr = S.r; }
+        }
+        const double nodex = X.x;
+        const bool okd = (nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT);
+        const bool oku = (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS);
+        const unsigned m3 = H_PRES | H_EX | H_ACT;
+        const unsigned samelay = __match_any_sync(FULL, lay) & gmask;
+        const unsigned samex = __match_any_sync(FULL, __double_as_longlong(sx)) & gmask;
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            // helper.py:30-63 compute_prior_probabilities
+            {
+                const bool el = (f & m3) == m3;
+                const unsigned elm = __ballot_sync(FULL, el);
+                if (okd && el) prior = recip_small(__popc(samelay & elm));
+            }
+            // helper.py:99-200 side norm + reweight + prune
+            {
+                const bool el = oku && (f & m3) == m3;
+                const bool left = el && sx < nodex;
+                const unsigned elm = __ballot_sync(FULL, el), leftm = __ballot_sync(FULL, left);
+                const unsigned grpm = samex & (left ? leftm : (elm & ~leftm));
+                const bool first = el && (__ffs(grpm) - 1 == lane);             // distinct x per side: len(set(coords))
+                const int normL = __popc(__ballot_sync(FULL, first && left) & gmask);
+                const int normR = __popc(__ballot_sync(FULL, first && !left) & gmask);
+                const unsigned lf = __shfl_sync(FULL, f, max(n - 1, 0), G);     // stale `neighbour_num`: LAST dict key
+                const bool any_el = (elm & gmask) != 0;
+                if (any_el && !(lf & H_EX) && gl == 0) referr |= GTF_REF_KEY;
+                const bool last_active = (lf & (H_EX | H_ACT)) == (H_EX | H_ACT);
+                const double x = el ? w * lik : 0.0;                            // denominator in dict order (helper.py:165-169)
+                double denom = 0.0;
+                for (int q = 0; q < nmax; q++) {
+                    const double xq = __shfl_sync(FULL, x, q, G);
+                    if (q < n) denom += xq;
+                }
+                if (el) {
+                    const int norm = last_active ? (left ? normL : normR) : 1;
+                    double rw = (w * lik * prior) / denom;
+                    if (norm != 1) rw = rw / (double)norm;
+                    lrn = norm; side = left ? 1 : 2;
+                    w = rw; ew = rw;
+                    f |= H_RW;
+                    if (rw < P.rw_thr) { f &= ~H_ACT; n_off++; }
+                }
+            }
+        }
+        // ---- clustering.py:193-307
+        bool clustered = false;
+        GtfState merged;
+        merged.a = merged.b = merged.c = merged.tau = merged.p00 = merged.p01 = merged.p11 = merged.p22 = 0.0;
+        double mprior = 0.0;
+        if (G < 32 && __any_sync(FULL, cl_node)) {
+            double thr = P.cl_kl;
+            if (P.use_lut && gv) {
+                const double ev = B.emp_var[i];
+                const int lb = (ev == ev) ? (int)floor(ev / 0.05) : 27;
+                thr = P.lut[max(0, min(27, lb))];
+            }
+            __syncwarp();
+            ss.v[0][lane] = mine.a; ss.v[1][lane] = mine.b; ss.v[2][lane] = mine.c; ss.v[3][lane] = mine.tau;
+            ss.v[4][lane] = mine.p00; ss.v[5][lane] = mine.p01; ss.v[6][lane] = mine.p11; ss.v[7][lane] = mine.p22;
+            ss.v[8][lane] = sx; ss.v[9][lane] = sz; ss.v[10][lane] = sr;
+            __syncwarp();
+            const int npairs = cl_node ? n * (n - 1) / 2 : 0;
+            const int rmax = ((int)__reduce_max_sync(FULL, (unsigned)npairs) + G - 1) / G;
+            double pv[R];
+            double lbest = INFINITY;
+            bool nz_any = false, nan_any = false;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                pv[r] = 0.0;
+                if (r < rmax) {
+                    const int p = r * G + gl;
+                    if (p < npairs) {
+                        int pi, pj;
+                        pair_decode(p, pi, pj);
+                        const int li = gbase + pi, lj = gbase + pj;
+                        GtfState si, sj;
+                        si.a = ss.v[0][li]; si.b = ss.v[1][li]; si.c = ss.v[2][li]; si.tau = ss.v[3][li];
+                        si.p00 = ss.v[4][li]; si.p01 = ss.v[5][li]; si.p11 = ss.v[6][li]; si.p22 = ss.v[7][li];
+                        sj.a = ss.v[0][lj]; sj.b = ss.v[1][lj]; sj.c = ss.v[2][lj]; sj.tau = ss.v[3][lj];
+                        sj.p00 = ss.v[4][lj]; sj.p01 = ss.v[5][lj]; sj.p11 = ss.v[6][lj]; sj.p22 = ss.v[7][lj];
+                        const double v = gtf_pair_chi2(si, sj, X.x, X.z, X.r, ss.v[8][li], ss.v[9][li], ss.v[10][li],
+                                                       ss.v[8][lj], ss.v[9][lj], ss.v[10][lj], g);
+                        pv[r] = v;
+                        if (v != 0.0) {               // np.nonzero keeps NaN, drops +-0 (clustering.py:119)
+                            nz_any = true;
+                            if (v != v) nan_any = true; else lbest = fmin(lbest, v);
+                        }
+                    }
+                }
+            }
+            nz_any = (__ballot_sync(FULL, nz_any) & gmask) != 0;
+            nan_any = (__ballot_sync(FULL, nan_any) & gmask) != 0;
+            if (cl_node && !nz_any && gl == 0) referr |= GTF_REF_EMPTY_MIN;    // np.min([]) -> ValueError
+            const double best = key_dbl(grp_min_u64<G>(dbl_key(lbest)));
+            bool go = cl_node && nz_any && !nan_any && best < P.cl_chi2;       // clustering.py:228 (nan < thr is False)
+            // np.where(distances == smallest): all tied positions in row-major order (clustering.py:122-123)
+            unsigned t1 = 1u << 30, t2 = 1u << 30, nm = 0, gone = 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int p = r * G + gl;
+                if (r < rmax && p < npairs && pv[r] == best) {
+                    int pi, pj;
+                    pair_decode(p, pi, pj);
+                    if (nm == 0) t1 = p; else if (nm == 1) t2 = p;
+                    nm++;
+                    gone |= (1u << pi) | (1u << pj);
+                }
+            }
+            const unsigned pfirst = grp_min_u32<G>(t1);
+            const unsigned p2 = grp_min_u32<G>(t1 == pfirst ? t2 : t1);
+            nm = grp_add_u32<G>(nm);
+            gone = grp_or_u32<G>(gone);
+            int idx0 = 0, idx1 = 0;
+            if (go) {
+                pair_decode((int)pfirst, idx0, idx1);       // unique minimum: idx = [row, col]
+                if (nm > 1) {                               // ties: idx = [rows..., cols...] -> idx[1] is the SECOND ROW
+                    int jj;
+                    pair_decode((int)p2, idx1, jj);
+                }
+            }
+            unsigned rem = go ? (((1u << n) - 1u) & ~gone) : 0u;
+            if (go && rem == 0) {                           // np.min([]) at :252
+                if (gl == 0) referr |= GTF_REF_EMPTY_MIN;
+                go = false;
+            }
+            if (__any_sync(FULL, go)) {
+                GtfInfo mine_i, M, t;
+                gtf_to_info(mine, mine_i);
+                grp_shfl_info<G>(mine_i, idx0, M);          // clustering.py:231-233: Sigma^-1 = S_i + S_j
+                grp_shfl_info<G>(mine_i, idx1, t);
+                gtf_info_add(M, t);
+                gtf_from_info(M, merged);
+                mprior = __shfl_sync(FULL, prior, idx0, G) + __shfl_sync(FULL, prior, idx1, G); // :234
+                bool live = go;
+                clustered = go;
+                while (__any_sync(FULL, live)) {
+                    const bool have = live && gl < n && ((rem >> gl) & 1u);
+                    const double kl = have ? gtf_kl_info(mine, mine_i, merged, M) : INFINITY; // clustering.py:107-112
+                    const bool nan_kl = (__ballot_sync(FULL, have && kl != kl) & gmask) != 0;  // list.index(nan) -> ValueError
+                    double bv;
+                    const int bk = grp_argmin<G>(kl, have, gmask, gbase, bv);                  // list.index: first occurrence
+                    const bool absorb = live && !nan_kl && bk >= 0 && bv < thr;                // clustering.py:261
+                    grp_shfl_info<G>(mine_i, max(bk, 0), t);
+                    const double pk = __shfl_sync(FULL, prior, max(bk, 0), G);
+                    if (live && nan_kl) {
+                        if (gl == 0) referr |= GTF_REF_NAN_INDEX;
+                        clustered = false;
+                        live = false;
+                    } else if (absorb) {
+                        gtf_info_add(M, t);                 // :263-265 merge_states(entry, merged)
+                        gtf_from_info(M, merged);
+                        mprior = pk + mprior;               // :266
+                        rem &= ~(1u << bk);
+                        if (rem == 0) live = false;         // :283
+                    } else
+                        live = false;
+                }
+                // un-absorbed components: their in-edge is deactivated (clustering.py:297-321)
+                if (clustered && gl < n && ((rem >> gl) & 1u) && (f & H_EX)) {
+                    f &= ~H_ACT;
+                    n_deact++;
+                }
+            }
+        }
+        // ---- degree (helper.py:67-73), mixture weights (helper.py:76-94), priors
+        const unsigned actm = __ballot_sync(FULL, (f & (H_PRES | H_EX | H_ACT)) == (H_PRES | H_EX | H_ACT)) & gmask;
+        const int deg = deg_np + __popc(actm);
+        const unsigned chgm = __ballot_sync(FULL, (f & (H_PRES | H_EX)) == (H_PRES | H_EX) && (((f & H_ACT) != 0) != ((f & H_ORIG) != 0))) & gmask;
+        if (gv && gl == 0) {
+            if (nf & NF_OK) B.degree[i] = deg;
+            n_act += deg;
+            n_chg += chg_np + __popc(chgm);
+        }
+        if (okd && (f & H_PRES)) w = recip_small(n);
+        {
+            const bool el = (f & m3) == m3;
+            const unsigned elm = __ballot_sync(FULL, el);
+            if (okd && el) prior = recip_small(__popc(samelay & elm));
+        }
+        // ---- store
+        if (valid) {
+            double2 *m = reinterpret_cast<double2 *>(K.meta + slot);
+            m[0] = make_double2(w, lik);
+            m[1] = make_double2(prior, __longlong_as_double(meta_tag(rank, side, lrn)));
+            if (f & H_RW) B.edge_w[slot] = ew; // helper.py:180
+            if ((f & H_ACT0) && !(f & H_ACT)) bm_clear(K.act_nx, slot);
+        }
+        if (clustered && gl == 0) {
+            MO.hm[i] = 1;
+            MO.m[0][i] = merged.a; MO.m[1][i] = merged.b; MO.m[2][i] = merged.c; MO.m[3][i] = merged.p00;
+            MO.m[4][i] = merged.p01; MO.m[5][i] = merged.p11; MO.m[6][i] = merged.p22; MO.m[7][i] = mprior;
+            n_merged++;
+        }
+        __syncwarp();
+    }
+    n_act = __reduce_add_sync(FULL, n_act); n_chg = __reduce_add_sync(FULL, n_chg);
+    n_off = __reduce_add_sync(FULL, n_off); n_deact = __reduce_add_sync(FULL, n_deact);
+    n_merged = __reduce_add_sync(FULL, n_merged); referr = __reduce_or_sync(FULL, referr);
+    if (lane == 0) {
+        if (n_act) atomicAdd(&s_cnt[CNT_ACTIVE], n_act);
+        if (n_chg) atomicAdd(&s_cnt[CNT_CHANGED], n_chg);
+        if (n_off) atomicAdd(&s_cnt[CNT_RWOFF], n_off);
+        if (n_deact) atomicAdd(&s_cnt[CNT_DEACT], n_deact);
+        if (n_merged) atomicAdd(&s_cnt[CNT_MERGED], n_merged);
+        if (referr) atomicOr(&s_cnt[CNT_REFERR], referr);
+    }
+    __syncthreads();
+    flush_counters(s_cnt, B.counters, tid);
+}
+
+// ------------------------------------------------------------------------------------------------ k_big
+// dicts with more than 32 entries: one 32-thread CTA per node, the generic shared-memory node program of gtf_tile.cuh
+// on a tile that holds just this node; lr_layer_norm lands in a shared array behind the tile.
+#define GTF_BIG_SMEM (sizeof(TileSmem) + 16 + sizeof(double) * GTF_TILE_SLOTS)
+__global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGeom g, MergedOut MO)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
+    double *lrn_s = reinterpret_cast<double *>(smem_raw + ((sizeof(TileSmem) + 15) & ~(size_t)15));
+    const int lane = threadIdx.x;
+    const int count = K.counts[PK_BIG];
+    const int32_t *list = K.hv_list + (size_t)HV_BINS * B.N;
+    for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+        const int i = list[idx];
+        const int gs0 = B.in_off[i], d = B.in_off[i + 1] - gs0;
+        if (lane < GTF_NCOUNTERS) sm.cnt[lane] = 0;
+        if (lane == 0) {
+            sm.nbeg[0] = 0; sm.nbeg[1] = (uint16_t)d;
+            unsigned nf = NF_DICT | B.node_ok[i];
+            if (B.has_uts[i]) nf |= NF_HASUTS;
+            sm.nflags[0] = (uint8_t)nf;
+        }
+        for (int ls = lane; ls < d; ls += 32) {
+            const int s = gs0 + ls;
+            const GeoRec gr = K.geo[s];
+            unsigned f = 0, sd = 0;
+            int rk = 0x7fffffff;
+            if (K.all_exist || bm_get(K.exists, s)) f |= F_EX;
+            if (bm_get(K.act_nx, s)) f |= F_ACT;
+            if (bm_get(K.act, s)) f |= F_ORIG;
+            if (bm_get(K.pres, s)) {
+                f |= F_PRES;
+                const MetaRec m = K.meta[s];
+                sd = SD_ORIGPRES | ((unsigned)m.side & 3u);
+                const double2 *st = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)s);
+                const double2 v0 = st[0], v1 = st[1], v2 = st[2], v3 = st[3];
+                sm.st[0][ls] = v0.x; sm.st[1][ls] = v0.y; sm.st[2][ls] = v1.x; sm.st[3][ls] = v1.y;
+                sm.st[4][ls] = v2.x; sm.st[5][ls] = v2.y; sm.st[6][ls] = v3.x; sm.st[7][ls] = v3.y;
+                sm.prior[ls] = m.prior; sm.w[ls] = m.w; sm.lik[ls] = m.lik;
+                rk = m.rank;
+                if (rk == GTF_NEWMARK) f |= F_NEW;
+            }
+            sm.src[ls] = gr.src;
+            sm.srcx[ls] = gr.sx;
+            sm.layer[ls] = gr.lay;
+            sm.rank[ls] = rk;
+            sm.side[ls] = (uint8_t)sd;
+            sm.flags[ls] = (uint8_t)f;
+            lrn_s[ls] = -1.0;
+        }
+        __syncwarp();
+        node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, true, MO.hm, MO.m, lrn_s);
+        __syncwarp();
+        unsigned n_act = 0, n_chg = 0;
+        for (int ls = lane; ls < d; ls += 32) {
+            const int s = gs0 + ls;
+            const unsigned f = sm.flags[ls];
+            const bool a = f & F_ACT, a0 = f & F_ORIG;
+            if (f & F_EX) { n_act += a; n_chg += a != a0; }
+            if (!a && bm_get(K.act_nx, s)) bm_clear(K.act_nx, s);
+            if (f & F_PRES) {
+                MetaRec m = K.meta[s];
+                m.prior = sm.prior[ls];
+                m.w = sm.w[ls];
+                m.rank = sm.rank[ls];
+                if (f & F_RW) m.side = (int8_t)(sm.side[ls] & 3);
+                if (lrn_s[ls] >= 0.0) m.lrn = (int16_t)lrn_s[ls];
+                K.meta[s] = m;
+            }
+        }
+        n_act = __reduce_add_sync(0xffffffffu, n_act);
+        n_chg = __reduce_add_sync(0xffffffffu, n_chg);
+        __syncwarp();
+        if (lane == 0) {
+            if (n_act) atomicAdd(&B.counters[CNT_ACTIVE], (unsigned long long)n_act);
+            if (n_chg) atomicAdd(&B.counters[CNT_CHANGED], (unsigned long long)n_chg);
+        }
+        flush_counters(sm.cnt, B.counters, lane);
+        __syncwarp();
+    }
+}

@@ -124,6 +124,8 @@ int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, g
  * and k_heavy): enable != 0 resets the accumulators; gtf_batch_timing returns averages over the calls since */
 int gtf_batch_set_timing(gtf_batch *b, int enable);
 int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms, double *heavy_ms, int *count);
+/* per-kernel averages of the packed pipeline: ms[0..3] = k_send, k_exec, k_node2, cooperative kernels (k_hv<*>, k_big) */
+int gtf_batch_timing_kernels(gtf_batch *b, double *ms, int n_ms, int *count);
 
 /* ---- candidate extraction ------------------------------------------------------------------- */
 /* extract/extract_track_candidates.py:332-346 CCA: weakly connected components over active edges ->
