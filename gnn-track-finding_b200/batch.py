@@ -147,17 +147,18 @@ class EventBatch(object):
         L.check(self.lib.gtf_remove_state_metadata(self.h, ctypes.byref(st)))
         return self._done(st)
 
-    def _iter_params(self, chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, KL_lut):
-        p = L.IterParams(chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, None)
+    def _iter_params(self, chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, KL_lut, record_chi2=False):
+        p = L.IterParams(chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, None, 1 if record_chi2 else 0)
         if KL_lut is not None:
             self._lut_keep = np.ascontiguousarray(KL_lut, np.float64)
             p.kl_lut = self._lut_keep.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         return p
 
     def iterate(self, max_iter=10, stop_when_converged=True, chi2_cut=2.0, cluster_chi2=1000.0, cluster_kl=100.0,
-                reweight_threshold=0.1, KL_lut=None):
-        """Fused iterations [message_passing, (prior, reweight) x2, cluster(updated states)]."""
-        p = self._iter_params(chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, KL_lut)
+                reweight_threshold=0.1, KL_lut=None, record_chi2=False):
+        """Fused iterations [message_passing, (prior, reweight) x2, cluster(updated states)].
+        record_chi2: also keep every message's gate chi2 in `uts_chi2` (diagnostic; the reference only logs it)."""
+        p = self._iter_params(chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, KL_lut, record_chi2)
         stats = (L.Stats * max_iter)()
         n = ctypes.c_int(0)
         L.check(self.lib.gtf_iterate(self.h, ctypes.byref(p), ctypes.byref(self.geom), max_iter,
@@ -184,6 +185,13 @@ class EventBatch(object):
         a, b_, c, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int(0)
         L.check(self.lib.gtf_batch_timing(self.h, ctypes.byref(a), ctypes.byref(b_), ctypes.byref(c), ctypes.byref(n)))
         return a.value, b_.value, c.value, n.value
+
+    def timing_kernels(self):
+        """{kernel: ms} averages of the packed pipeline: k_send, k_exec, k_node2, cooperative (k_hv<*> + k_big)"""
+        ms = (ctypes.c_double * 5)()
+        n = ctypes.c_int(0)
+        L.check(self.lib.gtf_batch_timing_kernels(self.h, ms, 5, ctypes.byref(n)))
+        return {"k_send": ms[0], "k_exec": ms[1], "k_node2": ms[2], "k_hv": ms[3], "n": n.value}
 
     def CCA(self):
         """extract_track_candidates.py:332: component label per node (smallest node index; -1 = removed)."""

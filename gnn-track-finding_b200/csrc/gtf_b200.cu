@@ -152,10 +152,10 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         DevPack &k = b->k;
         const int64_t words = ((int64_t)E + 31) / 32 + 2;
         DA(k.out_dst, E); DA(k.out_rev, E); DA(k.geo, E); DA(k.xyzr, N);
-        DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words);
-        DA(k.state, (int64_t)E * 8); DA(k.meta, E);
+        DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.fresh, words); DA(k.newb, words);
+        DA(k.state, (int64_t)E * 8); DA(k.meta, E); DA(k.tag, E);
         DA(k.msg_slot, E); DA(k.msg_src, E); DA(k.msg_dst, E); DA(k.msg_w, E);
-        DA(k.src_first, N); DA(k.src_cnt, N);
+        DA(k.msg_p11, E); DA(k.msg_vms, E);
         DA(k.hv_list, (int64_t)(HV_BINS + 1) * N);
         DA(k.counts, PK_NCOUNTS);
         b->pack_static_stale = true;
@@ -193,8 +193,8 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.state, k.meta, k.msg_slot,
-                      k.msg_src, k.msg_dst, k.msg_w, k.src_first, k.src_cnt, k.hv_list, k.counts};
+        void *pk[] = {k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.fresh, k.newb, k.state, k.meta, k.tag, k.msg_slot,
+                      k.msg_src, k.msg_dst, k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         cudaStreamDestroy(b->stream3);
         cudaEventDestroy(b->ev_fork2); cudaEventDestroy(b->ev_join2); cudaEventDestroy(b->ev_join3);
@@ -217,7 +217,7 @@ static int field_group(int f)
     case GTF_F_uts_present: return PG_PRES;
     case GTF_F_uts_rank: case GTF_F_uts_a: case GTF_F_uts_b: case GTF_F_uts_c: case GTF_F_uts_tau: case GTF_F_uts_p00:
     case GTF_F_uts_p01: case GTF_F_uts_p11: case GTF_F_uts_p22: case GTF_F_uts_lik: case GTF_F_uts_prior: case GTF_F_uts_w:
-    case GTF_F_uts_lrn: case GTF_F_uts_side: return PG_REC;
+    case GTF_F_uts_lrn: case GTF_F_uts_side: case GTF_F_edge_w: return PG_REC;
     default: return -1;
     }
 }
@@ -367,6 +367,34 @@ extern "C" int gtf_batch_finalize(gtf_batch *b)
     if (b->tile_begin) cudaFree(b->tile_begin);
     CK(cudaMalloc((void **)&b->tile_begin, sizeof(int32_t) * tiles.size()));
     CK(cudaMemcpyAsync(b->tile_begin, tiles.data(), sizeof(int32_t) * tiles.size(), cudaMemcpyHostToDevice, b->stream));
+    {
+        // k_send tiles over sources (whole sources, bounded out-edges)
+        std::vector<int32_t> out_off((size_t)b->N + 1);
+        CK(cudaMemcpyAsync(out_off.data(), b->f[GTF_F_out_off], sizeof(int32_t) * ((size_t)b->N + 1), cudaMemcpyDeviceToHost,
+                           b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        if (b->N && (out_off[0] != 0 || out_off[b->N] != b->E)) return fail(GTF_E_STATE, "gtf_batch_finalize: out_off does not span the slots");
+        std::vector<int32_t> st;
+        st.push_back(0);
+        int u = 0;
+        while (u < b->N) {
+            int start = u, edges = 0;
+            while (u < b->N && (u - start) < GTF_SEND_SRCS) {
+                int dg = out_off[u + 1] - out_off[u];
+                if (dg < 0) return fail(GTF_E_STATE, "gtf_batch_finalize: out_off not monotone");
+                if (dg > GTF_SEND_EDGES) return fail(GTF_E_DEGREE, "gtf_batch_finalize: node out-degree exceeds GTF_SEND_EDGES");
+                if (edges + dg > GTF_SEND_EDGES) break;
+                edges += dg;
+                u++;
+            }
+            st.push_back(u);
+        }
+        b->n_stiles = (int)st.size() - 1;
+        if (b->stile_begin) cudaFree(b->stile_begin);
+        CK(cudaMalloc((void **)&b->stile_begin, sizeof(int32_t) * st.size()));
+        CK(cudaMemcpyAsync(b->stile_begin, st.data(), sizeof(int32_t) * st.size(), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
     sync_dev_view(b);
     int r = recount_subs(b);
     if (r) return r;
@@ -675,9 +703,13 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
     if (b->timing) CK(cudaEventRecord(b->evk[0], s0));
     CK(cudaMemsetAsync(k.counts, 0, sizeof(int) * (PK_BIG + 1), s0));
     CK(cudaMemcpyAsync(k.act_nx, k.act, sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, s0));
-    if (b->N) k_send<<<(b->N + GTF_SEND_THREADS - 1) / GTF_SEND_THREADS, GTF_SEND_THREADS, 0, s0>>>(d, k);
+    CK(cudaMemsetAsync(k.fresh, 0, sizeof(uint32_t) * words, s0));
+    CK(cudaMemsetAsync(k.newb, 0, sizeof(uint32_t) * words, s0));
+    // accumulated p11 of nodes that send nothing this pass (quirk 2); k_send overwrites the senders
+    if (b->N) CK(cudaMemcpyAsync(d.m_p11_nx, d.m_p11, sizeof(double) * (size_t)b->N, cudaMemcpyDeviceToDevice, s0));
+    if (b->n_stiles) k_send<<<b->n_stiles, GTF_SEND_THREADS, 0, s0>>>(d, k, b->stile_begin, gg);
     if (b->timing) CK(cudaEventRecord(b->evk[1], s0));
-    if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * 2, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg);
+    if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * 2, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg, p->record_chi2);
     if (b->timing) CK(cudaEventRecord(b->evk[2], s0));
     if (b->N) k_node2<<<(b->N + GTF_NODE2_THREADS - 1) / GTF_NODE2_THREADS, GTF_NODE2_THREADS, 0, s0>>>(d, k, P);
     if (b->timing) CK(cudaEventRecord(b->evk[3], s0));

@@ -43,9 +43,12 @@ struct DevBatch {
 
 // ---- packed iteration layout (gtf_iter.cuh): per-slot records + bitmaps, built from / written back to the SoA
 // fields by k_pack_* / k_unpack_slots.  The SoA arrays stay the exchange format of the C-ABI.
-struct __align__(32) MetaRec {   // the part of an updated_track_states entry the re-weighting touches
-    double w, lik, prior;        // mixture_weight, likelihood, prior
-    int32_t rank;                // dict insertion stamp (GTF_NEWMARK: inserted by k_exec, stamp assigned by the node kernels)
+struct __align__(32) MetaRec {   // the part of an updated_track_states entry the re-weighting touches: one 32 B sector,
+    double w, lik, prior;        // always written whole (a partial-sector write costs a DRAM read-modify-write)
+    double ew;                   // G[src][dst]['mixture_weight'] (helper.py:180)
+};
+struct __align__(8) TagRec {     // rarely changing part of the entry: written only when a value changes
+    int32_t rank;                // dict insertion stamp
     int8_t side, pad;            // helper.py:129-139 'side' (0 none, 1 left, 2 right)
     int16_t lrn;                 // lr_layer_norm: -1 untouched since packing (SoA value stands), 0 NaN, k > 0 the integer norm
 };
@@ -65,12 +68,14 @@ struct DevPack {
     int all_exist;               // every slot is an existing edge (no ghost slot, no removed node)
     // mutable slot state
     uint32_t *act, *act_nx, *pres, *exists; // bitmaps over slots, 2 zero words of padding
+    uint32_t *fresh, *newb;      // entry (re)written / inserted by k_exec in this iteration (cleared every iteration)
     double *state;               // [E][8] a b c tau p00 p01 p11 p22
     MetaRec *meta;               // [E]
+    TagRec *tag;                 // [E]
     // message list of one iteration, source-major (a source's messages are contiguous, in successor order)
     int32_t *msg_slot, *msg_src, *msg_dst; // [E]  (msg_slot bit 31: the source has no seed entry for this neighbour)
     double *msg_w;               // [E] mixture weight carried by the message (extrapolate...py:384)
-    int32_t *src_first, *src_cnt; // [N] a source's range in the list
+    double *msg_p11, *msg_vms;   // [E] merged_cov[1,1] as the edge sees it (quirk 2), its multiple-scattering term
     int32_t *hv_list;            // [(HV_BINS + 1) * N] cooperative nodes binned by dict size: <=4, <=8, <=16, <=32, more
     int *counts;                 // [PK_NCOUNTS] messages, 4 bins, big, missing slots
 };
@@ -123,6 +128,8 @@ struct gtf_batch {
     unsigned long long *n_dead;
     int n_tiles, n_big;
     int32_t *tile_begin;
+    int n_stiles;
+    int32_t *stile_begin;      // k_send tiles: whole sources, <= GTF_SEND_SRCS sources and <= GTF_SEND_EDGES out-edges
     unsigned long long *h_counters; // pinned
     int64_t dev_bytes;
     // extraction scratch

@@ -35,6 +35,8 @@ __device__ __forceinline__ uint32_t bm_win(const uint32_t *bm, int p)
 __device__ __forceinline__ void bm_clear(uint32_t *bm, int s) { atomicAnd(&bm[s >> 5], ~(1u << (s & 31))); }
 __device__ __forceinline__ void bm_set(uint32_t *bm, int s) { atomicOr(&bm[s >> 5], 1u << (s & 31)); }
 
+__device__ __forceinline__ void l1_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void flush_counters(unsigned int *s_cnt, unsigned long long *counters, int tid)
 {
     if (tid < GTF_NCOUNTERS && s_cnt[tid]) {
@@ -75,9 +77,11 @@ __global__ void k_pack_slots(DevBatch B, DevPack K, int do_static, int do_act, i
         st[2] = make_double2(B.uts_p00[s], B.uts_p01[s]);
         st[3] = make_double2(B.uts_p11[s], B.uts_p22[s]);
         MetaRec m;
-        m.w = B.uts_w[s]; m.lik = B.uts_lik[s]; m.prior = B.uts_prior[s];
-        m.rank = B.uts_rank[s]; m.side = B.uts_side[s]; m.pad = 0; m.lrn = -1;
+        m.w = B.uts_w[s]; m.lik = B.uts_lik[s]; m.prior = B.uts_prior[s]; m.ew = B.edge_w[s];
         K.meta[s] = m;
+        TagRec t;
+        t.rank = B.uts_rank[s]; t.side = B.uts_side[s]; t.pad = 0; t.lrn = -1;
+        K.tag[s] = t;
     }
 }
 __global__ void k_pack_out(DevBatch B, DevPack K)
@@ -108,141 +112,207 @@ __global__ void k_unpack_slots(DevBatch B, DevPack K, int do_act, int do_pres, i
         B.uts_a[s] = v0.x; B.uts_b[s] = v0.y; B.uts_c[s] = v1.x; B.uts_tau[s] = v1.y;
         B.uts_p00[s] = v2.x; B.uts_p01[s] = v2.y; B.uts_p11[s] = v3.x; B.uts_p22[s] = v3.y;
         const MetaRec m = K.meta[s];
-        B.uts_w[s] = m.w; B.uts_lik[s] = m.lik; B.uts_prior[s] = m.prior;
-        B.uts_rank[s] = m.rank; B.uts_side[s] = m.side;
-        if (m.lrn >= 0) B.uts_lrn[s] = m.lrn == 0 ? NAN : (double)m.lrn;
+        B.uts_w[s] = m.w; B.uts_lik[s] = m.lik; B.uts_prior[s] = m.prior; B.edge_w[s] = m.ew;
+        const TagRec t = K.tag[s];
+        B.uts_rank[s] = t.rank; B.uts_side[s] = t.side;
+        if (t.lrn >= 0) B.uts_lrn[s] = t.lrn == 0 ? NAN : (double)t.lrn;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ k_send
-#define GTF_SEND_THREADS 128
-__global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack K)
+// One CTA owns a tile of whole sources (<= GTF_SEND_SRCS sources, <= GTF_SEND_EDGES out-edges; table built at
+// gtf_batch_finalize).
+//   phase 0  thread per source : offsets, "sends at all" flag (merged state, sub-graph in play), source of every edge
+//   phase 1  thread per edge   : does the edge carry a message?  (edge active and existing: extrapolate...py:416,425,431)
+//                                -> ordered compaction into shared memory
+//   phase 2  thread per message: Highland term var_ms (extrapolate...py:114-124), carried mixture weight (:384)
+//   phase 3  thread per source : merged_cov[1,1] as each edge sees it = node value + the terms of the source's earlier
+//                                active successors, summed left to right (quirk 2); the total stays on the node
+//   phase 4  thread per message: coalesced append to the global source-major list k_exec consumes densely
+#define GTF_SEND_THREADS 256
+#define GTF_SEND_EPT 3                                   // out-edges per thread
+#define GTF_SEND_EDGES (GTF_SEND_THREADS * GTF_SEND_EPT)
+#define GTF_SEND_SRCS 255                                // (+1 offsets: one per thread)
+struct SendSmem {
+    int off[GTF_SEND_SRCS + 1];
+    uint8_t ok[GTF_SEND_SRCS + 1];
+    uint8_t esrc[GTF_SEND_EDGES];                        // local source of every out-edge of the tile
+    int m_slot[GTF_SEND_EDGES], m_dst[GTF_SEND_EDGES], m_rev[GTF_SEND_EDGES];
+    uint8_t m_src[GTF_SEND_EDGES];
+    double m_vms[GTF_SEND_EDGES], m_w[GTF_SEND_EDGES], m_p11[GTF_SEND_EDGES];
+    uint16_t first[GTF_SEND_SRCS + 1], last[GTF_SEND_SRCS + 1]; // a source's message range in the tile list
+    int wsum[GTF_SEND_THREADS / 32];
+    int base;
+};
+__global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack K, const int32_t *__restrict__ stile, GtfGeom g)
 {
-    __shared__ int s_warp[GTF_SEND_THREADS / 32];
-    __shared__ int s_base;
+    __shared__ SendSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = blockIdx.x * GTF_SEND_THREADS + tid;
-    int cnt = 0, o0 = 0, o1 = 0;
-    const bool ok = u < B.N && B.has_merged[u] && (B.node_ok[u] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI);
-    if (ok) {
-        o0 = B.out_off[u]; o1 = B.out_off[u + 1];
-        for (int o = o0; o < o1; o++) {
-            const int s = B.out_slot[o];
-            cnt += bm_get(K.act, s) && (K.all_exist || bm_get(K.exists, s));
+    const int u0 = stile[blockIdx.x], ns = stile[blockIdx.x + 1] - u0;
+    // ---- phase 0
+    int my_off = 0, my_end = 0;
+    if (tid < ns) {
+        const int u = u0 + tid;
+        my_off = B.out_off[u]; my_end = B.out_off[u + 1];
+        sm.off[tid] = my_off;
+        if (tid == ns - 1) sm.off[ns] = my_end;
+        sm.ok[tid] = B.has_merged[u] && (B.node_ok[u] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI);
+        sm.first[tid] = 0xffff;
+    }
+    __syncthreads();
+    const int o_base = sm.off[0], ne = sm.off[ns] - o_base;
+    if (tid < ns)
+        for (int o = my_off; o < my_end; o++) sm.esrc[o - o_base] = (uint8_t)tid;
+    __syncthreads();
+    // ---- phase 1: GTF_SEND_EPT consecutive edges per thread keep the successor order
+    int slots[GTF_SEND_EPT], dsts[GTF_SEND_EPT], revs[GTF_SEND_EPT], cnt = 0;
+    unsigned mymask = 0;
+    const int e0 = tid * GTF_SEND_EPT;
+#pragma unroll
+    for (int j = 0; j < GTF_SEND_EPT; j++) slots[j] = e0 + j < ne ? B.out_slot[o_base + e0 + j] : -1;
+#pragma unroll
+    for (int j = 0; j < GTF_SEND_EPT; j++) {
+        dsts[j] = 0; revs[j] = -1;
+        if (e0 + j < ne) {
+            const int s = slots[j];
+            if (sm.ok[sm.esrc[e0 + j]] && bm_get(K.act, s) && (K.all_exist || bm_get(K.exists, s))) { mymask |= 1u << j; cnt++; }
         }
     }
+#pragma unroll
+    for (int j = 0; j < GTF_SEND_EPT; j++)
+        if ((mymask >> j) & 1u) { dsts[j] = K.out_dst[o_base + e0 + j]; revs[j] = K.out_rev[o_base + e0 + j]; }
     int incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 31) sm.wsum[warp] = incl;
     __syncthreads();
-    int woff = 0, total = 0;
+    int woff = 0, M = 0;
 #pragma unroll
     for (int w = 0; w < GTF_SEND_THREADS / 32; w++) {
-        if (w < warp) woff += s_warp[w];
-        total += s_warp[w];
+        if (w < warp) woff += sm.wsum[w];
+        M += sm.wsum[w];
     }
-    if (tid == 0 && total) s_base = atomicAdd(&K.counts[PK_MSG], total); // one global atomic per CTA
+    if (M == 0) return;
+    if (tid == 0) sm.base = atomicAdd(&K.counts[PK_MSG], M); // one global atomic per CTA
+    {
+        int pos = woff + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < GTF_SEND_EPT; j++)
+            if ((mymask >> j) & 1u) {
+                sm.m_slot[pos] = slots[j]; sm.m_dst[pos] = dsts[j]; sm.m_rev[pos] = revs[j]; sm.m_src[pos] = sm.esrc[e0 + j];
+                pos++;
+            }
+    }
     __syncthreads();
-    if (u >= B.N) return;
-    const int first = (total ? s_base : 0) + woff + incl - cnt;
-    K.src_first[u] = first;
-    K.src_cnt[u] = cnt;
-    if (cnt == 0) { B.m_p11_nx[u] = B.m_p11[u]; return; } // nothing accumulates on this node (quirk 2)
-    int q = first;
-    for (int o = o0; o < o1; o++) {
-        const int s = B.out_slot[o];
-        if (!(bm_get(K.act, s) && (K.all_exist || bm_get(K.exists, s)))) continue;
-        const int rs = K.out_rev[o];
+    // ---- phase 2
+    for (int q = tid; q < M; q += GTF_SEND_THREADS) {
+        const int sl = sm.m_src[q], u = u0 + sl, v = sm.m_dst[q], rs = sm.m_rev[q];
+        const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
+        const double a = B.m_a[u], b = B.m_b[u];
         const bool has = rs >= 0 && B.tse_present[rs];      // extrapolate...py:384: u's seed entry for this neighbour
-        K.msg_slot[q] = has ? s : (s | (int)0x80000000);
-        K.msg_src[q] = u;
-        K.msg_dst[q] = K.out_dst[o];
-        K.msg_w[q] = has ? B.tse_w[rs] : NAN;
-        q++;
+        sm.m_w[q] = has ? B.tse_w[rs] : NAN;
+        if (!has) sm.m_slot[q] |= (int)0x80000000;
+        sm.m_vms[q] = gtf_var_ms(a, b, V.x, V.r - U.r, V.z - U.z, U.z, g.endcap);
+        if (q == 0 || sm.m_src[q - 1] != sl) sm.first[sl] = (uint16_t)q;
+        if (q == M - 1 || sm.m_src[q + 1] != sl) sm.last[sl] = (uint16_t)q;
+    }
+    __syncthreads();
+    // ---- phase 3
+    if (tid < ns && sm.first[tid] != 0xffff) {
+        const int u = u0 + tid, q1 = sm.last[tid];
+        double p = B.m_p11[u];
+        for (int q = sm.first[tid]; q <= q1; q++) {
+            p += sm.m_vms[q];
+            sm.m_p11[q] = p;
+        }
+        B.m_p11_nx[u] = p;
+    }
+    __syncthreads();
+    // ---- phase 4
+    const int base = sm.base;
+    for (int q = tid; q < M; q += GTF_SEND_THREADS) {
+        const int gq = base + q;
+        K.msg_slot[gq] = sm.m_slot[q];
+        K.msg_src[gq] = u0 + sm.m_src[q];
+        K.msg_dst[gq] = sm.m_dst[q];
+        K.msg_w[gq] = sm.m_w[q];
+        K.msg_p11[gq] = sm.m_p11[q];
+        K.msg_vms[gq] = sm.m_vms[q];
     }
 }
 
 // ------------------------------------------------------------------------------------------------ k_exec
+// thread per message: extrapolate, chi2 gate, Kalman update (extrapolate_merged_states.py:26-402); writes the state
+// record and the weight record of the receiving dict entry, clears the activation bit of a gated edge.
 #ifndef GTF_EXEC_THREADS
 #define GTF_EXEC_THREADS 128
 #endif
 #ifndef GTF_EXEC_MINB
 #define GTF_EXEC_MINB 4
 #endif
-__device__ __noinline__ double var_ms_nb(double a, double b, double xk, double dr, double dz, double ez, double endcap)
-{
-    return gtf_var_ms(a, b, xk, dr, dz, ez, endcap);
-}
-__global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBatch B, DevPack K, double chi2_cut, GtfGeom g)
+__global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBatch B, DevPack K, double chi2_cut, GtfGeom g, int record_chi2)
 {
     __shared__ unsigned int s_cnt[GTF_NCOUNTERS];
-    const unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     if (tid < GTF_NCOUNTERS) s_cnt[tid] = 0;
     __syncthreads();
     const int count = K.counts[PK_MSG];
+    const int stride = gridDim.x * GTF_EXEC_THREADS;
     unsigned gated = 0, sent = 0;
-    for (int base = blockIdx.x * GTF_EXEC_THREADS + (tid & ~31); base < count; base += gridDim.x * GTF_EXEC_THREADS) {
-        const int q = base + lane;
-        const bool valid = q < count;
-        const int qq = valid ? q : count - 1;
-        const int sraw = K.msg_slot[qq], s = sraw & 0x7fffffff;
-        const int u = K.msg_src[qq], v = K.msg_dst[qq];
-        const int sf = K.src_first[u], sc = K.src_cnt[u];
+    // software pipeline: the loads of this thread's next message are issued between the two halves of the
+    // extrapolation, so their latency hides behind the covariance algebra (only 16 warps per SM fit the registers)
+    struct In {
+        int sraw;
+        double ux, uy, uz, ur, vx, vy, vz, vr, a, b, c, p00, p01, p22, w, p, vms;
+    };
+    auto load = [&](int q, In &x) {
+        const int sraw = K.msg_slot[q], u = K.msg_src[q], v = K.msg_dst[q];
         const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
-        const double a = B.m_a[u], bb = B.m_b[u], p11b = B.m_p11[u];
-        const double vms = gtf_var_ms(a, bb, V.x, V.r - U.r, V.z - U.z, U.z, g.endcap);
-        // merged_cov[1,1] accumulates var_ms over the source's active successors, left to right (quirk 2).
-        // Messages of this source that sit before this warp's first message: recompute their terms.
-        const int k0 = __shfl_sync(FULL, qq - sf, 0);
-        double acc0 = __shfl_sync(FULL, p11b, 0);
-        if (k0 > 0) {
-            const double a0 = __shfl_sync(FULL, a, 0), b0 = __shfl_sync(FULL, bb, 0);
-            const double ur0 = __shfl_sync(FULL, U.r, 0), uz0 = __shfl_sync(FULL, U.z, 0);
-            for (int off = 0; off < k0; off += 32) {
-                const int j = off + lane;
-                const int dj = K.msg_dst[j < k0 ? base - k0 + j : base];
-                const NodeXYZR W = K.xyzr[dj];
-                const double vj = var_ms_nb(a0, b0, W.x, W.r - ur0, W.z - uz0, uz0, g.endcap);
-                const int m = min(32, k0 - off);
-                for (int t = 0; t < m; t++) acc0 += __shfl_sync(FULL, vj, t);
-            }
-        }
-        const int first_lane = max(sf - base, 0);
-        double p = sf < base ? acc0 : p11b;
-        const int maxlen = (int)__reduce_max_sync(FULL, (unsigned)(valid ? lane - first_lane + 1 : 0));
-        for (int d = 0; d < maxlen; d++) {
-            const int sl = first_lane + d;
-            const double vj = __shfl_sync(FULL, vms, sl & 31);
-            if (sl <= lane) p += vj;
-        }
-        if (!valid) continue;
-        if (qq - sf == sc - 1) B.m_p11_nx[u] = p; // the total stays on the node
+        x.sraw = sraw;
+        x.ux = U.x; x.uy = U.y; x.uz = U.z; x.ur = U.r; x.vx = V.x; x.vy = V.y; x.vz = V.z; x.vr = V.r;
+        x.a = B.m_a[u]; x.b = B.m_b[u]; x.c = B.m_c[u]; x.p00 = B.m_p00[u]; x.p01 = B.m_p01[u]; x.p22 = B.m_p22[u];
+        x.w = K.msg_w[q]; x.p = K.msg_p11[q]; x.vms = K.msg_vms[q];
+    };
+    int q = blockIdx.x * GTF_EXEC_THREADS + tid;
+    In cur;
+    if (q < count) load(q, cur);
+    while (q < count) {
+        const int s = cur.sraw & 0x7fffffff;
+        const bool notse = cur.sraw < 0;
+        const double w = cur.w, p = cur.p, vms = cur.vms, p00 = cur.p00, p01 = cur.p01, p22 = cur.p22;
+        const double dr = cur.vr - cur.ur, dz = cur.vz - cur.uz, uz = cur.uz, vz = cur.vz;
+        GtfJac J;
+        gtf_extrap_jac(cur.ux, cur.uy, cur.vx, cur.vy, cur.a, cur.b, cur.c, J);
+        const int qn = q + stride;
+        if (qn < count) load(qn, cur);
         GtfExtrapOut o;
-        gtf_extrapolate(U.x, U.y, U.z, U.r, V.x, V.y, V.z, V.r, a, bb, B.m_c[u], B.m_p00[u], B.m_p01[u], p, B.m_p22[u], vms,
-                        chi2_cut, g, o);
-        B.uts_chi2[s] = o.chi2;
+        gtf_extrap_update(J, dr, dz, uz, vz, p00, p01, p, p22, vms, chi2_cut, g, o);
+        if (record_chi2) B.uts_chi2[s] = o.chi2; // diagnostic only (the reference appends it to a CSV): a partial-sector write
         sent++;
         if (o.pass) {
-            if (sraw < 0) atomicOr(&s_cnt[CNT_REFERR], (unsigned)GTF_REF_NO_TSE);
+            if (notse) atomicOr(&s_cnt[CNT_REFERR], (unsigned)GTF_REF_NO_TSE);
             double2 *st = reinterpret_cast<double2 *>(K.state + 8 * (size_t)s);
             st[0] = make_double2(o.s.a, o.s.b);
             st[1] = make_double2(o.s.c, o.s.tau);
             st[2] = make_double2(o.s.p00, o.s.p01);
             st[3] = make_double2(o.s.p11, o.s.p22);
-            MetaRec *m = K.meta + s;
-            *reinterpret_cast<double2 *>(m) = make_double2(K.msg_w[qq], o.lik);
-            m->prior = NAN;                                   // a fresh dict entry has no prior / lr_layer_norm / side yet
-            reinterpret_cast<int32_t *>(m)[7] = 0;            // side = 0, lrn = 0 (NaN)
-            if (!bm_get(K.pres, s)) { m->rank = GTF_NEWMARK; bm_set(K.pres, s); }
+            // a fresh dict entry has no prior / lr_layer_norm / side yet; its edge weight is set by the re-weighting
+            // that always follows in this iteration.  Whole-sector write; side / lrn / stamp live in the tag record,
+            // which the node kernels fix up guided by the `fresh` / `newb` bits.
+            double2 *m = reinterpret_cast<double2 *>(K.meta + s);
+            m[0] = make_double2(w, o.lik);
+            m[1] = make_double2(NAN, NAN);
+            const unsigned bit = 1u << (s & 31);
+            atomicOr(&K.fresh[s >> 5], bit);
+            if (!(atomicOr(&K.pres[s >> 5], bit) & bit)) atomicOr(&K.newb[s >> 5], bit);
         } else {
             bm_clear(K.act_nx, s); // :393
             gated++;
         }
+        q = qn;
     }
     if (sent) atomicAdd(&s_cnt[CNT_SENT], sent);
     if (gated) atomicAdd(&s_cnt[CNT_GATED], gated);
@@ -254,39 +324,38 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
 struct LEnt {          // one dict entry of a light node
     int s;             // slot
     unsigned f;        // H_*
-    int lay, rank, side, lrn;
+    int lay, rank, side, lrn, rank0, tag0;
     double sx, w, lik, prior, ew;
 };
+__device__ __forceinline__ int tag_pack(int rank_unused, int side, int lrn) { return (side & 0xff) | (lrn << 16); }
 __device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, int s, LEnt &e)
 {
     const double2 m0 = *reinterpret_cast<const double2 *>(K.meta + s);
     const double2 m1 = *(reinterpret_cast<const double2 *>(K.meta + s) + 1);
-    const long long tag = __double_as_longlong(m1.y);
+    const int2 tg = *reinterpret_cast<const int2 *>(K.tag + s);
     const GeoRec gr = K.geo[s];
     e.s = s;
-    e.w = m0.x; e.lik = m0.y; e.prior = m1.x;
-    e.rank = (int)(tag & 0xffffffffll);
-    e.side = (int)(int8_t)((tag >> 32) & 0xff);
-    e.lrn = (int)(int16_t)((tag >> 48) & 0xffff);
+    e.w = m0.x; e.lik = m0.y; e.prior = m1.x; e.ew = m1.y;
+    e.rank = tg.x; e.tag0 = tg.y;
+    e.side = (int)(int8_t)(tg.y & 0xff);
+    e.lrn = tg.y >> 16;
+    e.rank0 = tg.x;
     e.sx = gr.sx + 0.0; e.lay = gr.lay;
     unsigned f = H_PRES;
     if (K.all_exist || bm_get(K.exists, s)) f |= H_EX;
     if (bm_get(K.act_nx, s)) f |= H_ACT | H_ACT0;
     if (bm_get(K.act, s)) f |= H_ORIG;
-    if (e.rank == GTF_NEWMARK) f |= H_NEW;
+    if (bm_get(K.fresh, s)) { e.side = 0; e.lrn = 0; }   // entry rewritten by k_exec: no side / lr_layer_norm yet
+    if (bm_get(K.newb, s)) f |= H_NEW;
     e.f = f;
-    e.ew = 0.0;
-}
-__device__ __forceinline__ long long meta_tag(int rank, int side, int lrn)
-{
-    return (long long)(unsigned)rank | ((long long)(side & 0xff) << 32) | ((long long)(lrn & 0xffff) << 48);
 }
 __device__ __forceinline__ void lent_store(const DevBatch &B, const DevPack &K, const LEnt &e)
 {
     double2 *m = reinterpret_cast<double2 *>(K.meta + e.s);
     m[0] = make_double2(e.w, e.lik);
-    m[1] = make_double2(e.prior, __longlong_as_double(meta_tag(e.rank, e.side, e.lrn)));
-    if (e.f & H_RW) B.edge_w[e.s] = e.ew; // helper.py:180
+    m[1] = make_double2(e.prior, e.ew);                  // ew: helper.py:180
+    const int t1 = tag_pack(0, e.side, e.lrn);
+    if (e.rank != e.rank0 || t1 != e.tag0) *reinterpret_cast<int2 *>(K.tag + e.s) = make_int2(e.rank, t1);
     if ((e.f & H_ACT0) && !(e.f & H_ACT)) bm_clear(K.act_nx, e.s);
 }
 __device__ __forceinline__ void lent_prior(LEnt &a, LEnt &b, int n)
@@ -373,6 +442,7 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS) k_node2(DevBatch B, DevPack
                 LEnt a, b;
                 a.f = 0; b.f = 0; a.s = b.s = b0; a.lay = b.lay = -1; a.sx = b.sx = 0; a.w = b.w = a.lik = b.lik = 0;
                 a.prior = b.prior = a.ew = b.ew = 0; a.side = b.side = a.rank = b.rank = 0; a.lrn = b.lrn = -1;
+                a.rank0 = b.rank0 = a.tag0 = b.tag0 = 0;
                 if (n >= 1) lent_load(B, K, e0, a);
                 if (n == 2) lent_load(B, K, e1, b);
                 if (B.has_uts[i]) nf |= NF_HASUTS | NF_DICT;
@@ -537,23 +607,24 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         const bool valid = gv && gl < n;
         // ---- weight record, flags
         double w = 0.0, lik = 0.0, prior = 0.0, sx = 0.0, ew = 0.0;
-        int rank = 0x7fffffff, side = 0, lrn = -1, lay = -1000 - lane, src = 0;
+        int rank = 0x7fffffff, side = 0, lrn = -1, lay = -1000 - lane, src = 0, rank0 = 0, tag0 = 0;
         unsigned f = 0;
         if (valid) {
             const double2 m0 = *reinterpret_cast<const double2 *>(K.meta + slot);
             const double2 m1 = *(reinterpret_cast<const double2 *>(K.meta + slot) + 1);
-            const long long tag = __double_as_longlong(m1.y);
-            w = m0.x; lik = m0.y; prior = m1.x;
-            rank = (int)(tag & 0xffffffffll);
-            side = (int)(int8_t)((tag >> 32) & 0xff);
-            lrn = (int)(int16_t)((tag >> 48) & 0xffff);
+            const int2 tg = *reinterpret_cast<const int2 *>(K.tag + slot);
+            w = m0.x; lik = m0.y; prior = m1.x; ew = m1.y;
+            rank = tg.x; rank0 = tg.x; tag0 = tg.y;
+            side = (int)(int8_t)(tg.y & 0xff);
+            lrn = tg.y >> 16;
             const GeoRec gr = K.geo[slot];
             sx = gr.sx + 0.0; lay = gr.lay; src = gr.src;
             f = H_PRES;
             if (K.all_exist || bm_get(K.exists, slot)) f |= H_EX;
             if (bm_get(K.act_nx, slot)) f |= H_ACT | H_ACT0;
             if (bm_get(K.act, slot)) f |= H_ORIG;
-            if (rank == GTF_NEWMARK) f |= H_NEW;
+            if (bm_get(K.fresh, slot)) { side = 0; lrn = 0; } // entry rewritten by k_exec: no side / lr_layer_norm yet
+            if (bm_get(K.newb, slot)) f |= H_NEW;
         }
         // ---- new entries enter the dict in ascending source order (extrapolate...py:419-447)
         const unsigned newm = __ballot_sync(FULL, (f & H_NEW) != 0);
@@ -592,6 +663,8 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             side = (int)(int8_t)(sl2 & 0xff); lrn = sl2 >> 8;
             w = __shfl_sync(FULL, w, inv, G); lik = __shfl_sync(FULL, lik, inv, G);
             prior = __shfl_sync(FULL, prior, inv, G); sx = __shfl_sync(FULL, sx, inv, G);
+            ew = __shfl_sync(FULL, ew, inv, G);
+            rank0 = __shfl_sync(FULL, rank0, inv, G); tag0 = __shfl_sync(FULL, tag0, inv, G);
         }
         // ---- state record of my entry, node coordinates
         GtfState mine;
@@ -791,8 +864,9 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         if (valid) {
             double2 *m = reinterpret_cast<double2 *>(K.meta + slot);
             m[0] = make_double2(w, lik);
-            m[1] = make_double2(prior, __longlong_as_double(meta_tag(rank, side, lrn)));
-            if (f & H_RW) B.edge_w[slot] = ew; // helper.py:180
+            m[1] = make_double2(prior, ew);                      // ew: helper.py:180
+            const int t1 = tag_pack(0, side, lrn);
+            if (rank != rank0 || t1 != tag0) *reinterpret_cast<int2 *>(K.tag + slot) = make_int2(rank, t1);
             if ((f & H_ACT0) && !(f & H_ACT)) bm_clear(K.act_nx, slot);
         }
         if (clustered && gl == 0) {
@@ -821,12 +895,13 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
 // ------------------------------------------------------------------------------------------------ k_big
 // dicts with more than 32 entries: one 32-thread CTA per node, the generic shared-memory node program of gtf_tile.cuh
 // on a tile that holds just this node; lr_layer_norm lands in a shared array behind the tile.
-#define GTF_BIG_SMEM (sizeof(TileSmem) + 16 + sizeof(double) * GTF_TILE_SLOTS)
+#define GTF_BIG_SMEM (sizeof(TileSmem) + 16 + 2 * sizeof(double) * GTF_TILE_SLOTS)
 __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGeom g, MergedOut MO)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
     double *lrn_s = reinterpret_cast<double *>(smem_raw + ((sizeof(TileSmem) + 15) & ~(size_t)15));
+    double *ew_s = lrn_s + GTF_TILE_SLOTS;
     const int lane = threadIdx.x;
     const int count = K.counts[PK_BIG];
     const int32_t *list = K.hv_list + (size_t)HV_BINS * B.N;
@@ -851,14 +926,17 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
             if (bm_get(K.pres, s)) {
                 f |= F_PRES;
                 const MetaRec m = K.meta[s];
-                sd = SD_ORIGPRES | ((unsigned)m.side & 3u);
+                const TagRec t = K.tag[s];
+                const bool fresh = bm_get(K.fresh, s);
+                sd = SD_ORIGPRES | (fresh ? 0u : ((unsigned)t.side & 3u));
                 const double2 *st = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)s);
                 const double2 v0 = st[0], v1 = st[1], v2 = st[2], v3 = st[3];
                 sm.st[0][ls] = v0.x; sm.st[1][ls] = v0.y; sm.st[2][ls] = v1.x; sm.st[3][ls] = v1.y;
                 sm.st[4][ls] = v2.x; sm.st[5][ls] = v2.y; sm.st[6][ls] = v3.x; sm.st[7][ls] = v3.y;
                 sm.prior[ls] = m.prior; sm.w[ls] = m.w; sm.lik[ls] = m.lik;
-                rk = m.rank;
-                if (rk == GTF_NEWMARK) f |= F_NEW;
+                rk = t.rank;
+                if (bm_get(K.newb, s)) f |= F_NEW;
+                ew_s[ls] = m.ew;
             }
             sm.src[ls] = gr.src;
             sm.srcx[ls] = gr.sx;
@@ -869,7 +947,7 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
             lrn_s[ls] = -1.0;
         }
         __syncwarp();
-        node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, true, MO.hm, MO.m, lrn_s);
+        node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, true, MO.hm, MO.m, lrn_s, ew_s);
         __syncwarp();
         unsigned n_act = 0, n_chg = 0;
         for (int ls = lane; ls < d; ls += 32) {
@@ -879,13 +957,15 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
             if (f & F_EX) { n_act += a; n_chg += a != a0; }
             if (!a && bm_get(K.act_nx, s)) bm_clear(K.act_nx, s);
             if (f & F_PRES) {
-                MetaRec m = K.meta[s];
-                m.prior = sm.prior[ls];
-                m.w = sm.w[ls];
-                m.rank = sm.rank[ls];
-                if (f & F_RW) m.side = (int8_t)(sm.side[ls] & 3);
-                if (lrn_s[ls] >= 0.0) m.lrn = (int16_t)lrn_s[ls];
+                MetaRec m;
+                m.prior = sm.prior[ls]; m.w = sm.w[ls]; m.lik = sm.lik[ls]; m.ew = ew_s[ls];
                 K.meta[s] = m;
+                TagRec t = K.tag[s];
+                if (bm_get(K.fresh, s)) { t.side = 0; t.lrn = 0; }
+                t.rank = sm.rank[ls];
+                if (f & F_RW) t.side = (int8_t)(sm.side[ls] & 3);
+                if (lrn_s[ls] >= 0.0) t.lrn = (int16_t)lrn_s[ls];
+                K.tag[s] = t;
             }
         }
         n_act = __reduce_add_sync(0xffffffffu, n_act);

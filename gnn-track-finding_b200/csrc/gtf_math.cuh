@@ -89,9 +89,13 @@ struct GtfExtrapOut {
     int pass;
 };
 
-GTF_HD void gtf_extrapolate(double ux, double uy, double uz, double ur, double vx, double vy, double vz, double vr,
-                            double a, double b, double c, double p00, double p01, double p11_eff, double p22,
-                            double var_ms, double chi2_cut, const GtfGeom &g, GtfExtrapOut &o)
+// Split in two so a kernel can issue the next edge's loads between the halves: gtf_extrap_jac (geometry, Jacobian F,
+// once-propagated state) and gtf_extrap_update (covariance propagation, gate, filterpy predict + update, tau).
+struct GtfJac {
+    double f00, f01, f02, f10, f11, f12, f20, f21, f22;
+    double xe0, xe1, xe2;
+};
+GTF_HD void gtf_extrap_jac(double ux, double uy, double vx, double vy, double a, double b, double c, GtfJac &J)
 {
     // rotation into the source frame (:41,52) -- only x_A is live
     double rho = sqrt(ux * ux + uy * uy);
@@ -113,28 +117,33 @@ GTF_HD void gtf_extrapolate(double ux, double uy, double uz, double ur, double v
     double ds_dc = -sp * (1.0 + 2.0 * a * sp * xp * iV2) * iV;
     // da'/d. (:89-92)
     double den = cp + (2.0 * a + b) * sp, id = 1.0 / den, id2 = id * id, id4 = id2 * id2;
-    double f00 = (id2 * id) * (1.0 - (6.0 * a * sp) * (s_star + a * ds_da) * id);
-    double f01 = (-3.0 * a * sp * (2.0 * a * ds_db + 1.0)) * id4;
-    double f02 = (-6.0 * sp * ds_dc * a * a) * id4;
+    J.f00 = (id2 * id) * (1.0 - (6.0 * a * sp) * (s_star + a * ds_da) * id);
+    J.f01 = (-3.0 * a * sp * (2.0 * a * ds_db + 1.0)) * id4;
+    J.f02 = (-6.0 * sp * ds_dc * a * a) * id4;
     // db'/d. (:95-99)
     double w = 2.0 * a * s_star + b;
     den = cp + w * sp;
     id = 1.0 / den;
     double br = cp - (sp * (-sp + w * cp)) * id;
-    double f10 = (2.0 * (s_star + a * ds_da) * br) * id;
-    double f11 = ((1.0 + 2.0 * a * ds_da) * br) * id;
-    double f12 = (2.0 * a * ds_dc * br) * id;
+    J.f10 = (2.0 * (s_star + a * ds_da) * br) * id;
+    J.f11 = ((1.0 + 2.0 * a * ds_da) * br) * id;
+    J.f12 = (2.0 * a * ds_dc * br) * id;
     // dc'/d. (:102-105)
     br = cp * (2.0 * a + b) - sp;
-    double f20 = ds_da * br + s_star * s_star * cp;
-    double f21 = ds_db * br + s_star * cp;
-    double f22 = ds_dc * br + cp;
-
-    // first propagation (:129-130): x_e = F x, P_e = F P F^T with block P (p11 already carries the
-    // accumulated multiple-scattering term, :127-128)
-    double xe0 = f00 * a + f01 * b + f02 * c;
-    double xe1 = f10 * a + f11 * b + f12 * c;
-    double xe2 = f20 * a + f21 * b + f22 * c;
+    J.f20 = ds_da * br + s_star * s_star * cp;
+    J.f21 = ds_db * br + s_star * cp;
+    J.f22 = ds_dc * br + cp;
+    // first propagation of the state (:129): x_e = F x
+    J.xe0 = J.f00 * a + J.f01 * b + J.f02 * c;
+    J.xe1 = J.f10 * a + J.f11 * b + J.f12 * c;
+    J.xe2 = J.f20 * a + J.f21 * b + J.f22 * c;
+}
+GTF_HD void gtf_extrap_update(const GtfJac &J, double dr, double dz, double uz, double vz, double p00, double p01,
+                              double p11_eff, double p22, double var_ms, double chi2_cut, const GtfGeom &g, GtfExtrapOut &o)
+{
+    const double f00 = J.f00, f01 = J.f01, f02 = J.f02, f10 = J.f10, f11 = J.f11, f12 = J.f12, f20 = J.f20, f21 = J.f21,
+                 f22 = J.f22, xe0 = J.xe0, xe1 = J.xe1, xe2 = J.xe2;
+    // P_e = F P F^T with block P (p11 already carries the accumulated multiple-scattering term, :127-130)
 #define GTF_FPFT(ri0, ri1, ri2, rj0, rj1, rj2) \
     ((ri0) * (p00 * (rj0) + p01 * (rj1)) + (ri1) * (p01 * (rj0) + p11_eff * (rj1)) + (ri2) * p22 * (rj2))
     double e00 = GTF_FPFT(f00, f01, f02, f00, f01, f02);
@@ -185,9 +194,16 @@ GTF_HD void gtf_extrapolate(double ux, double uy, double uz, double ur, double v
     o.s.p01 = t01 - K1 * t02 + K0 * R * K1;
     o.s.p11 = t11 - K1 * t12 + K1 * R * K1;
     // tau and its variance (:326-365)
-    double dr = vr - ur, dz = vz - uz;
     o.s.tau = dz / dr;
     o.s.p22 = gtf_var_tau(dz, dr, uz, vz, g) + var_ms;
+}
+GTF_HD void gtf_extrapolate(double ux, double uy, double uz, double ur, double vx, double vy, double vz, double vr,
+                            double a, double b, double c, double p00, double p01, double p11_eff, double p22,
+                            double var_ms, double chi2_cut, const GtfGeom &g, GtfExtrapOut &o)
+{
+    GtfJac J;
+    gtf_extrap_jac(ux, uy, vx, vy, a, b, c, J);
+    gtf_extrap_update(J, vr - ur, vz - uz, uz, vz, p00, p01, p11_eff, p22, var_ms, chi2_cut, g, o);
 }
 
 // ------------------------------------------------------------------------------------------------

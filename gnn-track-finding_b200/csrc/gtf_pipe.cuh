@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(32) k_bignode(DevBatch B, Prog P, GtfGeom g)
             sm.flags[ls] = (uint8_t)f;
         }
         __syncwarp();
-        node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, true, hm_out, mo, B.uts_lrn + gs0);
+        node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, true, hm_out, mo, B.uts_lrn + gs0, B.edge_w + gs0);
         __syncwarp();
         unsigned n_act = 0, n_chg = 0;
         for (int ls = lane; ls < d; ls += 32) {

@@ -330,7 +330,7 @@ __device__ __forceinline__ bool node_cluster(SM &sm, double *Dw, int b0, int n, 
 // in-slots -- everything else runs the register-resident fast path below.
 __device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch B, const Prog P, const GtfGeom g, int i,
                                                   int ln, int s0, int warp, int lane, bool uts, uint8_t *hm_out,
-                                                  double *const *mo, double *lrn_base)
+                                                  double *const *mo, double *lrn_base, double *ew_base)
 {
     const int b0 = sm.nbeg[ln], b1 = sm.nbeg[ln + 1];
     unsigned nf = sm.nflags[ln];
@@ -381,7 +381,7 @@ __device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch B
         } else if (op == OP_RW) {
             if (uts && (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS)) {
                 if (n < 0) n = node_build_order(sm, b0, b1, lane);
-                node_reweight(sm, b0, b1, n, B.x[i], P.rw_thr, lane, B.edge_w + s0, lrn_base);
+                node_reweight(sm, b0, b1, n, B.x[i], P.rw_thr, lane, ew_base, lrn_base);
             }
         } else if (op == OP_CLUSTER) {
             if ((nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT)) {
@@ -914,7 +914,7 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
             if (q < nh) {
                 const int ln = sm.heavy[q], i = n0 + ln;
                 if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED, TileSmem>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
-                else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo, B.uts_lrn + s0);
+                else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo, B.uts_lrn + s0, B.edge_w + s0);
             } else {
                 const int idx = (q - nh) * 32 + lane;
                 if (idx < nl) {
@@ -931,7 +931,7 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
         for (int ln = warp; ln < nn;) {
             const int i = n0 + ln;
             if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED, TileSmem>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
-            else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo, B.uts_lrn + s0);
+            else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo, B.uts_lrn + s0, B.edge_w + s0);
             int nxt = 0;
             if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
             ln = __shfl_sync(0xffffffffu, nxt, 0);

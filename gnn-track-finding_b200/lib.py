@@ -29,7 +29,8 @@ class Stats(ctypes.Structure):
 
 class IterParams(ctypes.Structure):
     _fields_ = [("chi2_cut", ctypes.c_double), ("cluster_chi2", ctypes.c_double), ("cluster_kl", ctypes.c_double),
-                ("reweight_threshold", ctypes.c_double), ("kl_lut", ctypes.POINTER(ctypes.c_double))]
+                ("reweight_threshold", ctypes.c_double), ("kl_lut", ctypes.POINTER(ctypes.c_double)),
+                ("record_chi2", ctypes.c_int32)]
 
 
 def needs_build():

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GTF_ABI_VERSION 1
+#define GTF_ABI_VERSION 2
 
 #define GTF_E_CUDA (-1)    /* CUDA runtime error / no device */
 #define GTF_E_ARG (-2)     /* bad argument */
@@ -58,6 +58,9 @@ typedef struct {
     double cluster_chi2, cluster_kl; /* cluster on updated states run_gnn_trackml_mod.sh:112 (1000, 100) */
     double reweight_threshold;  /* helper.py:145 (0.1) */
     const double *kl_lut;       /* host pointer to 28 kl_max values or NULL (scalar threshold) */
+    int32_t record_chi2;        /* != 0: also store every message's gate chi2 in `uts_chi2` -- a diagnostic the reference
+                                   only appends to a CSV (extrapolate_merged_states.py:150-292), not part of the graph
+                                   state; off by default in the fused iteration (one scattered 8 B write per message) */
 } gtf_iter_params;
 
 int gtf_abi_version(void);

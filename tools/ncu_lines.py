@@ -17,7 +17,8 @@ for l in lines[start + 1:]:
         continue
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/', l)
     if m: off2line[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+flt = ["-k", os.environ["NCU_K"]] if os.environ.get("NCU_K") else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + flt, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split('\n')))
 hdr = rows[1]
 ia, isamp, iinst = hdr.index('Address'), hdr.index('# Samples'), hdr.index('Instructions Executed')
@@ -25,7 +26,7 @@ stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith('stall_') and 'N
 base = None
 agg = collections.defaultdict(lambda: [0, 0, collections.Counter()])
 for r in rows[2:]:
-    if len(r) <= iinst: continue
+    if len(r) <= iinst or r[ia] == 'Address': continue
     a = int(r[ia], 16)
     if base is None: base = a
     key = off2line.get(a - base, ('?', 0))

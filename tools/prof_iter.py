@@ -12,3 +12,4 @@ b.sync()
 b.set_timing(True)
 for _ in range(5): b.iterate_dry()
 print("prefix_ms, tile_ms, heavy_ms, n:", b.timing())
+print("kernels:", b.timing_kernels())
