@@ -62,7 +62,7 @@ enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_NCOUN
 
 struct DevPack {
     // static, derived from the topology and the hit coordinates
-    int32_t *out_dst, *out_rev;  // [E] out-CSR order: destination node / slot of the reverse edge (-1 none)
+    int32_t *out_dst, *out_rev, *out_src; // [E] out-CSR order: destination node / slot of the reverse edge (-1 none) / source
     GeoRec *geo;                 // [E]
     NodeXYZR *xyzr;              // [N]
     int all_exist;               // every slot is an existing edge (no ghost slot, no removed node)

@@ -561,7 +561,7 @@ template <int G> __device__ __forceinline__ void grp_shfl_info(const GtfInfo &in
 #ifndef GTF_HV_MINB
 #define GTF_HV_MINB 4
 #endif
-struct HvStage { double v[11][32]; }; // a b c tau p00 p01 p11 p22 sx sz sr of the warp's 32 entries
+struct HvStage { double v[13][32]; }; // a b c tau p00 p01 p11 p22 + GtfPairGeo (I T Q A C) of the warp's 32 entries
 
 template <int G>
 __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch B, DevPack K, Prog P, GtfGeom g, int bin,
@@ -577,6 +577,18 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
     const int gl = lane % G, gbase = lane - gl;
     const unsigned gmask = G == 32 ? FULL : (((1u << G) - 1u) << gbase);
     if (tid < GTF_NCOUNTERS) s_cnt[tid] = 0;
+#ifndef GTF_HV_NO_TABLES
+    // 1/k and the pair -> row table in shared memory: per-lane indices would serialise in the constant cache
+    __shared__ double s_recip[33];
+    __shared__ uint8_t s_pair_i[GTF_MAXD * (GTF_MAXD - 1) / 2];
+    if (tid < 33) s_recip[tid] = tid ? 1.0 / (double)tid : 0.0;
+    if (tid < GTF_MAXD * (GTF_MAXD - 1) / 2) s_pair_i[tid] = c_pair_i[tid];
+#define HV_RECIP(k) s_recip[k]
+#define HV_PAIR_DECODE(p, i, j) do { (i) = s_pair_i[p]; (j) = (p) - (i) * ((i) - 1) / 2; } while (0)
+#else
+#define HV_RECIP(k) recip_small(k)
+#define HV_PAIR_DECODE(p, i, j) pair_decode(p, i, j)
+#endif
     __syncthreads();
     const int count = K.counts[PK_HV0 + bin];
     const int32_t *list = K.hv_list + (size_t)bin * B.N;
@@ -693,7 +705,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             {
                 const bool el = (f & m3) == m3;
                 const unsigned elm = __ballot_sync(FULL, el);
-                if (okd && el) prior = recip_small(__popc(samelay & elm));
+                if (okd && el) prior = HV_RECIP(__popc(samelay & elm));
             }
             // helper.py:99-200 side norm + reweight + prune
             {
@@ -740,7 +752,11 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             __syncwarp();
             ss.v[0][lane] = mine.a; ss.v[1][lane] = mine.b; ss.v[2][lane] = mine.c; ss.v[3][lane] = mine.tau;
             ss.v[4][lane] = mine.p00; ss.v[5][lane] = mine.p01; ss.v[6][lane] = mine.p11; ss.v[7][lane] = mine.p22;
-            ss.v[8][lane] = sx; ss.v[9][lane] = sz; ss.v[10][lane] = sr;
+            {
+                GtfPairGeo pg;
+                gtf_pair_geo(sx, sz, sr, X.z, X.r, g, pg);
+                ss.v[8][lane] = pg.I; ss.v[9][lane] = pg.T; ss.v[10][lane] = pg.Q; ss.v[11][lane] = pg.A; ss.v[12][lane] = pg.C;
+            }
             __syncwarp();
             const int npairs = cl_node ? n * (n - 1) / 2 : 0;
             const int rmax = ((int)__reduce_max_sync(FULL, (unsigned)npairs) + G - 1) / G;
@@ -754,15 +770,17 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
                     const int p = r * G + gl;
                     if (p < npairs) {
                         int pi, pj;
-                        pair_decode(p, pi, pj);
+                        HV_PAIR_DECODE(p, pi, pj);
                         const int li = gbase + pi, lj = gbase + pj;
                         GtfState si, sj;
                         si.a = ss.v[0][li]; si.b = ss.v[1][li]; si.c = ss.v[2][li]; si.tau = ss.v[3][li];
                         si.p00 = ss.v[4][li]; si.p01 = ss.v[5][li]; si.p11 = ss.v[6][li]; si.p22 = ss.v[7][li];
                         sj.a = ss.v[0][lj]; sj.b = ss.v[1][lj]; sj.c = ss.v[2][lj]; sj.tau = ss.v[3][lj];
                         sj.p00 = ss.v[4][lj]; sj.p01 = ss.v[5][lj]; sj.p11 = ss.v[6][lj]; sj.p22 = ss.v[7][lj];
-                        const double v = gtf_pair_chi2(si, sj, X.x, X.z, X.r, ss.v[8][li], ss.v[9][li], ss.v[10][li],
-                                                       ss.v[8][lj], ss.v[9][lj], ss.v[10][lj], g);
+                        GtfPairGeo gi, gj;
+                        gi.I = ss.v[8][li]; gi.T = ss.v[9][li]; gi.Q = ss.v[10][li]; gi.A = ss.v[11][li]; gi.C = ss.v[12][li];
+                        gj.I = ss.v[8][lj]; gj.T = ss.v[9][lj]; gj.Q = ss.v[10][lj]; gj.A = ss.v[11][lj]; gj.C = ss.v[12][lj];
+                        const double v = gtf_pair_chi2_pre(si, sj, X.x, gi, gj, g);
                         pv[r] = v;
                         if (v != 0.0) {               // np.nonzero keeps NaN, drops +-0 (clustering.py:119)
                             nz_any = true;
@@ -783,7 +801,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
                 const int p = r * G + gl;
                 if (r < rmax && p < npairs && pv[r] == best) {
                     int pi, pj;
-                    pair_decode(p, pi, pj);
+                    HV_PAIR_DECODE(p, pi, pj);
                     if (nm == 0) t1 = p; else if (nm == 1) t2 = p;
                     nm++;
                     gone |= (1u << pi) | (1u << pj);
@@ -795,10 +813,10 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             gone = grp_or_u32<G>(gone);
             int idx0 = 0, idx1 = 0;
             if (go) {
-                pair_decode((int)pfirst, idx0, idx1);       // unique minimum: idx = [row, col]
+                HV_PAIR_DECODE((int)pfirst, idx0, idx1);       // unique minimum: idx = [row, col]
                 if (nm > 1) {                               // ties: idx = [rows..., cols...] -> idx[1] is the SECOND ROW
                     int jj;
-                    pair_decode((int)p2, idx1, jj);
+                    HV_PAIR_DECODE((int)p2, idx1, jj);
                 }
             }
             unsigned rem = go ? (((1u << n) - 1u) & ~gone) : 0u;
@@ -854,11 +872,11 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             n_act += deg;
             n_chg += chg_np + __popc(chgm);
         }
-        if (okd && (f & H_PRES)) w = recip_small(n);
+        if (okd && (f & H_PRES)) w = HV_RECIP(n);
         {
             const bool el = (f & m3) == m3;
             const unsigned elm = __ballot_sync(FULL, el);
-            if (okd && el) prior = recip_small(__popc(samelay & elm));
+            if (okd && el) prior = HV_RECIP(__popc(samelay & elm));
         }
         // ---- store
         if (valid) {
@@ -892,6 +910,8 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
     flush_counters(s_cnt, B.counters, tid);
 }
 
+#undef HV_RECIP
+#undef HV_PAIR_DECODE
 // ------------------------------------------------------------------------------------------------ k_big
 // dicts with more than 32 entries: one 32-thread CTA per node, the generic shared-memory node program of gtf_tile.cuh
 // on a tile that holds just this node; lr_layer_norm lands in a shared array behind the tile.

@@ -208,25 +208,42 @@ GTF_HD void gtf_extrapolate(double ux, double uy, double uz, double ur, double v
 
 // ------------------------------------------------------------------------------------------------
 // clustering.py:11-78 pairwise chi2 of components i ("neighbour1", b) and j ("neighbour2", c) at node a.
-GTF_HD double gtf_pair_chi2(const GtfState &si, const GtfState &sj, double xa, double za, double ra, double xb,
-                            double zb, double rb, double xc, double zc, double rc, const GtfGeom &g)
+// The tau part only needs per-component quantities (1/dr, tau, its measurement-error terms), so they are computed
+// once per component (gtf_pair_geo) and a pair costs two divisions instead of four.
+struct GtfPairGeo {
+    double I, T, Q, A, C; // 1/(r_e - r_a);  tau_e = (z_e - z_a) I;  tau_e I;  I^2 sigma_z,e^2;  Q^2 sigma_r,e^2
+};
+GTF_HD void gtf_pair_geo(double xe, double ze, double re, double za, double ra, const GtfGeom &g, GtfPairGeo &G)
+{
+    double sz = g.sigma0rz2, sr = g.sigma0rz;
+    if (fabs(xe) >= g.endcap) { sz = g.sigma0rz; sr = g.sigma0rz2; }     // abs(x), not abs(z): clustering.py:49-57
+    G.I = 1.0 / (re - ra);
+    G.T = (ze - za) * G.I;
+    G.Q = G.T * G.I;
+    G.A = G.I * G.I * sz * sz;
+    G.C = G.Q * G.Q * sr * sr;
+}
+GTF_HD double gtf_pair_chi2_pre(const GtfState &si, const GtfState &sj, double xa, const GtfPairGeo &Gb, const GtfPairGeo &Gc,
+                                const GtfGeom &g)
 {
     double r0 = si.a - sj.a, r1 = si.b - sj.b;
     double c00 = si.p00 + sj.p00, c01 = si.p01 + sj.p01, c11 = si.p11 + sj.p11;
     double det = c00 * c11 - c01 * c01;
     double d1 = (r0 * r0 * c11 - 2.0 * r0 * r1 * c01 + r1 * r1 * c00) / det;
-    double ib = 1.0 / (rb - ra), ic = 1.0 / (rc - ra);
-    double j2 = ib, j3 = -ic, j1 = -j3 - j2;
-    double j5 = -(zb - za) * ib * ib, j6 = (zc - za) * ic * ic, j4 = -j5 - j6;
-    double sza = g.sigma0rz2, szb = g.sigma0rz2, szc = g.sigma0rz2;
-    double sra = g.sigma0rz, srb = g.sigma0rz, src = g.sigma0rz;
-    if (fabs(xa) >= g.endcap) { sza = g.sigma0rz; sra = g.sigma0rz2; }    // abs(x), not abs(z): clustering.py:49-57
-    if (fabs(xb) >= g.endcap) { szb = g.sigma0rz; srb = g.sigma0rz2; }
-    if (fabs(xc) >= g.endcap) { szc = g.sigma0rz; src = g.sigma0rz2; }
-    double cdt = j1 * j1 * sza * sza + j2 * j2 * szb * szb + j3 * j3 * szc * szc + j4 * j4 * sra * sra +
-                 j5 * j5 * srb * srb + j6 * j6 * src * src;
-    double dtau = (zb - za) * ib - (zc - za) * ic;
+    double sza = g.sigma0rz2, sra = g.sigma0rz;
+    if (fabs(xa) >= g.endcap) { sza = g.sigma0rz; sra = g.sigma0rz2; }
+    double j1 = Gc.I - Gb.I, j4 = Gb.Q - Gc.Q;                            // d tau_b - tau_c / d(z_a, r_a)
+    double cdt = j1 * j1 * sza * sza + Gb.A + Gc.A + j4 * j4 * sra * sra + Gb.C + Gc.C;
+    double dtau = Gb.T - Gc.T;
     return d1 + dtau * dtau * (1.0 / cdt);
+}
+GTF_HD double gtf_pair_chi2(const GtfState &si, const GtfState &sj, double xa, double za, double ra, double xb,
+                            double zb, double rb, double xc, double zc, double rc, const GtfGeom &g)
+{
+    GtfPairGeo Gb, Gc;
+    gtf_pair_geo(xb, zb, rb, za, ra, g, Gb);
+    gtf_pair_geo(xc, zc, rc, za, ra, g, Gc);
+    return gtf_pair_chi2_pre(si, sj, xa, Gb, Gc, g);
 }
 
 // inverse of the 2x2 block: returns (i00, i01, i11)

@@ -18,6 +18,7 @@ for l in lines[start + 1:]:
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/', l)
     if m: off2line[int(m.group(1), 16)] = cur
 flt = ["-k", os.environ["NCU_K"]] if os.environ.get("NCU_K") else []
+if os.environ.get("NCU_SKIP"): flt += ["--launch-skip", os.environ["NCU_SKIP"], "--launch-count", "1"]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + flt, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split('\n')))
 hdr = rows[1]
