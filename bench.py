@@ -8,13 +8,14 @@ metric   directed edge-iterations/s of ONE fused iteration
           greedy KL clustering/merge, degree, mixture weights, priors]
          over a batch of independent cfg2-shaped events; an "edge-iteration" is one ACTIVE directed edge taken
          through the iteration.  events/s is reported beside it.
-step     gtf_iterate_dry: k_prefix + k_tile on the batch; it reads the committed state and writes the next
-         state into shadow buffers, so every step does identical work (idempotent).
+step     gtf_iterate_dry: the packed pipeline k_send -> k_exec -> k_node2 -> k_hv<G> on the batch; it reads the
+         committed state, rewrites the dict entries in place (same values every pass) and sends the merged states
+         to shadow buffers, so every step does identical work.
 value    device-resident throughput, CUDA events on the batch stream, max over ranks.
 e2e      the same iteration through the C-ABI from HOST buffers: pinned H2D of the iteration's mutable inputs,
          one committed gtf_iterate, D2H of the resulting state -- copies inside the timed region.
-roofline algorithmic bytes (264 B per active edge-iteration) / k_tile's average CUDA-event duration
-         vs the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+roofline algorithmic bytes (264 B per active edge-iteration) / the summed CUDA-event durations of all
+         kernels of the iteration vs the measured HBM copy bandwidth in MEASURED_PEAKS.json.
 Events shard across GPUs with no data-path collective (weak scaling); NCCL only carries the timing reduction
 and the final candidate-table gather (gtf_b200.shard).
 """
@@ -325,8 +326,10 @@ def main():
     b.set_timing(True)
     for _ in range(a.steps):
         b.iterate_dry()
-    prefix_ms, tile_ms, heavy_ms, _ = b.timing()
+    kt = b.timing_kernels()
     b.set_timing(False)
+    kern_ms = {k: kt[k] for k in ("k_send", "k_exec", "k_node2", "k_hv")}
+    iter_ms = sum(kern_ms.values())
     e2e_ms, h2d, d2h = (None, 0, 0)
     if not a.no_e2e:
         nch = max(1, min(a.e2e_chunks, a.events))
@@ -349,9 +352,11 @@ def main():
         peaks = json.load(open(pk_path)) if os.path.exists(pk_path) else {}
         peak = float(peaks.get("hbm_gbs", 6650.0))
         step_s = ms / a.steps / 1e3
-        ach = B_ALG * n_active / ((tile_ms + heavy_ms) / 1e3) / 1e9      # both kernels that touch the per-edge state
-        traffic, tr_path = None, os.path.join(REPO, "profiles", "r01_k_tile_traffic.json")
-        if os.path.exists(tr_path):   # dram__bytes_read+write of k_tile from the committed `ncu --set full` capture, per active edge
+        # the 264 algorithmic bytes cover the WHOLE iteration (extrapolate + update + reweight x2 + cluster), so they are
+        # charged against the sum of all its kernels (CUDA events recorded by the library on its stream around each)
+        ach = B_ALG * n_active / (iter_ms / 1e3) / 1e9
+        traffic, tr_path = None, os.path.join(REPO, "profiles", "r01_pipeline_traffic.json")
+        if os.path.exists(tr_path):   # dram__bytes_read+write of every pipeline kernel from the committed `ncu --set full` capture
             traffic = json.load(open(tr_path))["dram_bytes_per_active_edge"] * n_active
         out = {
             "metric": METRIC, "value": n_act_all / step_s, "unit": "edges/s", "n_gpus": world, "steps": a.steps,
@@ -363,14 +368,18 @@ def main():
                                    "distinct_events": min(a.distinct, a.events), "device_bytes": b.device_bytes()},
                        "l2": "per-step working set %.0f MB per GPU is larger than the 126 MB L2 (no flush needed)" % (
                            (B_ALG * n_active + 11.0 * b.E) / 1e6),
-                       "step": "gtf_iterate_dry = k_prefix + k_tile (fused load/E/R) + k_heavy (R+C of >=3-component nodes), idempotent"},
-            "gpu_launches": 3 * a.steps,
+                       "step": "gtf_iterate_dry = k_send (message list + scattering prefix) + k_exec (extrapolate, gate, Kalman "
+                               "update) + k_node2 (<= 2-component nodes: priors, reweight x2, prune) + k_hv<4|8|16|32> / k_big "
+                               "(>= 3-component nodes: the same + pairwise chi2 + greedy KL merge); reads the committed state, "
+                               "rewrites the dict entries in place, merged states to shadow buffers"},
+            "gpu_launches": 8 * a.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                         "traffic_source": "profiles/r01_k_tile_traffic.json (ncu capture at 16 events) x active edges of this launch",
+                         "traffic_source": "profiles/r01_pipeline_traffic.json (ncu --set full capture of all pipeline kernels at this "
+                                           "workload) x active edges of this launch",
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
-                         "kernel": "k_tile + k_heavy", "kernel_ms": tile_ms + heavy_ms, "k_tile_ms": tile_ms,
-                         "k_heavy_ms": heavy_ms, "k_prefix_ms": prefix_ms,
+                         "kernel": "whole iteration: k_send + k_exec + k_node2 + k_hv<4,8,16,32> (+ k_big)", "kernel_ms": iter_ms,
+                         "kernels_ms": kern_ms, "dominant": max(kern_ms, key=kern_ms.get),
                          "alg_bytes_per_launch": B_ALG * n_active},
             "iteration_stats": stats,
         }
