@@ -152,7 +152,7 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         DevPack &k = b->k;
         const int64_t words = ((int64_t)E + 31) / 32 + 2;
         DA(k.out_dst, E); DA(k.out_rev, E); DA(k.out_src, E); DA(k.geo, E); DA(k.xyzr, N);
-        DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.fresh, words); DA(k.newb, words);
+        DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.newb, words);
         DA(k.state, (int64_t)E * 8); DA(k.meta, E); DA(k.tag, E);
         DA(k.msg_slot, E); DA(k.msg_src, E); DA(k.msg_dst, E); DA(k.msg_w, E);
         DA(k.msg_p11, E); DA(k.msg_vms, E);
@@ -193,7 +193,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.out_src, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.fresh, k.newb, k.state, k.meta, k.tag, k.msg_slot,
+        void *pk[] = {k.out_src, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.newb, k.state, k.meta, k.tag, k.msg_slot,
                       k.msg_src, k.msg_dst, k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         cudaStreamDestroy(b->stream3);
@@ -701,12 +701,10 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
     const size_t words = ((size_t)b->E + 31) / 32 + 2;
     cudaStream_t s0 = b->stream;
     if (b->timing) CK(cudaEventRecord(b->evk[0], s0));
-    CK(cudaMemsetAsync(k.counts, 0, sizeof(int) * (PK_BIG + 1), s0));
-    CK(cudaMemcpyAsync(k.act_nx, k.act, sizeof(uint32_t) * words, cudaMemcpyDeviceToDevice, s0));
-    CK(cudaMemsetAsync(k.fresh, 0, sizeof(uint32_t) * words, s0));
-    CK(cudaMemsetAsync(k.newb, 0, sizeof(uint32_t) * words, s0));
-    // accumulated p11 of nodes that send nothing this pass (quirk 2); k_send overwrites the senders
-    if (b->N) CK(cudaMemcpyAsync(d.m_p11_nx, d.m_p11, sizeof(double) * (size_t)b->N, cudaMemcpyDeviceToDevice, s0));
+    {
+        const int nthr = (int)std::max<size_t>(words, (size_t)b->N);
+        k_begin<<<(nthr + 255) / 256, 256, 0, s0>>>(d, k, (int)words);
+    }
     if (b->n_stiles) k_send<<<b->n_stiles, GTF_SEND_THREADS, 0, s0>>>(d, k, b->stile_begin, gg);
     if (b->timing) CK(cudaEventRecord(b->evk[1], s0));
     if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * 2, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg, p->record_chi2);

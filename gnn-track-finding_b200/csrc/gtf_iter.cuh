@@ -119,6 +119,17 @@ __global__ void k_unpack_slots(DevBatch B, DevPack K, int do_act, int do_pres, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k_begin
+// start of an iteration: next activation bitmap := current, 'inserted this pass' bitmap := 0, list counters := 0,
+// accumulated p11 of the nodes carried over (k_send overwrites the ones that send; quirk 2)
+__global__ void k_begin(DevBatch B, DevPack K, int words)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < words) { K.act_nx[t] = K.act[t]; K.newb[t] = 0; }
+    if (t < B.N) B.m_p11_nx[t] = B.m_p11[t];
+    if (t <= PK_BIG) K.counts[t] = 0;
+}
+
 // ------------------------------------------------------------------------------------------------ k_send
 // One CTA owns a tile of whole sources (<= GTF_SEND_SRCS sources, <= GTF_SEND_EDGES out-edges; table built at
 // gtf_batch_finalize).
@@ -299,15 +310,14 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
             st[1] = make_double2(o.s.c, o.s.tau);
             st[2] = make_double2(o.s.p00, o.s.p01);
             st[3] = make_double2(o.s.p11, o.s.p22);
-            // a fresh dict entry has no prior / lr_layer_norm / side yet; its edge weight is set by the re-weighting
-            // that always follows in this iteration.  Whole-sector write; side / lrn / stamp live in the tag record,
-            // which the node kernels fix up guided by the `fresh` / `newb` bits.
+            // a fresh dict entry has no prior / lr_layer_norm / side yet (prior = NaN is what marks it for the node
+            // kernels, which reset side / lrn in the tag record); its edge weight is set by the re-weighting that always
+            // follows in this iteration.  Whole-sector write.
             double2 *m = reinterpret_cast<double2 *>(K.meta + s);
             m[0] = make_double2(w, o.lik);
             m[1] = make_double2(NAN, NAN);
             const unsigned bit = 1u << (s & 31);
-            atomicOr(&K.fresh[s >> 5], bit);
-            if (!(atomicOr(&K.pres[s >> 5], bit) & bit)) atomicOr(&K.newb[s >> 5], bit);
+            if (!(atomicOr(&K.pres[s >> 5], bit) & bit)) bm_set(K.newb, s);
         } else {
             bm_clear(K.act_nx, s); // :393
             gated++;
@@ -345,7 +355,7 @@ __device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, i
     if (K.all_exist || bm_get(K.exists, s)) f |= H_EX;
     if (bm_get(K.act_nx, s)) f |= H_ACT | H_ACT0;
     if (bm_get(K.act, s)) f |= H_ORIG;
-    if (bm_get(K.fresh, s)) { e.side = 0; e.lrn = 0; }   // entry rewritten by k_exec: no side / lr_layer_norm yet
+    if (e.prior != e.prior) { e.side = 0; e.lrn = 0; }   // entry just written by the extrapolation: no side / lr_layer_norm yet
     if (bm_get(K.newb, s)) f |= H_NEW;
     e.f = f;
 }
@@ -635,7 +645,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             if (K.all_exist || bm_get(K.exists, slot)) f |= H_EX;
             if (bm_get(K.act_nx, slot)) f |= H_ACT | H_ACT0;
             if (bm_get(K.act, slot)) f |= H_ORIG;
-            if (bm_get(K.fresh, slot)) { side = 0; lrn = 0; } // entry rewritten by k_exec: no side / lr_layer_norm yet
+            if (prior != prior) { side = 0; lrn = 0; }        // entry just written by the extrapolation: no side / lr_layer_norm yet
             if (bm_get(K.newb, slot)) f |= H_NEW;
         }
         // ---- new entries enter the dict in ascending source order (extrapolate...py:419-447)
@@ -915,13 +925,14 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
 // ------------------------------------------------------------------------------------------------ k_big
 // dicts with more than 32 entries: one 32-thread CTA per node, the generic shared-memory node program of gtf_tile.cuh
 // on a tile that holds just this node; lr_layer_norm lands in a shared array behind the tile.
-#define GTF_BIG_SMEM (sizeof(TileSmem) + 16 + 2 * sizeof(double) * GTF_TILE_SLOTS)
+#define GTF_BIG_SMEM (sizeof(TileSmem) + 16 + 2 * sizeof(double) * GTF_TILE_SLOTS + GTF_TILE_SLOTS)
 __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGeom g, MergedOut MO)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
     double *lrn_s = reinterpret_cast<double *>(smem_raw + ((sizeof(TileSmem) + 15) & ~(size_t)15));
     double *ew_s = lrn_s + GTF_TILE_SLOTS;
+    uint8_t *fresh_s = reinterpret_cast<uint8_t *>(ew_s + GTF_TILE_SLOTS);
     const int lane = threadIdx.x;
     const int count = K.counts[PK_BIG];
     const int32_t *list = K.hv_list + (size_t)HV_BINS * B.N;
@@ -940,6 +951,7 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
             const GeoRec gr = K.geo[s];
             unsigned f = 0, sd = 0;
             int rk = 0x7fffffff;
+            fresh_s[ls] = 0;
             if (K.all_exist || bm_get(K.exists, s)) f |= F_EX;
             if (bm_get(K.act_nx, s)) f |= F_ACT;
             if (bm_get(K.act, s)) f |= F_ORIG;
@@ -947,7 +959,8 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
                 f |= F_PRES;
                 const MetaRec m = K.meta[s];
                 const TagRec t = K.tag[s];
-                const bool fresh = bm_get(K.fresh, s);
+                const bool fresh = m.prior != m.prior;
+                if (fresh) fresh_s[ls] = 1;
                 sd = SD_ORIGPRES | (fresh ? 0u : ((unsigned)t.side & 3u));
                 const double2 *st = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)s);
                 const double2 v0 = st[0], v1 = st[1], v2 = st[2], v3 = st[3];
@@ -981,7 +994,7 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
                 m.prior = sm.prior[ls]; m.w = sm.w[ls]; m.lik = sm.lik[ls]; m.ew = ew_s[ls];
                 K.meta[s] = m;
                 TagRec t = K.tag[s];
-                if (bm_get(K.fresh, s)) { t.side = 0; t.lrn = 0; }
+                if (fresh_s[ls]) { t.side = 0; t.lrn = 0; }
                 t.rank = sm.rank[ls];
                 if (f & F_RW) t.side = (int8_t)(sm.side[ls] & 3);
                 if (lrn_s[ls] >= 0.0) t.lrn = (int16_t)lrn_s[ls];
