@@ -152,7 +152,7 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         DevPack &k = b->k;
         const int64_t words = ((int64_t)E + 31) / 32 + 2;
         DA(k.out_dst, E); DA(k.out_rev, E); DA(k.out_src, E); DA(k.geo, E); DA(k.xyzr, N);
-        DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.newb, words);
+        DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.pres0, words);
         DA(k.state, (int64_t)E * 8); DA(k.meta, E); DA(k.tag, E);
         DA(k.msg_slot, E); DA(k.msg_src, E); DA(k.msg_dst, E); DA(k.msg_w, E);
         DA(k.msg_p11, E); DA(k.msg_vms, E);
@@ -193,7 +193,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.out_src, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.newb, k.state, k.meta, k.tag, k.msg_slot,
+        void *pk[] = {k.out_src, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.tag, k.msg_slot,
                       k.msg_src, k.msg_dst, k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         cudaStreamDestroy(b->stream3);

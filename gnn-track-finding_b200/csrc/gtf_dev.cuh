@@ -68,7 +68,7 @@ struct DevPack {
     int all_exist;               // every slot is an existing edge (no ghost slot, no removed node)
     // mutable slot state
     uint32_t *act, *act_nx, *pres, *exists; // bitmaps over slots, 2 zero words of padding
-    uint32_t *newb;              // entry inserted by k_exec in this iteration (cleared every iteration)
+    uint32_t *pres0;             // presence bitmap as it was when the iteration started (an entry not in it is new)
     double *state;               // [E][8] a b c tau p00 p01 p11 p22
     MetaRec *meta;               // [E]
     TagRec *tag;                 // [E]

@@ -120,12 +120,12 @@ __global__ void k_unpack_slots(DevBatch B, DevPack K, int do_act, int do_pres, i
 }
 
 // ------------------------------------------------------------------------------------------------ k_begin
-// start of an iteration: next activation bitmap := current, 'inserted this pass' bitmap := 0, list counters := 0,
+// start of an iteration: next activation bitmap := current, snapshot of the presence bitmap, list counters := 0,
 // accumulated p11 of the nodes carried over (k_send overwrites the ones that send; quirk 2)
 __global__ void k_begin(DevBatch B, DevPack K, int words)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < words) { K.act_nx[t] = K.act[t]; K.newb[t] = 0; }
+    if (t < words) { K.act_nx[t] = K.act[t]; K.pres0[t] = K.pres[t]; }
     if (t < B.N) B.m_p11_nx[t] = B.m_p11[t];
     if (t <= PK_BIG) K.counts[t] = 0;
 }
@@ -316,8 +316,7 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
             double2 *m = reinterpret_cast<double2 *>(K.meta + s);
             m[0] = make_double2(w, o.lik);
             m[1] = make_double2(NAN, NAN);
-            const unsigned bit = 1u << (s & 31);
-            if (!(atomicOr(&K.pres[s >> 5], bit) & bit)) bm_set(K.newb, s);
+            bm_set(K.pres, s); // fire and forget; 'inserted this pass' = present now and not in the snapshot k_begin took
         } else {
             bm_clear(K.act_nx, s); // :393
             gated++;
@@ -356,7 +355,7 @@ __device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, i
     if (bm_get(K.act_nx, s)) f |= H_ACT | H_ACT0;
     if (bm_get(K.act, s)) f |= H_ORIG;
     if (e.prior != e.prior) { e.side = 0; e.lrn = 0; }   // entry just written by the extrapolation: no side / lr_layer_norm yet
-    if (bm_get(K.newb, s)) f |= H_NEW;
+    if (!bm_get(K.pres0, s)) f |= H_NEW;
     e.f = f;
 }
 __device__ __forceinline__ void lent_store(const DevBatch &B, const DevPack &K, const LEnt &e)
@@ -646,7 +645,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             if (bm_get(K.act_nx, slot)) f |= H_ACT | H_ACT0;
             if (bm_get(K.act, slot)) f |= H_ORIG;
             if (prior != prior) { side = 0; lrn = 0; }        // entry just written by the extrapolation: no side / lr_layer_norm yet
-            if (bm_get(K.newb, slot)) f |= H_NEW;
+            if (!bm_get(K.pres0, slot)) f |= H_NEW;
         }
         // ---- new entries enter the dict in ascending source order (extrapolate...py:419-447)
         const unsigned newm = __ballot_sync(FULL, (f & H_NEW) != 0);
@@ -968,7 +967,7 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
                 sm.st[4][ls] = v2.x; sm.st[5][ls] = v2.y; sm.st[6][ls] = v3.x; sm.st[7][ls] = v3.y;
                 sm.prior[ls] = m.prior; sm.w[ls] = m.w; sm.lik[ls] = m.lik;
                 rk = t.rank;
-                if (bm_get(K.newb, s)) f |= F_NEW;
+                if (!bm_get(K.pres0, s)) f |= F_NEW;
                 ew_s[ls] = m.ew;
             }
             sm.src[ls] = gr.src;
