@@ -409,7 +409,10 @@ __device__ __forceinline__ void lent_reweight(unsigned int *cnt, LEnt &a, LEnt &
 }
 
 #define GTF_NODE2_THREADS 256
-__global__ void __launch_bounds__(GTF_NODE2_THREADS) k_node2(DevBatch B, DevPack K, Prog P)
+#ifndef GTF_NODE2_MINB
+#define GTF_NODE2_MINB 4
+#endif
+__global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(DevBatch B, DevPack K, Prog P)
 {
     __shared__ unsigned int s_cnt[GTF_NCOUNTERS];
     __shared__ int s_n[HV_BINS + 1], s_base[HV_BINS + 1];
