@@ -35,6 +35,14 @@ __device__ __forceinline__ uint32_t bm_win(const uint32_t *bm, int p)
 __device__ __forceinline__ void bm_clear(uint32_t *bm, int s) { atomicAnd(&bm[s >> 5], ~(1u << (s & 31))); }
 __device__ __forceinline__ void bm_set(uint32_t *bm, int s) { atomicOr(&bm[s >> 5], 1u << (s & 31)); }
 
+// 16 B geometry record, streaming (read once per iteration)
+__device__ __forceinline__ GeoRec ld_geo(const GeoRec *p)
+{
+    const int4 v = __ldcs(reinterpret_cast<const int4 *>(p));
+    GeoRec g;
+    g.sx = __hiloint2double(v.y, v.x); g.lay = v.z; g.src = v.w;
+    return g;
+}
 __device__ __forceinline__ void l1_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void flush_counters(unsigned int *s_cnt, unsigned long long *counters, int tid)
@@ -280,12 +288,12 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
         double ux, uy, uz, ur, vx, vy, vz, vr, a, b, c, p00, p01, p22, w, p, vms;
     };
     auto load = [&](int q, In &x) {
-        const int sraw = K.msg_slot[q], u = K.msg_src[q], v = K.msg_dst[q];
+        const int sraw = __ldcs(K.msg_slot + q), u = __ldcs(K.msg_src + q), v = __ldcs(K.msg_dst + q);
         const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
         x.sraw = sraw;
         x.ux = U.x; x.uy = U.y; x.uz = U.z; x.ur = U.r; x.vx = V.x; x.vy = V.y; x.vz = V.z; x.vr = V.r;
         x.a = B.m_a[u]; x.b = B.m_b[u]; x.c = B.m_c[u]; x.p00 = B.m_p00[u]; x.p01 = B.m_p01[u]; x.p22 = B.m_p22[u];
-        x.w = K.msg_w[q]; x.p = K.msg_p11[q]; x.vms = K.msg_vms[q];
+        x.w = __ldcs(K.msg_w + q); x.p = __ldcs(K.msg_p11 + q); x.vms = __ldcs(K.msg_vms + q);
     };
     int q = blockIdx.x * GTF_EXEC_THREADS + tid;
     In cur;
@@ -306,16 +314,16 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
         if (o.pass) {
             if (notse) atomicOr(&s_cnt[CNT_REFERR], (unsigned)GTF_REF_NO_TSE);
             double2 *st = reinterpret_cast<double2 *>(K.state + 8 * (size_t)s);
-            st[0] = make_double2(o.s.a, o.s.b);
-            st[1] = make_double2(o.s.c, o.s.tau);
-            st[2] = make_double2(o.s.p00, o.s.p01);
-            st[3] = make_double2(o.s.p11, o.s.p22);
+            __stcs(st + 0, make_double2(o.s.a, o.s.b));
+            __stcs(st + 1, make_double2(o.s.c, o.s.tau));
+            __stcs(st + 2, make_double2(o.s.p00, o.s.p01));
+            __stcs(st + 3, make_double2(o.s.p11, o.s.p22));
             // a fresh dict entry has no prior / lr_layer_norm / side yet (prior = NaN is what marks it for the node
             // kernels, which reset side / lrn in the tag record); its edge weight is set by the re-weighting that always
             // follows in this iteration.  Whole-sector write.
             double2 *m = reinterpret_cast<double2 *>(K.meta + s);
-            m[0] = make_double2(w, o.lik);
-            m[1] = make_double2(NAN, NAN);
+            __stcs(m + 0, make_double2(w, o.lik));
+            __stcs(m + 1, make_double2(NAN, NAN));
             bm_set(K.pres, s); // fire and forget; 'inserted this pass' = present now and not in the snapshot k_begin took
         } else {
             bm_clear(K.act_nx, s); // :393
@@ -339,10 +347,10 @@ struct LEnt {          // one dict entry of a light node
 __device__ __forceinline__ int tag_pack(int rank_unused, int side, int lrn) { return (side & 0xff) | (lrn << 16); }
 __device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, int s, LEnt &e)
 {
-    const double2 m0 = *reinterpret_cast<const double2 *>(K.meta + s);
-    const double2 m1 = *(reinterpret_cast<const double2 *>(K.meta + s) + 1);
-    const int2 tg = *reinterpret_cast<const int2 *>(K.tag + s);
-    const GeoRec gr = K.geo[s];
+    const double2 m0 = __ldcs(reinterpret_cast<const double2 *>(K.meta + s));
+    const double2 m1 = __ldcs(reinterpret_cast<const double2 *>(K.meta + s) + 1);
+    const int2 tg = __ldcs(reinterpret_cast<const int2 *>(K.tag + s));
+    const GeoRec gr = ld_geo(K.geo + s);
     e.s = s;
     e.w = m0.x; e.lik = m0.y; e.prior = m1.x; e.ew = m1.y;
     e.rank = tg.x; e.tag0 = tg.y;
@@ -361,8 +369,8 @@ __device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, i
 __device__ __forceinline__ void lent_store(const DevBatch &B, const DevPack &K, const LEnt &e)
 {
     double2 *m = reinterpret_cast<double2 *>(K.meta + e.s);
-    m[0] = make_double2(e.w, e.lik);
-    m[1] = make_double2(e.prior, e.ew);                  // ew: helper.py:180
+    __stcs(m + 0, make_double2(e.w, e.lik));
+    __stcs(m + 1, make_double2(e.prior, e.ew));          // ew: helper.py:180
     const int t1 = tag_pack(0, e.side, e.lrn);
     if (e.rank != e.rank0 || t1 != e.tag0) *reinterpret_cast<int2 *>(K.tag + e.s) = make_int2(e.rank, t1);
     if ((e.f & H_ACT0) && !(e.f & H_ACT)) bm_clear(K.act_nx, e.s);
@@ -634,14 +642,14 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         int rank = 0x7fffffff, side = 0, lrn = -1, lay = -1000 - lane, src = 0, rank0 = 0, tag0 = 0;
         unsigned f = 0;
         if (valid) {
-            const double2 m0 = *reinterpret_cast<const double2 *>(K.meta + slot);
-            const double2 m1 = *(reinterpret_cast<const double2 *>(K.meta + slot) + 1);
-            const int2 tg = *reinterpret_cast<const int2 *>(K.tag + slot);
+            const double2 m0 = __ldcs(reinterpret_cast<const double2 *>(K.meta + slot));
+            const double2 m1 = __ldcs(reinterpret_cast<const double2 *>(K.meta + slot) + 1);
+            const int2 tg = __ldcs(reinterpret_cast<const int2 *>(K.tag + slot));
             w = m0.x; lik = m0.y; prior = m1.x; ew = m1.y;
             rank = tg.x; rank0 = tg.x; tag0 = tg.y;
             side = (int)(int8_t)(tg.y & 0xff);
             lrn = tg.y >> 16;
-            const GeoRec gr = K.geo[slot];
+            const GeoRec gr = ld_geo(K.geo + slot);
             sx = gr.sx + 0.0; lay = gr.lay; src = gr.src;
             f = H_PRES;
             if (K.all_exist || bm_get(K.exists, slot)) f |= H_EX;
@@ -700,7 +708,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         const bool cl_node = G < 32 && gv && (nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT) && n >= 3 && n <= GTF_MAXD; // clustering.py:207
         if (valid && cl_node) {
             const double2 *st = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)slot);
-            const double2 v0 = st[0], v1 = st[1], v2 = st[2], v3 = st[3];
+            const double2 v0 = __ldcs(st + 0), v1 = __ldcs(st + 1), v2 = __ldcs(st + 2), v3 = __ldcs(st + 3);
             mine.a = v0.x; mine.b = v0.y; mine.c = v1.x; mine.tau = v1.y;
             mine.p00 = v2.x; mine.p01 = v2.y; mine.p11 = v3.x; mine.p22 = v3.y;
             if (src >= 0) { const NodeXYZR S = K.xyzr[src]; sz = S.z; sr = S.r; }
@@ -893,8 +901,8 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         // ---- store
         if (valid) {
             double2 *m = reinterpret_cast<double2 *>(K.meta + slot);
-            m[0] = make_double2(w, lik);
-            m[1] = make_double2(prior, ew);                      // ew: helper.py:180
+            __stcs(m + 0, make_double2(w, lik));
+            __stcs(m + 1, make_double2(prior, ew));              // ew: helper.py:180
             const int t1 = tag_pack(0, side, lrn);
             if (rank != rank0 || t1 != tag0) *reinterpret_cast<int2 *>(K.tag + slot) = make_int2(rank, t1);
             if ((f & H_ACT0) && !(f & H_ACT)) bm_clear(K.act_nx, slot);
