@@ -151,7 +151,7 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         // packed iteration layout (gtf_iter.cuh)
         DevPack &k = b->k;
         const int64_t words = ((int64_t)E + 31) / 32 + 2;
-        DA(k.out_dst, E); DA(k.out_rev, E); DA(k.out_src, E); DA(k.geo, E); DA(k.xyzr, N);
+        DA(k.out_dst, E); DA(k.out_rev, E); DA(k.out_src, E); DA(k.geo, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N);
         DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.pres0, words);
         DA(k.state, (int64_t)E * 8); DA(k.meta, E); DA(k.tag, E);
         DA(k.msg_slot, E); DA(k.msg_src, E); DA(k.msg_dst, E); DA(k.msg_w, E);
@@ -159,7 +159,7 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         DA(k.hv_list, (int64_t)(HV_BINS + 1) * N);
         DA(k.counts, PK_NCOUNTS);
         b->pack_static_stale = true;
-        for (int q = 0; q < 3; q++) { b->pack_stale[q] = true; b->soa_stale[q] = false; }
+        for (int q = 0; q < PG_N; q++) { b->pack_stale[q] = true; b->soa_stale[q] = false; }
         const char *ie = getenv("GTF_ITER");   // experiments: 0 fused tile kernel, 1 SoA pipeline, default packed pipeline
         b->iter_mode = ie ? atoi(ie) : 2;
         CK(cudaStreamCreateWithFlags(&b->stream3, cudaStreamNonBlocking));
@@ -193,7 +193,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.out_src, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.tag, k.msg_slot,
+        void *pk[] = {k.mrec, k.mrec_nx, k.out_src, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.tag, k.msg_slot,
                       k.msg_src, k.msg_dst, k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         cudaStreamDestroy(b->stream3);
@@ -218,6 +218,8 @@ static int field_group(int f)
     case GTF_F_uts_rank: case GTF_F_uts_a: case GTF_F_uts_b: case GTF_F_uts_c: case GTF_F_uts_tau: case GTF_F_uts_p00:
     case GTF_F_uts_p01: case GTF_F_uts_p11: case GTF_F_uts_p22: case GTF_F_uts_lik: case GTF_F_uts_prior: case GTF_F_uts_w:
     case GTF_F_uts_lrn: case GTF_F_uts_side: case GTF_F_edge_w: return PG_REC;
+    case GTF_F_m_a: case GTF_F_m_b: case GTF_F_m_c: case GTF_F_m_p00: case GTF_F_m_p01: case GTF_F_m_p22: case GTF_F_m_prior:
+        return PG_NODE;
     default: return -1;
     }
 }
@@ -229,21 +231,25 @@ static bool field_is_pack_static(int f)
 // bring the SoA arrays of the groups in `mask` up to date (after packed iterations)
 static int soa_sync(gtf_batch *b, unsigned mask)
 {
-    int d[3];
-    bool any = false;
-    for (int q = 0; q < 3; q++) { d[q] = ((mask >> q) & 1u) && b->soa_stale[q]; any |= d[q] != 0; }
-    if (!any || !b->E) { for (int q = 0; q < 3; q++) if ((mask >> q) & 1u) b->soa_stale[q] = false; return 0; }
-    k_unpack_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, b->k, d[PG_ACT], d[PG_PRES], d[PG_REC]);
-    CK(cudaGetLastError());
-    for (int q = 0; q < 3; q++) if (d[q]) b->soa_stale[q] = false;
+    int d[PG_N];
+    for (int q = 0; q < PG_N; q++) d[q] = ((mask >> q) & 1u) && b->soa_stale[q];
+    if ((d[PG_ACT] || d[PG_PRES] || d[PG_REC]) && b->E) {
+        k_unpack_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, b->k, d[PG_ACT], d[PG_PRES], d[PG_REC]);
+        CK(cudaGetLastError());
+    }
+    if (d[PG_NODE] && b->N) {
+        k_unpack_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, b->k);
+        CK(cudaGetLastError());
+    }
+    for (int q = 0; q < PG_N; q++) if ((mask >> q) & 1u) b->soa_stale[q] = false;
     return 0;
 }
 // a stage that works on the SoA arrays is about to run: SoA current, packed copy invalid afterwards
 static int soa_for_stage(gtf_batch *b, bool writes)
 {
-    int r = soa_sync(b, 7u);
+    int r = soa_sync(b, (1u << PG_N) - 1u);
     if (r) return r;
-    if (writes) for (int q = 0; q < 3; q++) b->pack_stale[q] = true;
+    if (writes) for (int q = 0; q < PG_N; q++) b->pack_stale[q] = true;
     return 0;
 }
 
@@ -252,7 +258,7 @@ extern "C" int gtf_batch_upload(gtf_batch *b, int f, const void *host)
     if (!b || f < 0 || f >= GTF_NFIELDS || !host) return fail(GTF_E_ARG, "gtf_batch_upload: bad argument");
     CK(cudaSetDevice(b->device));
     const int grp = field_group(f);
-    if (grp == PG_REC) { int r = soa_sync(b, 1u << PG_REC); if (r) return r; }   // the other record fields must be current
+    if (grp == PG_REC || grp == PG_NODE) { int r = soa_sync(b, 1u << grp); if (r) return r; } // the group's other fields must be current
     if (f == GTF_F_alive) { int r = soa_sync(b, 1u << PG_ACT); if (r) return r; b->pack_stale[PG_ACT] = true; }
     CK(cudaMemcpyAsync(b->f[f], host, (size_t)gtf_field_bytes(b, f), cudaMemcpyHostToDevice, b->stream));
     if (grp >= 0) { b->soa_stale[grp] = false; b->pack_stale[grp] = true; }
@@ -662,13 +668,14 @@ static int ensure_packed(gtf_batch *b)
 {
     if (b->derived_dirty) TRY(recount_subs(b));
     const bool st = b->pack_static_stale;
-    const bool any = st || b->pack_stale[0] || b->pack_stale[1] || b->pack_stale[2];
+    const bool any = st || b->pack_stale[0] || b->pack_stale[1] || b->pack_stale[2] || b->pack_stale[PG_NODE];
     if (!any) return 0;
     DevPack &k = b->k;
     if (st) {
         if (b->E) k_pack_out<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k);
-        if (b->N) k_pack_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, k);
     }
+    if (b->N && (st || b->pack_stale[PG_NODE]))
+        k_pack_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, k, st, b->pack_stale[PG_NODE]);
     if (b->pack_stale[PG_ACT]) CK(cudaMemsetAsync(k.counts + PK_MISSING, 0, sizeof(int), b->stream));
     if (b->E)
         k_pack_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k, st, b->pack_stale[PG_ACT], b->pack_stale[PG_PRES],
@@ -681,7 +688,7 @@ static int ensure_packed(gtf_batch *b)
         k.all_exist = missing == 0;
     }
     b->pack_static_stale = false;
-    for (int q = 0; q < 3; q++) b->pack_stale[q] = false;
+    for (int q = 0; q < PG_N; q++) b->pack_stale[q] = false;
     return 0;
 }
 template <int G> static void launch_hv(gtf_batch *b, cudaStream_t s, const Prog &P, const GtfGeom &gg, int bin, const MergedOut &mo)
@@ -714,16 +721,9 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
     CK(cudaGetLastError());
     if (b->N) {
         MergedOut mo;
-        if (commit) {
-            mo.hm = d.has_merged;
-            mo.m[0] = d.m_a; mo.m[1] = d.m_b; mo.m[2] = d.m_c; mo.m[3] = d.m_p00; mo.m[4] = d.m_p01; mo.m[6] = d.m_p22;
-            mo.m[7] = d.m_prior;
-        } else {
-            mo.hm = d.has_merged_nx;
-            mo.m[0] = d.m_a_nx; mo.m[1] = d.m_b_nx; mo.m[2] = d.m_c_nx; mo.m[3] = d.m_p00_nx; mo.m[4] = d.m_p01_nx;
-            mo.m[6] = d.m_p22_nx; mo.m[7] = d.m_prior_nx;
-        }
-        mo.m[5] = d.m_p11_nx; // k_send / k_exec wrote every node's accumulated value there; a new cluster replaces it
+        mo.hm = commit ? d.has_merged : d.has_merged_nx;
+        mo.rec = commit ? k.mrec : k.mrec_nx;
+        mo.p11 = d.m_p11_nx; // k_begin / k_send wrote every node's accumulated value there; a new cluster replaces it
         // the bins are independent (disjoint nodes): run them side by side
         CK(cudaEventRecord(b->ev_fork2, s0));
         CK(cudaStreamWaitEvent(b->stream2, b->ev_fork2, 0));
@@ -750,6 +750,7 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
         b->t_prefix_ms += 0; b->t_count++;
     }
     for (int q = 0; q < 3; q++) b->soa_stale[q] = true; // (a dry pass also rewrites dict entries in place)
+    if (commit) b->soa_stale[PG_NODE] = true;
     if (commit) {
         std::swap(k.act, k.act_nx);
         std::swap(b->f[GTF_F_m_p11], *(void **)&d.m_p11_nx);

@@ -57,6 +57,8 @@ struct __align__(16) GeoRec {    // static per-slot view of the source hit
     int32_t lay, src;            // its layer id; its node index (-1: ghost slot)
 };
 struct __align__(32) NodeXYZR { double x, y, z, r; };
+struct __align__(32) MergedRec { double a, b, c, p00, p01, p22, prior, pad; }; // merged_state / merged_cov / merged_prior of a node
+                                                                             // (p11 lives in the m_p11 ping-pong pair: quirk 2)
 
 enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_NCOUNTS = 8 };
 
@@ -65,6 +67,7 @@ struct DevPack {
     int32_t *out_dst, *out_rev, *out_src; // [E] out-CSR order: destination node / slot of the reverse edge (-1 none) / source
     GeoRec *geo;                 // [E]
     NodeXYZR *xyzr;              // [N]
+    MergedRec *mrec, *mrec_nx;   // [N] merged state of every node (64 B: two whole sectors); _nx: shadow for uncommitted passes
     int all_exist;               // every slot is an existing edge (no ghost slot, no removed node)
     // mutable slot state
     uint32_t *act, *act_nx, *pres, *exists; // bitmaps over slots, 2 zero words of padding
@@ -85,7 +88,7 @@ enum {
 };
 
 // per-node program executed by the tile kernel
-enum { PG_ACT = 0, PG_PRES = 1, PG_REC = 2 };
+enum { PG_ACT = 0, PG_PRES = 1, PG_REC = 2, PG_NODE = 3, PG_N = 4 };
 enum { OP_END = 0, OP_E, OP_PRIOR, OP_RW, OP_CLUSTER, OP_DEGREE, OP_WEIGHTS, OP_POP };
 
 // write-back masks
@@ -152,7 +155,7 @@ struct gtf_batch {
     DevPack k;
     int iter_mode;             // 2 packed pipeline (default), 1 SoA multi-kernel pipeline, 0 single fused tile kernel
     bool pack_static_stale;    // topology / coordinates changed since the static part was built
-    bool pack_stale[3], soa_stale[3]; // per group (PG_ACT, PG_PRES, PG_REC): which side holds the newer state
+    bool pack_stale[4], soa_stale[4]; // per group (PG_ACT, PG_PRES, PG_REC, PG_NODE): which side holds the newer state
     cudaStream_t stream3;
     cudaEvent_t ev_fork2, ev_join2, ev_join3;
     cudaEvent_t evk[6];

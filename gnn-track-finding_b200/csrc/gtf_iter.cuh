@@ -100,13 +100,29 @@ __global__ void k_pack_out(DevBatch B, DevPack K)
     K.out_dst[o] = B.slot_dst[s];
     K.out_rev[o] = B.rev_slot[s];
 }
-__global__ void k_pack_nodes(DevBatch B, DevPack K)
+__global__ void k_pack_nodes(DevBatch B, DevPack K, int do_static, int do_merged)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.N) return;
-    NodeXYZR v;
-    v.x = B.x[i]; v.y = B.y[i]; v.z = B.z[i]; v.r = B.r[i];
-    K.xyzr[i] = v;
+    if (do_static) {
+        NodeXYZR v;
+        v.x = B.x[i]; v.y = B.y[i]; v.z = B.z[i]; v.r = B.r[i];
+        K.xyzr[i] = v;
+    }
+    if (do_merged) {
+        MergedRec m;
+        m.a = B.m_a[i]; m.b = B.m_b[i]; m.c = B.m_c[i]; m.p00 = B.m_p00[i]; m.p01 = B.m_p01[i]; m.p22 = B.m_p22[i];
+        m.prior = B.m_prior[i]; m.pad = 0.0;
+        K.mrec[i] = m;
+    }
+}
+__global__ void k_unpack_nodes(DevBatch B, DevPack K)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N) return;
+    const MergedRec m = K.mrec[i];
+    B.m_a[i] = m.a; B.m_b[i] = m.b; B.m_c[i] = m.c; B.m_p00[i] = m.p00; B.m_p01[i] = m.p01; B.m_p22[i] = m.p22;
+    B.m_prior[i] = m.prior;
 }
 __global__ void k_unpack_slots(DevBatch B, DevPack K, int do_act, int do_pres, int do_rec)
 {
@@ -230,7 +246,8 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack K
     for (int q = tid; q < M; q += GTF_SEND_THREADS) {
         const int sl = sm.m_src[q], u = u0 + sl, v = sm.m_dst[q], rs = sm.m_rev[q];
         const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
-        const double a = B.m_a[u], b = B.m_b[u];
+        const double2 ab = *reinterpret_cast<const double2 *>(K.mrec + u);
+        const double a = ab.x, b = ab.y;
         const bool has = rs >= 0 && B.tse_present[rs];      // extrapolate...py:384: u's seed entry for this neighbour
         sm.m_w[q] = has ? B.tse_w[rs] : NAN;
         if (!has) sm.m_slot[q] |= (int)0x80000000;
@@ -292,7 +309,9 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
         const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
         x.sraw = sraw;
         x.ux = U.x; x.uy = U.y; x.uz = U.z; x.ur = U.r; x.vx = V.x; x.vy = V.y; x.vz = V.z; x.vr = V.r;
-        x.a = B.m_a[u]; x.b = B.m_b[u]; x.c = B.m_c[u]; x.p00 = B.m_p00[u]; x.p01 = B.m_p01[u]; x.p22 = B.m_p22[u];
+        const double2 *mr = reinterpret_cast<const double2 *>(K.mrec + u);
+        const double2 r0 = mr[0], r1 = mr[1], r2 = mr[2];
+        x.a = r0.x; x.b = r0.y; x.c = r1.x; x.p00 = r1.y; x.p01 = r2.x; x.p22 = r2.y;
         x.w = __ldcs(K.msg_w + q); x.p = __ldcs(K.msg_p11 + q); x.vms = __ldcs(K.msg_vms + q);
     };
     int q = blockIdx.x * GTF_EXEC_THREADS + tid;
@@ -528,9 +547,20 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
 
 // ------------------------------------------------------------------------------------------------ k_hv<G>
 struct MergedOut {
-    uint8_t *hm;
-    double *m[8]; // a b c p00 p01 p11 p22 prior
+    uint8_t *hm;      // has_merged flags to set
+    MergedRec *rec;   // merged-state records to write (in place when the pass is committed, shadow otherwise)
+    double *p11;      // accumulated merged_cov[1,1] of the next state
 };
+__device__ __forceinline__ void merged_store(const MergedOut &MO, int i, const GtfState &m, double mprior)
+{
+    if (!MO.hm[i]) MO.hm[i] = 1;
+    double2 *r = reinterpret_cast<double2 *>(MO.rec + i);
+    r[0] = make_double2(m.a, m.b);
+    r[1] = make_double2(m.c, m.p00);
+    r[2] = make_double2(m.p01, m.p22);
+    r[3] = make_double2(mprior, 0.0);
+    MO.p11[i] = m.p11;
+}
 
 template <int G> __device__ __forceinline__ unsigned grp_min_u32(unsigned v)
 {
@@ -908,9 +938,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             if ((f & H_ACT0) && !(f & H_ACT)) bm_clear(K.act_nx, slot);
         }
         if (clustered && gl == 0) {
-            MO.hm[i] = 1;
-            MO.m[0][i] = merged.a; MO.m[1][i] = merged.b; MO.m[2][i] = merged.c; MO.m[3][i] = merged.p00;
-            MO.m[4][i] = merged.p01; MO.m[5][i] = merged.p11; MO.m[6][i] = merged.p22; MO.m[7][i] = mprior;
+            merged_store(MO, i, merged, mprior);
             n_merged++;
         }
         __syncwarp();
@@ -943,6 +971,8 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
     double *lrn_s = reinterpret_cast<double *>(smem_raw + ((sizeof(TileSmem) + 15) & ~(size_t)15));
     double *ew_s = lrn_s + GTF_TILE_SLOTS;
     uint8_t *fresh_s = reinterpret_cast<uint8_t *>(ew_s + GTF_TILE_SLOTS);
+    __shared__ double mscr[8];
+    __shared__ uint8_t hm_s[8];
     const int lane = threadIdx.x;
     const int count = K.counts[PK_BIG];
     const int32_t *list = K.hv_list + (size_t)HV_BINS * B.N;
@@ -990,7 +1020,17 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
             lrn_s[ls] = -1.0;
         }
         __syncwarp();
-        node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, true, MO.hm, MO.m, lrn_s, ew_s);
+        // the generic program writes mo[k][i]: point every mo[k] at a shared scratch (biased by -i), copy out afterwards
+        double *mo[8];
+        for (int k = 0; k < 8; k++) mo[k] = mscr + k - i;
+        node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, true, hm_s - i, mo, lrn_s, ew_s);
+        __syncwarp();
+        if (lane == 0 && (sm.nflags[0] & NF_CLUSTERED)) {
+            GtfState m;
+            m.a = mscr[0]; m.b = mscr[1]; m.c = mscr[2]; m.p00 = mscr[3]; m.p01 = mscr[4]; m.p11 = mscr[5]; m.p22 = mscr[6];
+            m.tau = 0.0;
+            merged_store(MO, i, m, mscr[7]);
+        }
         __syncwarp();
         unsigned n_act = 0, n_chg = 0;
         for (int ls = lane; ls < d; ls += 32) {
