@@ -109,8 +109,6 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
     b->N = N; b->E = E; b->S = S; b->device = device;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
     for (int f = 0; f < GTF_NFIELDS; f++) {
         size_t bytes = (size_t)field_count(b, f) * g_fields[f].elem;
         if (!bytes) bytes = 8;
@@ -123,26 +121,9 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
     DA(d.node_ok, N);
     DA(b->n_dead, 1);
     DA(d.slot_p11, E); DA(d.slot_vms, E); DA(d.node_p11tot, N);
-    DA(d.active_nx, E); DA(d.has_merged_nx, N);
-    DA(d.m_a_nx, N); DA(d.m_b_nx, N); DA(d.m_c_nx, N); DA(d.m_p00_nx, N); DA(d.m_p01_nx, N);
-    DA(d.m_p11_nx, N); DA(d.m_p22_nx, N); DA(d.m_prior_nx, N);
+    DA(d.has_merged_nx, N); DA(d.m_p11_nx, N);
     DA(d.counters, GTF_NCOUNTERS);
     {
-        // optional: run the cooperative (>= 3 component) nodes in their own kernel (k_heavy).  Measured on B200 it is
-        // slower than keeping them inside k_tile (0.36 + 0.14 ms vs 0.44 ms per 32 cfg2 events), so it is opt-in.
-        const char *e = getenv("GTF_SPLIT_HEAVY");
-        b->split_heavy = (e && e[0] == '1');
-        // default: the multi-kernel pipeline (faster on B200); GTF_PIPELINE=0 selects the single
-        // fused tile kernel (k_tile<true>)
-        const char *pe = getenv("GTF_PIPELINE");
-        b->pipeline = !(pe && pe[0] == '0');
-        DA(b->msg_list, E);
-        DA(b->big_list, N);
-        DA(b->pipe_counts, 2);
-        DA(b->heavy_list, N);
-        DA(b->heavy_slot, N);
-        if ((int64_t)E >= (1LL << 25)) b->split_heavy = false;   // packed (slot << 6 | degree) must fit an int32
-        DA(b->heavy_count, 2);
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         b->n_sm = prop.multiProcessorCount;
@@ -151,7 +132,7 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         // packed iteration layout (gtf_iter.cuh)
         DevPack &k = b->k;
         const int64_t words = ((int64_t)E + 31) / 32 + 2;
-        DA(k.out_dst, E); DA(k.out_rev, E); DA(k.out_src, E); DA(k.geo, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N);
+        DA(k.out_dst, E); DA(k.out_rev, E); DA(k.geo, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N);
         DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.pres0, words);
         DA(k.state, (int64_t)E * 8); DA(k.meta, E); DA(k.tag, E);
         DA(k.msg_slot, E); DA(k.msg_src, E); DA(k.msg_dst, E); DA(k.msg_w, E);
@@ -160,8 +141,6 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         DA(k.counts, PK_NCOUNTS);
         b->pack_static_stale = true;
         for (int q = 0; q < PG_N; q++) { b->pack_stale[q] = true; b->soa_stale[q] = false; }
-        const char *ie = getenv("GTF_ITER");   // experiments: 0 fused tile kernel, 1 SoA pipeline, default packed pipeline
-        b->iter_mode = ie ? atoi(ie) : 2;
         CK(cudaStreamCreateWithFlags(&b->stream3, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&b->ev_fork2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming));
@@ -184,16 +163,14 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     cudaStreamSynchronize(b->stream);
     for (int f = 0; f < GTF_NFIELDS; f++) cudaFree(b->f[f]);
     DevBatch &d = b->d;
-    void *extra[] = {d.sub_nalive, d.node_ok, b->n_dead, d.slot_p11, d.slot_vms, d.node_p11tot, d.active_nx, d.has_merged_nx, d.m_a_nx,
-                     d.m_b_nx, d.m_c_nx, d.m_p00_nx, d.m_p01_nx, d.m_p11_nx, d.m_p22_nx, d.m_prior_nx, d.counters,
-                     b->accepted_total, b->cand_root, b->sub_has_inactive, b->sub_first, b->sort_keys, b->sort_vals,
-                     b->sort_keys2, b->sort_vals2, b->pv_xy, b->pv_zr, b->acc_now, b->tags_a, b->tags_b,
-                     b->tile_begin, b->sort_tmp, b->heavy_list, b->heavy_slot, b->heavy_count, b->msg_list, b->big_list,
-                     b->pipe_counts};
+    void *extra[] = {d.sub_nalive, d.node_ok, b->n_dead, d.slot_p11, d.slot_vms, d.node_p11tot, d.has_merged_nx, d.m_p11_nx,
+                     d.counters, b->accepted_total, b->cand_root, b->sub_has_inactive, b->sub_first, b->sort_keys,
+                     b->sort_vals, b->sort_keys2, b->sort_vals2, b->pv_xy, b->pv_zr, b->acc_now, b->tags_a, b->tags_b,
+                     b->tile_begin, b->sort_tmp};
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.mrec, k.mrec_nx, k.out_src, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.tag, k.msg_slot,
+        void *pk[] = {k.mrec, k.mrec_nx, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.tag, k.msg_slot,
                       k.msg_src, k.msg_dst, k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         cudaStreamDestroy(b->stream3);
@@ -203,8 +180,6 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     cudaFreeHost(b->h_counters);
     cudaStreamDestroy(b->stream);
     cudaStreamDestroy(b->stream2);
-    cudaEventDestroy(b->ev_fork);
-    cudaEventDestroy(b->ev_join);
     delete b;
     return 0;
 }
@@ -404,9 +379,7 @@ extern "C" int gtf_batch_finalize(gtf_batch *b)
     sync_dev_view(b);
     int r = recount_subs(b);
     if (r) return r;
-    CK(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-    CK(cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-    CK(cudaFuncSetAttribute(k_bignode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CK(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     CK(cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GTF_BIG_SMEM));
     CK(cudaStreamSynchronize(b->stream));
     b->finalized = true;
@@ -450,18 +423,17 @@ static GtfGeom geom_default()
     return o;
 }
 
-static int launch_tile(gtf_batch *b, const Prog &P, const GtfGeom &g, bool fused = false)
+static int launch_tile(gtf_batch *b, const Prog &P, const GtfGeom &g)
 {
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized (call gtf_batch_finalize after uploading the topology)");
     CK(cudaSetDevice(b->device));
-    if (!fused) TRY_(soa_for_stage(b, true));
+    TRY_(soa_for_stage(b, true));
     if (b->n_tiles == 0) return 0;
     if (b->derived_dirty) {
         int r_ = recount_subs(b);
         if (r_) return r_;
     }
-    if (fused) k_tile<true><<<b->n_tiles, GTF_TILE_THREADS, sizeof(TileSmem), b->stream>>>(b->d, P, g);
-    else k_tile<false><<<b->n_tiles, GTF_TILE_THREADS, sizeof(TileSmem), b->stream>>>(b->d, P, g);
+    k_tile<<<b->n_tiles, GTF_TILE_THREADS, sizeof(TileSmem), b->stream>>>(b->d, P, g);
     CK(cudaGetLastError());
     return 0;
 }
@@ -639,7 +611,7 @@ extern "C" int gtf_remove_state_metadata(gtf_batch *b, gtf_stats *st)
 static Prog fused_prog(const gtf_iter_params *p)
 {
     Prog P = make_prog(GTF_KEY_UTS,
-                       WB_ACTIVE | WB_PRESENT | WB_STATE | WB_PRIOR | WB_W | WB_UTSX | WB_EDGEW | WB_MERGED_NX | WB_COUNT_ACTIVE,
+                       WB_ACTIVE | WB_PRESENT | WB_STATE | WB_PRIOR | WB_W | WB_UTSX | WB_EDGEW | WB_COUNT_ACTIVE,
                        {OP_E, OP_PRIOR, OP_RW, OP_PRIOR, OP_RW, OP_CLUSTER, OP_DEGREE, OP_WEIGHTS, OP_PRIOR});
     P.chi2_cut = p->chi2_cut;
     P.cl_chi2 = p->cluster_chi2;
@@ -647,21 +619,6 @@ static Prog fused_prog(const gtf_iter_params *p)
     P.rw_thr = p->reweight_threshold;
     if (p->kl_lut) { P.use_lut = 1; memcpy(P.lut, p->kl_lut, sizeof(double) * 28); }
     return P;
-}
-static void commit_next(gtf_batch *b)
-{
-    DevBatch &d = b->d;
-    std::swap(b->f[GTF_F_active], *(void **)&d.active_nx);
-    std::swap(b->f[GTF_F_has_merged], *(void **)&d.has_merged_nx);
-    std::swap(b->f[GTF_F_m_a], *(void **)&d.m_a_nx);
-    std::swap(b->f[GTF_F_m_b], *(void **)&d.m_b_nx);
-    std::swap(b->f[GTF_F_m_c], *(void **)&d.m_c_nx);
-    std::swap(b->f[GTF_F_m_p00], *(void **)&d.m_p00_nx);
-    std::swap(b->f[GTF_F_m_p01], *(void **)&d.m_p01_nx);
-    std::swap(b->f[GTF_F_m_p11], *(void **)&d.m_p11_nx);
-    std::swap(b->f[GTF_F_m_p22], *(void **)&d.m_p22_nx);
-    std::swap(b->f[GTF_F_m_prior], *(void **)&d.m_prior_nx);
-    sync_dev_view(b);
 }
 // ---- packed pipeline (gtf_iter.cuh) --------------------------------------------------------------------------------
 static int ensure_packed(gtf_batch *b)
@@ -747,7 +704,7 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
             CK(cudaEventElapsedTime(&t, b->evk[q], b->evk[q + 1]));
             b->t_k[q] += t;
         }
-        b->t_prefix_ms += 0; b->t_count++;
+        b->t_count++;
     }
     for (int q = 0; q < 3; q++) b->soa_stale[q] = true; // (a dry pass also rewrites dict entries in place)
     if (commit) b->soa_stale[PG_NODE] = true;
@@ -762,76 +719,10 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
 
 extern "C" int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st)
 {
-    if (b && p && g && b->finalized && b->iter_mode == 2) {
-        CK(cudaSetDevice(b->device));
-        return iterate_packed(b, p, geom_of(g), st, false);
-    }
-    if (b && b->finalized) TRY(soa_for_stage(b, true));
     if (!b || !p || !g) return fail(GTF_E_ARG, "gtf_iterate_dry: null argument");
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
     CK(cudaSetDevice(b->device));
-    TRY(counters_reset(b));
-    GtfGeom gg = geom_of(g);
-    const bool pipe = b->pipeline && (int64_t)b->E < (1LL << 25);
-    b->d.msg_list = b->msg_list;
-    b->d.msg_count = b->pipe_counts;
-    b->d.big_count = b->pipe_counts + 1;
-    if (b->timing) CK(cudaEventRecord(b->ev[0], b->stream));
-    if (pipe && b->E) {
-        // the message list only reads the committed state: build it beside the prefix on the second stream
-        if (b->derived_dirty) TRY(recount_subs(b));
-        CK(cudaMemsetAsync(b->pipe_counts, 0, 2 * sizeof(int), b->stream));
-        CK(cudaEventRecord(b->ev_fork, b->stream));
-        CK(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
-        k_msg_list<<<(b->E + GTF_PIPE_THREADS - 1) / GTF_PIPE_THREADS, GTF_PIPE_THREADS, 0, b->stream2>>>(b->d);
-        CK(cudaEventRecord(b->ev_join, b->stream2));
-    }
-    TRY(launch_prefix(b, gg));
-    if (pipe && b->E) CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
-    if (b->timing) CK(cudaEventRecord(b->ev[1], b->stream));
-    Prog P = fused_prog(p);
-    b->d.heavy_slot = b->heavy_slot;
-    b->d.heavy_count = b->heavy_count;
-    b->d.big_list = b->big_list;
-    if (pipe) {
-        // multi-kernel form: message list -> message execution -> thread-per-node -> cooperative nodes
-        b->d.heavy_list = b->heavy_list;
-        CK(cudaMemsetAsync(b->heavy_count, 0, 2 * sizeof(int), b->stream));
-        if (b->E) k_msg_exec<<<b->n_sm * 8, GTF_PIPE_THREADS, 0, b->stream>>>(b->d, P.chi2_cut, gg);
-        if (b->N) k_node<<<(b->N + GTF_NODE_THREADS - 1) / GTF_NODE_THREADS, GTF_NODE_THREADS, 0, b->stream>>>(b->d, P);
-        CK(cudaGetLastError());
-        if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
-        if (b->N) {
-            // the (few, long) > 32-slot cooperative nodes run beside k_heavy on the second stream
-            CK(cudaEventRecord(b->ev_fork, b->stream));
-            CK(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
-            k_bignode<<<b->n_sm * 2, 32, sizeof(TileSmem), b->stream2>>>(b->d, P, gg);
-            CK(cudaEventRecord(b->ev_join, b->stream2));
-            k_heavy<<<b->n_sm * GTF_HEAVY_MINB, GTF_HEAVY_WARPS * 32, 0, b->stream>>>(b->d, P, gg);
-            CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
-        }
-        CK(cudaGetLastError());
-    } else {
-        b->d.heavy_list = b->split_heavy ? b->heavy_list : nullptr;
-        if (b->split_heavy) CK(cudaMemsetAsync(b->heavy_count, 0, 2 * sizeof(int), b->stream));
-        TRY(launch_tile(b, P, gg, true));
-        if (b->timing) CK(cudaEventRecord(b->ev[2], b->stream));
-        if (b->split_heavy && b->n_tiles) {
-            k_heavy<<<b->n_sm * GTF_HEAVY_MINB, GTF_HEAVY_WARPS * 32, 0, b->stream>>>(b->d, P, gg);
-            CK(cudaGetLastError());
-        }
-    }
-    if (b->timing) {
-        CK(cudaEventRecord(b->ev[3], b->stream));
-        CK(cudaEventSynchronize(b->ev[3]));
-        float t0 = 0, t1 = 0, t2 = 0;
-        CK(cudaEventElapsedTime(&t0, b->ev[0], b->ev[1]));
-        CK(cudaEventElapsedTime(&t1, b->ev[1], b->ev[2]));
-        CK(cudaEventElapsedTime(&t2, b->ev[2], b->ev[3]));
-        b->t_prefix_ms += t0; b->t_tile_ms += t1; b->t_heavy_ms += t2; b->t_count++;
-    }
-    if (st) return counters_read(b, st);
-    return 0;
+    return iterate_packed(b, p, geom_of(g), st, false);
 }
 // per-kernel timing of the fused iteration with CUDA events on the batch stream (bench.py roofline):
 // enable=1 resets the accumulators; gtf_batch_timing returns the averages since then
@@ -839,30 +730,20 @@ extern "C" int gtf_batch_set_timing(gtf_batch *b, int enable)
 {
     if (!b) return fail(GTF_E_ARG, "null batch");
     CK(cudaSetDevice(b->device));
-    if (enable && !b->ev[0]) {
-        for (int k = 0; k < 4; k++) CK(cudaEventCreate(&b->ev[k]));
+    if (enable && !b->evk[0])
         for (int k = 0; k < 6; k++) CK(cudaEventCreate(&b->evk[k]));
-    }
     for (int k = 0; k < 5; k++) b->t_k[k] = 0.0;
     b->timing = enable != 0;
-    b->t_prefix_ms = b->t_tile_ms = b->t_heavy_ms = 0.0;
     b->t_count = 0;
     return 0;
 }
 extern "C" int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms, double *heavy_ms, int *count)
 {
     if (!b) return fail(GTF_E_ARG, "null batch");
-    int n = b->t_count ? b->t_count : 1;
-    if (b->iter_mode == 2) { // packed pipeline: k_send | k_exec + k_node2 | k_hv<*> + k_big
-        if (prefix_ms) *prefix_ms = b->t_k[0] / n;
-        if (tile_ms) *tile_ms = (b->t_k[1] + b->t_k[2]) / n;
-        if (heavy_ms) *heavy_ms = b->t_k[3] / n;
-        if (count) *count = b->t_count;
-        return 0;
-    }
-    if (prefix_ms) *prefix_ms = b->t_prefix_ms / n;
-    if (tile_ms) *tile_ms = b->t_tile_ms / n;
-    if (heavy_ms) *heavy_ms = b->t_heavy_ms / n;
+    int n = b->t_count ? b->t_count : 1; // k_begin + k_send | k_exec + k_node2 | k_hv<*> + k_big
+    if (prefix_ms) *prefix_ms = b->t_k[0] / n;
+    if (tile_ms) *tile_ms = (b->t_k[1] + b->t_k[2]) / n;
+    if (heavy_ms) *heavy_ms = b->t_k[3] / n;
     if (count) *count = b->t_count;
     return 0;
 }
@@ -879,16 +760,12 @@ extern "C" int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geo
                            gtf_stats *stats, int *n_done)
 {
     if (!b || !p || !g) return fail(GTF_E_ARG, "gtf_iterate: null argument");
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
+    CK(cudaSetDevice(b->device));
     int it = 0;
     for (; it < max_iter; it++) {
         gtf_stats st;
-        if (b->finalized && b->iter_mode == 2) {
-            CK(cudaSetDevice(b->device));
-            TRY(iterate_packed(b, p, geom_of(g), &st, true));
-        } else {
-            TRY(gtf_iterate_dry(b, p, g, &st));
-            commit_next(b);
-        }
+        TRY(iterate_packed(b, p, geom_of(g), &st, true));
         if (stats) stats[it] = st;
         if (stop_when_converged && st.active_changed == 0) { it++; break; }
     }

@@ -27,18 +27,11 @@ struct DevBatch {
     double *slot_p11;            // [E] merged_cov[1,1] as seen by this edge
     double *slot_vms;            // [E] var_ms of this edge
     double *node_p11tot;         // [N] merged_cov[1,1] after all successors
-    // "next" buffers of the fused iteration (ping-pong with active / has_merged / m_*)
-    uint8_t *active_nx, *has_merged_nx;
-    double *m_a_nx, *m_b_nx, *m_c_nx, *m_p00_nx, *m_p01_nx, *m_p11_nx, *m_p22_nx, *m_prior_nx;
+    // shadow buffers of the iteration: accumulated merged_cov[1,1] of the next state (ping-pong with m_p11, quirk 2);
+    // has_merged flags of an uncommitted pass
+    uint8_t *has_merged_nx;
+    double *m_p11_nx;
     unsigned long long *counters; // [GTF_NCOUNTERS]
-    // cooperative (>= 3 components) nodes of the fused iteration, filled by k_tile, consumed by k_heavy
-    int32_t *heavy_list; // [N] (nullptr: process them inside k_tile)
-    int32_t *heavy_slot; // [N] first slot << 6 | degree  (E < 2^25 slots per batch when the split is on)
-    int *heavy_count;    // [2]: count, next
-    // pipeline mode (gtf_pipe.cuh)
-    int32_t *msg_list;   // [E] slots that carry a message this iteration
-    int32_t *big_list;   // [N] cooperative nodes with more than 32 in-slots
-    int *msg_count, *big_count;
 };
 
 // ---- packed iteration layout (gtf_iter.cuh): per-slot records + bitmaps, built from / written back to the SoA
@@ -64,7 +57,7 @@ enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_NCOUN
 
 struct DevPack {
     // static, derived from the topology and the hit coordinates
-    int32_t *out_dst, *out_rev, *out_src; // [E] out-CSR order: destination node / slot of the reverse edge (-1 none) / source
+    int32_t *out_dst, *out_rev;  // [E] out-CSR order: destination node / slot of the reverse edge (-1 none)
     GeoRec *geo;                 // [E]
     NodeXYZR *xyzr;              // [N]
     MergedRec *mrec, *mrec_nx;   // [N] merged state of every node (64 B: two whole sectors); _nx: shadow for uncommitted passes
@@ -94,8 +87,7 @@ enum { OP_END = 0, OP_E, OP_PRIOR, OP_RW, OP_CLUSTER, OP_DEGREE, OP_WEIGHTS, OP_
 // write-back masks
 enum {
     WB_ACTIVE = 1, WB_PRESENT = 2, WB_STATE = 4, WB_PRIOR = 8, WB_W = 16, WB_UTSX = 32 /* lik, lrn, side, rank */,
-    WB_EDGEW = 64, WB_MERGED_NX = 128 /* fused: write every node's merged state to the *_nx buffers */,
-    WB_COUNT_ACTIVE = 256
+    WB_EDGEW = 64, WB_COUNT_ACTIVE = 256
 };
 
 struct Prog {
@@ -124,7 +116,6 @@ struct Prog {
 struct gtf_batch {
     int N, E, S, device;
     cudaStream_t stream, stream2;
-    cudaEvent_t ev_fork, ev_join;
     void *f[GTF_NFIELDS];
     DevBatch d;
     bool finalized, derived_dirty;
@@ -146,26 +137,16 @@ struct gtf_batch {
     double *pv_xy, *pv_zr;     // [N]
     uint8_t *acc_now;          // [N]
     int32_t *tags_a, *tags_b;  // [N]
-    // cooperative nodes of the fused iteration run in their own kernel (k_heavy) unless GTF_SPLIT_HEAVY=0
-    bool split_heavy;
-    int32_t *heavy_list, *heavy_slot;
-    int *heavy_count;
     int n_sm;
     // packed iteration layout
     DevPack k;
-    int iter_mode;             // 2 packed pipeline (default), 1 SoA multi-kernel pipeline, 0 single fused tile kernel
     bool pack_static_stale;    // topology / coordinates changed since the static part was built
     bool pack_stale[4], soa_stale[4]; // per group (PG_ACT, PG_PRES, PG_REC, PG_NODE): which side holds the newer state
     cudaStream_t stream3;
     cudaEvent_t ev_fork2, ev_join2, ev_join3;
     cudaEvent_t evk[6];
     double t_k[5];             // send, exec, node, heavy, (spare)
-    bool pipeline;             // GTF_PIPELINE=1: multi-kernel form of the fused iteration (gtf_pipe.cuh)
-    int32_t *msg_list, *big_list;
-    int *pipe_counts;          // [2]: messages, big nodes
-    // optional per-kernel timing of the fused iteration
+    // optional per-kernel timing of the iteration (CUDA events on the batch stream)
     bool timing;
-    cudaEvent_t ev[4];
-    double t_prefix_ms, t_tile_ms, t_heavy_ms;
     int t_count;
 };

@@ -1,4 +1,5 @@
-// gtf_tile.cuh -- the fused per-iteration kernel (and, with shorter programs, every per-stage kernel).
+// gtf_tile.cuh -- the per-stage kernel on the SoA fields: one launch = one reference stage (or a short chain of them).
+// The fused iteration runs on the packed layout instead (gtf_iter.cuh).
 //
 // One CTA owns a *tile*: a contiguous range of nodes (hits) and therefore a contiguous range of in-slots
 // (incoming edges / mixture components).  Phases:
@@ -10,8 +11,8 @@
 //               side-norm + reweight + prune (helper.py:99-200), pairwise chi2 + greedy KL clustering
 //               (clustering.py:193-307), degree / mixture weights (helper.py:67-94)
 //   4. store    thread-per-slot coalesced write-back of what the program changed
-// The program (list of OP_*) selects which of these run, so gtf_cluster / gtf_reweight / ... are the same
-// kernel with a one- or two-op program and gtf_iterate is the full list in one launch.
+// The program (list of OP_*) selects which of these run, so gtf_cluster / gtf_reweight / gtf_message_passing / ...
+// are the same kernel with a one- to six-op program.
 #pragma once
 #include "gtf_dev.cuh"
 
@@ -31,8 +32,6 @@
 #define NF_DICT 4u   // node has the working dict
 #define NF_HASUTS 8u
 #define NF_CLUSTERED 16u
-#define NF_DEFER 32u   // cooperative node handed to k_heavy (fused iteration)
-#define GTF_NEWMARK 0x7ffffffe // uts_rank of an entry inserted by k_tile whose dict position k_heavy still has to assign
 
 struct TileSmem {
     double st[8][GTF_TILE_SLOTS]; // a b c tau p00 p01 p11 p22 of the working dict entry
@@ -45,9 +44,7 @@ struct TileSmem {
     uint8_t nflags[GTF_TILE_NODES];
     double D[GTF_TILE_THREADS / 32][GTF_MAXD * (GTF_MAXD - 1) / 2 + 1];
     unsigned int cnt[GTF_NCOUNTERS];
-    int next_node, elist_n, heavy_n, light_n, defer_n, defer_base;
-    uint8_t heavy[GTF_TILE_NODES], light[GTF_TILE_NODES];
-    uint16_t ne0[GTF_TILE_NODES], ne1[GTF_TILE_NODES], ndeg[GTF_TILE_NODES]; // light nodes: their (<= 2) entries, active degree
+    int next_node, elist_n;
 };
 
 template <class SM>
@@ -426,17 +423,10 @@ __device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch B
     }
 }
 
-// the op list of the fused iteration (gtf_iterate): known at compile time in k_tile<true>
-__device__ __forceinline__ constexpr int fused_op(int k)
-{
-    return k == 0 ? OP_E : k == 1 ? OP_PRIOR : k == 2 ? OP_RW : k == 3 ? OP_PRIOR : k == 4 ? OP_RW
-         : k == 5 ? OP_CLUSTER : k == 6 ? OP_DEGREE : k == 7 ? OP_WEIGHTS : k == 8 ? OP_PRIOR : OP_END;
-}
-
 // register-resident per-node program for nodes with <= 32 in-slots: lane l owns slot b0 + l; counts,
 // same-layer / same-x groupings and dict positions come from ballots, MATCH.ANY and shuffles instead of
 // O(d^2) shared-memory loops.
-template <bool FUSED, class SM>
+template <class SM>
 __device__ __forceinline__ void node_program_fast(SM &sm, const DevBatch &B, const Prog &P, const GtfGeom &g, int i,
                                                   int ln, int s0, int warp, int lane, bool uts, uint8_t *hm_out,
                                                   double *const *mo)
@@ -463,7 +453,7 @@ __device__ __forceinline__ void node_program_fast(SM &sm, const DevBatch &B, con
 
 #pragma unroll
     for (int k = 0; k < 12; k++) {
-        const int op = FUSED ? fused_op(k) : P.ops[k];
+        const int op = P.ops[k];
         if (op == OP_END) break;
         bool need_order = (op == OP_RW || op == OP_CLUSTER || op == OP_WEIGHTS);
         if (op == OP_E) {
@@ -590,144 +580,6 @@ __device__ __forceinline__ void node_program_fast(SM &sm, const DevBatch &B, con
 }
 
 
-// thread-per-node program of the fused iteration for nodes whose dict holds at most two entries (~87 % of
-// the nodes of a cfg2 event): no clustering can happen (clustering.py:207 needs >= 3), priors / side norms /
-// reweighting reduce to closed forms over two entries, so one thread does the whole node and a warp does
-// 32 nodes at once.  Same op order as fused_op(): E-rank, PRIOR, RW, PRIOR, RW, (CLUSTER: skip), DEGREE,
-// WEIGHTS, PRIOR.
-struct LightEntry {
-    int ls;
-    unsigned f;
-    int lay;
-    double sx, w, lik, prior;
-    int side;
-};
-__device__ __forceinline__ void light_load(const TileSmem &sm, int ls, LightEntry &e)
-{
-    e.ls = ls;
-    e.f = sm.flags[ls];
-    e.lay = sm.layer[ls];
-    e.sx = sm.srcx[ls] + 0.0;
-    e.w = sm.w[ls]; e.lik = sm.lik[ls]; e.prior = sm.prior[ls];
-    e.side = 0;
-}
-__device__ __forceinline__ void light_prior(LightEntry &a, LightEntry &b, int n)
-{
-    const unsigned m3 = F_PRES | F_EX | F_ACT;
-    bool ea = (a.f & m3) == m3, eb = n == 2 && (b.f & m3) == m3;
-    bool same = ea && eb && a.lay == b.lay;
-    if (ea) a.prior = same ? 0.5 : 1.0; // helper.py:61: 1/len(group)
-    if (eb) b.prior = same ? 0.5 : 1.0;
-}
-__device__ __forceinline__ void light_reweight(unsigned int *cnt, LightEntry &a, LightEntry &b, int n, double nodex, double thr,
-                                               double *edge_w_tile, double *lrn_tile)
-{
-    const unsigned m3 = F_PRES | F_EX | F_ACT;
-    bool ea = (a.f & m3) == m3, eb = n == 2 && (b.f & m3) == m3;
-    if (!ea && !eb) return;
-    bool la = a.sx < nodex, lb = b.sx < nodex;
-    // len(set(x)) per side (helper.py:127,134)
-    double norm_a = 1.0, norm_b = 1.0;
-    if (ea && eb && la == lb && a.sx != b.sx) { norm_a = 2.0; norm_b = 2.0; }
-    // stale `neighbour_num`: the last dict key gates the norms (helper.py:131,138)
-    unsigned lf = n == 2 ? b.f : a.f;
-    if (!(lf & F_EX)) atomicOr(&cnt[CNT_REFERR], (unsigned)GTF_REF_KEY);
-    bool last_active = (lf & (F_EX | F_ACT)) == (F_EX | F_ACT);
-    double denom = 0.0; // dict order (helper.py:165-169)
-    if (ea) denom += a.w * a.lik;
-    if (eb) denom += b.w * b.lik;
-    unsigned off = 0;
-    if (ea) {
-        double norm = last_active ? norm_a : 1.0;
-        double rw = (a.w * a.lik * a.prior) / denom;
-        if (norm != 1.0) rw = rw / norm;
-        lrn_tile[a.ls] = norm; a.side = la ? 1 : 2; a.w = rw;
-        edge_w_tile[a.ls] = rw;
-        a.f |= F_RW;
-        if (rw < thr) { a.f &= ~F_ACT; off++; } else a.f |= F_ACT;
-    }
-    if (eb) {
-        double norm = last_active ? norm_b : 1.0;
-        double rw = (b.w * b.lik * b.prior) / denom;
-        if (norm != 1.0) rw = rw / norm;
-        lrn_tile[b.ls] = norm; b.side = lb ? 1 : 2; b.w = rw;
-        edge_w_tile[b.ls] = rw;
-        b.f |= F_RW;
-        if (rw < thr) { b.f &= ~F_ACT; off++; } else b.f |= F_ACT;
-    }
-    if (off) atomicAdd(&cnt[CNT_RWOFF], off);
-}
-__device__ __forceinline__ void light_store(TileSmem &sm, const LightEntry &e, int rank)
-{
-    sm.flags[e.ls] = (uint8_t)e.f;
-    sm.rank[e.ls] = rank;
-    sm.w[e.ls] = e.w;
-    sm.prior[e.ls] = e.prior;
-    if (e.f & F_RW) sm.side[e.ls] = (uint8_t)((sm.side[e.ls] & SD_ORIGPRES) | e.side);
-}
-// one light node (classified by the caller: n <= 2 dict entries at local slots e0, e1; deg0 = active in-degree
-// before the reweight passes)
-__device__ __forceinline__ void node_program_light(TileSmem &sm, const DevBatch &B, const Prog &P, int i, int ln, int s0)
-{
-    const int b0 = sm.nbeg[ln];
-    unsigned nf = sm.nflags[ln];
-    const int e0 = sm.ne0[ln], e1 = sm.ne1[ln];
-    const int n = (e0 != 0xffff) + (e1 != 0xffff);
-    if (!(nf & NF_OK)) return; // every op is guarded by NF_OK
-    LightEntry a, b;
-    a.f = 0; b.f = 0; a.ls = b.ls = b0; a.lay = b.lay = -1; a.sx = b.sx = 0; a.w = b.w = a.lik = b.lik = 0;
-    a.prior = b.prior = 0; a.side = b.side = 0;
-    int ra = 0, rb = 0;
-    if (n >= 1) { light_load(sm, e0, a); ra = sm.rank[e0]; }
-    if (n == 2) { light_load(sm, e1, b); rb = sm.rank[e1]; }
-    // OP_E: new entries enter the dict in ascending source order (extrapolate...py:419-447)
-    int nnew = ((a.f & F_NEW) != 0) + ((b.f & F_NEW) != 0);
-    if (nnew) {
-        int nxt = B.uts_next[i];
-        if (nnew == 2) {
-            bool a_first = sm.src[e0] < sm.src[e1];
-            ra = nxt + (a_first ? 0 : 1);
-            rb = nxt + (a_first ? 1 : 0);
-        } else if (a.f & F_NEW) ra = nxt; else rb = nxt;
-        B.uts_next[i] = nxt + nnew;
-        B.has_uts[i] = 1;
-        nf |= NF_DICT | NF_HASUTS;
-    }
-    if (n == 2 && rb < ra) { LightEntry t = a; a = b; b = t; int r = ra; ra = rb; rb = r; } // dict order
-    const bool rdict = (nf & (NF_MULTI | NF_DICT)) == (NF_MULTI | NF_DICT);
-    const bool ruts = (nf & (NF_MULTI | NF_HASUTS)) == (NF_MULTI | NF_HASUTS);
-    const double nodex = B.x[i];
-    if (n) {
-        if (rdict) light_prior(a, b, n);
-        if (ruts) light_reweight(sm.cnt, a, b, n, nodex, P.rw_thr, B.edge_w + s0, B.uts_lrn + s0);
-        if (rdict) light_prior(a, b, n);
-        if (ruts) light_reweight(sm.cnt, a, b, n, nodex, P.rw_thr, B.edge_w + s0, B.uts_lrn + s0);
-    }
-    // OP_WEIGHTS, final OP_PRIOR
-    if (rdict) {
-        if (n == 0) atomicOr(&sm.cnt[CNT_REFERR], (unsigned)GTF_REF_ZERO_DIV);
-        else {
-            double mw = n == 2 ? 0.5 : 1.0;
-            a.w = mw;
-            b.w = mw;
-            light_prior(a, b, n);
-        }
-    }
-    // OP_DEGREE (after all pruning): entries that lost their activation in the reweight passes
-    int lost = 0;
-    if (n >= 1) {
-        lost += (sm.flags[a.ls] & (F_EX | F_ACT)) == (F_EX | F_ACT) && (a.f & (F_EX | F_ACT)) != (F_EX | F_ACT);
-        light_store(sm, a, ra);
-    }
-    if (n == 2) {
-        lost += (sm.flags[b.ls] & (F_EX | F_ACT)) == (F_EX | F_ACT) && (b.f & (F_EX | F_ACT)) != (F_EX | F_ACT);
-        light_store(sm, b, rb);
-    }
-    B.degree[i] = (int)sm.ndeg[ln] - lost;
-    (void)b0;
-}
-
-template <bool FUSED>
 __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBatch B, Prog P, GtfGeom g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -736,14 +588,13 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
     const int n0 = B.tile_begin[blockIdx.x], n1 = B.tile_begin[blockIdx.x + 1];
     const int nn = n1 - n0;
     const int s0 = B.in_off[n0], ns = B.in_off[n1] - s0;
-    const bool uts = FUSED ? true : (P.key == GTF_KEY_UTS);
-    const int wb = FUSED ? (WB_ACTIVE | WB_PRESENT | WB_STATE | WB_PRIOR | WB_W | WB_UTSX | WB_MERGED_NX | WB_COUNT_ACTIVE) : P.wb;
-    bool has_E = FUSED;
-    if (!FUSED)
-        for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) has_E |= P.ops[k] == OP_E;
+    const bool uts = P.key == GTF_KEY_UTS;
+    const int wb = P.wb;
+    bool has_E = false;
+    for (int k = 0; k < 12 && P.ops[k] != OP_END; k++) has_E |= P.ops[k] == OP_E;
 
     if (tid < GTF_NCOUNTERS) sm.cnt[tid] = 0;
-    if (tid == 0) { sm.next_node = GTF_TILE_THREADS / 32; sm.elist_n = 0; sm.heavy_n = 0; sm.light_n = 0; sm.defer_n = 0; sm.defer_base = 0; }
+    if (tid == 0) { sm.next_node = GTF_TILE_THREADS / 32; sm.elist_n = 0; }
     __syncthreads();
     // ---------------------------------------------------------------- node table
     for (int ln = tid; ln <= nn; ln += GTF_TILE_THREADS) {
@@ -869,107 +720,30 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
     }
 
     // ---------------------------------------------------------------- node programs (warp per node, dynamic)
-    uint8_t *hm_out = (wb & WB_MERGED_NX) ? B.has_merged_nx : B.has_merged;
-    double *const mo[8] = {(wb & WB_MERGED_NX) ? B.m_a_nx : B.m_a,     (wb & WB_MERGED_NX) ? B.m_b_nx : B.m_b,
-                           (wb & WB_MERGED_NX) ? B.m_c_nx : B.m_c,     (wb & WB_MERGED_NX) ? B.m_p00_nx : B.m_p00,
-                           (wb & WB_MERGED_NX) ? B.m_p01_nx : B.m_p01, (wb & WB_MERGED_NX) ? B.m_p11_nx : B.m_p11,
-                           (wb & WB_MERGED_NX) ? B.m_p22_nx : B.m_p22, (wb & WB_MERGED_NX) ? B.m_prior_nx : B.m_prior};
-    if (FUSED) {
-        // classify (thread per node, one scan of its slots): dict entries, active in-degree
-        for (int ln = tid; ln < nn; ln += GTF_TILE_THREADS) {
-            const int b0 = sm.nbeg[ln], b1 = sm.nbeg[ln + 1];
-            int e0 = 0xffff, e1 = 0xffff, np = 0, deg = 0;
-            for (int t = b0; t < b1; t++) {
-                unsigned f = sm.flags[t];
-                deg += (f & (F_EX | F_ACT)) == (F_EX | F_ACT);
-                if (f & F_PRES) {
-                    if (np == 0) e0 = t; else if (np == 1) e1 = t;
-                    np++;
-                }
-            }
-            sm.ne0[ln] = (uint16_t)e0; sm.ne1[ln] = (uint16_t)e1; sm.ndeg[ln] = (uint16_t)deg;
-            if (np > 2) {
-                if (B.heavy_list && b1 - b0 <= 32) { // cooperative node: its own kernel (k_heavy), off this CTA's critical path
-                    sm.light[GTF_TILE_NODES - 1 - atomicAdd(&sm.defer_n, 1)] = (uint8_t)ln; // deferred list grows from the top
-                    sm.nflags[ln] |= NF_DEFER;
-                } else
-                    sm.heavy[atomicAdd(&sm.heavy_n, 1)] = (uint8_t)ln;
-            } else
-                sm.light[atomicAdd(&sm.light_n, 1)] = (uint8_t)ln;
-        }
-        __syncthreads();
-        // hand the deferred nodes to k_heavy: ONE global atomic per tile reserves the range
-        if (sm.defer_n) {
-            if (tid == 0) sm.defer_base = atomicAdd(B.heavy_count, sm.defer_n);
-            __syncthreads();
-            for (int q = tid; q < sm.defer_n; q += GTF_TILE_THREADS) {
-                const int ln = sm.light[GTF_TILE_NODES - 1 - q];
-                B.heavy_list[sm.defer_base + q] = n0 + ln;
-                B.heavy_slot[sm.defer_base + q] = ((s0 + sm.nbeg[ln]) << 6) | (sm.nbeg[ln + 1] - sm.nbeg[ln]);
-            }
-        }
-        // one work queue: cooperative (warp-per-node) items first, then chunks of 32 light nodes (thread-per-node)
-        const int nh = sm.heavy_n, nl = sm.light_n, nitems = nh + (nl + 31) / 32;
-        for (int q = warp; q < nitems;) {
-            if (q < nh) {
-                const int ln = sm.heavy[q], i = n0 + ln;
-                if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED, TileSmem>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
-                else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo, B.uts_lrn + s0, B.edge_w + s0);
-            } else {
-                const int idx = (q - nh) * 32 + lane;
-                if (idx < nl) {
-                    const int ln = sm.light[idx];
-                    node_program_light(sm, B, P, n0 + ln, ln, s0);
-                }
-                __syncwarp();
-            }
-            int nxt = 0;
-            if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
-            q = __shfl_sync(0xffffffffu, nxt, 0);
-        }
-    } else {
-        for (int ln = warp; ln < nn;) {
-            const int i = n0 + ln;
-            if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<FUSED, TileSmem>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
-            else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo, B.uts_lrn + s0, B.edge_w + s0);
-            int nxt = 0;
-            if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
-            ln = __shfl_sync(0xffffffffu, nxt, 0);
-        }
+    uint8_t *hm_out = B.has_merged;
+    double *const mo[8] = {B.m_a, B.m_b, B.m_c, B.m_p00, B.m_p01, B.m_p11, B.m_p22, B.m_prior};
+    for (int ln = warp; ln < nn;) {
+        const int i = n0 + ln;
+        if (sm.nbeg[ln + 1] - sm.nbeg[ln] <= 32) node_program_fast<TileSmem>(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo);
+        else node_program_generic(sm, B, P, g, i, ln, s0, warp, lane, uts, hm_out, mo, B.uts_lrn + s0, B.edge_w + s0);
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&sm.next_node, 1);
+        ln = __shfl_sync(0xffffffffu, nxt, 0);
     }
     __syncthreads();
 
     // ---------------------------------------------------------------- store
-    // merged state of nodes without a new cluster result is carried to the next buffers, with the
-    // multiple-scattering term the reference accumulates on the node attribute (quirk 2)
-    if (wb & WB_MERGED_NX) {
-        for (int ln = tid; ln < nn; ln += GTF_TILE_THREADS) {
-            if (sm.nflags[ln] & NF_CLUSTERED) continue;
-            int i = n0 + ln;
-            uint8_t h = B.has_merged[i];
-            hm_out[i] = h;
-            if (h) {
-                mo[0][i] = B.m_a[i]; mo[1][i] = B.m_b[i]; mo[2][i] = B.m_c[i]; mo[3][i] = B.m_p00[i];
-                mo[4][i] = B.m_p01[i]; mo[6][i] = B.m_p22[i]; mo[7][i] = B.m_prior[i];
-                mo[5][i] = has_E ? B.node_p11tot[i] : B.m_p11[i];
-            }
-        }
-    }
-    uint8_t *act_out = (wb & WB_MERGED_NX) ? B.active_nx : B.active;
+    uint8_t *act_out = B.active;
     unsigned n_act = 0, n_chg = 0;
     for (int ls = tid; ls < ns; ls += GTF_TILE_THREADS) {
         int s = s0 + ls;
         unsigned f = sm.flags[ls];
         bool a = f & F_ACT, a0 = f & F_ORIG;
-        const bool deferred = FUSED && (sm.nflags[sm.dstl[ls]] & NF_DEFER);
-        if ((f & F_EX) && !deferred) {
+        if (f & F_EX) {
             n_act += a;
             n_chg += a != a0;
         }
-        if (wb & WB_ACTIVE) {
-            if (wb & WB_MERGED_NX) act_out[s] = a ? 1 : 0;
-            else if (a != a0) act_out[s] = a ? 1 : 0;
-        }
+        if ((wb & WB_ACTIVE) && a != a0) act_out[s] = a ? 1 : 0;
         if (uts) {
             if (wb & WB_PRESENT) {
                 if (f & F_NEW) B.uts_present[s] = 1;
@@ -979,7 +753,7 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
                 B.uts_a[s] = sm.st[0][ls]; B.uts_b[s] = sm.st[1][ls]; B.uts_c[s] = sm.st[2][ls]; B.uts_tau[s] = sm.st[3][ls];
                 B.uts_p00[s] = sm.st[4][ls]; B.uts_p01[s] = sm.st[5][ls]; B.uts_p11[s] = sm.st[6][ls]; B.uts_p22[s] = sm.st[7][ls];
                 B.uts_lik[s] = sm.lik[ls];
-                if (f & F_NEW) B.uts_rank[s] = deferred ? GTF_NEWMARK : sm.rank[ls];
+                if (f & F_NEW) B.uts_rank[s] = sm.rank[ls];
             }
             if (f & F_PRES) {
                 if (wb & WB_PRIOR) B.uts_prior[s] = sm.prior[ls];
@@ -998,105 +772,6 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
         }
     }
     if (wb & WB_COUNT_ACTIVE) {
-        if (n_act) atomicAdd(&sm.cnt[CNT_ACTIVE], n_act);
-        if (n_chg) atomicAdd(&sm.cnt[CNT_CHANGED], n_chg);
-    }
-    __syncthreads();
-    if (tid < GTF_NCOUNTERS && sm.cnt[tid]) {
-        if (tid == CNT_REFERR) atomicOr(&B.counters[tid], (unsigned long long)sm.cnt[tid]);
-        else atomicAdd(&B.counters[tid], (unsigned long long)sm.cnt[tid]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_heavy: the cooperative nodes (>= 3 mixture components, <= 32 in-slots) of the fused iteration, one warp per
-// node, pulled from the list k_tile filled.  Same register-resident node program (node_program_fast) on a
-// per-warp 32-slot mini tile; no CTA-wide barriers, so a 15-component node no longer stalls a whole tile.
-#define GTF_HEAVY_WARPS 4
-#ifndef GTF_HEAVY_MINB
-#define GTF_HEAVY_MINB 6
-#endif
-struct HeavySmem {
-    double st[8][GTF_HEAVY_WARPS * 32];
-    double prior[GTF_HEAVY_WARPS * 32], w[GTF_HEAVY_WARPS * 32], lik[GTF_HEAVY_WARPS * 32], srcx[GTF_HEAVY_WARPS * 32];
-    int32_t src[GTF_HEAVY_WARPS * 32], rank[GTF_HEAVY_WARPS * 32], layer[GTF_HEAVY_WARPS * 32];
-    uint16_t ordl[GTF_HEAVY_WARPS * 32];
-    uint8_t flags[GTF_HEAVY_WARPS * 32], side[GTF_HEAVY_WARPS * 32];
-    uint16_t nbeg[2 * GTF_HEAVY_WARPS];
-    uint8_t nflags[2 * GTF_HEAVY_WARPS];
-    double D[GTF_HEAVY_WARPS][GTF_MAXD * (GTF_MAXD - 1) / 2 + 1];
-    unsigned int cnt[GTF_NCOUNTERS];
-};
-
-__global__ void __launch_bounds__(GTF_HEAVY_WARPS * 32, GTF_HEAVY_MINB) k_heavy(DevBatch B, Prog P, GtfGeom g)
-{
-    __shared__ HeavySmem sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < GTF_NCOUNTERS) sm.cnt[tid] = 0;
-    __syncthreads();
-    uint8_t *hm_out = B.has_merged_nx;
-    double *const mo[8] = {B.m_a_nx, B.m_b_nx, B.m_c_nx, B.m_p00_nx, B.m_p01_nx, B.m_p11_nx, B.m_p22_nx, B.m_prior_nx};
-    const int count = B.heavy_count[0];
-    const int b0 = warp * 32, ls = b0 + lane;
-    unsigned n_act = 0, n_chg = 0;
-    const int nwarps = gridDim.x * GTF_HEAVY_WARPS;
-    for (int idx = blockIdx.x * GTF_HEAVY_WARPS + warp; idx < count; idx += nwarps) { // static striding: no contended atomic
-        const int i = B.heavy_list[idx];
-        const int packed = B.heavy_slot[idx];
-        const int gs0 = packed >> 6, d = packed & 63;
-        const bool valid = lane < d;
-        const int s = gs0 + lane;
-        if (lane == 0) {
-            sm.nbeg[2 * warp] = (uint16_t)b0;
-            sm.nbeg[2 * warp + 1] = (uint16_t)(b0 + d);
-            unsigned nf = NF_DICT | B.node_ok[i];
-            if (B.has_uts[i]) nf |= NF_HASUTS;
-            sm.nflags[2 * warp] = (uint8_t)nf;
-        }
-        if (valid) {
-            int src = B.in_src[s];
-            unsigned f = 0;
-            if (src >= 0 && (B.all_alive || (B.alive[src] && B.alive[i]))) f |= F_EX;
-            if (B.active_nx[s] == 1) f |= F_ACT;      // after the extrapolation gate of k_tile
-            if (B.active[s] == 1) f |= F_ORIG;
-            unsigned sd = 0;
-            int rk = 0x7fffffff;
-            if (B.uts_present[s]) {
-                f |= F_PRES;
-                sd = SD_ORIGPRES | ((unsigned)B.uts_side[s] & 3u);
-                sm.st[0][ls] = B.uts_a[s]; sm.st[1][ls] = B.uts_b[s]; sm.st[2][ls] = B.uts_c[s]; sm.st[3][ls] = B.uts_tau[s];
-                sm.st[4][ls] = B.uts_p00[s]; sm.st[5][ls] = B.uts_p01[s]; sm.st[6][ls] = B.uts_p11[s]; sm.st[7][ls] = B.uts_p22[s];
-                sm.prior[ls] = B.uts_prior[s]; sm.w[ls] = B.uts_w[s]; sm.lik[ls] = B.uts_lik[s];
-                rk = B.uts_rank[s];
-                if (rk == GTF_NEWMARK) f |= F_NEW;
-            }
-            sm.src[ls] = src;
-            sm.srcx[ls] = src >= 0 ? B.x[src] : 0.0;
-            sm.layer[ls] = src >= 0 ? B.layer[src] : -1;
-            sm.rank[ls] = rk;
-            sm.side[ls] = (uint8_t)sd;
-            sm.flags[ls] = (uint8_t)f;
-        }
-        __syncwarp();
-        node_program_fast<true, HeavySmem>(sm, B, P, g, i, 2 * warp, gs0 - b0, warp, lane, true, hm_out, mo);
-        __syncwarp();
-        if (valid) {
-            unsigned f = sm.flags[ls];
-            bool a = f & F_ACT, a0 = f & F_ORIG;
-            if (f & F_EX) { n_act += a; n_chg += a != a0; }
-            B.active_nx[s] = a ? 1 : 0;
-            if (f & F_PRES) {
-                B.uts_prior[s] = sm.prior[ls];
-                B.uts_w[s] = sm.w[ls];
-                if (f & F_RW) B.uts_side[s] = (int8_t)(sm.side[ls] & 3);
-                if (f & F_NEW) B.uts_rank[s] = sm.rank[ls];
-            }
-        }
-        __syncwarp();
-    }
-    n_act = __reduce_add_sync(0xffffffffu, n_act);
-    n_chg = __reduce_add_sync(0xffffffffu, n_chg);
-    if (lane == 0) {
         if (n_act) atomicAdd(&sm.cnt[CNT_ACTIVE], n_act);
         if (n_chg) atomicAdd(&sm.cnt[CNT_CHANGED], n_chg);
     }
@@ -1130,4 +805,3 @@ __global__ void k_prefix(DevBatch B, GtfGeom g)
     B.node_p11tot[u] = p;
 }
 
-#include "gtf_pipe.cuh"

@@ -9,7 +9,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO = os.environ.get("GTF_LIB") or os.path.join(CSRC, "libgtf_b200.so")   # GTF_LIB: experiment builds
-SOURCES = ["gtf_b200.cu", "gtf_tile.cuh", "gtf_pipe.cuh", "gtf_iter.cuh", "gtf_dev.cuh", "gtf_math.cuh"]
+SOURCES = ["gtf_b200.cu", "gtf_tile.cuh", "gtf_iter.cuh", "gtf_dev.cuh", "gtf_math.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
 

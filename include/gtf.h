@@ -112,19 +112,24 @@ int gtf_extrapolate_stage(gtf_batch *b, double chi2_cut, const gtf_geom *g, gtf_
 /* update/remove_state_metadata.py:31-53 */
 int gtf_remove_state_metadata(gtf_batch *b, gtf_stats *st);
 
-/* ---- fused iteration: [message_passing, prior, reweight, prior, reweight, cluster(updated states)] --- */
-/* Per iteration: k_prefix (per-source multiple-scattering prefix), k_tile (fused load + extrapolate/update + per-node
- * reweight/prune), k_heavy (nodes holding >= 3 components: reweight + clustering, one warp per node).  Runs `max_iter` iterations or
- * stops early when an iteration leaves the active-edge bitmap unchanged (SURVEY.md §8d "converged").
- * stats[i] receives iteration i's counters (may be NULL); *n_done the number of iterations run. */
+/* ---- fused iteration: [message_passing, prior, reweight, prior, reweight, cluster(updated states), degree, weights, priors] --- */
+/* Runs on a packed copy of the mutable state (activation / presence bitmaps, 64 B state + 32 B weight records per dict
+ * entry, 64 B merged-state records per node) that the library builds from the fields on entry and writes back lazily
+ * when a field is downloaded or a per-stage entry point is called.  Per iteration: k_send (message list + per-source
+ * multiple-scattering prefix), k_exec (extrapolate, chi2 gate, Kalman update), k_node2 (nodes holding <= 2 components:
+ * priors, reweight x2, prune), k_hv<4|8|16|32> / k_big (>= 3 components: the same + pairwise chi2 + greedy KL merge).
+ * Runs `max_iter` iterations or stops early when an iteration leaves the active-edge bitmap unchanged (SURVEY.md §8d
+ * "converged").  stats[i] receives iteration i's counters (may be NULL); *n_done the number of iterations run. */
 int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, int max_iter, int stop_when_converged,
                 gtf_stats *stats, int *n_done);
-/* the same fused iteration, ONE pass, reading the current state and writing the next state into the
- * batch's shadow buffers WITHOUT committing it (idempotent: benchmark / profiling entry point) */
+/* the same iteration, ONE pass, NOT committed: reads the current state, rewrites the dict entries in place (with the
+ * same values on every call) and sends activation flags / merged states / accumulated p11 to shadow buffers, so the
+ * next call does identical work (benchmark / profiling entry point; the stats are those of a committed pass) */
 int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st);
 
-/* per-kernel timing of the fused iteration (CUDA events recorded on the batch stream around k_prefix, k_tile
- * and k_heavy): enable != 0 resets the accumulators; gtf_batch_timing returns averages over the calls since */
+/* per-kernel timing of the iteration (CUDA events recorded on the batch stream): enable != 0 resets the
+ * accumulators; gtf_batch_timing returns averages over the calls since: prefix_ms = k_begin + k_send,
+ * tile_ms = k_exec + k_node2, heavy_ms = k_hv<*> + k_big */
 int gtf_batch_set_timing(gtf_batch *b, int enable);
 int gtf_batch_timing(gtf_batch *b, double *prefix_ms, double *tile_ms, double *heavy_ms, int *count);
 /* per-kernel averages of the packed pipeline: ms[0..3] = k_send, k_exec, k_node2, cooperative kernels (k_hv<*>, k_big) */
