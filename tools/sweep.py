@@ -34,13 +34,15 @@ def point(n_tracks, degree, n_events, steps=20):
     b.set_timing(True)
     for _ in range(steps):
         b.iterate_dry()
-    pre, tile, heavy, _ = b.timing()
+    kt = b.timing_kernels()
+    kern = {k: kt[k] for k in ("k_send", "k_exec", "k_node2", "k_hv")}
+    it_ms = sum(kern.values())
     deg = np.diff(hb["in_off"])
     out = {"tracks_per_event": n_tracks, "events": n_events, "target_degree": degree, "hits": b.N, "directed_edges": b.E,
-           "mean_degree": float(deg.mean()), "active_edges": n_active, "k_prefix_ms": pre, "k_tile_ms": tile + heavy,
-           "active_edge_iterations_per_s": n_active / ((pre + tile + heavy) / 1e3),
-           "all_edges_per_s": b.E / ((pre + tile + heavy) / 1e3),
-           "roofline_frac": bench.B_ALG * n_active / ((tile + heavy) / 1e3) / 1e9 / PEAK}
+           "mean_degree": float(deg.mean()), "active_edges": n_active, "kernels_ms": kern, "iteration_ms": it_ms,
+           "active_edge_iterations_per_s": n_active / (it_ms / 1e3),
+           "all_edges_per_s": b.E / (it_ms / 1e3),
+           "roofline_frac": bench.B_ALG * n_active / (it_ms / 1e3) / 1e9 / PEAK}
     b.close()
     return out
 
