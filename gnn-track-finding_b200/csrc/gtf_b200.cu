@@ -135,7 +135,7 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         DA(k.out_dst, E); DA(k.out_rev, E); DA(k.geo, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N);
         DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.pres0, words);
         DA(k.state, (int64_t)E * 8); DA(k.meta, E); DA(k.tag, E);
-        DA(k.msg_slot, E); DA(k.msg_src, E); DA(k.msg_dst, E); DA(k.msg_w, E);
+        DA(k.msg_desc, E); DA(k.msg_w, E);
         DA(k.msg_p11, E); DA(k.msg_vms, E);
         DA(k.hv_list, (int64_t)(HV_BINS + 1) * N);
         DA(k.counts, PK_NCOUNTS);
@@ -170,8 +170,8 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.mrec, k.mrec_nx, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.tag, k.msg_slot,
-                      k.msg_src, k.msg_dst, k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
+        void *pk[] = {k.mrec, k.mrec_nx, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.tag, k.msg_desc,
+                      k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         cudaStreamDestroy(b->stream3);
         cudaEventDestroy(b->ev_fork2); cudaEventDestroy(b->ev_join2); cudaEventDestroy(b->ev_join3);

@@ -69,7 +69,7 @@ struct DevPack {
     MetaRec *meta;               // [E]
     TagRec *tag;                 // [E]
     // message list of one iteration, source-major (a source's messages are contiguous, in successor order)
-    int32_t *msg_slot, *msg_src, *msg_dst; // [E]  (msg_slot bit 31: the source has no seed entry for this neighbour)
+    int4 *msg_desc;              // [E] (slot, source, destination, -); slot bit 31: the source has no seed entry for this neighbour
     double *msg_w;               // [E] mixture weight carried by the message (extrapolate...py:384)
     double *msg_p11, *msg_vms;   // [E] merged_cov[1,1] as the edge sees it (quirk 2), its multiple-scattering term
     int32_t *hv_list;            // [(HV_BINS + 1) * N] cooperative nodes binned by dict size: <=4, <=8, <=16, <=32, more

@@ -271,9 +271,7 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack K
     const int base = sm.base;
     for (int q = tid; q < M; q += GTF_SEND_THREADS) {
         const int gq = base + q;
-        K.msg_slot[gq] = sm.m_slot[q];
-        K.msg_src[gq] = u0 + sm.m_src[q];
-        K.msg_dst[gq] = sm.m_dst[q];
+        K.msg_desc[gq] = make_int4(sm.m_slot[q], u0 + sm.m_src[q], sm.m_dst[q], 0);
         K.msg_w[gq] = sm.m_w[q];
         K.msg_p11[gq] = sm.m_p11[q];
         K.msg_vms[gq] = sm.m_vms[q];
@@ -298,16 +296,23 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
     const int count = K.counts[PK_MSG];
     const int stride = gridDim.x * GTF_EXEC_THREADS;
     unsigned gated = 0, sent = 0;
-    // software pipeline: the loads of this thread's next message are issued between the two halves of the
-    // extrapolation, so their latency hides behind the covariance algebra (only 16 warps per SM fit the registers)
+    // software pipeline, two stages deep: the DESCRIPTOR (slot, source, destination) of the message after next travels
+    // to shared memory with cp.async (no register held), the GATHERS it indexes for the next message are issued between
+    // the two halves of the extrapolation, so both latencies hide behind the algebra (only 16 warps per SM fit the
+    // 128 registers)
     struct In {
         int sraw;
         double ux, uy, uz, ur, vx, vy, vz, vr, a, b, c, p00, p01, p22, w, p, vms;
     };
-    auto load = [&](int q, In &x) {
-        const int sraw = __ldcs(K.msg_slot + q), u = __ldcs(K.msg_src + q), v = __ldcs(K.msg_dst + q);
+    __shared__ int4 s_desc[GTF_EXEC_THREADS];
+    const unsigned s_addr = (unsigned)__cvta_generic_to_shared(&s_desc[tid]);
+    auto fetch_desc = [&](int q) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n cp.async.commit_group;" ::"r"(s_addr), "l"(K.msg_desc + q) : "memory");
+    };
+    auto load = [&](int q, const int4 d, In &x) {
+        const int u = d.y, v = d.z;
         const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
-        x.sraw = sraw;
+        x.sraw = d.x;
         x.ux = U.x; x.uy = U.y; x.uz = U.z; x.ur = U.r; x.vx = V.x; x.vy = V.y; x.vz = V.z; x.vr = V.r;
         const double2 *mr = reinterpret_cast<const double2 *>(K.mrec + u);
         const double2 r0 = mr[0], r1 = mr[1], r2 = mr[2];
@@ -316,7 +321,10 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
     };
     int q = blockIdx.x * GTF_EXEC_THREADS + tid;
     In cur;
-    if (q < count) load(q, cur);
+    if (q < count) {
+        load(q, __ldcs(K.msg_desc + q), cur);
+        if (q + stride < count) fetch_desc(q + stride);
+    }
     while (q < count) {
         const int s = cur.sraw & 0x7fffffff;
         const bool notse = cur.sraw < 0;
@@ -325,7 +333,12 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
         GtfJac J;
         gtf_extrap_jac(cur.ux, cur.uy, cur.vx, cur.vy, cur.a, cur.b, cur.c, J);
         const int qn = q + stride;
-        if (qn < count) load(qn, cur);
+        if (qn < count) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const int4 d = s_desc[tid];                 // descriptor of the next message: fetched one iteration ago
+            if (qn + stride < count) fetch_desc(qn + stride);
+            load(qn, d, cur);
+        }
         GtfExtrapOut o;
         gtf_extrap_update(J, dr, dz, uz, vz, p00, p01, p, p22, vms, chi2_cut, g, o);
         if (record_chi2) B.uts_chi2[s] = o.chi2; // diagnostic only (the reference appends it to a CSV): a partial-sector write
