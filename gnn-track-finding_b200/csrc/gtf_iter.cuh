@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
                 const bool rdict = (nf & (NF_MULTI | NF_DICT)) == (NF_MULTI | NF_DICT);
                 const bool ruts = (nf & (NF_MULTI | NF_HASUTS)) == (NF_MULTI | NF_HASUTS);
                 if (n) {
-                    const double nodex = K.xyzr[i].x;
+                    const double nodex = B.x[i];
                     if (rdict) lent_prior(a, b, n);
                     if (ruts) lent_reweight(s_cnt, a, b, n, nodex, P.rw_thr);
                     if (rdict) lent_prior(a, b, n);

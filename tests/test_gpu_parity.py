@@ -309,6 +309,49 @@ def test_packed_layout_stays_in_sync_with_the_fields():
     assert np.array_equal(b.CCA(), ob.cca())
 
 
+def test_copies_of_an_event_inside_a_large_batch_evolve_identically():
+    """size-independent property at batch scale: events are independent, so the copies of one generated event inside a
+    tiled batch (the benchmark's construction) must end in BIT-identical states whatever tile / CTA / list position
+    they land on, and one copy must match the oracle run on that event alone"""
+    import bench
+    n_ev, distinct, tracks = 48, 3, 400
+    hb = bench.build_batch(n_ev, tracks, 5000, distinct)
+    b = gpu_batch(hb)
+    b.seed()
+    b.cluster(0, 1.0, 2.0)
+    stats = b.iterate(max_iter=3, stop_when_converged=False)
+    out = state_of(b)
+    # node / slot range of every event (events are concatenated)
+    first_sub = np.searchsorted(out["sub_event"], np.arange(n_ev + 1))
+    node0 = out["sub_off"][first_sub]
+    slot0 = out["in_off"][node0]
+    node_fields = ["has_merged", "degree", "has_uts", "uts_next"] + ["m_" + k for k in ("a", "b", "c", "p00", "p01", "p11", "p22", "prior")]
+    slot_fields = ["active", "uts_present", "uts_rank", "uts_side", "edge_w"] + \
+                  ["uts_" + k for k in ("a", "b", "c", "tau", "p00", "p01", "p11", "p22", "lik", "prior", "w", "lrn")]
+    for e in range(distinct, n_ev):
+        r = e % distinct
+        for f in node_fields:
+            assert np.array_equal(out[f][node0[e]:node0[e + 1]], out[f][node0[r]:node0[r + 1]], equal_nan=True), (e, f)
+        for f in slot_fields:
+            assert np.array_equal(out[f][slot0[e]:slot0[e + 1]], out[f][slot0[r]:slot0[r + 1]], equal_nan=True), (e, f)
+    for k in ("nodes_merged", "edges_sent", "edges_gated", "active_edges"):
+        assert stats[-1][k] % (n_ev // distinct) == 0
+    # and the first event against the oracle
+    one = bench.build_batch(1, tracks, 5000, 1)
+    ob = ol.OracleBatch(one)
+    ob.seed()
+    ob.cluster(0, 1.0, 2.0)
+    for _ in range(3):
+        ob.extrapolate_stage(2.0)
+        ob.cluster(1, 1000.0, 100.0)
+    n1, s1 = int(node0[1]), int(slot0[1])
+    assert np.array_equal(out["active"][:s1], ob.hb["active"])
+    assert np.array_equal(out["has_merged"][:n1], ob.hb["has_merged"])
+    assert np.array_equal(out["uts_present"][:s1], ob.hb["uts_present"])
+    m = ob.hb["has_merged"] > 0
+    assert gu.rel_err(out["m_a"][:n1][m], ob.hb["m_a"][m], gu.field_floor(ob.hb["m_a"][m])) <= 1e-7
+
+
 def test_gate_chi2_is_recorded_on_request():
     """uts_chi2 is a diagnostic (the reference appends it to a CSV): the fused iteration stores it only when asked"""
     hb = synth_batch(1, 300, 2650)
