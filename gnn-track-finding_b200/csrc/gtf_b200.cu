@@ -132,9 +132,9 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         // packed iteration layout (gtf_iter.cuh)
         DevPack &k = b->k;
         const int64_t words = ((int64_t)E + 31) / 32 + 2;
-        DA(k.out_dst, E); DA(k.out_rev, E); DA(k.geo, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N);
+        DA(k.out_dst, E); DA(k.out_rev, E); DA(k.aux, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N);
         DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.pres0, words);
-        DA(k.state, (int64_t)E * 8); DA(k.meta, E); DA(k.tag, E);
+        DA(k.state, (int64_t)E * 8); DA(k.meta, E);
         DA(k.msg_desc, E); DA(k.msg_w, E);
         DA(k.msg_p11, E); DA(k.msg_vms, E);
         DA(k.hv_list, (int64_t)(HV_BINS + 1) * N);
@@ -170,7 +170,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.mrec, k.mrec_nx, k.out_dst, k.out_rev, k.geo, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.tag, k.msg_desc,
+        void *pk[] = {k.mrec, k.mrec_nx, k.out_dst, k.out_rev, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
                       k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         cudaStreamDestroy(b->stream3);

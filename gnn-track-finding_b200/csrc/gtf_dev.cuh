@@ -49,6 +49,7 @@ struct __align__(16) GeoRec {    // static per-slot view of the source hit
     double sx;                   // x of the source hit
     int32_t lay, src;            // its layer id; its node index (-1: ghost slot)
 };
+struct __align__(32) AuxRec { GeoRec g; TagRec t; int32_t pad[2]; };
 struct __align__(32) NodeXYZR { double x, y, z, r; };
 struct __align__(32) MergedRec { double a, b, c, p00, p01, p22, prior, pad; }; // merged_state / merged_cov / merged_prior of a node
                                                                              // (p11 lives in the m_p11 ping-pong pair: quirk 2)
@@ -58,7 +59,7 @@ enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_NCOUN
 struct DevPack {
     // static, derived from the topology and the hit coordinates
     int32_t *out_dst, *out_rev;  // [E] out-CSR order: destination node / slot of the reverse edge (-1 none)
-    GeoRec *geo;                 // [E]
+    AuxRec *aux;                 // [E] geometry + tag
     NodeXYZR *xyzr;              // [N]
     MergedRec *mrec, *mrec_nx;   // [N] merged state of every node (64 B: two whole sectors); _nx: shadow for uncommitted passes
     int all_exist;               // every slot is an existing edge (no ghost slot, no removed node)
@@ -67,7 +68,6 @@ struct DevPack {
     uint32_t *pres0;             // presence bitmap as it was when the iteration started (an entry not in it is new)
     double *state;               // [E][8] a b c tau p00 p01 p11 p22
     MetaRec *meta;               // [E]
-    TagRec *tag;                 // [E]
     // message list of one iteration, source-major (a source's messages are contiguous, in successor order)
     int4 *msg_desc;              // [E] (slot, source, destination, -); slot bit 31: the source has no seed entry for this neighbour
     double *msg_w;               // [E] mixture weight carried by the message (extrapolate...py:384)

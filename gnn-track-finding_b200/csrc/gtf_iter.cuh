@@ -35,6 +35,9 @@ __device__ __forceinline__ uint32_t bm_win(const uint32_t *bm, int p)
 __device__ __forceinline__ void bm_clear(uint32_t *bm, int s) { atomicAnd(&bm[s >> 5], ~(1u << (s & 31))); }
 __device__ __forceinline__ void bm_set(uint32_t *bm, int s) { atomicOr(&bm[s >> 5], 1u << (s & 31)); }
 
+// per-slot auxiliary record: static geometry of the source hit (16 B) and the rarely written tag (8 B) share one sector
+__device__ __forceinline__ GeoRec *geo_p(const DevPack &K, int s) { return &K.aux[s].g; }
+__device__ __forceinline__ TagRec *tag_p(const DevPack &K, int s) { return &K.aux[s].t; }
 // 16 B geometry record, streaming (read once per iteration)
 __device__ __forceinline__ GeoRec ld_geo(const GeoRec *p)
 {
@@ -76,7 +79,7 @@ __global__ void k_pack_slots(DevBatch B, DevPack K, int do_static, int do_act, i
         gr.sx = src >= 0 ? B.x[src] : 0.0;
         gr.lay = src >= 0 ? B.layer[src] : -1;
         gr.src = src;
-        K.geo[s] = gr;
+        (*geo_p(K, s)) = gr;
     }
     if (do_rec) {
         double2 *st = reinterpret_cast<double2 *>(K.state + 8 * (size_t)s);
@@ -89,7 +92,7 @@ __global__ void k_pack_slots(DevBatch B, DevPack K, int do_static, int do_act, i
         K.meta[s] = m;
         TagRec t;
         t.rank = B.uts_rank[s]; t.side = B.uts_side[s]; t.pad = 0; t.lrn = -1;
-        K.tag[s] = t;
+        (*tag_p(K, s)) = t;
     }
 }
 __global__ void k_pack_out(DevBatch B, DevPack K)
@@ -137,7 +140,7 @@ __global__ void k_unpack_slots(DevBatch B, DevPack K, int do_act, int do_pres, i
         B.uts_p00[s] = v2.x; B.uts_p01[s] = v2.y; B.uts_p11[s] = v3.x; B.uts_p22[s] = v3.y;
         const MetaRec m = K.meta[s];
         B.uts_w[s] = m.w; B.uts_lik[s] = m.lik; B.uts_prior[s] = m.prior; B.edge_w[s] = m.ew;
-        const TagRec t = K.tag[s];
+        const TagRec t = (*tag_p(K, s));
         B.uts_rank[s] = t.rank; B.uts_side[s] = t.side;
         if (t.lrn >= 0) B.uts_lrn[s] = t.lrn == 0 ? NAN : (double)t.lrn;
     }
@@ -381,8 +384,8 @@ __device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, i
 {
     const double2 m0 = __ldcs(reinterpret_cast<const double2 *>(K.meta + s));
     const double2 m1 = __ldcs(reinterpret_cast<const double2 *>(K.meta + s) + 1);
-    const int2 tg = __ldcs(reinterpret_cast<const int2 *>(K.tag + s));
-    const GeoRec gr = ld_geo(K.geo + s);
+    const int2 tg = __ldcs(reinterpret_cast<const int2 *>(tag_p(K, s)));
+    const GeoRec gr = ld_geo(geo_p(K, s));
     e.s = s;
     e.w = m0.x; e.lik = m0.y; e.prior = m1.x; e.ew = m1.y;
     e.rank = tg.x; e.tag0 = tg.y;
@@ -404,7 +407,7 @@ __device__ __forceinline__ void lent_store(const DevBatch &B, const DevPack &K, 
     __stcs(m + 0, make_double2(e.w, e.lik));
     __stcs(m + 1, make_double2(e.prior, e.ew));          // ew: helper.py:180
     const int t1 = tag_pack(0, e.side, e.lrn);
-    if (e.rank != e.rank0 || t1 != e.tag0) *reinterpret_cast<int2 *>(K.tag + e.s) = make_int2(e.rank, t1);
+    if (e.rank != e.rank0 || t1 != e.tag0) *reinterpret_cast<int2 *>(tag_p(K, e.s)) = make_int2(e.rank, t1);
     if ((e.f & H_ACT0) && !(e.f & H_ACT)) bm_clear(K.act_nx, e.s);
 }
 __device__ __forceinline__ void lent_prior(LEnt &a, LEnt &b, int n)
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
                 if (nnew) { // new entries enter the dict in ascending source order (extrapolate...py:419-447)
                     const int nxt = B.uts_next[i];
                     if (nnew == 2) {
-                        const bool a_first = K.geo[e0].src < K.geo[e1].src;
+                        const bool a_first = (*geo_p(K, e0)).src < (*geo_p(K, e1)).src;
                         a.rank = nxt + (a_first ? 0 : 1);
                         b.rank = nxt + (a_first ? 1 : 0);
                     } else if (a.f & H_NEW) a.rank = nxt; else b.rank = nxt;
@@ -687,12 +690,12 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         if (valid) {
             const double2 m0 = __ldcs(reinterpret_cast<const double2 *>(K.meta + slot));
             const double2 m1 = __ldcs(reinterpret_cast<const double2 *>(K.meta + slot) + 1);
-            const int2 tg = __ldcs(reinterpret_cast<const int2 *>(K.tag + slot));
+            const int2 tg = __ldcs(reinterpret_cast<const int2 *>(tag_p(K, slot)));
             w = m0.x; lik = m0.y; prior = m1.x; ew = m1.y;
             rank = tg.x; rank0 = tg.x; tag0 = tg.y;
             side = (int)(int8_t)(tg.y & 0xff);
             lrn = tg.y >> 16;
-            const GeoRec gr = ld_geo(K.geo + slot);
+            const GeoRec gr = ld_geo(geo_p(K, slot));
             sx = gr.sx + 0.0; lay = gr.lay; src = gr.src;
             f = H_PRES;
             if (K.all_exist || bm_get(K.exists, slot)) f |= H_EX;
@@ -947,7 +950,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             __stcs(m + 0, make_double2(w, lik));
             __stcs(m + 1, make_double2(prior, ew));              // ew: helper.py:180
             const int t1 = tag_pack(0, side, lrn);
-            if (rank != rank0 || t1 != tag0) *reinterpret_cast<int2 *>(K.tag + slot) = make_int2(rank, t1);
+            if (rank != rank0 || t1 != tag0) *reinterpret_cast<int2 *>(tag_p(K, slot)) = make_int2(rank, t1);
             if ((f & H_ACT0) && !(f & H_ACT)) bm_clear(K.act_nx, slot);
         }
         if (clustered && gl == 0) {
@@ -1001,7 +1004,7 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
         }
         for (int ls = lane; ls < d; ls += 32) {
             const int s = gs0 + ls;
-            const GeoRec gr = K.geo[s];
+            const GeoRec gr = (*geo_p(K, s));
             unsigned f = 0, sd = 0;
             int rk = 0x7fffffff;
             fresh_s[ls] = 0;
@@ -1011,7 +1014,7 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
             if (bm_get(K.pres, s)) {
                 f |= F_PRES;
                 const MetaRec m = K.meta[s];
-                const TagRec t = K.tag[s];
+                const TagRec t = (*tag_p(K, s));
                 const bool fresh = m.prior != m.prior;
                 if (fresh) fresh_s[ls] = 1;
                 sd = SD_ORIGPRES | (fresh ? 0u : ((unsigned)t.side & 3u));
@@ -1056,12 +1059,12 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGe
                 MetaRec m;
                 m.prior = sm.prior[ls]; m.w = sm.w[ls]; m.lik = sm.lik[ls]; m.ew = ew_s[ls];
                 K.meta[s] = m;
-                TagRec t = K.tag[s];
+                TagRec t = (*tag_p(K, s));
                 if (fresh_s[ls]) { t.side = 0; t.lrn = 0; }
                 t.rank = sm.rank[ls];
                 if (f & F_RW) t.side = (int8_t)(sm.side[ls] & 3);
                 if (lrn_s[ls] >= 0.0) t.lrn = (int16_t)lrn_s[ls];
-                K.tag[s] = t;
+                (*tag_p(K, s)) = t;
             }
         }
         n_act = __reduce_add_sync(0xffffffffu, n_act);
