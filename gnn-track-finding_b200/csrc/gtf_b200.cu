@@ -132,7 +132,7 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         // packed iteration layout (gtf_iter.cuh)
         DevPack &k = b->k;
         const int64_t words = ((int64_t)E + 31) / 32 + 2;
-        DA(k.out_dst, E); DA(k.out_rev, E); DA(k.aux, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N);
+        DA(k.out_dst, E); DA(k.orec, E); DA(k.aux, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N);
         DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.pres0, words);
         DA(k.state, (int64_t)E * 8); DA(k.meta, E);
         DA(k.msg_desc, E); DA(k.msg_w, E);
@@ -170,7 +170,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.mrec, k.mrec_nx, k.out_dst, k.out_rev, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
+        void *pk[] = {k.mrec, k.mrec_nx, k.out_dst, k.orec, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
                       k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         cudaStreamDestroy(b->stream3);
@@ -201,7 +201,8 @@ static int field_group(int f)
 static bool field_is_pack_static(int f)
 {
     return f == GTF_F_x || f == GTF_F_y || f == GTF_F_z || f == GTF_F_r || f == GTF_F_layer || f == GTF_F_in_src ||
-           f == GTF_F_slot_dst || f == GTF_F_out_slot || f == GTF_F_rev_slot || f == GTF_F_in_off || f == GTF_F_out_off;
+           f == GTF_F_slot_dst || f == GTF_F_out_slot || f == GTF_F_rev_slot || f == GTF_F_in_off || f == GTF_F_out_off ||
+           f == GTF_F_tse_w || f == GTF_F_tse_present; // (the carried seed weights live in the per-out-edge records)
 }
 // bring the SoA arrays of the groups in `mask` up to date (after packed iterations)
 static int soa_sync(gtf_batch *b, unsigned mask)
@@ -224,7 +225,10 @@ static int soa_for_stage(gtf_batch *b, bool writes)
 {
     int r = soa_sync(b, (1u << PG_N) - 1u);
     if (r) return r;
-    if (writes) for (int q = 0; q < PG_N; q++) b->pack_stale[q] = true;
+    if (writes) {
+        for (int q = 0; q < PG_N; q++) b->pack_stale[q] = true;
+        b->pack_static_stale = true; // seed weights (tse_w) may change: per-out-edge records are rebuilt
+    }
     return 0;
 }
 

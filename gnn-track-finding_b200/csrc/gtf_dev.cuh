@@ -51,6 +51,12 @@ struct __align__(16) GeoRec {    // static per-slot view of the source hit
 };
 struct __align__(32) AuxRec { GeoRec g; TagRec t; int32_t pad[2]; };
 struct __align__(32) NodeXYZR { double x, y, z, r; };
+// per out-edge (successor order), static between per-stage calls: what a message needs besides the source's merged state
+struct __align__(32) OutRec {
+    double sin_t, xk, rdz;       // sin(theta) of the segment, x of the destination hit, |dr| / |dz|  (Highland term, extrapolate...py:114-124)
+    double w;                    // mixture weight the message carries = the source's seed entry for this neighbour (:384); GTF_NO_TSE bits: none
+};
+#define GTF_NO_TSE_BITS 0x7ff8dead00000001ll
 struct __align__(32) MergedRec { double a, b, c, p00, p01, p22, prior, pad; }; // merged_state / merged_cov / merged_prior of a node
                                                                              // (p11 lives in the m_p11 ping-pong pair: quirk 2)
 
@@ -58,7 +64,8 @@ enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_NCOUN
 
 struct DevPack {
     // static, derived from the topology and the hit coordinates
-    int32_t *out_dst, *out_rev;  // [E] out-CSR order: destination node / slot of the reverse edge (-1 none)
+    int32_t *out_dst;            // [E] out-CSR order: destination node
+    OutRec *orec;                // [E] out-CSR order
     AuxRec *aux;                 // [E] geometry + tag
     NodeXYZR *xyzr;              // [N]
     MergedRec *mrec, *mrec_nx;   // [N] merged state of every node (64 B: two whole sectors); _nx: shadow for uncommitted passes
@@ -140,7 +147,7 @@ struct gtf_batch {
     int n_sm;
     // packed iteration layout
     DevPack k;
-    bool pack_static_stale;    // topology / coordinates changed since the static part was built
+    bool pack_static_stale;    // topology / coordinates / seed weights changed since the static part was built
     bool pack_stale[4], soa_stale[4]; // per group (PG_ACT, PG_PRES, PG_REC, PG_NODE): which side holds the newer state
     cudaStream_t stream3;
     cudaEvent_t ev_fork2, ev_join2, ev_join3;

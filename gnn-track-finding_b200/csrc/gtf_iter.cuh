@@ -100,8 +100,14 @@ __global__ void k_pack_out(DevBatch B, DevPack K)
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= B.E) return;
     const int s = B.out_slot[o];
-    K.out_dst[o] = B.slot_dst[s];
-    K.out_rev[o] = B.rev_slot[s];
+    const int u = B.in_src[s], v = B.slot_dst[s], rs = B.rev_slot[s];
+    K.out_dst[o] = v;
+    OutRec r;
+    gtf_var_ms_geo(B.r[v] - B.r[u], B.z[v] - B.z[u], r.sin_t, r.rdz);
+    r.xk = B.x[v];
+    const bool has = rs >= 0 && B.tse_present[rs];          // extrapolate...py:384: u's seed entry for this neighbour
+    r.w = has ? B.tse_w[rs] : __longlong_as_double(GTF_NO_TSE_BITS);
+    K.orec[o] = r;
 }
 __global__ void k_pack_nodes(DevBatch B, DevPack K, int do_static, int do_merged)
 {
@@ -167,15 +173,19 @@ __global__ void k_begin(DevBatch B, DevPack K, int words)
 //   phase 3  thread per source : merged_cov[1,1] as each edge sees it = node value + the terms of the source's earlier
 //                                active successors, summed left to right (quirk 2); the total stays on the node
 //   phase 4  thread per message: coalesced append to the global source-major list k_exec consumes densely
+#ifndef GTF_SEND_THREADS
 #define GTF_SEND_THREADS 256
+#endif
+#ifndef GTF_SEND_EPT
 #define GTF_SEND_EPT 3                                   // out-edges per thread
+#endif
 #define GTF_SEND_EDGES (GTF_SEND_THREADS * GTF_SEND_EPT)
-#define GTF_SEND_SRCS 255                                // (+1 offsets: one per thread)
+#define GTF_SEND_SRCS (GTF_SEND_THREADS - 1)             // (+1 offsets: one per thread; <= 255: uint8 source index)
 struct SendSmem {
     int off[GTF_SEND_SRCS + 1];
     uint8_t ok[GTF_SEND_SRCS + 1];
     uint8_t esrc[GTF_SEND_EDGES];                        // local source of every out-edge of the tile
-    int m_slot[GTF_SEND_EDGES], m_dst[GTF_SEND_EDGES], m_rev[GTF_SEND_EDGES];
+    int m_slot[GTF_SEND_EDGES], m_dst[GTF_SEND_EDGES], m_o[GTF_SEND_EDGES];
     uint8_t m_src[GTF_SEND_EDGES];
     double m_vms[GTF_SEND_EDGES], m_w[GTF_SEND_EDGES], m_p11[GTF_SEND_EDGES];
     uint16_t first[GTF_SEND_SRCS + 1], last[GTF_SEND_SRCS + 1]; // a source's message range in the tile list
@@ -203,14 +213,14 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack K
         for (int o = my_off; o < my_end; o++) sm.esrc[o - o_base] = (uint8_t)tid;
     __syncthreads();
     // ---- phase 1: GTF_SEND_EPT consecutive edges per thread keep the successor order
-    int slots[GTF_SEND_EPT], dsts[GTF_SEND_EPT], revs[GTF_SEND_EPT], cnt = 0;
+    int slots[GTF_SEND_EPT], dsts[GTF_SEND_EPT], cnt = 0;
     unsigned mymask = 0;
     const int e0 = tid * GTF_SEND_EPT;
 #pragma unroll
     for (int j = 0; j < GTF_SEND_EPT; j++) slots[j] = e0 + j < ne ? B.out_slot[o_base + e0 + j] : -1;
 #pragma unroll
     for (int j = 0; j < GTF_SEND_EPT; j++) {
-        dsts[j] = 0; revs[j] = -1;
+        dsts[j] = 0;
         if (e0 + j < ne) {
             const int s = slots[j];
             if (sm.ok[sm.esrc[e0 + j]] && bm_get(K.act, s) && (K.all_exist || bm_get(K.exists, s))) { mymask |= 1u << j; cnt++; }
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack K
     }
 #pragma unroll
     for (int j = 0; j < GTF_SEND_EPT; j++)
-        if ((mymask >> j) & 1u) { dsts[j] = K.out_dst[o_base + e0 + j]; revs[j] = K.out_rev[o_base + e0 + j]; }
+        if ((mymask >> j) & 1u) dsts[j] = K.out_dst[o_base + e0 + j];
     int incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -240,21 +250,21 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack K
 #pragma unroll
         for (int j = 0; j < GTF_SEND_EPT; j++)
             if ((mymask >> j) & 1u) {
-                sm.m_slot[pos] = slots[j]; sm.m_dst[pos] = dsts[j]; sm.m_rev[pos] = revs[j]; sm.m_src[pos] = sm.esrc[e0 + j];
+                sm.m_slot[pos] = slots[j]; sm.m_dst[pos] = dsts[j]; sm.m_o[pos] = o_base + e0 + j; sm.m_src[pos] = sm.esrc[e0 + j];
                 pos++;
             }
     }
     __syncthreads();
     // ---- phase 2
     for (int q = tid; q < M; q += GTF_SEND_THREADS) {
-        const int sl = sm.m_src[q], u = u0 + sl, v = sm.m_dst[q], rs = sm.m_rev[q];
-        const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
+        const int sl = sm.m_src[q], u = u0 + sl;
+        const double4 *rp = reinterpret_cast<const double4 *>(K.orec + sm.m_o[q]);   // one sector, in successor order
+        const double2 r0 = *reinterpret_cast<const double2 *>(rp), r1 = *(reinterpret_cast<const double2 *>(rp) + 1);
         const double2 ab = *reinterpret_cast<const double2 *>(K.mrec + u);
-        const double a = ab.x, b = ab.y;
-        const bool has = rs >= 0 && B.tse_present[rs];      // extrapolate...py:384: u's seed entry for this neighbour
-        sm.m_w[q] = has ? B.tse_w[rs] : NAN;
+        const bool has = __double_as_longlong(r1.y) != GTF_NO_TSE_BITS;
+        sm.m_w[q] = has ? r1.y : NAN;
         if (!has) sm.m_slot[q] |= (int)0x80000000;
-        sm.m_vms[q] = gtf_var_ms(a, b, V.x, V.r - U.r, V.z - U.z, U.z, g.endcap);
+        sm.m_vms[q] = gtf_var_ms_pre(ab.x, ab.y, r0.y, r0.x, r1.x, B.z[u], g.endcap);
         if (q == 0 || sm.m_src[q - 1] != sl) sm.first[sl] = (uint16_t)q;
         if (q == M - 1 || sm.m_src[q + 1] != sl) sm.last[sl] = (uint16_t)q;
     }

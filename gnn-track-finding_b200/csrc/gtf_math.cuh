@@ -43,6 +43,25 @@ GTF_HD double gtf_var_ms(double a, double b, double xk, double dr, double dz, do
     return v;
 }
 
+// the same with the per-edge geometry (sin(theta) = |dr| / hypot(dr, dz) and the end-cap ratio |dr| / |dz|) computed
+// once per edge instead of per message: same operations in the same order as gtf_var_ms
+GTF_HD void gtf_var_ms_geo(double dr, double dz, double &sin_t, double &rdz)
+{
+    double hyp = sqrt(dr * dr + dz * dz);
+    sin_t = fabs(dr) / hyp;
+    rdz = fabs(dr) / fabs(dz);
+}
+GTF_HD double gtf_var_ms_pre(double a, double b, double xk, double sin_t, double rdz, double endcap_side_z, double endcap)
+{
+    double kb = 2.0 * a * xk + b;
+    double t = 1.0 + kb * kb;
+    double kappa = (2.0 * a) / (t * sqrt(t));
+    double q = (13.6 * 1e-3 * 0.1414213562373095048801688724 * kappa) / 0.3; // sqrt(0.02)
+    double v = sin_t * (q * q);
+    if (fabs(endcap_side_z) >= endcap) v = v * rdz;
+    return v;
+}
+
 // variance of tau = dz/dr from the four measurement errors (helper.py:317-330, extrapolate...py:344-358)
 GTF_HD double gtf_var_tau(double dz, double dr, double z_node, double z_nb, const GtfGeom &g)
 {
