@@ -219,7 +219,7 @@ class E2EChunk(object):
             L.check(self.b.lib.gtf_batch_upload(self.b.h, self.F.FIELD_ID[k], ctypes.c_void_p(t.data_ptr())))
 
     def compute(self):
-        self.b.iterate(max_iter=1, stop_when_converged=False)
+        self.b.iterate(max_iter=1, stop_when_converged=False, want_stats=False)   # asynchronous: no counter read-back
 
     def download(self):
         from gtf_b200 import lib as L

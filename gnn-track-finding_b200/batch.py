@@ -155,12 +155,16 @@ class EventBatch(object):
         return p
 
     def iterate(self, max_iter=10, stop_when_converged=True, chi2_cut=2.0, cluster_chi2=1000.0, cluster_kl=100.0,
-                reweight_threshold=0.1, KL_lut=None, record_chi2=False):
+                reweight_threshold=0.1, KL_lut=None, record_chi2=False, want_stats=True):
         """Fused iterations [message_passing, (prior, reweight) x2, cluster(updated states)].
-        record_chi2: also keep every message's gate chi2 in `uts_chi2` (diagnostic; the reference only logs it)."""
+        record_chi2: also keep every message's gate chi2 in `uts_chi2` (diagnostic; the reference only logs it).
+        want_stats=False (with stop_when_converged=False): no counter read-back, the call returns without synchronising."""
         p = self._iter_params(chi2_cut, cluster_chi2, cluster_kl, reweight_threshold, KL_lut, record_chi2)
-        stats = (L.Stats * max_iter)()
         n = ctypes.c_int(0)
+        if not want_stats and not stop_when_converged:
+            L.check(self.lib.gtf_iterate(self.h, ctypes.byref(p), ctypes.byref(self.geom), max_iter, 0, None, ctypes.byref(n)))
+            return []
+        stats = (L.Stats * max_iter)()
         L.check(self.lib.gtf_iterate(self.h, ctypes.byref(p), ctypes.byref(self.geom), max_iter,
                                      1 if stop_when_converged else 0, stats, ctypes.byref(n)))
         out = [stats[i].as_dict() for i in range(n.value)]

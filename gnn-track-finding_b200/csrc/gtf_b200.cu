@@ -642,12 +642,6 @@ static int ensure_packed(gtf_batch *b)
         k_pack_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k, st, b->pack_stale[PG_ACT], b->pack_stale[PG_PRES],
                                                                 b->pack_stale[PG_REC]);
     CK(cudaGetLastError());
-    if (b->pack_stale[PG_ACT]) {
-        int missing = 0;
-        CK(cudaMemcpyAsync(&missing, k.counts + PK_MISSING, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-        CK(cudaStreamSynchronize(b->stream));
-        k.all_exist = missing == 0;
-    }
     b->pack_static_stale = false;
     for (int q = 0; q < PG_N; q++) b->pack_stale[q] = false;
     return 0;
@@ -767,9 +761,11 @@ extern "C" int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geo
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
     CK(cudaSetDevice(b->device));
     int it = 0;
+    const bool need = stats != nullptr || stop_when_converged; // without either the call stays asynchronous (no counter read-back)
     for (; it < max_iter; it++) {
         gtf_stats st;
-        TRY(iterate_packed(b, p, geom_of(g), &st, true));
+        memset(&st, 0, sizeof(st));
+        TRY(iterate_packed(b, p, geom_of(g), need ? &st : nullptr, true));
         if (stats) stats[it] = st;
         if (stop_when_converged && st.active_changed == 0) { it++; break; }
     }

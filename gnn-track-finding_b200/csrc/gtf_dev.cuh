@@ -69,7 +69,7 @@ struct DevPack {
     AuxRec *aux;                 // [E] geometry + tag
     NodeXYZR *xyzr;              // [N]
     MergedRec *mrec, *mrec_nx;   // [N] merged state of every node (64 B: two whole sectors); _nx: shadow for uncommitted passes
-    int all_exist;               // every slot is an existing edge (no ghost slot, no removed node)
+    int all_exist;               // every slot is an existing edge (no ghost slot, no removed node): set on the device from counts[PK_MISSING]
     // mutable slot state
     uint32_t *act, *act_nx, *pres, *exists; // bitmaps over slots, 2 zero words of padding
     uint32_t *pres0;             // presence bitmap as it was when the iteration started (an entry not in it is new)

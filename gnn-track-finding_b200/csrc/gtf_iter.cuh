@@ -192,8 +192,10 @@ struct SendSmem {
     int wsum[GTF_SEND_THREADS / 32];
     int base;
 };
-__global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack K, const int32_t *__restrict__ stile, GtfGeom g)
+__global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack Kin, const int32_t *__restrict__ stile, GtfGeom g)
 {
+    DevPack K = Kin;
+    K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
     __shared__ SendSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int u0 = stile[blockIdx.x], ns = stile[blockIdx.x + 1] - u0;
@@ -465,8 +467,10 @@ __device__ __forceinline__ void lent_reweight(unsigned int *cnt, LEnt &a, LEnt &
 #ifndef GTF_NODE2_MINB
 #define GTF_NODE2_MINB 4
 #endif
-__global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(DevBatch B, DevPack K, Prog P)
+__global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(DevBatch B, DevPack Kin, Prog P)
 {
+    DevPack K = Kin;
+    K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
     __shared__ unsigned int s_cnt[GTF_NCOUNTERS];
     __shared__ int s_n[HV_BINS + 1], s_base[HV_BINS + 1];
     __shared__ int s_list[HV_BINS + 1][GTF_NODE2_THREADS];
@@ -640,9 +644,11 @@ template <int G> __device__ __forceinline__ void grp_shfl_info(const GtfInfo &in
 struct HvStage { double v[13][32]; }; // a b c tau p00 p01 p11 p22 + GtfPairGeo (I T Q A C) of the warp's 32 entries
 
 template <int G>
-__global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch B, DevPack K, Prog P, GtfGeom g, int bin,
+__global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch B, DevPack Kin, Prog P, GtfGeom g, int bin,
                                                                          MergedOut MO)
 {
+    DevPack K = Kin;
+    K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
     constexpr int NG = 32 / G;                                   // nodes per warp
     constexpr int MAXN = G == 4 ? 4 : G == 8 ? 8 : 15;           // largest dict that can cluster in this bin
     constexpr int R = (MAXN * (MAXN - 1) / 2 + G - 1) / G;       // pair rounds
@@ -990,8 +996,10 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
 // dicts with more than 32 entries: one 32-thread CTA per node, the generic shared-memory node program of gtf_tile.cuh
 // on a tile that holds just this node; lr_layer_norm lands in a shared array behind the tile.
 #define GTF_BIG_SMEM (sizeof(TileSmem) + 16 + 2 * sizeof(double) * GTF_TILE_SLOTS + GTF_TILE_SLOTS)
-__global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack K, Prog P, GtfGeom g, MergedOut MO)
+__global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack Kin, Prog P, GtfGeom g, MergedOut MO)
 {
+    DevPack K = Kin;
+    K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
     double *lrn_s = reinterpret_cast<double *>(smem_raw + ((sizeof(TileSmem) + 15) & ~(size_t)15));
