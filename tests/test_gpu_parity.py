@@ -207,6 +207,40 @@ def test_converged_loop_and_candidates_vs_oracle():
     assert gu.rel_err(pxy_g, pxy_o) <= 1e-7 and gu.rel_err(pzr_g, pzr_o) <= 1e-7
 
 
+def test_iterate_after_extraction_vs_oracle():
+    """extraction removes the accepted candidates' nodes: the packed iteration afterwards must treat their edges as
+    non-existing (existing-edge bitmap, one-node sub-graphs, fragments) exactly like the reference's graph surgery"""
+    hb = synth_batch(2, 200, 2350, eta_max=1.0)
+    ob = ol.OracleBatch(hb)
+    ob.seed()
+    ob.cluster(0, 1.0, 2.0)
+    b = gpu_batch(hb)
+    b.seed()
+    b.cluster(0, 1.0, 2.0)
+    # nodes that lose every neighbour make the reference itself raise (1/len({}), helper.py:90) AFTER it has mutated the
+    # graph; both sides record the condition and carry on, and the states must still agree
+    b.raise_ref_errors = False
+    removed = 0
+    for rnd in range(3):
+        for _ in range(2):
+            ob.extrapolate_stage(2.0)
+            ob.cluster(1, 1000.0, 100.0)
+        b.iterate(max_iter=2, stop_when_converged=False)
+        n_o, acc_o, _, _ = ob.extract()
+        n_g, acc_g, _, _ = b.extract()
+        assert n_o == n_g and np.array_equal(acc_o, acc_g), rnd
+        removed += int(acc_g.sum())
+        ob.remove_state_metadata()      # pops the dict entries of removed neighbours, like the reference's schedule
+        b.remove_state_metadata()       # (run_gnn_trackml_mod.sh:131-139); without it the reference raises KeyError
+        assert gu.compare_states(state_of(b), ob.hb, ("alive", "active", "merged", "uts", "degree"), rtol=1e-7) == [], rnd
+    assert removed > 0
+    ob.extrapolate_stage(2.0)
+    ob.cluster(1, 1000.0, 100.0)
+    b.iterate(max_iter=1, stop_when_converged=False)
+    assert gu.compare_states(state_of(b), ob.hb, ("alive", "active", "merged", "uts", "degree"), rtol=1e-7) == []
+    assert np.array_equal(b.CCA(), ob.cca())
+
+
 def test_stage_wrappers_on_networkx_graphs():
     """the reference-signature wrappers (gtf_b200.stages) on nx.DiGraph lists give the same graphs as the
     device-resident EventBatch path"""
