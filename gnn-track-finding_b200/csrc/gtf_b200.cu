@@ -142,6 +142,8 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         b->pack_static_stale = true;
         for (int q = 0; q < PG_N; q++) { b->pack_stale[q] = true; b->soa_stale[q] = false; }
         CK(cudaStreamCreateWithFlags(&b->stream3, cudaStreamNonBlocking));
+        const char *ge = getenv("GTF_GRAPH");
+        b->use_graph = !(ge && ge[0] == '0');
         CK(cudaEventCreateWithFlags(&b->ev_fork2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b->ev_join3, cudaEventDisableTiming));
@@ -173,6 +175,9 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
         void *pk[] = {k.mrec, k.mrec_nx, k.out_dst, k.orec, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
                       k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
+        for (int c = 0; c < 2; c++)
+            for (int q = 0; q < 2; q++)
+                if (b->graphs[c][q].exec) cudaGraphExecDestroy(b->graphs[c][q].exec);
         cudaStreamDestroy(b->stream3);
         cudaEventDestroy(b->ev_fork2); cudaEventDestroy(b->ev_join2); cudaEventDestroy(b->ev_join3);
         for (int q = 0; q < 6; q++) if (b->evk[q]) cudaEventDestroy(b->evk[q]);
@@ -650,29 +655,26 @@ template <int G> static void launch_hv(gtf_batch *b, cudaStream_t s, const Prog 
 {
     k_hv<G><<<b->n_sm * GTF_HV_MINB, GTF_HV_WARPS * 32, 0, s>>>(b->d, b->k, P, gg, bin, mo);
 }
-// one iteration on the packed layout.  commit: the next state becomes the current one (merged states are written in
-// place, the activation bitmap and the accumulated p11 swap); otherwise the merged states of this pass go to the shadow
-// buffers and nothing the next pass reads is changed (profiling / benchmark entry point).
-static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom &gg, gtf_stats *st, bool commit)
+// the kernel launches of one iteration (k_begin .. k_hv / k_big), issued on the batch stream (and forked onto the side
+// streams for the independent bins); also the body that is captured into a CUDA graph
+static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int record_chi2, bool commit, bool timed)
 {
-    TRY(ensure_packed(b));
-    TRY(counters_reset(b));
     DevPack &k = b->k;
     DevBatch &d = b->d;
-    const Prog P = fused_prog(p);
     const size_t words = ((size_t)b->E + 31) / 32 + 2;
     cudaStream_t s0 = b->stream;
-    if (b->timing) CK(cudaEventRecord(b->evk[0], s0));
+    CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS, s0));
+    if (timed) CK(cudaEventRecord(b->evk[0], s0));
     {
         const int nthr = (int)std::max<size_t>(words, (size_t)b->N);
         k_begin<<<(nthr + 255) / 256, 256, 0, s0>>>(d, k, (int)words);
     }
     if (b->n_stiles) k_send<<<b->n_stiles, GTF_SEND_THREADS, 0, s0>>>(d, k, b->stile_begin, gg);
-    if (b->timing) CK(cudaEventRecord(b->evk[1], s0));
-    if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * 2, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg, p->record_chi2);
-    if (b->timing) CK(cudaEventRecord(b->evk[2], s0));
+    if (timed) CK(cudaEventRecord(b->evk[1], s0));
+    if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * 2, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg, record_chi2);
+    if (timed) CK(cudaEventRecord(b->evk[2], s0));
     if (b->N) k_node2<<<(b->N + GTF_NODE2_THREADS - 1) / GTF_NODE2_THREADS, GTF_NODE2_THREADS, 0, s0>>>(d, k, P);
-    if (b->timing) CK(cudaEventRecord(b->evk[3], s0));
+    if (timed) CK(cudaEventRecord(b->evk[3], s0));
     CK(cudaGetLastError());
     if (b->N) {
         MergedOut mo;
@@ -694,15 +696,50 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
         CK(cudaStreamWaitEvent(s0, b->ev_join2, 0));
         CK(cudaStreamWaitEvent(s0, b->ev_join3, 0));
     }
-    if (b->timing) {
-        CK(cudaEventRecord(b->evk[4], s0));
-        CK(cudaEventSynchronize(b->evk[4]));
-        for (int q = 0; q < 4; q++) {
-            float t = 0;
-            CK(cudaEventElapsedTime(&t, b->evk[q], b->evk[q + 1]));
-            b->t_k[q] += t;
+    if (timed) CK(cudaEventRecord(b->evk[4], s0));
+    return 0;
+}
+// one iteration on the packed layout.  commit: the next state becomes the current one (merged states are written in
+// place, the activation bitmap and the accumulated p11 swap); otherwise the merged states of this pass go to the shadow
+// buffers and nothing the next pass reads is changed (profiling / benchmark entry point).
+// The launch sequence is replayed from a CUDA graph (one per {committed, not} x {ping-pong parity}, re-captured when
+// the parameters change): nine dependent launches cost more than the kernels themselves on a single event.
+static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom &gg, gtf_stats *st, bool commit)
+{
+    TRY(ensure_packed(b));
+    DevPack &k = b->k;
+    DevBatch &d = b->d;
+    const Prog P = fused_prog(p);
+    cudaStream_t s0 = b->stream;
+    if (b->timing || !b->use_graph) {
+        TRY(issue_iteration(b, P, gg, p->record_chi2, commit, b->timing));
+        if (b->timing) {
+            CK(cudaEventSynchronize(b->evk[4]));
+            for (int q = 0; q < 4; q++) {
+                float t = 0;
+                CK(cudaEventElapsedTime(&t, b->evk[q], b->evk[q + 1]));
+                b->t_k[q] += t;
+            }
+            b->t_count++;
         }
-        b->t_count++;
+    } else {
+        IterGraph &G = b->graphs[commit ? 1 : 0][b->parity];
+        const bool same = G.exec && memcmp(&G.P, &P, sizeof(Prog)) == 0 && memcmp(&G.g, &gg, sizeof(GtfGeom)) == 0 &&
+                          G.record_chi2 == p->record_chi2 && G.n_stiles == b->n_stiles && G.stile == (const void *)b->stile_begin;
+        if (!same) {
+            if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+            int r = issue_iteration(b, P, gg, p->record_chi2, commit, false);
+            cudaError_t e = cudaStreamEndCapture(s0, &graph);
+            if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+            if (e != cudaSuccess) return fail(GTF_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&G.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return fail(GTF_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+            G.P = P; G.g = gg; G.record_chi2 = p->record_chi2; G.n_stiles = b->n_stiles; G.stile = (const void *)b->stile_begin;
+        }
+        CK(cudaGraphLaunch(G.exec, s0));
     }
     for (int q = 0; q < 3; q++) b->soa_stale[q] = true; // (a dry pass also rewrites dict entries in place)
     if (commit) b->soa_stale[PG_NODE] = true;
@@ -710,6 +747,7 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
         std::swap(k.act, k.act_nx);
         std::swap(b->f[GTF_F_m_p11], *(void **)&d.m_p11_nx);
         sync_dev_view(b);
+        b->parity ^= 1;
     }
     if (st) return counters_read(b, st);
     return 0;

@@ -120,6 +120,15 @@ struct Prog {
 #define GTF_TILE_MINB 2
 #endif
 
+// a captured iteration (issue_iteration in gtf_b200.cu) and the parameters it was captured with
+struct IterGraph {
+    cudaGraphExec_t exec;
+    Prog P;
+    GtfGeom g;
+    int record_chi2, n_stiles;
+    const void *stile;
+};
+
 struct gtf_batch {
     int N, E, S, device;
     cudaStream_t stream, stream2;
@@ -152,6 +161,9 @@ struct gtf_batch {
     cudaStream_t stream3;
     cudaEvent_t ev_fork2, ev_join2, ev_join3;
     cudaEvent_t evk[6];
+    bool use_graph;            // replay the iteration from a CUDA graph (GTF_GRAPH=0: plain launches)
+    int parity;                // which half of the ping-pong pairs (act / act_nx, m_p11 / m_p11_nx) is current
+    IterGraph graphs[2][2];    // [committed][parity]
     double t_k[5];             // send, exec, node, heavy, (spare)
     // optional per-kernel timing of the iteration (CUDA events on the batch stream)
     bool timing;

@@ -118,8 +118,10 @@ int gtf_remove_state_metadata(gtf_batch *b, gtf_stats *st);
  * when a field is downloaded or a per-stage entry point is called.  Per iteration: k_send (message list + per-source
  * multiple-scattering prefix), k_exec (extrapolate, chi2 gate, Kalman update), k_node2 (nodes holding <= 2 components:
  * priors, reweight x2, prune), k_hv<4|8|16|32> / k_big (>= 3 components: the same + pairwise chi2 + greedy KL merge).
+ * The launch sequence is replayed from a CUDA graph (environment GTF_GRAPH=0: plain launches).
  * Runs `max_iter` iterations or stops early when an iteration leaves the active-edge bitmap unchanged (SURVEY.md §8d
- * "converged").  stats[i] receives iteration i's counters (may be NULL); *n_done the number of iterations run. */
+ * "converged").  stats[i] receives iteration i's counters (may be NULL); *n_done the number of iterations run.
+ * With stats == NULL and stop_when_converged == 0 the call does not synchronise (no counter read-back). */
 int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, int max_iter, int stop_when_converged,
                 gtf_stats *stats, int *n_done);
 /* the same iteration, ONE pass, NOT committed: reads the current state, rewrites the dict entries in place (with the

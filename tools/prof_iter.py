@@ -13,3 +13,13 @@ b.set_timing(True)
 for _ in range(5): b.iterate_dry()
 print("prefix_ms, tile_ms, heavy_ms, n:", b.timing())
 print("kernels:", b.timing_kernels())
+
+import time
+b.set_timing(False)
+for _ in range(5): b.iterate_dry()
+b.sync()
+t0 = time.perf_counter()
+n = 300
+for _ in range(n): b.iterate_dry()
+b.sync()
+print("wall ms per uncommitted iteration (no timing events):", (time.perf_counter() - t0) / n * 1e3)
