@@ -109,12 +109,10 @@ class EventBatch(object):
         L.check(self.lib.gtf_query_node_degree(self.h))
 
     def seed(self):
-        """event_conversion.py:87-96: seed, activate, priors, weights, degree."""
-        self.compute_track_state_estimates()
-        self.initialize_edge_activation()
-        self.compute_prior_probabilities(0)
-        self.compute_mixture_weights(0)
-        self.query_node_degree_in_edges()
+        """event_conversion.py:87-96: seed, activate, priors, weights, degree (one call, three kernel launches)."""
+        st = L.Stats()
+        L.check(self.lib.gtf_seed_all(self.h, ctypes.byref(self.geom), ctypes.byref(st)))
+        return self._done(st)
 
     def cluster(self, track_state_key, chi2_threshold, KL_threshold, KL_lut=None):
         st = L.Stats()
@@ -202,15 +200,20 @@ class EventBatch(object):
         L.check(self.lib.gtf_components(self.h))
         return self.download(["label"])["label"]
 
-    def extract(self, pval=0.01, numhits=4, sep3d=10.0, merge_dist=8.0):
-        acc = np.zeros(self.N, np.uint8)
-        pxy = np.zeros(self.N)
-        pzr = np.zeros(self.N)
+    def extract(self, pval=0.01, numhits=4, sep3d=10.0, merge_dist=8.0, want_arrays=True):
+        """extract_track_candidates.py:402-467.  Returns (n accepted nodes, accepted flags, p-values xy, p-values zr);
+        want_arrays=False skips the three per-node host arrays (returns None for them)."""
         n = ctypes.c_int32(0)
         dp = ctypes.POINTER(ctypes.c_double)
+        acc = pxy = pzr = None
+        if want_arrays:
+            acc = np.zeros(self.N, np.uint8)
+            pxy = np.zeros(self.N)
+            pzr = np.zeros(self.N)
         L.check(self.lib.gtf_extract(self.h, ctypes.byref(self.geom), pval, numhits, sep3d, merge_dist, ctypes.byref(n),
-                                     acc.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), pxy.ctypes.data_as(dp),
-                                     pzr.ctypes.data_as(dp)))
+                                     acc.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) if want_arrays else None,
+                                     pxy.ctypes.data_as(dp) if want_arrays else None,
+                                     pzr.ctypes.data_as(dp) if want_arrays else None))
         L.check(self.lib.gtf_batch_sync(self.h))
         return n.value, acc, pxy, pzr
 
@@ -228,5 +231,4 @@ class EventBatch(object):
         rows = np.zeros((max(n.value, 1), 3), np.int32)
         L.check(self.lib.gtf_candidates(self.h, rows.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), max(n.value, 1),
                                         ctypes.byref(n)))
-        rows = rows[:n.value]
-        return rows[np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))]
+        return rows[:n.value]   # sorted by (event, candidate, node) on the device

@@ -168,7 +168,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     void *extra[] = {d.sub_nalive, d.node_ok, b->n_dead, d.slot_p11, d.slot_vms, d.node_p11tot, d.has_merged_nx, d.m_p11_nx,
                      d.counters, b->accepted_total, b->cand_root, b->sub_has_inactive, b->sub_first, b->sort_keys,
                      b->sort_vals, b->sort_keys2, b->sort_vals2, b->pv_xy, b->pv_zr, b->acc_now, b->tags_a, b->tags_b,
-                     b->tile_begin, b->sort_tmp};
+                     b->tile_begin, b->sort_tmp, b->cand_rows};
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
@@ -298,7 +298,10 @@ extern "C" int64_t gtf_batch_device_bytes(const gtf_batch *b) { return b ? b->de
 __global__ void k_sub_count(DevBatch B)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B.N && B.alive[i]) atomicAdd(&B.sub_nalive[B.sub[i]], 1);
+    // consecutive nodes mostly share a sub-graph: one atomic per distinct sub-graph in the warp
+    const int sg = (i < B.N && B.alive[i]) ? B.sub[i] : -1 - (int)(threadIdx.x & 31);
+    const unsigned same = __match_any_sync(0xffffffffu, sg);
+    if (sg >= 0 && (int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&B.sub_nalive[sg], __popc(same));
 }
 __global__ void k_node_ok(DevBatch B, unsigned long long *n_dead)
 {
@@ -518,6 +521,17 @@ extern "C" int gtf_seed(gtf_batch *b, const gtf_geom *g)
     if (b->N) k_seed_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d);
     CK(cudaGetLastError());
     return 0;
+}
+/* event_conversion.py:87-96 in one call: seed, initialize_edge_activation, compute_prior_probabilities, compute_mixture_weights,
+ * node degrees -- the last three as ONE launch of the per-stage kernel */
+extern "C" int gtf_seed_all(gtf_batch *b, const gtf_geom *g, gtf_stats *st)
+{
+    TRY(gtf_seed(b, g));
+    CK(cudaMemsetAsync(b->f[GTF_F_active], 1, (size_t)(b->E ? b->E : 0), b->stream));
+    TRY(counters_reset(b));
+    Prog P = make_prog(GTF_KEY_TSE, WB_PRIOR | WB_W, {OP_PRIOR, OP_WEIGHTS, OP_DEGREE});
+    TRY(launch_tile(b, P, geom_default()));
+    return counters_read(b, st);
 }
 
 extern "C" int gtf_initialize_edge_activation(gtf_batch *b)
@@ -843,7 +857,10 @@ __global__ void k_cca_init(DevBatch B, uint8_t *has_inactive, int32_t *first)
 __global__ void k_cca_first(DevBatch B, int32_t *first)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B.N && B.alive[i]) atomicMin(&first[B.sub[i]], i);
+    // consecutive nodes mostly share a sub-graph: one atomic per distinct sub-graph in the warp (its lowest lane = lowest index)
+    const int sg = (i < B.N && B.alive[i]) ? B.sub[i] : -1 - (int)(threadIdx.x & 31);
+    const unsigned same = __match_any_sync(0xffffffffu, sg);
+    if (sg >= 0 && (int)(threadIdx.x & 31) == __ffs(same) - 1) atomicMin(&first[sg], i);
 }
 __global__ void k_cca_edges(DevBatch B, uint8_t *has_inactive)
 {
@@ -1085,17 +1102,26 @@ extern "C" int gtf_tag_propagate(gtf_batch *b, double threshold, int32_t *tags, 
 }
 
 // ------------------------------------------------------------------------------------------------ candidate table
-__global__ void k_cand_rows(DevBatch B, const uint8_t *acc_total, const int32_t *root, int32_t *rows, long long cap,
+// candidate table: keys = candidate id (root node index) of accepted nodes, INT_MAX otherwise; a stable radix sort by key
+// leaves the accepted nodes first, grouped by candidate, ascending node index inside a candidate -- and candidates in
+// event order, because events own contiguous node ranges
+__global__ void k_cand_keys(DevBatch B, const uint8_t *acc_total, const int32_t *root, int32_t *keys, int32_t *vals,
                             unsigned long long *count)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B.N || !acc_total[i]) return;
-    unsigned long long k = atomicAdd(count, 1ull);
-    if ((long long)k < cap) {
-        rows[3 * k + 0] = B.sub_event[B.sub[i]];
-        rows[3 * k + 1] = root[i];
-        rows[3 * k + 2] = i;
-    }
+    const bool a = i < B.N && acc_total[i];
+    if (i < B.N) { keys[i] = a ? root[i] : 0x7fffffff; vals[i] = i; }
+    const unsigned m = __ballot_sync(0xffffffffu, a);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+__global__ void k_cand_rows(DevBatch B, const int32_t *keys, const int32_t *vals, int32_t *rows, long long n)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = vals[k];
+    rows[3 * k + 0] = B.sub_event[B.sub[i]];
+    rows[3 * k + 1] = keys[k];
+    rows[3 * k + 2] = i;
 }
 extern "C" int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_rows, int64_t *n_rows)
 {
@@ -1103,20 +1129,33 @@ extern "C" int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_row
     CK(cudaSetDevice(b->device));
     *n_rows = 0;
     if (b->N == 0) return 0;
-    int32_t *rows = nullptr;
-    int64_t cap = cap_rows > 0 && table_host ? cap_rows : 0;
-    if (cap) CK(cudaMalloc((void **)&rows, sizeof(int32_t) * 3 * (size_t)cap));
     TRY(counters_reset(b));
-    k_cand_rows<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, b->accepted_total, b->cand_root, rows, (long long)cap,
+    k_cand_keys<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, b->accepted_total, b->cand_root, b->sort_keys, b->sort_vals,
                                                            b->d.counters);
     CK(cudaGetLastError());
+    const bool fill = cap_rows > 0 && table_host;
+    if (fill) {
+        size_t need = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, b->sort_keys, b->sort_keys2, b->sort_vals, b->sort_vals2, b->N, 0, 32,
+                                           b->stream));
+        if (need > b->sort_tmp_bytes) {
+            if (b->sort_tmp) cudaFree(b->sort_tmp);
+            CK(cudaMalloc(&b->sort_tmp, need));
+            b->sort_tmp_bytes = need;
+        }
+        CK(cub::DeviceRadixSort::SortPairs(b->sort_tmp, need, b->sort_keys, b->sort_keys2, b->sort_vals, b->sort_vals2, b->N, 0,
+                                           32, b->stream));
+    }
     TRY(counters_read(b, nullptr));
     *n_rows = (int64_t)b->h_counters[0];
-    if (cap) {
-        int64_t nw = *n_rows < cap ? *n_rows : cap;
-        CK(cudaMemcpyAsync(table_host, rows, sizeof(int32_t) * 3 * (size_t)nw, cudaMemcpyDeviceToHost, b->stream));
+    if (fill && *n_rows > 0) {
+        const int64_t nw = *n_rows < cap_rows ? *n_rows : cap_rows;
+        // rows are staged in the (now free) unsorted key / value buffers plus the tag scratch: 3 N int32 are needed
+        if (!b->cand_rows) CK(cudaMalloc((void **)&b->cand_rows, sizeof(int32_t) * 3 * (size_t)b->N));
+        k_cand_rows<<<(unsigned)((nw + 255) / 256), 256, 0, b->stream>>>(b->d, b->sort_keys2, b->sort_vals2, b->cand_rows, (long long)nw);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(table_host, b->cand_rows, sizeof(int32_t) * 3 * (size_t)nw, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
-        cudaFree(rows);
     }
     return 0;
 }

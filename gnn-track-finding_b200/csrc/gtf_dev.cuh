@@ -153,6 +153,7 @@ struct gtf_batch {
     double *pv_xy, *pv_zr;     // [N]
     uint8_t *acc_now;          // [N]
     int32_t *tags_a, *tags_b;  // [N]
+    int32_t *cand_rows;        // [3 N] candidate table staging (allocated on first use)
     int n_sm;
     // packed iteration layout
     DevPack k;

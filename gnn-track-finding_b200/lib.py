@@ -83,6 +83,7 @@ def lib():
         "gtf_batch_stream": (ctypes.c_int, [vp, ctypes.POINTER(vp)]),
         "gtf_batch_device_bytes": (i64, [vp]),
         "gtf_seed": (ctypes.c_int, [vp, pg]),
+        "gtf_seed_all": (ctypes.c_int, [vp, pg, ps]),
         "gtf_initialize_edge_activation": (ctypes.c_int, [vp]),
         "gtf_compute_prior_probabilities": (ctypes.c_int, [vp, ctypes.c_int]),
         "gtf_compute_mixture_weights": (ctypes.c_int, [vp, ctypes.c_int, ps]),

@@ -91,6 +91,9 @@ int64_t gtf_batch_device_bytes(const gtf_batch *b);
 /* ---- per-stage entry points (same effect as the reference function named) ---------------------- */
 /* utilities/helper.py:238-452 compute_track_state_estimates (slot order supplies the neighbour order) */
 int gtf_seed(gtf_batch *b, const gtf_geom *g);
+/* event_conversion.py:87-96 in one call: gtf_seed + initialize_edge_activation + compute_prior_probabilities(seeds) +
+ * compute_mixture_weights(seeds) + node degrees (the last three as one kernel launch) */
+int gtf_seed_all(gtf_batch *b, const gtf_geom *g, gtf_stats *st);
 /* utilities/helper.py:24-25 initialize_edge_activation */
 int gtf_initialize_edge_activation(gtf_batch *b);
 /* utilities/helper.py:30-63 compute_prior_probabilities(GraphList, key) */
@@ -149,8 +152,9 @@ int gtf_extract(gtf_batch *b, const gtf_geom *g, double pval_cut, int numhits, d
 /* tag_propagation/tag_propagation.py:64-164: Jacobi max-label propagation from lower-radius successors until
  * the fraction of flipped tags <= threshold.  tags: host i32[N], in = initial tag, out = final tag. */
 int gtf_tag_propagate(gtf_batch *b, double threshold, int32_t *tags, int max_sweeps, int *n_sweeps);
-/* rows (event_id, candidate_id = root node index, node index) of every node accepted so far; device-side
- * compaction, table copied to host.  Returns the row count in *n_rows (may exceed cap; only cap rows written). */
+/* rows (event_id, candidate_id = root node index, node index) of every node accepted so far, sorted by (event, candidate,
+ * node) on the device (radix sort by candidate id), table copied to host.  Returns the row count in *n_rows (may exceed
+ * cap; only cap rows written); table_host == NULL: count only. */
 int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_rows, int64_t *n_rows);
 
 #ifdef __cplusplus
