@@ -26,6 +26,11 @@ struct GtfState {          // one Gaussian component: parabola (a,b,c), slope ta
 };
 
 GTF_HD double gtf_sq(double v) { return v * v; }
+#ifdef __CUDA_ARCH__
+#define GTF_RSQRT(x) rsqrt(x)
+#else
+#define GTF_RSQRT(x) (1.0 / sqrt(x))
+#endif
 
 // Highland multiple-scattering variance of the track direction (helper.py:402-415,
 // extrapolate_merged_states.py:114-124, extract_track_candidates.py:244-255).
@@ -36,8 +41,9 @@ GTF_HD double gtf_var_ms(double a, double b, double xk, double dr, double dz, do
     double sin_t = fabs(dr) / hyp;
     double kb = 2.0 * a * xk + b;
     double t = 1.0 + kb * kb;
-    double kappa = (2.0 * a) / (t * sqrt(t));
-    double q = (13.6 * 1e-3 * 0.1414213562373095048801688724 * kappa) / 0.3; // sqrt(0.02)
+    double rt = GTF_RSQRT(t);
+    double kappa = (2.0 * a) * (rt * rt * rt);                                // 2a / t^(3/2)
+    double q = (13.6 * 1e-3 * 0.1414213562373095048801688724 / 0.3) * kappa;  // sqrt(0.02); constant folded
     double v = sin_t * (q * q);
     if (fabs(endcap_side_z) >= endcap) v = v * (fabs(dr) / fabs(dz));
     return v;
@@ -55,8 +61,9 @@ GTF_HD double gtf_var_ms_pre(double a, double b, double xk, double sin_t, double
 {
     double kb = 2.0 * a * xk + b;
     double t = 1.0 + kb * kb;
-    double kappa = (2.0 * a) / (t * sqrt(t));
-    double q = (13.6 * 1e-3 * 0.1414213562373095048801688724 * kappa) / 0.3; // sqrt(0.02)
+    double rt = GTF_RSQRT(t);
+    double kappa = (2.0 * a) * (rt * rt * rt);                                // 2a / t^(3/2)
+    double q = (13.6 * 1e-3 * 0.1414213562373095048801688724 / 0.3) * kappa;  // sqrt(0.02); constant folded
     double v = sin_t * (q * q);
     if (fabs(endcap_side_z) >= endcap) v = v * rdz;
     return v;
@@ -116,21 +123,21 @@ struct GtfJac {
 };
 GTF_HD void gtf_extrap_jac(double ux, double uy, double vx, double vy, double a, double b, double c, GtfJac &J)
 {
-    // rotation into the source frame (:41,52) -- only x_A is live
-    double rho = sqrt(ux * ux + uy * uy);
-    double irho = 1.0 / rho;                                                    // one reciprocal instead of two quotients
-    double ca = rho > 0.0 ? ux * irho : 1.0, sa = rho > 0.0 ? uy * irho : 0.0;
+    // rotation into the source frame (:41,52) -- only x_A is live; 1/rho and 1/h as reciprocal square roots
+    double rho2 = ux * ux + uy * uy;
+    double irho = GTF_RSQRT(rho2);
+    double ca = rho2 > 0.0 ? ux * irho : 1.0, sa = rho2 > 0.0 ? uy * irho : 0.0;
     double xA = (vx - ux) * ca + (vy - uy) * sa;
     // phi between the two radius vectors (:59): sin/cos taken algebraically
     double cr = ux * vy - uy * vx, dt = ux * vx + uy * vy;
-    double h = sqrt(cr * cr + dt * dt);
-    double ih = 1.0 / h;
-    double sp = h > 0.0 ? cr * ih : 0.0, cp = h > 0.0 ? dt * ih : 1.0;
+    double h2 = cr * cr + dt * dt;
+    double ih = GTF_RSQRT(h2);
+    double sp = h2 > 0.0 ? cr * ih : 0.0, cp = h2 > 0.0 ? dt * ih : 1.0;
     double xp = xA + c * sp, Vx = cp + b * sp, Ax = a * sp;                     // :63-65
     double Vx2 = Vx * Vx;
-    double s_star = (-xp * (2.0 * Vx2 + Ax * xp)) / (2.0 * Vx2 * Vx);           // :68
-    // ds*/d(a,b,c) (:82-86); numer == xp, denom == Vx
     double iV = 1.0 / Vx, iV2 = iV * iV;
+    double s_star = (-xp * (2.0 * Vx2 + Ax * xp)) * (0.5 * iV2 * iV);           // :68 (one reciprocal of Vx serves all)
+    // ds*/d(a,b,c) (:82-86); numer == xp, denom == Vx
     double ds_da = -(sp * xp * xp) * iV2 * iV;
     double ds_db = (sp * xp) * (1.0 + 3.0 * a * sp * xp * iV2) * iV2;
     double ds_dc = -sp * (1.0 + 2.0 * a * sp * xp * iV2) * iV;
@@ -180,7 +187,7 @@ GTF_HD void gtf_extrap_update(const GtfJac &J, double dr, double dz, double uz, 
     o.var_ms = var_ms;
     o.pass = chi2 <= chi2_cut;                                                  // :298 (NaN -> fail)
     if (!o.pass) return;
-    o.lik = exp(-0.5 * chi2) / sqrt(2.0 * 3.14159265358979323846 * fabs(S));    // :302-304
+    o.lik = exp(-0.5 * chi2) * GTF_RSQRT(2.0 * 3.14159265358979323846 * fabs(S)); // :302-304 (1/sqrt as one op)
     // filterpy predict(): F applied a second time, + Q = diag(0, var_ms, 0)    (:321)
     double x0 = f00 * xe0 + f01 * xe1 + f02 * xe2;
     double x1 = f10 * xe0 + f11 * xe1 + f12 * xe2;
@@ -213,8 +220,15 @@ GTF_HD void gtf_extrap_update(const GtfJac &J, double dr, double dz, double uz, 
     o.s.p01 = t01 - K1 * t02 + K0 * R * K1;
     o.s.p11 = t11 - K1 * t12 + K1 * R * K1;
     // tau and its variance (:326-365)
-    o.s.tau = dz / dr;
-    o.s.p22 = gtf_var_tau(dz, dr, uz, vz, g) + var_ms;
+    // one reciprocal of dr serves tau and both Jacobian terms of var(tau) (each within 1 ulp of the quotient)
+    {
+        double sr = g.sigma0rz, sz = g.sigma0rz2, srn = g.sigma0rz, szn = g.sigma0rz2;
+        if (fabs(uz) >= g.endcap) { sz = g.sigma0rz; sr = g.sigma0rz2; }
+        if (fabs(vz) >= g.endcap) { szn = g.sigma0rz; srn = g.sigma0rz2; }
+        double j1 = 1.0 / dr, tau = dz * j1, j3 = tau * j1;
+        o.s.tau = tau;
+        o.s.p22 = (j1 * j1 * (sz * sz) + j1 * j1 * (szn * szn) + j3 * j3 * (sr * sr) + j3 * j3 * (srn * srn)) + var_ms;
+    }
 }
 GTF_HD void gtf_extrapolate(double ux, double uy, double uz, double ur, double vx, double vy, double vz, double vr,
                             double a, double b, double c, double p00, double p01, double p11_eff, double p22,
