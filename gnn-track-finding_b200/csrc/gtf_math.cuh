@@ -262,13 +262,14 @@ GTF_HD double gtf_pair_chi2_pre(const GtfState &si, const GtfState &sj, double x
     double r0 = si.a - sj.a, r1 = si.b - sj.b;
     double c00 = si.p00 + sj.p00, c01 = si.p01 + sj.p01, c11 = si.p11 + sj.p11;
     double det = c00 * c11 - c01 * c01;
-    double d1 = (r0 * r0 * c11 - 2.0 * r0 * r1 * c01 + r1 * r1 * c00) / det;
+    double num = r0 * r0 * c11 - 2.0 * r0 * r1 * c01 + r1 * r1 * c00;
     double sza = g.sigma0rz2, sra = g.sigma0rz;
     if (fabs(xa) >= g.endcap) { sza = g.sigma0rz; sra = g.sigma0rz2; }
     double j1 = Gc.I - Gb.I, j4 = Gb.Q - Gc.Q;                            // d tau_b - tau_c / d(z_a, r_a)
     double cdt = j1 * j1 * sza * sza + Gb.A + Gc.A + j4 * j4 * sra * sra + Gb.C + Gc.C;
     double dtau = Gb.T - Gc.T;
-    return d1 + dtau * dtau * (1.0 / cdt);
+    // num / det + dtau^2 / cdt over one common denominator: one division per pair
+    return (num * cdt + dtau * dtau * det) / (det * cdt);
 }
 GTF_HD double gtf_pair_chi2(const GtfState &si, const GtfState &sj, double xa, double za, double ra, double xb,
                             double zb, double rb, double xc, double zc, double rc, const GtfGeom &g)
@@ -467,8 +468,14 @@ struct GtfInfo {
 };
 GTF_HD void gtf_to_info(const GtfState &s, GtfInfo &I)
 {
-    gtf_inv2(s.p00, s.p01, s.p11, I.s00, I.s01, I.s11);
-    I.sq = 1.0 / s.p22;
+    // 1/det and 1/p22 from one reciprocal of their product
+    double det = s.p00 * s.p11 - s.p01 * s.p01;
+    double r = 1.0 / (det * s.p22);
+    double id = r * s.p22;
+    I.s00 = s.p11 * id;
+    I.s01 = -s.p01 * id;
+    I.s11 = s.p00 * id;
+    I.sq = r * det;
     I.v0 = I.s00 * s.a + I.s01 * s.b;
     I.v1 = I.s01 * s.a + I.s11 * s.b;
     I.vc = I.sq * s.c;
@@ -481,8 +488,14 @@ GTF_HD void gtf_info_add(GtfInfo &m, const GtfInfo &e)
 }
 GTF_HD void gtf_from_info(const GtfInfo &I, GtfState &s)
 {
-    gtf_inv2(I.s00, I.s01, I.s11, s.p00, s.p01, s.p11);
-    s.p22 = 1.0 / I.sq;
+    // 1/det and 1/sq from one reciprocal of their product
+    double det = I.s00 * I.s11 - I.s01 * I.s01;
+    double r = 1.0 / (det * I.sq);
+    double id = r * I.sq;
+    s.p00 = I.s11 * id;
+    s.p01 = -I.s01 * id;
+    s.p11 = I.s00 * id;
+    s.p22 = r * det;
     s.a = s.p00 * I.v0 + s.p01 * I.v1;
     s.b = s.p01 * I.v0 + s.p11 * I.v1;
     s.c = s.p22 * I.vc;
