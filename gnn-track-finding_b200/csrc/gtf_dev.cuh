@@ -136,7 +136,7 @@ struct gtf_batch {
     DevBatch d;
     bool finalized, derived_dirty;
     unsigned long long *n_dead;
-    int n_tiles, n_big;
+    int n_tiles;
     int32_t *tile_begin;
     int n_stiles;
     int32_t *stile_begin;      // k_send tiles: whole sources, <= GTF_SEND_SRCS sources and <= GTF_SEND_EDGES out-edges

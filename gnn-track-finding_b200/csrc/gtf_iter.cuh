@@ -46,7 +46,6 @@ __device__ __forceinline__ GeoRec ld_geo(const GeoRec *p)
     g.sx = __hiloint2double(v.y, v.x); g.lay = v.z; g.src = v.w;
     return g;
 }
-__device__ __forceinline__ void l1_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void flush_counters(unsigned int *s_cnt, unsigned long long *counters, int tid)
 {
@@ -391,7 +390,8 @@ struct LEnt {          // one dict entry of a light node
     int lay, rank, side, lrn, rank0, tag0;
     double sx, w, lik, prior, ew;
 };
-__device__ __forceinline__ int tag_pack(int rank_unused, int side, int lrn) { return (side & 0xff) | (lrn << 16); }
+// second word of the tag record: side in byte 0, lr_layer_norm code in the upper half
+__device__ __forceinline__ int tag_pack(int side, int lrn) { return (side & 0xff) | (lrn << 16); }
 __device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, int s, LEnt &e)
 {
     const double2 m0 = __ldcs(reinterpret_cast<const double2 *>(K.meta + s));
@@ -418,7 +418,7 @@ __device__ __forceinline__ void lent_store(const DevBatch &B, const DevPack &K, 
     double2 *m = reinterpret_cast<double2 *>(K.meta + e.s);
     __stcs(m + 0, make_double2(e.w, e.lik));
     __stcs(m + 1, make_double2(e.prior, e.ew));          // ew: helper.py:180
-    const int t1 = tag_pack(0, e.side, e.lrn);
+    const int t1 = tag_pack(e.side, e.lrn);
     if (e.rank != e.rank0 || t1 != e.tag0) *reinterpret_cast<int2 *>(tag_p(K, e.s)) = make_int2(e.rank, t1);
     if ((e.f & H_ACT0) && !(e.f & H_ACT)) bm_clear(K.act_nx, e.s);
 }
@@ -659,7 +659,6 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
     const int gl = lane % G, gbase = lane - gl;
     const unsigned gmask = G == 32 ? FULL : (((1u << G) - 1u) << gbase);
     if (tid < GTF_NCOUNTERS) s_cnt[tid] = 0;
-#ifndef GTF_HV_NO_TABLES
     // 1/k and the pair -> row table in shared memory: per-lane indices would serialise in the constant cache
     __shared__ double s_recip[33];
     __shared__ uint8_t s_pair_i[GTF_MAXD * (GTF_MAXD - 1) / 2];
@@ -667,10 +666,6 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
     if (tid < GTF_MAXD * (GTF_MAXD - 1) / 2) s_pair_i[tid] = c_pair_i[tid];
 #define HV_RECIP(k) s_recip[k]
 #define HV_PAIR_DECODE(p, i, j) do { (i) = s_pair_i[p]; (j) = (p) - (i) * ((i) - 1) / 2; } while (0)
-#else
-#define HV_RECIP(k) recip_small(k)
-#define HV_PAIR_DECODE(p, i, j) pair_decode(p, i, j)
-#endif
     __syncthreads();
     const int count = K.counts[PK_HV0 + bin];
     const int32_t *list = K.hv_list + (size_t)bin * B.N;
@@ -965,7 +960,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             double2 *m = reinterpret_cast<double2 *>(K.meta + slot);
             __stcs(m + 0, make_double2(w, lik));
             __stcs(m + 1, make_double2(prior, ew));              // ew: helper.py:180
-            const int t1 = tag_pack(0, side, lrn);
+            const int t1 = tag_pack(side, lrn);
             if (rank != rank0 || t1 != tag0) *reinterpret_cast<int2 *>(tag_p(K, slot)) = make_int2(rank, t1);
             if ((f & H_ACT0) && !(f & H_ACT)) bm_clear(K.act_nx, slot);
         }
