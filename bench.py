@@ -372,7 +372,7 @@ def main():
                                "update) + k_node2 (<= 2-component nodes: priors, reweight x2, prune) + k_hv<4|8|16|32> / k_big "
                                "(>= 3-component nodes: the same + pairwise chi2 + greedy KL merge); reads the committed state, "
                                "rewrites the dict entries in place, merged states to shadow buffers"},
-            "gpu_launches": 8 * a.steps,
+            "gpu_launches": 9 * a.steps,   # k_begin, k_send, k_exec, k_node2, k_hv<4|8|16|32>, k_big (replayed from one CUDA graph)
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "traffic_source": "profiles/r01_pipeline_traffic.json (ncu --set full capture of all pipeline kernels at this "
