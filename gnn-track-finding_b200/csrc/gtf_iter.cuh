@@ -1,20 +1,22 @@
 // gtf_iter.cuh -- one message-passing iteration on the packed layout (DevPack, gtf_dev.cuh):
-//   k_send     thread per source  : which out-edges carry a message (extrapolate...py:416,425,431) -> compact
-//                                   source-major message list (a source's messages contiguous, successor order)
-//   k_exec     thread per message : multiple-scattering term + its per-source running sum (quirk 2, sequential order
-//                                   kept with warp shuffles), extrapolate, chi2 gate, Kalman update
-//                                   (extrapolate_merged_states.py:26-402); writes the 64 B state record and the
-//                                   32 B weight record of the receiving dict entry
-//   k_node     thread per node    : scans the node's bits; <= 2 dict entries -> closed-form priors / side norms /
+//   k_begin    thread per word/node: next activation bitmap := current, presence snapshot, counters, carried p11
+//   k_send     CTA per source tile : which out-edges carry a message (extrapolate...py:416,425,431), Highland term from
+//                                   the per-out-edge static records, the per-source running sum of merged_cov[1,1]
+//                                   (quirk 2, summed in successor order) -> compact source-major message list
+//   k_exec     thread per message : extrapolate, chi2 gate, Kalman update (extrapolate_merged_states.py:26-402);
+//                                   writes the 64 B state record and the 32 B weight record of the receiving dict
+//                                   entry; software-pipelined (cp.async descriptors, gathers between the two halves)
+//   k_node2    thread per node    : scans the node's bits; <= 2 dict entries -> closed-form priors / side norms /
 //                                   re-weighting / pruning right here (helper.py:30-200); >= 3 -> binned lists
 //   k_hv<G>    G lanes per node   : cooperative nodes (3..32 entries), G = 4, 8, 16, 32 lanes per node, entries in
 //                                   registers in dict order: priors, re-weighting, pairwise chi2 + greedy KL merge
 //                                   (clustering.py:193-307), degree, mixture weights, priors
 //   k_big      CTA per node       : more than 32 entries (generic shared-memory program of gtf_tile.cuh)
-//   k_pack_* / k_unpack_slots     : SoA fields <-> packed records and bitmaps
+//   k_pack_* / k_unpack_*         : SoA fields <-> packed records and bitmaps
 // Activation / presence flags are bitmaps (1.6 MB per 12.8 M slots: L2 resident, so the scattered tests of k_send
-// and the per-node scans cost no DRAM traffic); state and weights are array-of-records so a dict entry is read
-// and written as whole 32 B sectors.
+// and the per-node scans cost no DRAM traffic); state, weights, geometry + tag and merged states are
+// array-of-records so that an entry is read and written as whole 32 B sectors (a scattered 8 B store is a DRAM
+// read-modify-write).
 #pragma once
 
 #define H_EX 1u
