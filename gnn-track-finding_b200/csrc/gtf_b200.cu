@@ -144,6 +144,8 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         CK(cudaStreamCreateWithFlags(&b->stream3, cudaStreamNonBlocking));
         const char *ge = getenv("GTF_GRAPH");
         b->use_graph = !(ge && ge[0] == '0');
+        b->force_pending = true;
+        b->force_dev = -1;
         CK(cudaEventCreateWithFlags(&b->ev_fork2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b->ev_join3, cudaEventDisableTiming));
@@ -650,6 +652,7 @@ static int ensure_packed(gtf_batch *b)
     const bool st = b->pack_static_stale;
     const bool any = st || b->pack_stale[0] || b->pack_stale[1] || b->pack_stale[2] || b->pack_stale[PG_NODE];
     if (!any) return 0;
+    b->force_pending = true; // the packed state changes from outside: the next committed iteration evaluates every node
     DevPack &k = b->k;
     if (st) {
         if (b->E) k_pack_out<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k);
@@ -725,6 +728,17 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
     DevBatch &d = b->d;
     const Prog P = fused_prog(p);
     cudaStream_t s0 = b->stream;
+    {
+        // nodes without an active in-edge are skipped (k_node2) unless every node has to be evaluated: after a (re)pack,
+        // when the thresholds changed, and in uncommitted passes (their results go to shadow buffers)
+        const bool changed = !b->have_last_prog || memcmp(&b->last_prog, &P, sizeof(Prog)) != 0 || memcmp(&b->last_geom, &gg, sizeof(GtfGeom)) != 0;
+        const int fv = (b->force_pending || changed || !commit) ? 1 : 0;
+        if (fv != b->force_dev) {
+            CK(cudaMemsetAsync(k.counts + PK_FORCE, fv ? 0xff : 0, sizeof(int), s0));
+            b->force_dev = fv;
+        }
+        if (commit) { b->last_prog = P; b->last_geom = gg; b->have_last_prog = true; b->force_pending = false; }
+    }
     if (b->timing || !b->use_graph) {
         TRY(issue_iteration(b, P, gg, p->record_chi2, commit, b->timing));
         if (b->timing) {

@@ -57,10 +57,12 @@ struct __align__(32) OutRec {
     double w;                    // mixture weight the message carries = the source's seed entry for this neighbour (:384); GTF_NO_TSE bits: none
 };
 #define GTF_NO_TSE_BITS 0x7ff8dead00000001ll
-struct __align__(32) MergedRec { double a, b, c, p00, p01, p22, prior, pad; }; // merged_state / merged_cov / merged_prior of a node
-                                                                             // (p11 lives in the m_p11 ping-pong pair: quirk 2)
+struct __align__(32) MergedRec {  // merged_state / merged_cov / merged_prior of a node
+    double a, b, c, p00, p01, p22, prior;
+    double cl_p11;                // merged_cov[1,1] of the cluster formed at the node's last evaluation, NaN: none.  (The live
+};                                // value accumulates multiple scattering in the m_p11 ping-pong pair: quirk 2.)
 
-enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_NCOUNTS = 8 };
+enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_FORCE = 7, PK_NCOUNTS = 8 };
 
 struct DevPack {
     // static, derived from the topology and the hit coordinates
@@ -80,7 +82,7 @@ struct DevPack {
     double *msg_w;               // [E] mixture weight carried by the message (extrapolate...py:384)
     double *msg_p11, *msg_vms;   // [E] merged_cov[1,1] as the edge sees it (quirk 2), its multiple-scattering term
     int32_t *hv_list;            // [(HV_BINS + 1) * N] cooperative nodes binned by dict size: <=4, <=8, <=16, <=32, more
-    int *counts;                 // [PK_NCOUNTS] messages, 4 bins, big, missing slots
+    int *counts;                 // [PK_NCOUNTS] messages, 4 bins, big, missing slots, 'evaluate every node' flag
 };
 
 enum {
@@ -162,6 +164,11 @@ struct gtf_batch {
     cudaStream_t stream3;
     cudaEvent_t ev_fork2, ev_join2, ev_join3;
     cudaEvent_t evk[6];
+    bool force_pending;        // the packed state changed from outside: the next committed iteration evaluates every node
+    int force_dev;             // value of counts[PK_FORCE] on the device (-1 unknown)
+    bool have_last_prog;       // thresholds / geometry of the last committed iteration (a change re-evaluates every node)
+    Prog last_prog;
+    GtfGeom last_geom;
     bool use_graph;            // replay the iteration from a CUDA graph (GTF_GRAPH=0: plain launches)
     int parity;                // which half of the ping-pong pairs (act / act_nx, m_p11 / m_p11_nx) is current
     IterGraph graphs[2][2];    // [committed][parity]

@@ -122,7 +122,7 @@ __global__ void k_pack_nodes(DevBatch B, DevPack K, int do_static, int do_merged
     if (do_merged) {
         MergedRec m;
         m.a = B.m_a[i]; m.b = B.m_b[i]; m.c = B.m_c[i]; m.p00 = B.m_p00[i]; m.p01 = B.m_p01[i]; m.p22 = B.m_p22[i];
-        m.prior = B.m_prior[i]; m.pad = 0.0;
+        m.prior = B.m_prior[i]; m.cl_p11 = NAN;
         K.mrec[i] = m;
     }
 }
@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
         unsigned nf = B.node_ok[i];
         const int b0 = B.in_off[i], b1 = B.in_off[i + 1];
         int np = 0, e0 = -1, e1 = -1, deg = 0, chg = 0;
+        unsigned a0_any = 0;
         for (int c = b0; c < b1; c += 32) {
             const int nb = min(32, b1 - c);
             const unsigned mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
@@ -494,6 +495,7 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
             const unsigned an = bm_win(K.act_nx, c) & ex, a0 = bm_win(K.act, c) & ex;
             deg += __popc(an);
             chg += __popc(an ^ a0);
+            a0_any |= a0;
             if (pr) {
                 if (np == 0) {
                     e0 = c + __ffs(pr) - 1;
@@ -504,7 +506,18 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
                 np += __popc(pr);
             }
         }
-        if (np > 2 && (nf & NF_OK)) {
+        // A node without an active in-edge at the start of the iteration receives no message and changes no flag: its
+        // program would reproduce its last evaluation bit for bit (same entries, same priors, same cluster).  It is
+        // skipped -- except that a cluster's merged_cov[1,1] is re-created by every evaluation while the node keeps
+        // sending (quirk 2), so that value is restored.  After anything changed the packed state from outside, every
+        // node is evaluated once (PK_FORCE).
+        const bool is_static = a0_any == 0 && !K.counts[PK_FORCE];
+        if (is_static) {
+            if (np > 2 && (nf & NF_OK)) {
+                const double cp = K.mrec[i].cl_p11;
+                if (cp == cp) B.m_p11_nx[i] = cp;
+            }
+        } else if (np > 2 && (nf & NF_OK)) {
             const int bin = np <= 4 ? 0 : np <= 8 ? 1 : np <= 16 ? 2 : np <= 32 ? 3 : 4;
             s_list[bin][atomicAdd(&s_n[bin], 1)] = i;
         } else {
@@ -590,8 +603,13 @@ __device__ __forceinline__ void merged_store(const MergedOut &MO, int i, const G
     r[0] = make_double2(m.a, m.b);
     r[1] = make_double2(m.c, m.p00);
     r[2] = make_double2(m.p01, m.p22);
-    r[3] = make_double2(mprior, 0.0);
+    r[3] = make_double2(mprior, m.p11);
     MO.p11[i] = m.p11;
+}
+// the node was evaluated and formed no cluster: remember that (static nodes are skipped later, see k_node2)
+__device__ __forceinline__ void merged_none(const MergedOut &MO, int i)
+{
+    if (MO.rec[i].cl_p11 == MO.rec[i].cl_p11) MO.rec[i].cl_p11 = NAN;
 }
 
 template <int G> __device__ __forceinline__ unsigned grp_min_u32(unsigned v)
@@ -966,9 +984,12 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             if (rank != rank0 || t1 != tag0) *reinterpret_cast<int2 *>(tag_p(K, slot)) = make_int2(rank, t1);
             if ((f & H_ACT0) && !(f & H_ACT)) bm_clear(K.act_nx, slot);
         }
-        if (clustered && gl == 0) {
-            merged_store(MO, i, merged, mprior);
-            n_merged++;
+        if (gv && gl == 0) {
+            if (clustered) {
+                merged_store(MO, i, merged, mprior);
+                n_merged++;
+            } else
+                merged_none(MO, i);
         }
         __syncwarp();
     }
@@ -1056,13 +1077,15 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack Kin, Prog P, Gtf
         for (int k = 0; k < 8; k++) mo[k] = mscr + k - i;
         node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, true, hm_s - i, mo, lrn_s, ew_s);
         __syncwarp();
-        if (lane == 0 && (sm.nflags[0] & NF_CLUSTERED)) {
-            GtfState m;
-            m.a = mscr[0]; m.b = mscr[1]; m.c = mscr[2]; m.p00 = mscr[3]; m.p01 = mscr[4]; m.p11 = mscr[5]; m.p22 = mscr[6];
-            m.tau = 0.0;
-            merged_store(MO, i, m, mscr[7]);
+        if (lane == 0) {
+            if (sm.nflags[0] & NF_CLUSTERED) {
+                GtfState m;
+                m.a = mscr[0]; m.b = mscr[1]; m.c = mscr[2]; m.p00 = mscr[3]; m.p01 = mscr[4]; m.p11 = mscr[5]; m.p22 = mscr[6];
+                m.tau = 0.0;
+                merged_store(MO, i, m, mscr[7]);
+            } else
+                merged_none(MO, i);
         }
-        __syncwarp();
         unsigned n_act = 0, n_chg = 0;
         for (int ls = lane; ls < d; ls += 32) {
             const int s = gs0 + ls;

@@ -45,6 +45,8 @@ typedef struct {
 typedef struct {
     int64_t nodes_merged;       /* nodes that got a (new) merged state        clustering.py:291-294 */
     int64_t edges_deactivated;  /* un-absorbed components switched off        clustering.py:311-321 */
+                                /* (gtf_iterate counts the nodes it evaluated: from the second committed iteration on, nodes
+                                   without an active in-edge are skipped -- their evaluation would change nothing) */
     int64_t edges_sent;         /* extrapolate_validate calls                 extrapolate...py:433  */
     int64_t edges_gated;        /* chi2 > cut                                 extrapolate...py:393  */
     int64_t edges_reweight_off; /* weight < threshold                         helper.py:186-187     */
