@@ -62,6 +62,9 @@ struct __align__(32) MergedRec {  // merged_state / merged_cov / merged_prior of
     double cl_p11;                // merged_cov[1,1] of the cluster formed at the node's last evaluation, NaN: none.  (The live
 };                                // value accumulates multiple scattering in the m_p11 ping-pong pair: quirk 2.)
 
+static_assert(sizeof(MetaRec) == 32 && sizeof(AuxRec) == 32 && sizeof(NodeXYZR) == 32 && sizeof(OutRec) == 32 && sizeof(MergedRec) == 64,
+              "packed records are whole 32 B sectors");
+
 enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_FORCE = 7, PK_NCOUNTS = 8 };
 
 struct DevPack {
