@@ -1173,3 +1173,67 @@ extern "C" int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_row
     }
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ pairwise KL diagnostic
+// KLDistance between every pair of components of every group (node) with general 3x3 covariances: the inner function of
+// the reference's KL-LUT training-data generator (learn_KL_*_model: compute_KL_distance.py:11-21,
+// clustering_updated_states_test.py:175-233).  One thread per pair; output order: group by group, (i, j < i) row-major.
+__global__ void k_kl_pairs(const double *mean, const double *cov, const int32_t *off, const long long *poff, int n_groups,
+                           double *out, long long n_pairs)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    int lo = 0, hi = n_groups;             // group of pair p: last group whose first pair is <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (poff[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int q = (int)(p - poff[lo]);
+    int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
+    while (i * (i - 1) / 2 > q) i--;
+    while ((i + 1) * i / 2 <= q) i++;
+    const int j = q - i * (i - 1) / 2;
+    const int a = off[lo] + i, b = off[lo] + j;
+    out[p] = gtf_kl_general(mean + 3 * (size_t)a, cov + 9 * (size_t)a, mean + 3 * (size_t)b, cov + 9 * (size_t)b);
+}
+extern "C" int gtf_kl_pairs(int device, const double *mean, const double *cov, const int32_t *off, int32_t n_groups,
+                            double *out, int64_t cap, int64_t *n_pairs)
+{
+    if (!mean || !cov || !off || !n_pairs || n_groups < 0) return fail(GTF_E_ARG, "gtf_kl_pairs: bad argument");
+    if (gtf_device_count() <= device || device < 0) return fail(GTF_E_CUDA, "gtf_kl_pairs: no such CUDA device");
+    CK(cudaSetDevice(device));
+    std::vector<long long> poff((size_t)n_groups + 1, 0);
+    for (int gidx = 0; gidx < n_groups; gidx++) {
+        const long long n = off[gidx + 1] - off[gidx];
+        if (n < 0) return fail(GTF_E_ARG, "gtf_kl_pairs: offsets not monotone");
+        poff[gidx + 1] = poff[gidx] + n * (n - 1) / 2;
+    }
+    const long long np = poff[n_groups];
+    *n_pairs = np;
+    if (!out || np == 0) return 0;
+    if (cap < np) return fail(GTF_E_ARG, "gtf_kl_pairs: output buffer too small");
+    const size_t M = (size_t)off[n_groups];
+    double *d_mean = nullptr, *d_cov = nullptr, *d_out = nullptr;
+    int32_t *d_off = nullptr;
+    long long *d_poff = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto done = [&](int rc) {
+        cudaFree(d_mean); cudaFree(d_cov); cudaFree(d_out); cudaFree(d_off); cudaFree(d_poff);
+        return rc;
+    };
+#define CKF(call) do { e = (call); if (e != cudaSuccess) return done(fail(GTF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e))); } while (0)
+    CKF(cudaMalloc((void **)&d_mean, sizeof(double) * 3 * (M ? M : 1)));
+    CKF(cudaMalloc((void **)&d_cov, sizeof(double) * 9 * (M ? M : 1)));
+    CKF(cudaMalloc((void **)&d_out, sizeof(double) * (size_t)np));
+    CKF(cudaMalloc((void **)&d_off, sizeof(int32_t) * ((size_t)n_groups + 1)));
+    CKF(cudaMalloc((void **)&d_poff, sizeof(long long) * ((size_t)n_groups + 1)));
+    CKF(cudaMemcpy(d_mean, mean, sizeof(double) * 3 * M, cudaMemcpyHostToDevice));
+    CKF(cudaMemcpy(d_cov, cov, sizeof(double) * 9 * M, cudaMemcpyHostToDevice));
+    CKF(cudaMemcpy(d_off, off, sizeof(int32_t) * ((size_t)n_groups + 1), cudaMemcpyHostToDevice));
+    CKF(cudaMemcpy(d_poff, poff.data(), sizeof(long long) * ((size_t)n_groups + 1), cudaMemcpyHostToDevice));
+    k_kl_pairs<<<(unsigned)((np + 255) / 256), 256>>>(d_mean, d_cov, d_off, d_poff, n_groups, d_out, np);
+    CKF(cudaGetLastError());
+    CKF(cudaMemcpy(out, d_out, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost));
+#undef CKF
+    return done(0);
+}

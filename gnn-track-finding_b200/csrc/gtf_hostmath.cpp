@@ -46,6 +46,7 @@ void gtfh_merge(const double *s1, const double *s2, double *out8)
     out8[4] = m.p00; out8[5] = m.p01; out8[6] = m.p11; out8[7] = m.p22;
 }
 double gtfh_kl(const double *s1, const double *s2) { return gtf_kl(st(s1), st(s2)); }
+double gtfh_kl_general(const double *m1, const double *c1, const double *m2, const double *c2) { return gtf_kl_general(m1, c1, m2, c2); }
 }
 
 extern "C" void gtfh_track_fit(double *co4, int n, double sigma0xy, double sigma0rz, double endcap, double sep3d,

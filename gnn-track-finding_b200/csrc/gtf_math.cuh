@@ -329,6 +329,31 @@ GTF_HD double gtf_kl(const GtfState &s1, const GtfState &s2)
     return tr + (d0 * d0 * s00 + 2.0 * d0 * d1 * s01 + d1 * d1 * s11 + d2 * d2 * (q1 + q2));
 }
 
+// KLDistance for GENERAL 3x3 covariances (the LUT training-data generator seeds components with full matrices:
+// learn_KL_parabolic_model/.../utils.py:221-299, compute_KL_distance.py:11-21): closed-form cofactor inverse; the
+// "trace" is again of the element-wise product (clustering.py:93).  Pinned by the reference's shipped golden CSV.
+GTF_HD void gtf_inv3_general(const double *c, double *o)
+{
+    double c00 = c[4] * c[8] - c[5] * c[7], c01 = c[5] * c[6] - c[3] * c[8], c02 = c[3] * c[7] - c[4] * c[6];
+    double id = 1.0 / (c[0] * c00 + c[1] * c01 + c[2] * c02);
+    o[0] = c00 * id; o[1] = (c[2] * c[7] - c[1] * c[8]) * id; o[2] = (c[1] * c[5] - c[2] * c[4]) * id;
+    o[3] = c01 * id; o[4] = (c[0] * c[8] - c[2] * c[6]) * id; o[5] = (c[2] * c[3] - c[0] * c[5]) * id;
+    o[6] = c02 * id; o[7] = (c[1] * c[6] - c[0] * c[7]) * id; o[8] = (c[0] * c[4] - c[1] * c[3]) * id;
+}
+GTF_HD double gtf_kl_general(const double *m1, const double *c1, const double *m2, const double *c2)
+{
+    double i1[9], i2[9];
+    gtf_inv3_general(c1, i1);
+    gtf_inv3_general(c2, i2);
+    double tr = 0.0;
+    for (int k = 0; k < 3; k++) tr += (c1[4 * k] - c2[4 * k]) * (i2[4 * k] - i1[4 * k]);
+    double d0 = m1[0] - m2[0], d1 = m1[1] - m2[1], d2 = m1[2] - m2[2];
+    double t0 = d0 * (i1[0] + i2[0]) + d1 * (i1[3] + i2[3]) + d2 * (i1[6] + i2[6]);   // row vector times matrix first
+    double t1 = d0 * (i1[1] + i2[1]) + d1 * (i1[4] + i2[4]) + d2 * (i1[7] + i2[7]);
+    double t2 = d0 * (i1[2] + i2[2]) + d1 * (i1[5] + i2[5]) + d2 * (i1[8] + i2[8]);
+    return tr + (t0 * d0 + t1 * d1 + t2 * d2);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Candidate quality gate (extract/extract_track_candidates.py:172-328).
 

@@ -99,6 +99,7 @@ def lib():
         "gtf_batch_set_timing": (ctypes.c_int, [vp, ctypes.c_int]),
         "gtf_batch_timing": (ctypes.c_int, [vp, dp, dp, dp, ctypes.POINTER(ctypes.c_int)]),
         "gtf_batch_timing_kernels": (ctypes.c_int, [vp, dp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+        "gtf_kl_pairs": (ctypes.c_int, [ctypes.c_int, dp, dp, ctypes.POINTER(i32), i32, dp, i64, ctypes.POINTER(i64)]),
         "gtf_components": (ctypes.c_int, [vp]),
         "gtf_extract": (ctypes.c_int, [vp, pg, dbl, ctypes.c_int, dbl, dbl, ctypes.POINTER(i32),
                                        ctypes.POINTER(ctypes.c_uint8), dp, dp]),

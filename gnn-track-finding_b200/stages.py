@@ -138,3 +138,25 @@ def CCA(subCopy):
     for i, l in enumerate(lab):
         comps.setdefault(int(l), []).append(int(orig[i]))
     return [subCopy.subgraph(nodes).copy() for _, nodes in sorted(comps.items())]
+
+
+def KLDistance_pairs(means, covs, offsets, device=0):
+    """Pairwise `KLDistance` (clustering.py:90-94, general 3x3 covariances) between the components of every group, on the
+    GPU -- the inner loop of the reference's KL-threshold LUT training-data generator (compute_KL_distance.py:11-21).
+    means: (M, 3), covs: (M, 3, 3) or (M, 9), offsets: (G + 1,) component ranges.  Returns the KL values of all pairs
+    (i, j < i), group by group."""
+    import ctypes
+    from . import lib as L
+    means = np.ascontiguousarray(means, np.float64).reshape(-1, 3)
+    covs = np.ascontiguousarray(covs, np.float64).reshape(-1, 9)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    assert len(means) == len(covs) and len(offsets) >= 1 and offsets[-1] <= len(means)
+    lib = L.lib()
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+    n = ctypes.c_int64(0)
+    args = (device, means.ctypes.data_as(dp), covs.ctypes.data_as(dp), offsets.ctypes.data_as(ip), len(offsets) - 1)
+    L.check(lib.gtf_kl_pairs(*args, None, 0, ctypes.byref(n)))
+    out = np.empty(n.value, np.float64)
+    if n.value:
+        L.check(lib.gtf_kl_pairs(*args, out.ctypes.data_as(dp), n.value, ctypes.byref(n)))
+    return out

@@ -159,6 +159,15 @@ int gtf_tag_propagate(gtf_batch *b, double threshold, int32_t *tags, int max_swe
  * cap; only cap rows written); table_host == NULL: count only. */
 int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_rows, int64_t *n_rows);
 
+/* ---- diagnostic: pairwise KL between the components of every group (general 3x3 covariances) ------------------- */
+/* The inner function of the reference's KL-threshold LUT training-data generator (learn_KL_linear_model /
+ * learn_KL_parabolic_model: compute_KL_distance.py:11-21, clustering_updated_states_test.py:175-233; KLDistance with the
+ * element-wise trace of clustering/clustering.py:90-94).  mean: host f64[M][3], cov: host f64[M][9], off: host i32[G+1]
+ * (components of group g are off[g]..off[g+1]).  Writes KL(i, j) for j < i, group by group, to out (host f64[*n_pairs];
+ * out == NULL: count only).  Needs no batch. */
+int gtf_kl_pairs(int device, const double *mean, const double *cov, const int32_t *off, int32_t n_groups, double *out,
+                 int64_t cap, int64_t *n_pairs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -443,3 +443,27 @@ def test_cfg5_degree_sweep_vs_oracle(deg):
 
 def dict_orders_equal(a, b):
     return gu.dict_order(a) == gu.dict_order(b)
+
+
+def test_pairwise_kl_kernel_reproduces_the_reference_golden_csv():
+    """the reference's one shipped known-answer file (7,574 KL values of its LUT training-data generator)
+    through the GPU kernel behind gtf_kl_pairs / stages.KLDistance_pairs: same values as a sorted multiset (1e-9), and
+    pair for pair against the oracle"""
+    import ctypes
+    from gtf_b200 import stages
+    fx = np.load(gu.GOLDEN + "/kl_parabolic_known_answer.npz")
+    mean, cov, off = fx["mean"], fx["cov"].reshape(-1, 9), fx["off"]
+    got = stages.KLDistance_pairs(mean, cov, off)
+    assert len(got) == 7574
+    assert gu.rel_err(np.sort(got), fx["kl_sorted"]) <= 1e-9
+    L = ol.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    want = []
+    for a, b in zip(off[:-1], off[1:]):
+        for i in range(a, b):
+            for j in range(a, i):
+                mi, ci, mj, cj = (np.ascontiguousarray(x) for x in (mean[i], cov[i], mean[j], cov[j]))
+                want.append(L.gtfo_kl_distance(mi.ctypes.data_as(dp), ci.ctypes.data_as(dp), mj.ctypes.data_as(dp),
+                                               cj.ctypes.data_as(dp)))
+    assert gu.rel_err(got, np.array(want)) <= 1e-9
+    assert len(stages.KLDistance_pairs(mean[:0], cov[:0], np.zeros(1, np.int32))) == 0

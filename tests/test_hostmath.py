@@ -195,3 +195,24 @@ def test_information_form_clustering_matches_reference(hm, name, prev, stage, ke
     assert n_checked > (20 if key == "tse" else -1), n_checked
     print(name, stage, "nodes", n_checked, "worst rel err %.3g" % worst)
     assert worst <= gu.RTOL, worst
+
+
+def test_general_kl_known_answer_from_reference_csv(hm):
+    """the kernel algebra for general 3x3 covariances (gtf_kl_general, closed-form cofactor inverse) reproduces the
+    reference's shipped golden vector (1_events_training_data.csv, 7,574 KL values) as a sorted multiset"""
+    import ctypes
+    fx = np.load(gu.GOLDEN + "/kl_parabolic_known_answer.npz")
+    dp = ctypes.POINTER(ctypes.c_double)
+    hm.gtfh_kl_general.restype = ctypes.c_double
+    hm.gtfh_kl_general.argtypes = [dp] * 4
+    mean, cov, off = fx["mean"], fx["cov"].reshape(-1, 9), fx["off"]
+    out = []
+    for a, b in zip(off[:-1], off[1:]):
+        for i in range(a, b):
+            for j in range(a, i):
+                mi, ci, mj, cj = (np.ascontiguousarray(x) for x in (mean[i], cov[i], mean[j], cov[j]))
+                out.append(hm.gtfh_kl_general(mi.ctypes.data_as(dp), ci.ctypes.data_as(dp), mj.ctypes.data_as(dp),
+                                              cj.ctypes.data_as(dp)))
+    got = np.sort(np.array(out))
+    assert len(got) == 7574
+    assert gu.rel_err(got, fx["kl_sorted"]) <= 1e-9
