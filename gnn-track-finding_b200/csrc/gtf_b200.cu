@@ -140,6 +140,7 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
         DA(k.hv_list, (int64_t)(HV_BINS + 1) * N);
         DA(k.counts, PK_NCOUNTS);
         b->pack_static_stale = true;
+        b->exists_stale = true;
         for (int q = 0; q < PG_N; q++) { b->pack_stale[q] = true; b->soa_stale[q] = false; }
         CK(cudaStreamCreateWithFlags(&b->stream3, cudaStreamNonBlocking));
         const char *ge = getenv("GTF_GRAPH");
@@ -235,6 +236,7 @@ static int soa_for_stage(gtf_batch *b, bool writes)
     if (writes) {
         for (int q = 0; q < PG_N; q++) b->pack_stale[q] = true;
         b->pack_static_stale = true; // seed weights (tse_w) may change: per-out-edge records are rebuilt
+        b->exists_stale = true;      // nodes may have been removed
     }
     return 0;
 }
@@ -245,7 +247,10 @@ extern "C" int gtf_batch_upload(gtf_batch *b, int f, const void *host)
     CK(cudaSetDevice(b->device));
     const int grp = field_group(f);
     if (grp == PG_REC || grp == PG_NODE) { int r = soa_sync(b, 1u << grp); if (r) return r; } // the group's other fields must be current
-    if (f == GTF_F_alive) { int r = soa_sync(b, 1u << PG_ACT); if (r) return r; b->pack_stale[PG_ACT] = true; }
+    if (f == GTF_F_alive) { // the existing-edge bitmap is rebuilt from alive (together with the activation bitmap) at the next pack
+        int r = soa_sync(b, 1u << PG_ACT); if (r) return r;
+        b->pack_stale[PG_ACT] = true; b->exists_stale = true;
+    }
     CK(cudaMemcpyAsync(b->f[f], host, (size_t)gtf_field_bytes(b, f), cudaMemcpyHostToDevice, b->stream));
     if (grp >= 0) { b->soa_stale[grp] = false; b->pack_stale[grp] = true; }
     if (field_is_pack_static(f)) b->pack_static_stale = true;
@@ -650,7 +655,7 @@ static int ensure_packed(gtf_batch *b)
 {
     if (b->derived_dirty) TRY(recount_subs(b));
     const bool st = b->pack_static_stale;
-    const bool any = st || b->pack_stale[0] || b->pack_stale[1] || b->pack_stale[2] || b->pack_stale[PG_NODE];
+    const bool any = st || b->exists_stale || b->pack_stale[0] || b->pack_stale[1] || b->pack_stale[2] || b->pack_stale[PG_NODE];
     if (!any) return 0;
     b->force_pending = true; // the packed state changes from outside: the next committed iteration evaluates every node
     DevPack &k = b->k;
@@ -659,10 +664,17 @@ static int ensure_packed(gtf_batch *b)
     }
     if (b->N && (st || b->pack_stale[PG_NODE]))
         k_pack_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, k, st, b->pack_stale[PG_NODE]);
-    if (b->pack_stale[PG_ACT]) CK(cudaMemsetAsync(k.counts + PK_MISSING, 0, sizeof(int), b->stream));
-    if (b->E)
-        k_pack_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k, st, b->pack_stale[PG_ACT], b->pack_stale[PG_PRES],
-                                                                b->pack_stale[PG_REC]);
+    if (!st && !b->exists_stale && !b->pack_stale[PG_REC]) {
+        // only the flag bytes changed (a host that uploads them every iteration): bytes -> bits, nothing else
+        if (b->E && (b->pack_stale[PG_ACT] || b->pack_stale[PG_PRES]))
+            k_pack_bits<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k, b->pack_stale[PG_ACT], b->pack_stale[PG_PRES]);
+    } else {
+        const bool act = b->pack_stale[PG_ACT] || b->exists_stale;
+        if (act) CK(cudaMemsetAsync(k.counts + PK_MISSING, 0, sizeof(int), b->stream));
+        if (b->E)
+            k_pack_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k, st, act, b->pack_stale[PG_PRES], b->pack_stale[PG_REC]);
+        b->exists_stale = false;
+    }
     CK(cudaGetLastError());
     b->pack_static_stale = false;
     for (int q = 0; q < PG_N; q++) b->pack_stale[q] = false;

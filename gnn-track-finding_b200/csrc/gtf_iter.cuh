@@ -96,6 +96,19 @@ __global__ void k_pack_slots(DevBatch B, DevPack K, int do_static, int do_act, i
         (*tag_p(K, s)) = t;
     }
 }
+// activation / presence bytes -> bitmaps only (the existing-edge bitmap and everything else is current): the per-step
+// path of a host that uploads the flags every iteration
+__global__ void k_pack_bits(DevBatch B, DevPack K, int do_act, int do_pres)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = s < B.E;
+    const unsigned mact = __ballot_sync(0xffffffffu, do_act && in && B.active[s] == 1);
+    const unsigned mpres = __ballot_sync(0xffffffffu, do_pres && in && B.uts_present[s] != 0);
+    if ((threadIdx.x & 31) == 0 && in) {
+        if (do_act) K.act[s >> 5] = mact;
+        if (do_pres) K.pres[s >> 5] = mpres;
+    }
+}
 __global__ void k_pack_out(DevBatch B, DevPack K)
 {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
