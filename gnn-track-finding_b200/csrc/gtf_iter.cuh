@@ -478,7 +478,9 @@ __device__ __forceinline__ void lent_reweight(unsigned int *cnt, LEnt &a, LEnt &
     if (off) atomicAdd(&cnt[CNT_RWOFF], off);
 }
 
+#ifndef GTF_NODE2_THREADS
 #define GTF_NODE2_THREADS 256
+#endif
 #ifndef GTF_NODE2_MINB
 #define GTF_NODE2_MINB 4
 #endif
