@@ -1,0 +1,50 @@
+"""randomised parity sweep on the GPU: several event shapes / degrees / eta ranges, committed iterations in different
+groupings (1+1+.., all at once, with downloads, dry passes and per-stage calls in between) against the oracle.
+Usage (on a B200): python tools/stress_parity.py [n_cases] [seed]"""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+import numpy as np
+import gtf_b200
+from gtf_b200 import synth
+import golden_util as gu
+import oracle_lib as ol
+
+WHAT = ("alive", "active", "merged", "uts", "degree", "edge_w")
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 12345)
+bad_total = 0
+for case in range(n_cases):
+    n_ev = int(rng.integers(1, 4))
+    tracks = int(rng.choice([60, 150, 400]))
+    deg = float(rng.choice([3.0, 6.0, 10.0, 16.0, 28.0]))
+    eta = float(rng.choice([0.5, 1.0]))
+    hbs = [synth.event_to_host(synth.barrel_event(tracks, seed=int(rng.integers(1, 10**6)), eta_max=eta, target_degree=deg), e)
+           for e in range(n_ev)]
+    hb = synth.concat_host_batches(hbs)
+    hb.pop("truth"); hb.pop("orig_id")
+    ob = ol.OracleBatch(hb); ob.seed(); ob.cluster(0, 1.0, 2.0)
+    b = gtf_b200.EventBatch(hb); b.raise_ref_errors = False
+    b.seed(); b.cluster(0, 1.0, 2.0)
+    plan = rng.choice(["single", "burst", "mixed"])
+    n_it = 5
+    for _ in range(n_it):
+        ob.extrapolate_stage(2.0); ob.cluster(1, 1000.0, 100.0)
+    if plan == "single":
+        for _ in range(n_it): b.iterate(max_iter=1, stop_when_converged=False)
+    elif plan == "burst":
+        b.iterate(max_iter=n_it, stop_when_converged=False)
+    else:
+        b.iterate(max_iter=2, stop_when_converged=False)
+        b.iterate_dry(); b.download(["uts_w", "active"])
+        b.iterate(max_iter=1, stop_when_converged=False, want_stats=False)
+        b.iterate_dry()
+        b.iterate(max_iter=2, stop_when_converged=False)
+    bad = gu.compare_states(b.download(), ob.hb, WHAT, rtol=1e-7)
+    same_cca = bool(np.array_equal(b.CCA(), ob.cca()))
+    deg_max = int(np.diff(hb["in_off"]).max())
+    print("case %d: events %d tracks %d degree %.0f (max in-degree %d) eta %.1f plan %-6s -> %s%s" %
+          (case, n_ev, tracks, deg, deg_max, eta, plan, "ok" if not bad else bad, "" if same_cca else " CCA DIFFERS"), flush=True)
+    bad_total += bool(bad) + (not same_cca)
+    b.close()
+print("stress parity:", "ALL OK" if bad_total == 0 else "%d FAILURES" % bad_total)
