@@ -133,3 +133,42 @@ def test_wide_nodes_take_the_generic_path():
     ob, b, errs = run_both(hb)
     assert errs == ob.err == 0
     assert gu.compare_states(b.download(), ob.hb, ALL, rtol=1e-7) == []
+
+
+@pytest.mark.parametrize("seed", [11, 22, 33, 44])
+def test_randomised_iteration_plans_vs_oracle(seed):
+    """random event shape / in-degree (wide nodes reach k_big) and a random way of issuing five committed iterations
+    (singly, as one burst, or mixed with uncommitted passes, partial downloads and the asynchronous call): same state
+    as the oracle's five iterations (tools/stress_parity.py is the long form of this test)"""
+    rng = np.random.default_rng(seed)
+    n_ev, tracks = int(rng.integers(1, 4)), int(rng.choice([60, 150]))
+    deg, eta = float(rng.choice([3.0, 10.0, 16.0, 28.0])), float(rng.choice([0.5, 1.0]))
+    hbs = [synth.event_to_host(synth.barrel_event(tracks, seed=int(rng.integers(1, 10**6)), eta_max=eta, target_degree=deg), e)
+           for e in range(n_ev)]
+    hb = synth.concat_host_batches(hbs)
+    hb.pop("truth")
+    hb.pop("orig_id")
+    ob = ol.OracleBatch(hb)
+    ob.seed()
+    ob.cluster(0, 1.0, 2.0)
+    b = gtf_b200.EventBatch(hb, raise_ref_errors=False)
+    b.seed()
+    b.cluster(0, 1.0, 2.0)
+    for _ in range(5):
+        ob.extrapolate_stage(2.0)
+        ob.cluster(1, 1000.0, 100.0)
+    plan = rng.choice(["single", "burst", "mixed"])
+    if plan == "single":
+        for _ in range(5):
+            b.iterate(max_iter=1, stop_when_converged=False)
+    elif plan == "burst":
+        b.iterate(max_iter=5, stop_when_converged=False)
+    else:
+        b.iterate(max_iter=2, stop_when_converged=False)
+        b.iterate_dry()
+        b.download(["uts_w", "active"])
+        b.iterate(max_iter=1, stop_when_converged=False, want_stats=False)
+        b.iterate_dry()
+        b.iterate(max_iter=2, stop_when_converged=False)
+    assert gu.compare_states(b.download(), ob.hb, ("alive", "active", "merged", "uts", "degree", "edge_w"), rtol=1e-7) == []
+    assert np.array_equal(b.CCA(), ob.cca())
