@@ -672,7 +672,10 @@ template <int G> __device__ __forceinline__ void grp_shfl_info(const GtfInfo &in
     out.vc = __shfl_sync(FULL, in.vc, src, G); out.vt = __shfl_sync(FULL, in.vt, src, G);
 }
 
+#ifndef GTF_HV_WARPS
 #define GTF_HV_WARPS 4
+#endif
+static_assert(GTF_HV_WARPS * 32 >= GTF_MAXD * (GTF_MAXD - 1) / 2, "one thread per entry of the pair table");
 #ifndef GTF_HV_MINB
 #define GTF_HV_MINB 4
 #endif
