@@ -355,9 +355,16 @@ def main():
         # the 264 algorithmic bytes cover the WHOLE iteration (extrapolate + update + reweight x2 + cluster), so they are
         # charged against the sum of all its kernels (CUDA events recorded by the library on its stream around each)
         ach = B_ALG * n_active / (iter_ms / 1e3) / 1e9
-        traffic, tr_path = None, os.path.join(REPO, "profiles", "r01_pipeline_traffic.json")
+        traffic, kdram, tr_path = None, None, os.path.join(REPO, "profiles", "r01_pipeline_traffic.json")
         if os.path.exists(tr_path):   # dram__bytes_read+write of every pipeline kernel from the committed `ncu --set full` capture
-            traffic = json.load(open(tr_path))["dram_bytes_per_active_edge"] * n_active
+            tj = json.load(open(tr_path))
+            traffic = tj["dram_bytes_per_active_edge"] * n_active
+            # measured DRAM bytes of each kernel (scaled to this launch's active edges) / its live CUDA-event time / peak
+            scale = n_active / float(tj["active_edges"])
+            grp = {"k_send": ("k_begin", "k_send"), "k_exec": ("k_exec",), "k_node2": ("k_node2",),
+                   "k_hv": ("k_hv<8>", "k_hv<16>", "k_hv<4>", "k_hv<32>", "k_big")}
+            kdram = {k: sum(tj["kernels"].get(n, {}).get("dram_bytes", 0.0) for n in names) * scale / (kern_ms[k] / 1e3) / 1e9 / peak
+                     for k, names in grp.items() if kern_ms[k] > 0}
         out = {
             "metric": METRIC, "value": n_act_all / step_s, "unit": "edges/s", "n_gpus": world, "steps": a.steps,
             "warmup": warm, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -379,7 +386,7 @@ def main():
                                            "workload) x active edges of this launch",
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
                          "kernel": "whole iteration: k_send + k_exec + k_node2 + k_hv<4,8,16,32> (+ k_big)", "kernel_ms": iter_ms,
-                         "kernels_ms": kern_ms, "dominant": max(kern_ms, key=kern_ms.get),
+                         "kernels_ms": kern_ms, "dominant": max(kern_ms, key=kern_ms.get), "kernels_dram_frac": kdram,
                          "alg_bytes_per_launch": B_ALG * n_active},
             "iteration_stats": stats,
         }
