@@ -41,6 +41,7 @@ def empty_host_batch(N, E, S):
         "uts_side": np.zeros(E, np.int8),
         "has_merged": np.zeros(N, np.uint8), "degree": np.zeros(N, np.int32),
         "has_uts": np.zeros(N, np.uint8), "in_key": np.zeros(E, np.int64),
+        "emp_var": np.full(N, np.nan),
     }
     for f in F64_FIELDS_TSE:
         hb["tse_" + f] = np.full(E, np.nan)
@@ -138,6 +139,8 @@ def graphs_to_host(graphs, events=None):
             hb["orig_id"][i] = n
             hb["sub"][i] = gi
             hb["degree"][i] = attr.get("degree", 0)
+            if "xy_edge_gradient_mean_var" in attr:          # helper.py:446 (np.mean, np.var) of the xy edge gradients
+                hb["emp_var"][i] = attr["xy_edge_gradient_mean_var"][1]
             hb["in_off"][i] = s
             tse = attr.get("track_state_estimates", {})
             uts = attr.get("updated_track_states", None)

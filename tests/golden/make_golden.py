@@ -31,7 +31,7 @@ import gtf_b200  # noqa: E402
 from gtf_b200 import nxio, synth, fields  # noqa: E402
 
 TOPO = ("x", "y", "z", "r", "layer", "volume", "truth", "orig_id", "sub", "sub_off", "sub_event", "in_off",
-        "in_src", "slot_dst", "out_off", "out_slot", "rev_slot", "in_key")
+        "in_src", "slot_dst", "out_off", "out_slot", "rev_slot", "in_key", "emp_var")
 MUTABLE = [f for f, _, _ in fields.FIELDS if f not in TOPO and f not in ("label", "emp_var", "uts_chi2")]
 
 EVENTS = {
@@ -39,8 +39,10 @@ EVENTS = {
     "barrel40_eta1": dict(n_tracks=40, seed=2001, eta_max=1.0, target_degree=10.0),
     "barrel25_deg6": dict(n_tracks=25, seed=2002, eta_max=0.5, target_degree=6.0),
     "barrel100_cfg1": dict(n_tracks=100, seed=1000, eta_max=0.5, target_degree=10.0),
+    # BASELINE configs[1] size: 1000 tracks -> 10k hits / 100k directed edges (several minutes of reference time)
+    "barrel1000_cfg2": dict(n_tracks=1000, seed=2000, eta_max=0.5, target_degree=10.0),
 }
-COMPACT = {"barrel100_cfg1"}   # decisions + merged states only (keeps the fixture small)
+COMPACT = {"barrel100_cfg1", "barrel1000_cfg2"}   # decisions + merged states only (keeps the fixture small)
 
 
 def canonicalize(canon, snap, prev, graphs_alive_subs):

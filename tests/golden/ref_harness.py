@@ -141,6 +141,65 @@ def run_cluster(in_dir, out_dir, key, chi2_thr, kl_thr, P=PARAMS, it=1):
     return load_graphs(out_dir)
 
 
+class NodeKLThreshold(object):
+    """LUT-threshold mode (SURVEY.md 8c last row): the reference's own `cluster()` with `KL_threshold` swapped per node.
+    Passed as the `KL_threshold` argument; `smallest_dist < KL_threshold` (clustering.py:261) on a numpy scalar defers to
+    this object's reflected comparison (`__array_ufunc__ = None`), which reads the node being processed from the calling
+    frame (`node_attr`, clustering.py:195) and looks its threshold up: bin = floor(emp_var / 0.05) clipped to 0..27,
+    emp_var = node['xy_edge_gradient_mean_var'][1] (helper.py:446)."""
+    __array_ufunc__ = None
+
+    def __init__(self, lut):
+        self.lut = [float(v) for v in lut]
+        self.seen = 0
+
+    def threshold_of(self, attr):
+        import math
+        ev = attr["xy_edge_gradient_mean_var"][1]
+        b = 27 if ev != ev else int(math.floor(ev / 0.05))
+        return self.lut[max(0, min(27, b))]
+
+    def __gt__(self, other):
+        self.seen += 1
+        return bool(other < self.threshold_of(sys._getframe(1).f_locals["node_attr"]))
+
+
+def run_cluster_lut(in_dir, out_dir, key, chi2_thr, lut, P=PARAMS, it=1):
+    from clustering import clustering as cl
+    os.makedirs(out_dir, exist_ok=True)
+    thr = NodeKLThreshold(lut)
+    with quiet(os.path.dirname(out_dir.rstrip("/"))):
+        cl.cluster(in_dir, out_dir, key, chi2_thr, thr, None, it, False, P["sigma0rz"], P["sigma0rz2"], P["endcap"])
+    assert thr.seen > 0
+    return load_graphs(out_dir)
+
+
+def run_tag_propagation(graph, scratch=None):
+    """tag_propagation/tag_propagation.py executed UNMODIFIED on `graph` (saved as 0_subgraph.gpickle in a scratch cwd).
+    The script is module-level code; its tail indexes unique_colours[200] (:208-209, IndexError on small graphs) after the
+    labels are final, so the IndexError is caught and the result read from the script's namespace.
+    Returns ({node: final tag}, number of sweeps, size of the work list)."""
+    import networkx as nx
+    path = os.path.join(REF, "tag_propagation", "tag_propagation.py")
+    scratch = scratch or tempfile.mkdtemp(prefix="gtf_tag_")
+    nx.write_gpickle(graph, os.path.join(scratch, "0_subgraph.gpickle"))
+    saved = {n: getattr(nx, n) for n in ("draw_networkx_edges", "draw_networkx_nodes", "draw_networkx_labels")}
+    for n in saved:
+        setattr(nx, n, lambda *a, **k: None)      # they import matplotlib.collections internally
+    ns = {"__name__": "__tag_propagation__", "__file__": path}
+    try:
+        with quiet(scratch):
+            try:
+                exec(compile(open(path).read(), path, "exec"), ns)
+            except IndexError:
+                pass
+    finally:
+        for n, f in saved.items():
+            setattr(nx, n, f)
+    g = ns["current_endcap_graph"]
+    return {int(n): int(g.nodes[n]["tags"][-1]) for n in g.nodes()}, len(ns["frac_tags_flipped"]), ns["total_number_of_nodes_to_process"]
+
+
 def _call_main(mod, argv, cwd):
     old = sys.argv
     sys.argv = [mod.__name__] + [str(a) for a in argv]
