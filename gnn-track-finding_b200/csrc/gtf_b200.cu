@@ -102,6 +102,7 @@ static void sync_dev_view(gtf_batch *b)
     d.tile_begin = b->tile_begin;
 }
 
+static int batch_alloc(gtf_batch *b);
 extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf_batch **out)
 {
     if (!out || N < 0 || E < 0 || S < 0) return fail(GTF_E_ARG, "gtf_batch_create: bad sizes");
@@ -110,6 +111,20 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
     gtf_batch *b = new gtf_batch();
     memset((void *)b, 0, sizeof(*b));
     b->N = N; b->E = E; b->S = S; b->device = device;
+    int rc = batch_alloc(b);
+    if (rc) {                      // every pointer is zero-initialised: a partial batch is safe to destroy
+        const std::string msg = g_err;
+        gtf_batch_destroy(b);
+        cudaGetLastError();
+        g_err = msg;
+        return rc;
+    }
+    *out = b;
+    return 0;
+}
+static int batch_alloc(gtf_batch *b)
+{
+    const int N = b->N, E = b->E, S = b->S, device = b->device;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking));
     for (int f = 0; f < GTF_NFIELDS; f++) {
@@ -160,7 +175,6 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
     CK(cudaMallocHost((void **)&b->h_counters, sizeof(unsigned long long) * GTF_NCOUNTERS));
     sync_dev_view(b);
     CK(cudaStreamSynchronize(b->stream));
-    *out = b;
     return 0;
 }
 
@@ -168,7 +182,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
 {
     if (!b) return 0;
     cudaSetDevice(b->device);
-    cudaStreamSynchronize(b->stream);
+    if (b->stream) cudaStreamSynchronize(b->stream);
     for (int f = 0; f < GTF_NFIELDS; f++) cudaFree(b->f[f]);
     DevBatch &d = b->d;
     void *extra[] = {d.sub_nalive, d.node_ok, b->n_dead, d.slot_p11, d.slot_vms, d.node_p11tot, d.has_merged_nx, d.m_p11_nx,
@@ -184,13 +198,15 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
         for (int c = 0; c < 2; c++)
             for (int q = 0; q < 2; q++)
                 if (b->graphs[c][q].exec) cudaGraphExecDestroy(b->graphs[c][q].exec);
-        cudaStreamDestroy(b->stream3);
-        cudaEventDestroy(b->ev_fork2); cudaEventDestroy(b->ev_join2); cudaEventDestroy(b->ev_join3);
+        if (b->stream3) cudaStreamDestroy(b->stream3);
+        if (b->ev_fork2) cudaEventDestroy(b->ev_fork2);
+        if (b->ev_join2) cudaEventDestroy(b->ev_join2);
+        if (b->ev_join3) cudaEventDestroy(b->ev_join3);
         for (int q = 0; q < 6; q++) if (b->evk[q]) cudaEventDestroy(b->evk[q]);
     }
-    cudaFreeHost(b->h_counters);
-    cudaStreamDestroy(b->stream);
-    cudaStreamDestroy(b->stream2);
+    if (b->h_counters) cudaFreeHost(b->h_counters);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->stream2) cudaStreamDestroy(b->stream2);
     delete b;
     return 0;
 }
@@ -258,6 +274,7 @@ extern "C" int gtf_batch_upload(gtf_batch *b, int f, const void *host)
     if (grp >= 0) { b->soa_stale[grp] = false; b->pack_stale[grp] = true; }
     if (field_is_pack_static(f)) b->pack_static_stale = true;
     if (f == GTF_F_alive || f == GTF_F_sub_state || f == GTF_F_sub) b->derived_dirty = true;
+    if (f == GTF_F_has_merged || f == GTF_F_uts_next || f == GTF_F_has_uts || f == GTF_F_m_p11) b->force_pending = true;
     return 0;
 }
 extern "C" int gtf_batch_download_async(gtf_batch *b, int f, void *host)
@@ -286,7 +303,14 @@ extern "C" int gtf_batch_device_ptr(gtf_batch *b, int f, void **dptr)
         if (r) return r;
         b->pack_stale[grp] = true;
     }
+    if (f == GTF_F_alive) { // (same invalidation as gtf_batch_upload: the caller may write through the pointer)
+        CK(cudaSetDevice(b->device));
+        int r = soa_sync(b, 1u << PG_ACT); if (r) return r;
+        b->pack_stale[PG_ACT] = true; b->exists_stale = true;
+    }
     if (field_is_pack_static(f)) b->pack_static_stale = true;
+    if (f == GTF_F_alive || f == GTF_F_sub_state || f == GTF_F_sub) b->derived_dirty = true;
+    if (f == GTF_F_has_merged || f == GTF_F_uts_next || f == GTF_F_has_uts || f == GTF_F_m_p11) b->force_pending = true;
     *dptr = b->f[f];
     return 0;
 }
@@ -960,7 +984,26 @@ __global__ void k_extract_gate(DevBatch B, const int32_t *keys, const int32_t *v
     if (key == 0x7fffffff || (pos > 0 && keys[pos - 1] == key)) return;
     int n = 1;
     while (pos + n < B.N && keys[pos + n] == key) n++;
-    if (n < numhits || n > GTF_MAX_CAND) return; // :415; > 64 nodes cannot be one-hit-per-layer
+    if (n < numhits) return; // :415
+    if (n > GTF_MAX_CAND) {
+        // A component this large passes the one-hit-per-layer test (:427-429, with at most two close pairs :58-151) only
+        // on a detector with more than GTF_MAX_CAND - 2 distinct (volume, layer) ids.  Prove the rejection on its first
+        // nodes (duplicates inside a subset are duplicates of the whole); if that fails, say so instead of skipping.
+        const int K = min(n, 3 * GTF_MAX_CAND);
+        int n2 = 0, bad = 0;
+        for (int p = 0; p < K && !bad && n2 <= 2; p++) {
+            const int mp = vals[pos + p], lp = B.volume[mp] * 1000 + B.layer[mp];
+            int cnt = 0, first = 1;
+            for (int q = 0; q < K; q++) {
+                const int mq = vals[pos + q];
+                if (B.volume[mq] * 1000 + B.layer[mq] == lp) { cnt++; if (q < p) first = 0; }
+            }
+            if (!first) continue;
+            if (cnt == 2) n2++; else if (cnt != 1) bad = 1;
+        }
+        if (!bad && n2 <= 2) atomicOr(&B.counters[CNT_REFERR], (unsigned long long)GTF_STATUS_CAND_OVERFLOW);
+        return;
+    }
     int mem[GTF_MAX_CAND];
     int lay[GTF_MAX_CAND];
     double co[GTF_MAX_CAND][4];
@@ -1069,6 +1112,10 @@ extern "C" int gtf_extract(gtf_batch *b, const gtf_geom *g, double pval_cut, int
     k_extract_apply<<<nb, 256, 0, b->stream>>>(b->d, b->acc_now, b->accepted_total, b->d.counters + CNT_MERGED);
     TRY(recount_subs(b));
     if (b->S) k_sub_state<<<(b->S + 255) / 256, 256, 0, b->stream>>>(b->d, numhits);
+    // sub-graphs that just became fragments / empty leave the list (extract...py:463-467): their nodes are no longer in play
+    // for any later stage, so the per-node flags derived from sub_state are rebuilt
+    CK(cudaMemsetAsync(b->n_dead, 0, sizeof(unsigned long long), b->stream));
+    k_node_ok<<<nb, 256, 0, b->stream>>>(b->d, b->n_dead);
     CK(cudaGetLastError());
     if (accepted) CK(cudaMemcpyAsync(accepted, b->acc_now, (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
     if (pval_xy) CK(cudaMemcpyAsync(pval_xy, b->pv_xy, sizeof(double) * (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
@@ -1076,6 +1123,8 @@ extern "C" int gtf_extract(gtf_batch *b, const gtf_geom *g, double pval_cut, int
     gtf_stats st;
     TRY(counters_read(b, &st));
     if (n_accepted) *n_accepted = (int32_t)st.nodes_merged;
+    if (st.ref_errors & GTF_STATUS_CAND_OVERFLOW)
+        return fail(GTF_E_DEGREE, "gtf_extract: a component with more than GTF_MAX_CAND (64) nodes could be a one-hit-per-layer candidate");
     return 0;
 }
 

@@ -35,6 +35,9 @@ extern "C" {
 #define GTF_REF_ZERO_DIV 4  /* 1/len({})                 utilities/helper.py:90            ZeroDivisionError */
 #define GTF_REF_KEY 8       /* G[u][v] on a removed edge utilities/helper.py:131,138       KeyError          */
 #define GTF_REF_NO_TSE 16   /* missing seed entry        extrapolate/extrapolate_merged_states.py:384 KeyError */
+/* not a reference error: gtf_extract met a component of more than 64 nodes that could still be one-hit-per-layer (a
+ * detector with > 62 distinct (volume, layer) ids); the call fails with GTF_E_DEGREE instead of skipping it silently */
+#define GTF_STATUS_CAND_OVERFLOW 32
 
 typedef struct gtf_batch gtf_batch;
 
@@ -131,7 +134,10 @@ int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, int m
                 gtf_stats *stats, int *n_done);
 /* the same iteration, ONE pass, NOT committed: reads the current state, rewrites the dict entries in place (with the
  * same values on every call) and sends activation flags / merged states / accumulated p11 to shadow buffers, so the
- * next call does identical work (benchmark / profiling entry point; the stats are those of a committed pass) */
+ * next call does identical work (benchmark / profiling entry point; the stats are those of a committed pass).
+ * Side effects that DO persist: the dict entries written by the pass (presence bits, state / weight records, insertion
+ * stamps `uts_rank`, `uts_next`, `has_uts`) -- exactly what a committed pass would write, and what the next pass
+ * overwrites with the same values; the activation flags, merged states and accumulated merged_cov[1,1] do not change. */
 int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st);
 
 /* per-kernel timing of the iteration (CUDA events recorded on the batch stream): enable != 0 resets the
@@ -148,7 +154,10 @@ int gtf_batch_timing_kernels(gtf_batch *b, double *ms, int n_ms, int *count);
 int gtf_components(gtf_batch *b);
 /* extract/extract_track_candidates.py:402-467: components -> one-hit-per-layer / close-pair merge /
  * KF fit p-value gate -> accepted nodes removed, sub-graph states updated.
- * accepted (u8[N]), pval_xy / pval_zr (f64[N], at the component's root index) are optional host outputs. */
+ * accepted (u8[N]), pval_xy / pval_zr (f64[N], at the component's root index) are optional host outputs.
+ * A candidate holds at most 64 nodes (one hit per (volume, layer) id plus two close pairs: enough for any detector with
+ * <= 62 such ids, TrackML has 48); larger components are rejected after their layer duplicates are proven, else the call
+ * fails with GTF_E_DEGREE. */
 int gtf_extract(gtf_batch *b, const gtf_geom *g, double pval_cut, int numhits, double sep3d, double merge_dist,
                 int32_t *n_accepted, uint8_t *accepted, double *pval_xy, double *pval_zr);
 /* tag_propagation/tag_propagation.py:64-164: Jacobi max-label propagation from lower-radius successors until

@@ -135,4 +135,56 @@ def compare_states(got, want, what, rtol=RTOL, chained=None):
         e = rel_err(got["edge_w"][m], want["edge_w"][m])
         if not e <= rtol:
             bad.append("edge_w rel err %.3g" % e)
+    bad += compare_frozen(got, want, what, rtol)
     return bad
+
+
+def compare_frozen(got, want, what, rtol=RTOL):
+    """Nodes that are NOT in play (extracted, or in a sub-graph that left the list as a fragment / empty:
+    extract_track_candidates.py:460-467) are never touched again by the reference: their rows -- and the dict entries
+    stored at them -- must still hold what they held when they left play."""
+    bad = []
+    dead = ~inplay_nodes(want)
+    dead_slot = dead[want["slot_dst"]]
+    if not dead.any():
+        return bad
+    node_f, slot_f = [], []
+    if "merged" in what:
+        node_f += ["has_merged", "m_a", "m_b", "m_c", "m_p00", "m_p01", "m_p11", "m_p22", "m_prior"]
+    if "degree" in what:
+        node_f += ["degree"]
+    if "active" in what:
+        slot_f += ["active"]
+    if "edge_w" in what:
+        slot_f += ["edge_w"]
+    for key in ("tse", "uts"):
+        if key in what:
+            slot_f += [key + "_present"] + ["%s_%s" % (key, f) for f in ("a", "b", "c", "tau", "p00", "p01", "p11", "p22", "prior", "w")]
+    if "uts" in what:
+        slot_f += ["uts_lik", "uts_lrn", "uts_side"]
+        node_f += ["has_uts"]
+    for f in node_f:
+        m = dead & (want["has_merged"] > 0) & (got["has_merged"] > 0) if f.startswith("m_") else dead
+        if not _same(got[f][m], want[f][m], rtol):
+            bad.append("out-of-play nodes: %s changed" % f)
+    for f in slot_f:
+        m = dead_slot
+        if f.startswith(("tse_", "uts_")) and not f.endswith("_present"):
+            pk = f[:3] + "_present"
+            m = m & (want[pk] > 0) & (got[pk] > 0)
+        if f in ("active", "edge_w"):
+            m = m & edge_exists_at_exit(want)
+        if not _same(got[f][m], want[f][m], rtol):
+            bad.append("out-of-play slots: %s changed" % f)
+    return bad
+
+
+def edge_exists_at_exit(hb):
+    """slots whose source is a real node (not a ghost row)"""
+    return hb["in_src"] >= 0
+
+
+def _same(a, b, rtol):
+    if a.dtype.kind == "f":
+        return rel_err(a, b) <= rtol
+    return np.array_equal(a, b)

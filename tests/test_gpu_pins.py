@@ -63,3 +63,42 @@ def test_cfg2_size_schedule_vs_reference():
     unmodified reference: every decision and candidate set bit-exact"""
     from test_gpu_parity import test_full_schedule_vs_reference
     test_full_schedule_vs_reference("barrel1000_cfg2")
+
+
+def test_fragment_subgraphs_leave_play_vs_oracle():
+    """sub-graphs left with 1..3 nodes after an extraction become fragments (extract_track_candidates.py:463-467) and are
+    dropped from the list: no later stage may touch their nodes, count their edges or raise for them.  Small sparse events
+    (61 sub-graphs) leave fragments and empty sub-graphs after every extraction; states (incl. the frozen rows of the
+    out-of-play nodes) and the per-iteration counters are compared with the oracle."""
+    import oracle_lib as ol
+    from test_gpu_parity import synth_batch
+    hb = synth_batch(6, 20, 3100, target_degree=4.0)
+    ob = ol.OracleBatch(hb)
+    b = gtf_b200.EventBatch(hb, raise_ref_errors=False)
+    ob.seed()
+    b.seed()
+    ob.cluster(0, 1.0, 2.0)
+    b.cluster(0, 1.0, 2.0)
+    W = ("alive", "active", "merged", "uts", "degree", "edge_w")
+    seen_fragment = False
+    for rnd in range(3):
+        n_o, acc_o, _, _ = ob.extract()
+        n_g, acc_g, _, _ = b.extract()
+        assert n_o == n_g and np.array_equal(acc_o, acc_g), rnd
+        if rnd:
+            ob.remove_state_metadata()
+            b.remove_state_metadata()
+        seen_fragment |= bool((ob.hb["sub_state"] == 1).any())
+        for it in range(2):
+            s0 = (ob.stats.edges_sent, ob.stats.edges_gated, ob.stats.edges_reweight_off)
+            ob.extrapolate_stage(2.0)
+            ob.cluster(1, 1000.0, 100.0)
+            st = b.iterate(max_iter=1, stop_when_converged=False)[0]
+            assert gu.compare_states(state_of(b), ob.hb, W, rtol=1e-7) == [], (rnd, it)
+            assert st["edges_sent"] == ob.stats.edges_sent - s0[0], (rnd, it)
+            assert st["edges_gated"] == ob.stats.edges_gated - s0[1], (rnd, it)
+            assert st["edges_reweight_off"] == ob.stats.edges_reweight_off - s0[2], (rnd, it)
+            ex = gu.edge_exists(ob.hb) & gu.inplay_nodes(ob.hb)[ob.hb["slot_dst"]]
+            assert st["active_edges"] == int((ob.hb["active"][ex] == 1).sum()), (rnd, it)
+            assert st["ref_errors"] == ob.err, (rnd, it)
+    assert seen_fragment
