@@ -19,18 +19,61 @@ _REF_EXC = ((1, ValueError, "np.min of an empty array (clustering.py:116,120)"),
             (16, KeyError, "missing track_state_estimates entry (extrapolate_merged_states.py:384)"))
 
 
+class _DeviceArray(object):
+    """numpy-style view of device memory for `torch.as_tensor(..., device='cuda')` (__cuda_array_interface__)"""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+        self._owner = owner
+
+
 class EventBatch(object):
     def __init__(self, host_batch, device=0, geom=(0.3, 0.4, 0.6, 550.0), raise_ref_errors=True):
+        """Batch with an arbitrary (possibly mid-pipeline) state: every array of gtf_fields.h is uploaded.  For freshly
+        converted events use `EventBatch.with_capacity(...)` + `load_events(...)`: 44 B per hit + 8 B per edge cross PCIe
+        and everything else is initialised on the device."""
         hb = F.complete_host_batch(host_batch)
         self.N, self.E, self.S = len(hb["x"]), len(hb["in_src"]), len(hb["sub_off"]) - 1
+        self._create(device, geom, raise_ref_errors)
+        self.upload(hb)
+        L.check(self.lib.gtf_batch_finalize(self.h))
+
+    def _create(self, device, geom, raise_ref_errors):
         self.lib = L.lib()
         self.h = ctypes.c_void_p()
+        self.device = device
         L.check(self.lib.gtf_batch_create(self.N, self.E, self.S, device, ctypes.byref(self.h)))
         self.geom = L.Geom(*geom)
         self.raise_ref_errors = raise_ref_errors
         self.last_stats = None
-        self.upload(hb)
-        L.check(self.lib.gtf_batch_finalize(self.h))
+
+    @classmethod
+    def with_capacity(cls, n_nodes, n_slots, n_subgraphs, device=0, geom=(0.3, 0.4, 0.6, 550.0), raise_ref_errors=True):
+        """an empty batch that `load_events` fills (and refills: one allocation serves a stream of batches)"""
+        self = cls.__new__(cls)
+        self.N, self.E, self.S = int(n_nodes), int(n_slots), int(n_subgraphs)
+        self._create(device, geom, raise_ref_errors)
+        return self
+
+    def load_events(self, ev):
+        """event_conversion.py:40-112 on the device: `ev` holds the arrays of lib.EVENT_ARRAYS (hits + in-CSR in dict order +
+        out-CSR in successor order, e.g. synth.event_to_host / ingest.load_event_csv output; pinned torch tensors or numpy
+        arrays of the exact dtype are passed through without a copy).  Asynchronous on the batch stream."""
+        e = L.Events()
+        keep = []
+        for name, dt in L.EVENT_ARRAYS:
+            a = ev[name]
+            if hasattr(a, "data_ptr"):                   # torch tensor (pinned host memory)
+                ptr = a.data_ptr()
+            else:
+                a = np.ascontiguousarray(a, dtype=dt)
+                ptr = a.ctypes.data
+            keep.append(a)
+            setattr(e, name, ctypes.cast(ctypes.c_void_p(ptr), dict(L.Events._fields_)[name]))
+        e.n_nodes, e.n_slots, e.n_subgraphs = len(ev["x"]), len(ev["in_src"]), len(ev["sub_event"])
+        L.check(self.lib.gtf_batch_load_events(self.h, ctypes.byref(e)))
+        self.N, self.E, self.S = e.n_nodes, e.n_slots, e.n_subgraphs
+        self._loaded = keep                              # the copies are asynchronous: keep the sources alive
 
     # ---- data movement
     def upload(self, hb, names=None):
@@ -70,6 +113,9 @@ class EventBatch(object):
     def device_bytes(self):
         return int(self.lib.gtf_batch_device_bytes(self.h))
 
+    def iteration_launches(self):
+        return int(self.lib.gtf_batch_iteration_launches(self.h))
+
     def close(self):
         if self.h:
             self.lib.gtf_batch_destroy(self.h)
@@ -108,8 +154,12 @@ class EventBatch(object):
     def query_node_degree_in_edges(self):
         L.check(self.lib.gtf_query_node_degree(self.h))
 
-    def seed(self):
-        """event_conversion.py:87-96: seed, activate, priors, weights, degree (one call, three kernel launches)."""
+    def seed(self, want_stats=True):
+        """event_conversion.py:87-96: seed, activate, priors, weights, degree (one call, three kernel launches).
+        want_stats=False: no counter read-back (asynchronous)."""
+        if not want_stats:
+            L.check(self.lib.gtf_seed_all(self.h, ctypes.byref(self.geom), None))
+            return None
         st = L.Stats()
         L.check(self.lib.gtf_seed_all(self.h, ctypes.byref(self.geom), ctypes.byref(st)))
         return self._done(st)
@@ -223,6 +273,22 @@ class EventBatch(object):
         L.check(self.lib.gtf_tag_propagate(self.h, threshold, tags.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                                            max_sweeps, ctypes.byref(n)))
         return n.value, tags
+
+    def candidates_into(self, rows):
+        """the candidate table into a caller-owned (cap, 3) int32 host array (pinned: one D2H copy); returns the row count"""
+        n = ctypes.c_int64(0)
+        ptr = rows.data_ptr() if hasattr(rows, "data_ptr") else rows.ctypes.data
+        L.check(self.lib.gtf_candidates(self.h, ctypes.cast(ctypes.c_void_p(ptr), ctypes.POINTER(ctypes.c_int32)),
+                                        int(rows.shape[0]), ctypes.byref(n)))
+        return n.value
+
+    def candidates_device(self):
+        """the candidate table left on the device: an object exposing __cuda_array_interface__ ((n, 3) int32; valid until
+        the next candidates call) -- `torch.as_tensor(t, device="cuda")` hands it to NCCL (shard.gather_candidates)"""
+        n = ctypes.c_int64(0)
+        p = ctypes.c_void_p()
+        L.check(self.lib.gtf_candidates_device(self.h, ctypes.byref(p), ctypes.byref(n)))
+        return _DeviceArray(p.value or 0, (n.value, 3), "<i4", self) if n.value else None
 
     def candidates(self):
         """(event_id, candidate_id, node_index) rows of all nodes accepted so far, sorted."""

@@ -111,6 +111,7 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
     gtf_batch *b = new gtf_batch();
     memset((void *)b, 0, sizeof(*b));
     b->N = N; b->E = E; b->S = S; b->device = device;
+    b->capN = N; b->capE = E; b->capS = S;
     int rc = batch_alloc(b);
     if (rc) {                      // every pointer is zero-initialised: a partial batch is safe to destroy
         const std::string msg = g_err;
@@ -168,11 +169,16 @@ static int batch_alloc(gtf_batch *b)
         CK(cudaEventCreateWithFlags(&b->ev_fork2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b->ev_join3, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b->ev_tiles, cudaEventDisableTiming));
     }
     DA(b->accepted_total, N); DA(b->cand_root, N); DA(b->sub_has_inactive, S); DA(b->sub_first, S);
     DA(b->sort_keys, N); DA(b->sort_vals, N); DA(b->sort_keys2, N); DA(b->sort_vals2, N);
     DA(b->pv_xy, N); DA(b->pv_zr, N); DA(b->acc_now, N); DA(b->tags_a, N); DA(b->tags_b, N);
+    DA(b->tile_begin, (int64_t)N + 2); DA(b->stile_begin, (int64_t)N + 2);   // at most one tile per node (+ sentinel)
     CK(cudaMallocHost((void **)&b->h_counters, sizeof(unsigned long long) * GTF_NCOUNTERS));
+    CK(cudaMallocHost((void **)&b->h_tiles, sizeof(int32_t) * 2 * ((size_t)N + 2)));
+    CK(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CK(cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GTF_BIG_SMEM));
     sync_dev_view(b);
     CK(cudaStreamSynchronize(b->stream));
     return 0;
@@ -202,9 +208,11 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
         if (b->ev_fork2) cudaEventDestroy(b->ev_fork2);
         if (b->ev_join2) cudaEventDestroy(b->ev_join2);
         if (b->ev_join3) cudaEventDestroy(b->ev_join3);
+        if (b->ev_tiles) cudaEventDestroy(b->ev_tiles);
         for (int q = 0; q < 6; q++) if (b->evk[q]) cudaEventDestroy(b->evk[q]);
     }
     if (b->h_counters) cudaFreeHost(b->h_counters);
+    if (b->h_tiles) cudaFreeHost(b->h_tiles);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->stream2) cudaStreamDestroy(b->stream2);
     delete b;
@@ -327,6 +335,7 @@ extern "C" int gtf_batch_stream(gtf_batch *b, void **s)
     return 0;
 }
 extern "C" int64_t gtf_batch_device_bytes(const gtf_batch *b) { return b ? b->dev_bytes : 0; }
+extern "C" int64_t gtf_batch_iteration_launches(const gtf_batch *b) { return b ? b->launches : 0; }
 
 // alive nodes per sub-graph
 __global__ void k_sub_count(DevBatch B)
@@ -366,6 +375,53 @@ static int recount_subs(gtf_batch *b)
     return 0;
 }
 
+// node tiles of the per-stage kernel (whole nodes, <= GTF_TILE_NODES nodes, <= GTF_TILE_SLOTS in-slots) and source tiles of
+// k_send (whole sources, <= GTF_SEND_SRCS sources, <= GTF_SEND_EDGES out-edges) from the two CSR offset arrays on the host
+static int build_tiles(gtf_batch *b, const int32_t *in_off, const int32_t *out_off)
+{
+    const int N = b->N;
+    if (N && (in_off[0] != 0 || in_off[N] != b->E)) return fail(GTF_E_STATE, "in_off does not span the slots");
+    if (N && (out_off[0] != 0 || out_off[N] != b->E)) return fail(GTF_E_STATE, "out_off does not span the slots");
+    if (b->ev_tiles_used) CK(cudaEventSynchronize(b->ev_tiles));   // the previous upload out of the staging buffer is done
+    int32_t *t0 = b->h_tiles, *t1 = b->h_tiles + ((size_t)b->capN + 2);
+    int nt = 0, i = 0;
+    t0[0] = 0;
+    while (i < N) {
+        int start = i, slots = 0;
+        while (i < N && (i - start) < GTF_TILE_NODES) {
+            const int d = in_off[i + 1] - in_off[i];
+            if (d < 0) return fail(GTF_E_STATE, "in_off not monotone");
+            if (d > GTF_TILE_SLOTS) return fail(GTF_E_DEGREE, "node in-degree exceeds GTF_TILE_SLOTS");
+            if (slots + d > GTF_TILE_SLOTS) break;
+            slots += d;
+            i++;
+        }
+        t0[++nt] = i;
+    }
+    int ns = 0, u = 0;
+    t1[0] = 0;
+    while (u < N) {
+        int start = u, edges = 0;
+        while (u < N && (u - start) < GTF_SEND_SRCS) {
+            const int dg = out_off[u + 1] - out_off[u];
+            if (dg < 0) return fail(GTF_E_STATE, "out_off not monotone");
+            if (dg > GTF_SEND_EDGES) return fail(GTF_E_DEGREE, "node out-degree exceeds GTF_SEND_EDGES");
+            if (edges + dg > GTF_SEND_EDGES) break;
+            edges += dg;
+            u++;
+        }
+        t1[++ns] = u;
+    }
+    b->n_tiles = nt;
+    b->n_stiles = ns;
+    b->topo_gen++;
+    CK(cudaMemcpyAsync(b->tile_begin, t0, sizeof(int32_t) * ((size_t)nt + 1), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(b->stile_begin, t1, sizeof(int32_t) * ((size_t)ns + 1), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaEventRecord(b->ev_tiles, b->stream));
+    b->ev_tiles_used = true;
+    return 0;
+}
+
 extern "C" int gtf_batch_finalize(gtf_batch *b)
 {
     if (!b) return fail(GTF_E_ARG, "null batch");
@@ -374,60 +430,101 @@ extern "C" int gtf_batch_finalize(gtf_batch *b)
     CK(cudaMemcpyAsync(in_off.data(), b->f[GTF_F_in_off], sizeof(int32_t) * ((size_t)b->N + 1), cudaMemcpyDeviceToHost,
                        b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    if (b->N && (in_off[0] != 0 || in_off[b->N] != b->E)) return fail(GTF_E_STATE, "gtf_batch_finalize: in_off does not span the slots");
-    std::vector<int32_t> tiles;
-    tiles.push_back(0);
-    int i = 0;
-    while (i < b->N) {
-        int start = i, slots = 0;
-        while (i < b->N && (i - start) < GTF_TILE_NODES) {
-            int d = in_off[i + 1] - in_off[i];
-            if (d < 0) return fail(GTF_E_STATE, "gtf_batch_finalize: in_off not monotone");
-            if (d > GTF_TILE_SLOTS) return fail(GTF_E_DEGREE, "gtf_batch_finalize: node in-degree exceeds GTF_TILE_SLOTS");
-            if (slots + d > GTF_TILE_SLOTS) break;
-            slots += d;
-            i++;
-        }
-        tiles.push_back(i);
-    }
-    b->n_tiles = (int)tiles.size() - 1;
-    if (b->tile_begin) cudaFree(b->tile_begin);
-    CK(cudaMalloc((void **)&b->tile_begin, sizeof(int32_t) * tiles.size()));
-    CK(cudaMemcpyAsync(b->tile_begin, tiles.data(), sizeof(int32_t) * tiles.size(), cudaMemcpyHostToDevice, b->stream));
-    {
-        // k_send tiles over sources (whole sources, bounded out-edges)
-        std::vector<int32_t> out_off((size_t)b->N + 1);
-        CK(cudaMemcpyAsync(out_off.data(), b->f[GTF_F_out_off], sizeof(int32_t) * ((size_t)b->N + 1), cudaMemcpyDeviceToHost,
-                           b->stream));
-        CK(cudaStreamSynchronize(b->stream));
-        if (b->N && (out_off[0] != 0 || out_off[b->N] != b->E)) return fail(GTF_E_STATE, "gtf_batch_finalize: out_off does not span the slots");
-        std::vector<int32_t> st;
-        st.push_back(0);
-        int u = 0;
-        while (u < b->N) {
-            int start = u, edges = 0;
-            while (u < b->N && (u - start) < GTF_SEND_SRCS) {
-                int dg = out_off[u + 1] - out_off[u];
-                if (dg < 0) return fail(GTF_E_STATE, "gtf_batch_finalize: out_off not monotone");
-                if (dg > GTF_SEND_EDGES) return fail(GTF_E_DEGREE, "gtf_batch_finalize: node out-degree exceeds GTF_SEND_EDGES");
-                if (edges + dg > GTF_SEND_EDGES) break;
-                edges += dg;
-                u++;
-            }
-            st.push_back(u);
-        }
-        b->n_stiles = (int)st.size() - 1;
-        if (b->stile_begin) cudaFree(b->stile_begin);
-        CK(cudaMalloc((void **)&b->stile_begin, sizeof(int32_t) * st.size()));
-        CK(cudaMemcpyAsync(b->stile_begin, st.data(), sizeof(int32_t) * st.size(), cudaMemcpyHostToDevice, b->stream));
-        CK(cudaStreamSynchronize(b->stream));
-    }
+    std::vector<int32_t> out_off((size_t)b->N + 1);
+    CK(cudaMemcpyAsync(out_off.data(), b->f[GTF_F_out_off], sizeof(int32_t) * ((size_t)b->N + 1), cudaMemcpyDeviceToHost,
+                       b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    TRY_(build_tiles(b, in_off.data(), out_off.data()));
     sync_dev_view(b);
     int r = recount_subs(b);
     if (r) return r;
-    CK(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-    CK(cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GTF_BIG_SMEM));
     CK(cudaStreamSynchronize(b->stream));
+    b->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device-side ingest
+// event_conversion.py:40-112 hands the stages a freshly built graph: every node alive, every sub-graph in play, no state
+// dicts yet.  The host supplies only what defines the events (hits + the two CSR orders); everything else is derived or
+// initialised here, on the device.
+__global__ void k_derive_slot_dst(DevBatch B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.N) return;
+    for (int s = B.in_off[i]; s < B.in_off[i + 1]; s++) B.slot_dst[s] = i;
+}
+// rev_slot[s] for s = (u -> v): the slot of (v -> u), i.e. the in-slot of u whose source is v (-1: one-directional edge)
+__global__ void k_derive_rev_slot(DevBatch B)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B.E) return;
+    const int u = B.in_src[s], v = B.slot_dst[s];
+    int rs = -1;
+    if (u >= 0)
+        for (int t = B.in_off[u]; t < B.in_off[u + 1]; t++)
+            if (B.in_src[t] == v) { rs = t; break; }
+    B.rev_slot[s] = rs;
+}
+extern "C" int gtf_batch_load_events(gtf_batch *b, const gtf_events *ev)
+{
+    if (!b || !ev) return fail(GTF_E_ARG, "gtf_batch_load_events: null argument");
+    const int N = ev->n_nodes, E = ev->n_slots, S = ev->n_subgraphs;
+    if (N < 0 || E < 0 || S < 0 || N > b->capN || E > b->capE || S > b->capS)
+        return fail(GTF_E_ARG, "gtf_batch_load_events: the events exceed the capacity the batch was created with");
+    if (!ev->x || !ev->y || !ev->z || !ev->r || !ev->layer || !ev->volume || !ev->sub || !ev->sub_off || !ev->sub_event ||
+        !ev->in_off || !ev->in_src || !ev->out_off || !ev->out_slot)
+        return fail(GTF_E_ARG, "gtf_batch_load_events: missing array");
+    CK(cudaSetDevice(b->device));
+    b->N = N; b->E = E; b->S = S;
+    b->finalized = false;
+    cudaStream_t st = b->stream;
+    // 1. the events: one asynchronous copy per array (pinned host memory makes them overlap the host work below)
+    struct Up { int f; const void *p; } ups[] = {
+        {GTF_F_x, ev->x}, {GTF_F_y, ev->y}, {GTF_F_z, ev->z}, {GTF_F_r, ev->r}, {GTF_F_layer, ev->layer},
+        {GTF_F_volume, ev->volume}, {GTF_F_sub, ev->sub}, {GTF_F_sub_off, ev->sub_off}, {GTF_F_sub_event, ev->sub_event},
+        {GTF_F_in_off, ev->in_off}, {GTF_F_in_src, ev->in_src}, {GTF_F_out_off, ev->out_off}, {GTF_F_out_slot, ev->out_slot}};
+    bool given[GTF_NFIELDS] = {false};
+    for (const Up &u : ups) {
+        const size_t bytes = (size_t)gtf_field_bytes(b, u.f);
+        if (bytes) CK(cudaMemcpyAsync(b->f[u.f], u.p, bytes, cudaMemcpyHostToDevice, st));
+        given[u.f] = true;
+    }
+    // 2. every other array: the value a freshly converted event has (absent = NaN / -1 / 0; alive = 1)
+    given[GTF_F_slot_dst] = given[GTF_F_rev_slot] = true;   // derived below
+    for (int f = 0; f < GTF_NFIELDS; f++) {
+        if (given[f]) continue;
+        const size_t bytes = (size_t)gtf_field_bytes(b, f);
+        if (!bytes) continue;
+        int v = 0;
+        if (g_fields[f].elem == 8 || f == GTF_F_uts_rank || f == GTF_F_label) v = 0xff;   // all-ones: NaN as f64, -1 as i32
+        if (f == GTF_F_alive) v = 1;
+        CK(cudaMemsetAsync(b->f[f], v, bytes, st));
+    }
+    if (N) {
+        CK(cudaMemsetAsync(b->accepted_total, 0, (size_t)N, st));
+        CK(cudaMemsetAsync(b->d.has_merged_nx, 0, (size_t)N, st));
+    }
+    // 3. tiles from the host copies of the offsets (while the copies fly), derived topology on the device
+    TRY_(build_tiles(b, ev->in_off, ev->out_off));
+    sync_dev_view(b);
+    if (N) k_derive_slot_dst<<<(N + 255) / 256, 256, 0, st>>>(b->d);
+    if (E) k_derive_rev_slot<<<(E + 255) / 256, 256, 0, st>>>(b->d);
+    // 4. per-sub-graph counters / node flags (every node alive: no read-back needed)
+    CK(cudaMemsetAsync(b->d.sub_nalive, 0, sizeof(int32_t) * (S ? S : 1), st));
+    CK(cudaMemsetAsync(b->n_dead, 0, sizeof(unsigned long long), st));
+    if (N) {
+        k_sub_count<<<(N + 255) / 256, 256, 0, st>>>(b->d);
+        k_node_ok<<<(N + 255) / 256, 256, 0, st>>>(b->d, b->n_dead);
+    }
+    CK(cudaGetLastError());
+    b->d.all_alive = 1;
+    b->derived_dirty = false;
+    // 5. the packed copy is rebuilt from the fields at the next iteration
+    b->pack_static_stale = true;
+    b->exists_stale = true;
+    for (int q = 0; q < PG_N; q++) { b->pack_stale[q] = true; b->soa_stale[q] = false; }
+    b->force_pending = true;
+    b->have_last_prog = false;
     b->finalized = true;
     return 0;
 }
@@ -565,7 +662,7 @@ extern "C" int gtf_seed_all(gtf_batch *b, const gtf_geom *g, gtf_stats *st)
     TRY(counters_reset(b));
     Prog P = make_prog(GTF_KEY_TSE, WB_PRIOR | WB_W, {OP_PRIOR, OP_WEIGHTS, OP_DEGREE});
     TRY(launch_tile(b, P, geom_default()));
-    return counters_read(b, st);
+    return st ? counters_read(b, st) : 0;   // st == NULL: no read-back, the call stays asynchronous
 }
 
 extern "C" int gtf_initialize_edge_activation(gtf_batch *b)
@@ -608,7 +705,7 @@ extern "C" int gtf_cluster(gtf_batch *b, int key, double chi2_thr, double kl_thr
     P.cl_kl = kl_thr;
     if (kl_lut) { P.use_lut = 1; memcpy(P.lut, kl_lut, sizeof(double) * 28); }
     TRY(launch_tile(b, P, geom_of(g)));
-    return counters_read(b, st);
+    return st ? counters_read(b, st) : 0;   // st == NULL: no read-back, the call stays asynchronous
 }
 extern "C" int gtf_message_passing(gtf_batch *b, double chi2_cut, const gtf_geom *g, gtf_stats *st)
 {
@@ -753,6 +850,7 @@ static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int r
         CK(cudaStreamWaitEvent(s0, b->ev_join3, 0));
     }
     if (timed) CK(cudaEventRecord(b->evk[4], s0));
+    b->launches_per_iter = 1 + (b->n_stiles ? 1 : 0) + (b->E ? 1 : 0) + (b->N ? 6 : 0); // k_begin, k_send, k_exec, k_node2 + k_hv x4 + k_big
     return 0;
 }
 // one iteration on the packed layout.  commit: the next state becomes the current one (merged states are written in
@@ -792,7 +890,8 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
     } else {
         IterGraph &G = b->graphs[commit ? 1 : 0][b->parity];
         const bool same = G.exec && memcmp(&G.P, &P, sizeof(Prog)) == 0 && memcmp(&G.g, &gg, sizeof(GtfGeom)) == 0 &&
-                          G.record_chi2 == p->record_chi2 && G.n_stiles == b->n_stiles && G.stile == (const void *)b->stile_begin;
+                          G.record_chi2 == p->record_chi2 && G.n_stiles == b->n_stiles && G.stile == (const void *)b->stile_begin &&
+                          G.topo_gen == b->topo_gen;
         if (!same) {
             if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
             cudaGraph_t graph = nullptr;
@@ -805,9 +904,11 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return fail(GTF_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
             G.P = P; G.g = gg; G.record_chi2 = p->record_chi2; G.n_stiles = b->n_stiles; G.stile = (const void *)b->stile_begin;
+            G.topo_gen = b->topo_gen;
         }
         CK(cudaGraphLaunch(G.exec, s0));
     }
+    b->launches += b->launches_per_iter;
     for (int q = 0; q < 3; q++) b->soa_stale[q] = true; // (a dry pass also rewrites dict entries in place)
     if (commit) b->soa_stale[PG_NODE] = true;
     if (commit) {
@@ -1201,17 +1302,15 @@ __global__ void k_cand_rows(DevBatch B, const int32_t *keys, const int32_t *vals
     rows[3 * k + 1] = keys[k];
     rows[3 * k + 2] = i;
 }
-extern "C" int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_rows, int64_t *n_rows)
+// count, sort and materialise the rows on the device; *n_rows rows at b->cand_rows (fill == false: count only)
+static int candidates_build(gtf_batch *b, bool fill, int64_t cap_rows, int64_t *n_rows)
 {
-    if (!b || !n_rows) return fail(GTF_E_ARG, "gtf_candidates: null argument");
-    CK(cudaSetDevice(b->device));
     *n_rows = 0;
     if (b->N == 0) return 0;
     TRY(counters_reset(b));
     k_cand_keys<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, b->accepted_total, b->cand_root, b->sort_keys, b->sort_vals,
                                                            b->d.counters);
     CK(cudaGetLastError());
-    const bool fill = cap_rows > 0 && table_host;
     if (fill) {
         size_t need = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, need, b->sort_keys, b->sort_keys2, b->sort_vals, b->sort_vals2, b->N, 0, 32,
@@ -1228,13 +1327,32 @@ extern "C" int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_row
     *n_rows = (int64_t)b->h_counters[0];
     if (fill && *n_rows > 0) {
         const int64_t nw = *n_rows < cap_rows ? *n_rows : cap_rows;
-        // rows are staged in the (now free) unsorted key / value buffers plus the tag scratch: 3 N int32 are needed
-        if (!b->cand_rows) CK(cudaMalloc((void **)&b->cand_rows, sizeof(int32_t) * 3 * (size_t)b->N));
+        if (!b->cand_rows) CK(cudaMalloc((void **)&b->cand_rows, sizeof(int32_t) * 3 * (size_t)(b->capN ? b->capN : 1)));
         k_cand_rows<<<(unsigned)((nw + 255) / 256), 256, 0, b->stream>>>(b->d, b->sort_keys2, b->sort_vals2, b->cand_rows, (long long)nw);
         CK(cudaGetLastError());
+    }
+    return 0;
+}
+extern "C" int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_rows, int64_t *n_rows)
+{
+    if (!b || !n_rows) return fail(GTF_E_ARG, "gtf_candidates: null argument");
+    CK(cudaSetDevice(b->device));
+    const bool fill = cap_rows > 0 && table_host;
+    TRY(candidates_build(b, fill, cap_rows, n_rows));
+    if (fill && *n_rows > 0) {
+        const int64_t nw = *n_rows < cap_rows ? *n_rows : cap_rows;
         CK(cudaMemcpyAsync(table_host, b->cand_rows, sizeof(int32_t) * 3 * (size_t)nw, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
     }
+    return 0;
+}
+extern "C" int gtf_candidates_device(gtf_batch *b, int32_t **rows_dev, int64_t *n_rows)
+{
+    if (!b || !n_rows || !rows_dev) return fail(GTF_E_ARG, "gtf_candidates_device: null argument");
+    CK(cudaSetDevice(b->device));
+    TRY(candidates_build(b, true, (int64_t)b->N, n_rows));
+    CK(cudaStreamSynchronize(b->stream));
+    *rows_dev = b->cand_rows;
     return 0;
 }
 

@@ -132,10 +132,16 @@ struct IterGraph {
     GtfGeom g;
     int record_chi2, n_stiles;
     const void *stile;
+    int topo_gen;              // batch topology generation the kernel arguments (N, E, grids) were captured for
 };
 
 struct gtf_batch {
     int N, E, S, device;
+    int capN, capE, capS;      // allocated capacity (gtf_batch_create); gtf_batch_load_events may load smaller batches
+    int topo_gen;              // incremented whenever N / E / S or a tile table changes
+    int32_t *h_tiles;          // pinned staging for the two tile tables
+    cudaEvent_t ev_tiles;      // the upload out of h_tiles
+    bool ev_tiles_used;
     cudaStream_t stream, stream2;
     void *f[GTF_NFIELDS];
     DevBatch d;
@@ -180,4 +186,6 @@ struct gtf_batch {
     // optional per-kernel timing of the iteration (CUDA events on the batch stream)
     bool timing;
     int t_count;
+    long long launches;        // kernels launched by packed iterations so far (graph replays count their kernel nodes)
+    int launches_per_iter;
 };

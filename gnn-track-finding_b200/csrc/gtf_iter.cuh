@@ -586,8 +586,10 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
                 }
                 B.degree[i] = deg;
             }
-            n_act = deg;
-            n_chg = chg;
+            if (nf & NF_OK) {          // (edges of fragment sub-graphs left the list with their graph: not counted)
+                n_act = deg;
+                n_chg = chg;
+            }
         }
     }
     n_act = __reduce_add_sync(0xffffffffu, n_act);

@@ -33,6 +33,18 @@ class IterParams(ctypes.Structure):
                 ("record_chi2", ctypes.c_int32)]
 
 
+class Events(ctypes.Structure):
+    """gtf_events (include/gtf.h): host pointers to the arrays that define a batch of freshly converted events"""
+    _I, _D = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)
+    _fields_ = [("n_nodes", ctypes.c_int32), ("n_slots", ctypes.c_int32), ("n_subgraphs", ctypes.c_int32),
+                ("x", _D), ("y", _D), ("z", _D), ("r", _D), ("layer", _I), ("volume", _I), ("sub", _I), ("sub_off", _I),
+                ("sub_event", _I), ("in_off", _I), ("in_src", _I), ("out_off", _I), ("out_slot", _I)]
+
+
+EVENT_ARRAYS = (("x", "f8"), ("y", "f8"), ("z", "f8"), ("r", "f8"), ("layer", "i4"), ("volume", "i4"), ("sub", "i4"),
+                ("sub_off", "i4"), ("sub_event", "i4"), ("in_off", "i4"), ("in_src", "i4"), ("out_off", "i4"), ("out_slot", "i4"))
+
+
 def needs_build():
     if not os.path.exists(SO):
         return True
@@ -79,9 +91,12 @@ def lib():
         "gtf_batch_download_async": (ctypes.c_int, [vp, ctypes.c_int, vp]),
         "gtf_batch_device_ptr": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp)]),
         "gtf_batch_finalize": (ctypes.c_int, [vp]),
+        "gtf_batch_load_events": (ctypes.c_int, [vp, ctypes.POINTER(Events)]),
+        "gtf_candidates_device": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]),
         "gtf_batch_sync": (ctypes.c_int, [vp]),
         "gtf_batch_stream": (ctypes.c_int, [vp, ctypes.POINTER(vp)]),
         "gtf_batch_device_bytes": (i64, [vp]),
+        "gtf_batch_iteration_launches": (i64, [vp]),
         "gtf_seed": (ctypes.c_int, [vp, pg]),
         "gtf_seed_all": (ctypes.c_int, [vp, pg, ps]),
         "gtf_initialize_edge_activation": (ctypes.c_int, [vp]),

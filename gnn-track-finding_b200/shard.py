@@ -18,29 +18,41 @@ def partition_events(edge_counts, world_size):
     return [sorted(x) for x in out]
 
 
-def gather_candidates(rows, device=None, dst=0):
+def gather_candidates(rows, device=None, dst=0, sort=True, info=None):
     """Variable-length gather of (k, 3) int32 candidate tables to rank `dst` (all_gather of the row counts,
-    then all_gather of the padded tables: ~12 B per hit, negligible on NVLink).  Returns the concatenated,
-    lexicographically sorted table on `dst`, None elsewhere.  Without an initialised process group it is
-    the identity."""
+    then all_gather of the padded tables: ~12 B per hit, negligible on NVLink).  `rows`: numpy array, or a torch tensor
+    already on the device (EventBatch.candidates_device(): no host round trip before NCCL).  Returns the concatenated
+    table on `dst` (lexicographically sorted unless sort=False), None elsewhere.  `info` (dict) receives the per-rank row
+    counts and the bytes every rank contributed.  Without an initialised process group it is the identity."""
     import torch
     import torch.distributed as dist
-    rows = np.ascontiguousarray(rows, np.int32).reshape(-1, 3)
+    is_t = hasattr(rows, "is_cuda")
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return rows[np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))]
+        out = rows.detach().cpu().numpy() if is_t else np.ascontiguousarray(rows, np.int32)
+        out = out.reshape(-1, 3)
+        if info is not None:
+            info.update(counts=[out.shape[0]], bytes=0)
+        return out[np.lexsort((out[:, 2], out[:, 1], out[:, 0]))] if sort else out
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
-    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+    if is_t:
+        t = rows.reshape(-1, 3).to(dev)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(rows, np.int32).reshape(-1, 3)).to(dev)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)
     counts = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(counts, n)
     counts = [int(c.item()) for c in counts]
     cap = max(max(counts), 1)
     pad = torch.zeros((cap, 3), dtype=torch.int32, device=dev)
-    if rows.shape[0]:
-        pad[:rows.shape[0]] = torch.from_numpy(rows).to(dev)
-    bufs = [torch.zeros_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad)
+    if t.shape[0]:
+        pad[:t.shape[0]] = t
+    bufs = torch.empty((world, cap, 3), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(bufs, pad) if dist.get_backend() == "nccl" else dist.all_gather(list(bufs.unbind(0)), pad)
+    if info is not None:
+        info.update(counts=counts, bytes=int(cap) * 12)
     if rank != dst:
         return None
-    allrows = np.concatenate([b[:c].cpu().numpy() for b, c in zip(bufs, counts)], axis=0)
-    return allrows[np.lexsort((allrows[:, 2], allrows[:, 1], allrows[:, 0]))]
+    host = bufs.cpu().numpy()
+    allrows = np.concatenate([host[r, :c] for r, c in enumerate(counts)], axis=0)
+    return allrows[np.lexsort((allrows[:, 2], allrows[:, 1], allrows[:, 0]))] if sort else allrows

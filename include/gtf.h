@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GTF_ABI_VERSION 2
+#define GTF_ABI_VERSION 3
 
 #define GTF_E_CUDA (-1)    /* CUDA runtime error / no device */
 #define GTF_E_ARG (-2)     /* bad argument */
@@ -89,9 +89,29 @@ int gtf_batch_device_ptr(gtf_batch *b, int field_id, void **dptr);
 /* after the topology arrays (in_off, in_src, slot_dst, out_off, out_slot, rev_slot, sub, sub_off,
  * sub_state, alive) are uploaded: builds the node tiles and per-sub-graph counters */
 int gtf_batch_finalize(gtf_batch *b);
+/* ---- device-side ingest: a whole batch of freshly converted events in ONE call --------------------------------------
+ * What trackml_mod/event_conversion.py:40-112 + utilities/helper.py:465-520 (construct_graph) hand to the stages: hits and
+ * the directed graph, nothing else.  The host supplies only the arrays that DEFINE the events (44 B per hit + 8 B per
+ * directed edge; pinned memory makes the copies asynchronous); slot_dst / rev_slot are derived on the device, every
+ * node is alive, every sub-graph in play, all state arrays start absent (NaN / -1 / 0), the tiles are built, and the batch
+ * is finalized.  n_nodes / n_slots / n_subgraphs may be smaller than the capacity given to gtf_batch_create, so one batch
+ * object (and its device memory) serves a stream of batches.  Follow with gtf_seed_all, gtf_cluster, gtf_iterate, ... */
+typedef struct {
+    int32_t n_nodes, n_slots, n_subgraphs;
+    const double *x, *y, *z, *r;       /* [N] hit coordinates                         GNN_Measurement.py:1-9            */
+    const int32_t *layer, *volume;     /* [N] in_volume_layer_id, volume_id           utilities/helper.py:497-508       */
+    const int32_t *sub;                /* [N] sub-graph of the node                   event_conversion.py:76-84         */
+    const int32_t *sub_off;            /* [S+1] node range of each sub-graph                                             */
+    const int32_t *sub_event;          /* [S] event id of each sub-graph (candidate table)                              */
+    const int32_t *in_off, *in_src;    /* [N+1], [E] in-CSR by destination, dict (insertion) order  helper.py:280,375    */
+    const int32_t *out_off, *out_slot; /* [N+1], [E] out-CSR by source, successor order   extrapolate...py:430          */
+} gtf_events;
+int gtf_batch_load_events(gtf_batch *b, const gtf_events *ev);
 int gtf_batch_sync(gtf_batch *b);
 int gtf_batch_stream(gtf_batch *b, void **cuda_stream);
 int64_t gtf_batch_device_bytes(const gtf_batch *b);
+/* kernels launched by gtf_iterate / gtf_iterate_dry on this batch so far (a CUDA-graph replay counts its kernel nodes) */
+int64_t gtf_batch_iteration_launches(const gtf_batch *b);
 
 /* ---- per-stage entry points (same effect as the reference function named) ---------------------- */
 /* utilities/helper.py:238-452 compute_track_state_estimates (slot order supplies the neighbour order) */
@@ -167,6 +187,9 @@ int gtf_tag_propagate(gtf_batch *b, double threshold, int32_t *tags, int max_swe
  * node) on the device (radix sort by candidate id), table copied to host.  Returns the row count in *n_rows (may exceed
  * cap; only cap rows written); table_host == NULL: count only. */
 int gtf_candidates(gtf_batch *b, int32_t *table_host, int64_t cap_rows, int64_t *n_rows);
+/* the same table left on the device (valid until the next gtf_candidates* call on this batch): *rows_dev points at
+ * n_rows x 3 int32 -- what a multi-GPU driver hands to NCCL for the final gather */
+int gtf_candidates_device(gtf_batch *b, int32_t **rows_dev, int64_t *n_rows);
 
 /* ---- diagnostic: pairwise KL between the components of every group (general 3x3 covariances) ------------------- */
 /* The inner function of the reference's KL-threshold LUT training-data generator (learn_KL_linear_model /

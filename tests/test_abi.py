@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_field_table_matches_header():
     lib = L.lib()
-    assert lib.gtf_abi_version() == 2
+    assert lib.gtf_abi_version() == 3
     assert lib.gtf_field_count() == len(F.FIELDS)
     for i, (name, _, _) in enumerate(F.FIELDS):
         assert lib.gtf_field_name(i).decode() == name

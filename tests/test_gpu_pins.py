@@ -102,3 +102,41 @@ def test_fragment_subgraphs_leave_play_vs_oracle():
             assert st["active_edges"] == int((ob.hb["active"][ex] == 1).sum()), (rnd, it)
             assert st["ref_errors"] == ob.err, (rnd, it)
     assert seen_fragment
+
+
+def test_load_events_equals_full_upload_and_batch_reuse():
+    """gtf_batch_load_events (hits + the two CSR orders only; slot_dst / rev_slot / initial state on the device) gives the
+    same batch as uploading every array of gtf_fields.h, bit for bit, through the whole schedule; the same batch object then
+    takes a second, smaller set of events (capacity reuse) without leaking state from the first"""
+    from test_gpu_parity import synth_batch
+    from gtf_b200 import driver
+
+    def run(b):
+        b.seed()
+        b.cluster("track_state_estimates", 1.0, 2.0)
+        st = b.iterate(max_iter=4, stop_when_converged=False)
+        n = b.extract()[0]
+        return st, n, b.download(), b.candidates()
+
+    def same(x, y):
+        assert x[0] == y[0] and x[1] == y[1]
+        for k in x[2]:
+            assert np.array_equal(x[2][k], y[2][k], equal_nan=True), k
+        assert np.array_equal(x[3], y[3])
+
+    hb1 = synth_batch(3, 150, 5100, eta_max=1.0)
+    hb2 = synth_batch(2, 90, 5200)
+    ref1, ref2 = run(gtf_b200.EventBatch(hb1)), run(gtf_b200.EventBatch(hb2))
+    b = gtf_b200.EventBatch.with_capacity(len(hb1["x"]) + 7, len(hb1["in_src"]) + 11, len(hb1["sub_event"]) + 3)
+    b.load_events(hb1)
+    got = b.download(["slot_dst", "rev_slot", "alive", "sub_state", "uts_rank", "label"])
+    assert np.array_equal(got["slot_dst"], hb1["slot_dst"]) and np.array_equal(got["rev_slot"], hb1["rev_slot"])
+    assert got["alive"].all() and not got["sub_state"].any() and (got["uts_rank"] == -1).all() and (got["label"] == -1).all()
+    same(run(b), ref1)
+    t = b.candidates_device()
+    import torch
+    assert np.array_equal(torch.as_tensor(t, device="cuda").cpu().numpy(), ref1[3])
+    b.load_events(hb2)
+    same(run(b), ref2)
+    b.load_events(hb1)
+    same(run(b), ref1)
