@@ -96,6 +96,11 @@ def concat_events(pool, ids):
     return synth.concat_host_batches(hbs)
 
 
+def build_batch(n_events, n_tracks, seed0, distinct):
+    """`n_events` events tiled from `distinct` generated ones (seeds seed0, seed0 + 1, ...), event ids 0 .. n_events - 1"""
+    return concat_events(event_pool(n_tracks, min(distinct, n_events), seed0), range(n_events))
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \

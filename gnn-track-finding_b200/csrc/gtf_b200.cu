@@ -79,7 +79,7 @@ extern "C" int64_t gtf_field_bytes(const gtf_batch *b, int f)
 // ------------------------------------------------------------------------------------------------ batch
 template <typename T> static int dalloc(gtf_batch *b, T **p, int64_t count)
 {
-    size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+    size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T) + 64;   // (+64: bulk copies read whole 16 B blocks around a range)
     CK(cudaMalloc((void **)p, bytes));
     CK(cudaMemsetAsync(*p, 0, bytes, b->stream));
     b->dev_bytes += bytes;
@@ -129,8 +129,7 @@ static int batch_alloc(gtf_batch *b)
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking));
     for (int f = 0; f < GTF_NFIELDS; f++) {
-        size_t bytes = (size_t)field_count(b, f) * g_fields[f].elem;
-        if (!bytes) bytes = 8;
+        size_t bytes = (size_t)field_count(b, f) * g_fields[f].elem + 64;   // (+64: see dalloc)
         CK(cudaMalloc(&b->f[f], bytes));
         CK(cudaMemsetAsync(b->f[f], 0, bytes, b->stream));
         b->dev_bytes += bytes;
@@ -151,7 +150,7 @@ static int batch_alloc(gtf_batch *b)
         // packed iteration layout (gtf_iter.cuh)
         DevPack &k = b->k;
         const int64_t words = ((int64_t)E + 31) / 32 + 2;
-        DA(k.out_dst, E); DA(k.orec, E); DA(k.aux, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N);
+        DA(k.out_dst, E); DA(k.orec, E); DA(k.aux, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N); DA(k.srec, (int64_t)N + 1);
         DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.pres0, words);
         DA(k.state, (int64_t)E * 8); DA(k.meta, E);
         DA(k.msg_desc, E); DA(k.msg_w, E);
@@ -174,9 +173,10 @@ static int batch_alloc(gtf_batch *b)
     DA(b->accepted_total, N); DA(b->cand_root, N); DA(b->sub_has_inactive, S); DA(b->sub_first, S);
     DA(b->sort_keys, N); DA(b->sort_vals, N); DA(b->sort_keys2, N); DA(b->sort_vals2, N);
     DA(b->pv_xy, N); DA(b->pv_zr, N); DA(b->acc_now, N); DA(b->tags_a, N); DA(b->tags_b, N);
-    DA(b->tile_begin, (int64_t)N + 2); DA(b->stile_begin, (int64_t)N + 2);   // at most one tile per node (+ sentinel)
+    DA(b->tile_begin, (int64_t)N + 2); DA(b->stile_begin, 4 * ((int64_t)N + 2)); // at most one tile per node (+ sentinel); int4 per k_send tile
     CK(cudaMallocHost((void **)&b->h_counters, sizeof(unsigned long long) * GTF_NCOUNTERS));
-    CK(cudaMallocHost((void **)&b->h_tiles, sizeof(int32_t) * 2 * ((size_t)N + 2)));
+    CK(cudaMallocHost((void **)&b->h_tiles, sizeof(int32_t) * 5 * ((size_t)N + 2)));
+    CK(cudaFuncSetAttribute(k_send, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SendSmem)));
     CK(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     CK(cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GTF_BIG_SMEM));
     sync_dev_view(b);
@@ -198,7 +198,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.mrec, k.mrec_nx, k.out_dst, k.orec, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
+        void *pk[] = {k.srec, k.mrec, k.mrec_nx, k.out_dst, k.orec, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
                       k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         for (int c = 0; c < 2; c++)
@@ -399,8 +399,7 @@ static int build_tiles(gtf_batch *b, const int32_t *in_off, const int32_t *out_o
         t0[++nt] = i;
     }
     int ns = 0, u = 0;
-    t1[0] = 0;
-    while (u < N) {
+    while (u < N) {     // descriptor per tile: (first source, sources, first out-edge, out-edges)
         int start = u, edges = 0;
         while (u < N && (u - start) < GTF_SEND_SRCS) {
             const int dg = out_off[u + 1] - out_off[u];
@@ -410,13 +409,14 @@ static int build_tiles(gtf_batch *b, const int32_t *in_off, const int32_t *out_o
             edges += dg;
             u++;
         }
-        t1[++ns] = u;
+        t1[4 * ns + 0] = start; t1[4 * ns + 1] = u - start; t1[4 * ns + 2] = out_off[start]; t1[4 * ns + 3] = edges;
+        ns++;
     }
     b->n_tiles = nt;
     b->n_stiles = ns;
     b->topo_gen++;
     CK(cudaMemcpyAsync(b->tile_begin, t0, sizeof(int32_t) * ((size_t)nt + 1), cudaMemcpyHostToDevice, b->stream));
-    CK(cudaMemcpyAsync(b->stile_begin, t1, sizeof(int32_t) * ((size_t)ns + 1), cudaMemcpyHostToDevice, b->stream));
+    if (ns) CK(cudaMemcpyAsync(b->stile_begin, t1, sizeof(int32_t) * 4 * (size_t)ns, cudaMemcpyHostToDevice, b->stream));
     CK(cudaEventRecord(b->ev_tiles, b->stream));
     b->ev_tiles_used = true;
     return 0;
@@ -787,7 +787,7 @@ static int ensure_packed(gtf_batch *b)
         if (b->E) k_pack_out<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k);
     }
     if (b->N && (st || b->pack_stale[PG_NODE]))
-        k_pack_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d, k, st, b->pack_stale[PG_NODE]);
+        k_pack_nodes<<<(b->N + 256) / 256, 256, 0, b->stream>>>(b->d, k, st, b->pack_stale[PG_NODE]);   // N + 1 threads: srec sentinel
     if (!st && !b->exists_stale && !b->pack_stale[PG_REC]) {
         // only the flag bytes changed (a host that uploads them every iteration): bytes -> bits, nothing else
         if (b->E && (b->pack_stale[PG_ACT] || b->pack_stale[PG_PRES]))
@@ -822,7 +822,9 @@ static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int r
         const int nthr = (int)std::max<size_t>(words, (size_t)b->N);
         k_begin<<<(nthr + 255) / 256, 256, 0, s0>>>(d, k, (int)words);
     }
-    if (b->n_stiles) k_send<<<b->n_stiles, GTF_SEND_THREADS, 0, s0>>>(d, k, b->stile_begin, gg);
+    if (b->n_stiles)
+        k_send<<<std::min(b->n_stiles, b->n_sm * GTF_SEND_MINB), GTF_SEND_THREADS, sizeof(SendSmem), s0>>>(
+            d, k, reinterpret_cast<const int4 *>(b->stile_begin), b->n_stiles, gg);
     if (timed) CK(cudaEventRecord(b->evk[1], s0));
     if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * GTF_EXEC_WAVES, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg, record_chi2);
     if (timed) CK(cudaEventRecord(b->evk[2], s0));

@@ -57,6 +57,10 @@ struct __align__(32) OutRec {
     double w;                    // mixture weight the message carries = the source's seed entry for this neighbour (:384); GTF_NO_TSE bits: none
 };
 #define GTF_NO_TSE_BITS 0x7ff8dead00000001ll
+struct __align__(16) SrcRec {     // static per-source record of k_send: one 16 B read instead of two arrays
+    double z;                     // z of the hit (end-cap side of the Highland term)
+    int32_t off, pad;             // out_off[u]
+};
 struct __align__(32) MergedRec {  // merged_state / merged_cov / merged_prior of a node
     double a, b, c, p00, p01, p22, prior;
     double cl_p11;                // merged_cov[1,1] of the cluster formed at the node's last evaluation, NaN: none.  (The live
@@ -73,6 +77,7 @@ struct DevPack {
     OutRec *orec;                // [E] out-CSR order
     AuxRec *aux;                 // [E] geometry + tag
     NodeXYZR *xyzr;              // [N]
+    SrcRec *srec;                // [N + 1]
     MergedRec *mrec, *mrec_nx;   // [N] merged state of every node (64 B: two whole sectors); _nx: shadow for uncommitted passes
     int all_exist;               // every slot is an existing edge (no ghost slot, no removed node): set on the device from counts[PK_MISSING]
     // mutable slot state
@@ -150,7 +155,8 @@ struct gtf_batch {
     int n_tiles;
     int32_t *tile_begin;
     int n_stiles;
-    int32_t *stile_begin;      // k_send tiles: whole sources, <= GTF_SEND_SRCS sources and <= GTF_SEND_EDGES out-edges
+    int32_t *stile_begin;      // k_send tiles as int4 (first source, sources, first out-edge, out-edges): whole sources,
+                               // <= GTF_SEND_SRCS sources and <= GTF_SEND_EDGES out-edges
     unsigned long long *h_counters; // pinned
     int64_t dev_bytes;
     // extraction scratch

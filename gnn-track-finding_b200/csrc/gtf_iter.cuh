@@ -126,6 +126,11 @@ __global__ void k_pack_out(DevBatch B, DevPack K)
 __global__ void k_pack_nodes(DevBatch B, DevPack K, int do_static, int do_merged)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (do_static && i <= B.N) {
+        SrcRec r;
+        r.z = i < B.N ? B.z[i] : 0.0; r.off = B.out_off[i]; r.pad = 0;
+        K.srec[i] = r;
+    }
     if (i >= B.N) return;
     if (do_static) {
         NodeXYZR v;
@@ -178,9 +183,14 @@ __global__ void k_begin(DevBatch B, DevPack K, int words)
 }
 
 // ------------------------------------------------------------------------------------------------ k_send
-// One CTA owns a tile of whole sources (<= GTF_SEND_SRCS sources, <= GTF_SEND_EDGES out-edges; table built at
-// gtf_batch_finalize).
-//   phase 0  thread per source : offsets, "sends at all" flag (merged state, sub-graph in play), source of every edge
+// Persistent CTAs, one tile of whole sources (<= GTF_SEND_SRCS sources, <= GTF_SEND_EDGES out-edges; descriptor table built
+// by build_tiles) per loop trip, software-pipelined one tile ahead:
+//   prefetch   everything a tile reads that is CONTIGUOUS in memory travels global -> shared with cp.async.bulk (TMA unit,
+//              completion on an mbarrier), issued by one thread while the CTA still works on the previous tile: the
+//              out-CSR range (out_slot, out_dst), the per-source static records (z, out_off), has_merged / node_ok flags
+//              and the accumulated merged_cov[1,1]; the sources' (a, b) are gathered with 16 B cp.async.  What is left on
+//              the dependent chain of a tile: the activation-bit tests (L2) and the per-message record gather.
+//   phase 0  thread per source : "sends at all" flag (merged state, sub-graph in play), source of every edge
 //   phase 1  thread per edge   : does the edge carry a message?  (edge active and existing: extrapolate...py:416,425,431)
 //                                -> ordered compaction into shared memory
 //   phase 2  thread per message: Highland term var_ms (extrapolate...py:114-124), carried mixture weight (:384)
@@ -193,118 +203,218 @@ __global__ void k_begin(DevBatch B, DevPack K, int words)
 #ifndef GTF_SEND_EPT
 #define GTF_SEND_EPT 3                                   // out-edges per thread
 #endif
+#ifndef GTF_SEND_MINB
+#define GTF_SEND_MINB 4
+#endif
 #define GTF_SEND_EDGES (GTF_SEND_THREADS * GTF_SEND_EPT)
 #define GTF_SEND_SRCS (GTF_SEND_THREADS - 1)             // (+1 offsets: one per thread; <= 255: uint8 source index)
-struct SendSmem {
-    int off[GTF_SEND_SRCS + 1];
-    uint8_t ok[GTF_SEND_SRCS + 1];
-    uint8_t esrc[GTF_SEND_EDGES];                        // local source of every out-edge of the tile
-    int m_slot[GTF_SEND_EDGES], m_dst[GTF_SEND_EDGES], m_o[GTF_SEND_EDGES];
-    uint8_t m_src[GTF_SEND_EDGES];
-    double m_vms[GTF_SEND_EDGES], m_w[GTF_SEND_EDGES], m_p11[GTF_SEND_EDGES];
+#define GTF_SEND_MPT ((GTF_SEND_EDGES + GTF_SEND_THREADS - 1) / GTF_SEND_THREADS)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy (16 B aligned, size a multiple of 16), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct SendStage {                                       // what one tile reads, as it lies in global memory
+    int32_t slot[GTF_SEND_EDGES + 8];                    // out_slot range, from the 16 B boundary below the tile's first edge
+    int32_t dst[GTF_SEND_EDGES + 8];                     // out_dst, same range
+    SrcRec srec[GTF_SEND_SRCS + 1];                      // (z, out_off) of the tile's sources + the one after
+    double2 ab[GTF_SEND_SRCS + 1];                       // merged (a, b) of the sources
+    double p11[GTF_SEND_SRCS + 3];                       // merged_cov[1,1], from the 16 B boundary below the first source
+    uint8_t hm[GTF_SEND_SRCS + 33], nok[GTF_SEND_SRCS + 33]; // has_merged / node flags, from the 16 B boundary below
+};
+struct SendWork {
+    double m_vms[GTF_SEND_EDGES], m_p11[GTF_SEND_EDGES];
+    uint16_t m_le[GTF_SEND_EDGES];                       // local out-edge of every message
     uint16_t first[GTF_SEND_SRCS + 1], last[GTF_SEND_SRCS + 1]; // a source's message range in the tile list
+    uint8_t esrc[GTF_SEND_EDGES];                        // local source of every out-edge of the tile
+    uint8_t m_src[GTF_SEND_EDGES];
+    uint8_t ok[GTF_SEND_SRCS + 1];
     int wsum[GTF_SEND_THREADS / 32];
     int base;
 };
-__global__ void __launch_bounds__(GTF_SEND_THREADS) k_send(DevBatch B, DevPack Kin, const int32_t *__restrict__ stile, GtfGeom g)
+struct __align__(16) SendSmem {
+    SendStage st[2];
+    SendWork w;
+    uint64_t full[2];
+};
+static_assert(offsetof(SendStage, dst) % 16 == 0 && offsetof(SendStage, srec) % 16 == 0 && offsetof(SendStage, ab) % 16 == 0 &&
+              offsetof(SendStage, p11) % 16 == 0 && offsetof(SendStage, hm) % 16 == 0 && offsetof(SendStage, nok) % 16 == 0 &&
+              sizeof(SendStage) % 16 == 0, "bulk-copy destinations are 16 B aligned");
+
+// issue the loads of tile `d` = (first source, sources, first out-edge, out-edges) into stage `st`
+__device__ __forceinline__ void send_prefetch(const DevBatch &B, const DevPack &K, SendStage &st, uint64_t *bar, const int4 d, int tid)
+{
+    const int u0 = d.x, ns = d.y, o0 = d.z, ne = d.w;
+    if (tid == 0) {
+        // the stage was last read through the generic proxy (previous tile, finished at a CTA barrier); order those reads
+        // before the asynchronous-proxy writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const int oa = o0 & ~3, on = ((o0 + ne + 3) & ~3) - oa;
+        const int ua = u0 & ~15, un = ((u0 + ns + 15) & ~15) - ua;
+        const int pa = u0 & ~1, pn = ((u0 + ns + 1) & ~1) - pa;
+        const unsigned b_edges = 4u * on, b_src = 16u * (ns + 1), b_fl = (unsigned)un, b_p = 8u * pn;
+        mbar_expect_tx(bar, 2 * b_edges + b_src + 2 * b_fl + b_p);
+        if (on) {
+            bulk_g2s(st.slot, B.out_slot + oa, b_edges, bar);
+            bulk_g2s(st.dst, K.out_dst + oa, b_edges, bar);
+        }
+        bulk_g2s(st.srec, K.srec + u0, b_src, bar);
+        bulk_g2s(st.hm, B.has_merged + ua, b_fl, bar);
+        bulk_g2s(st.nok, B.node_ok + ua, b_fl, bar);
+        bulk_g2s(st.p11, B.m_p11 + pa, b_p, bar);
+    }
+    if (tid < ns)                                        // merged (a, b): first 16 B of the 64 B node record
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&st.ab[tid])), "l"(K.mrec + u0 + tid) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBatch B, DevPack Kin, const int4 *__restrict__ tdesc, int n_tiles,
+                                                                         GtfGeom g)
 {
     DevPack K = Kin;
     K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
-    __shared__ SendSmem sm;
+    extern __shared__ __align__(16) unsigned char send_raw[];
+    SendSmem &S = *reinterpret_cast<SendSmem *>(send_raw);
+    SendWork &sm = S.w;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u0 = stile[blockIdx.x], ns = stile[blockIdx.x + 1] - u0;
-    // ---- phase 0
-    int my_off = 0, my_end = 0;
-    if (tid < ns) {
-        const int u = u0 + tid;
-        my_off = B.out_off[u]; my_end = B.out_off[u + 1];
-        sm.off[tid] = my_off;
-        if (tid == ns - 1) sm.off[ns] = my_end;
-        sm.ok[tid] = B.has_merged[u] && (B.node_ok[u] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI);
-        sm.first[tid] = 0xffff;
+    const int G = gridDim.x;
+    if (tid == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int o_base = sm.off[0], ne = sm.off[ns] - o_base;
-    if (tid < ns)
-        for (int o = my_off; o < my_end; o++) sm.esrc[o - o_base] = (uint8_t)tid;
-    __syncthreads();
-    // ---- phase 1: GTF_SEND_EPT consecutive edges per thread keep the successor order
-    int slots[GTF_SEND_EPT], dsts[GTF_SEND_EPT], cnt = 0;
-    unsigned mymask = 0;
-    const int e0 = tid * GTF_SEND_EPT;
-#pragma unroll
-    for (int j = 0; j < GTF_SEND_EPT; j++) slots[j] = e0 + j < ne ? B.out_slot[o_base + e0 + j] : -1;
-#pragma unroll
-    for (int j = 0; j < GTF_SEND_EPT; j++) {
-        dsts[j] = 0;
-        if (e0 + j < ne) {
-            const int s = slots[j];
-            if (sm.ok[sm.esrc[e0 + j]] && bm_get(K.act, s) && (K.all_exist || bm_get(K.exists, s))) { mymask |= 1u << j; cnt++; }
+    int t = blockIdx.x;
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    int4 d_cur = t < n_tiles ? tdesc[t] : zero4;
+    int4 d_nxt = t + G < n_tiles ? tdesc[t + G] : zero4;
+    if (t < n_tiles) send_prefetch(B, K, S.st[0], &S.full[0], d_cur, tid);
+    for (int it = 0; t < n_tiles; t += G, it++) {
+        const int s = it & 1;
+        SendStage &st = S.st[s];
+        // the next tile travels while this one is processed (its stage was released by the barrier that ended the previous trip)
+        const int tn = t + G;
+        if (tn < n_tiles) send_prefetch(B, K, S.st[s ^ 1], &S.full[s ^ 1], d_nxt, tid);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const int4 d_nn = tn + G < n_tiles ? tdesc[tn + G] : zero4;     // descriptor after next: a register prefetch
+        asm volatile("cp.async.wait_group 1;" ::: "memory");          // this tile's (a, b) gathers (issued one trip ago)
+        mbar_wait(&S.full[s], (unsigned)(it >> 1) & 1u);
+        const int u0 = d_cur.x, ns = d_cur.y, o_base = d_cur.z, ne = d_cur.w;
+        const int epad = o_base & 3, upad = u0 & 15, ppad = u0 & 1;
+        // ---- phase 0
+        if (tid < ns) {
+            const int my_off = st.srec[tid].off - o_base, my_end = st.srec[tid + 1].off - o_base;
+            sm.ok[tid] = st.hm[upad + tid] && (st.nok[upad + tid] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI);
+            sm.first[tid] = 0xffff;
+            for (int o = my_off; o < my_end; o++) sm.esrc[o] = (uint8_t)tid;
         }
-    }
+        __syncthreads();
+        // ---- phase 1: GTF_SEND_EPT consecutive edges per thread keep the successor order
+        int cnt = 0;
+        unsigned mymask = 0;
+        const int e0 = tid * GTF_SEND_EPT;
 #pragma unroll
-    for (int j = 0; j < GTF_SEND_EPT; j++)
-        if ((mymask >> j) & 1u) dsts[j] = K.out_dst[o_base + e0 + j];
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) sm.wsum[warp] = incl;
-    __syncthreads();
-    int woff = 0, M = 0;
-#pragma unroll
-    for (int w = 0; w < GTF_SEND_THREADS / 32; w++) {
-        if (w < warp) woff += sm.wsum[w];
-        M += sm.wsum[w];
-    }
-    if (M == 0) return;
-    if (tid == 0) sm.base = atomicAdd(&K.counts[PK_MSG], M); // one global atomic per CTA
-    {
-        int pos = woff + incl - cnt;
-#pragma unroll
-        for (int j = 0; j < GTF_SEND_EPT; j++)
-            if ((mymask >> j) & 1u) {
-                sm.m_slot[pos] = slots[j]; sm.m_dst[pos] = dsts[j]; sm.m_o[pos] = o_base + e0 + j; sm.m_src[pos] = sm.esrc[e0 + j];
-                pos++;
+        for (int j = 0; j < GTF_SEND_EPT; j++) {
+            if (e0 + j < ne) {
+                const int sl = st.slot[epad + e0 + j];
+                if (sm.ok[sm.esrc[e0 + j]] && bm_get(K.act, sl) && (K.all_exist || bm_get(K.exists, sl))) { mymask |= 1u << j; cnt++; }
             }
-    }
-    __syncthreads();
-    // ---- phase 2
-    for (int q = tid; q < M; q += GTF_SEND_THREADS) {
-        const int sl = sm.m_src[q], u = u0 + sl;
-        const double4 *rp = reinterpret_cast<const double4 *>(K.orec + sm.m_o[q]);   // one sector, in successor order
-        const double2 r0 = *reinterpret_cast<const double2 *>(rp), r1 = *(reinterpret_cast<const double2 *>(rp) + 1);
-        const double2 ab = *reinterpret_cast<const double2 *>(K.mrec + u);
-        const bool has = __double_as_longlong(r1.y) != GTF_NO_TSE_BITS;
-        sm.m_w[q] = has ? r1.y : NAN;
-        if (!has) sm.m_slot[q] |= (int)0x80000000;
-        sm.m_vms[q] = gtf_var_ms_pre(ab.x, ab.y, r0.y, r0.x, r1.x, B.z[u], g.endcap);
-        if (q == 0 || sm.m_src[q - 1] != sl) sm.first[sl] = (uint16_t)q;
-        if (q == M - 1 || sm.m_src[q + 1] != sl) sm.last[sl] = (uint16_t)q;
-    }
-    __syncthreads();
-    // ---- phase 3
-    if (tid < ns && sm.first[tid] != 0xffff) {
-        const int u = u0 + tid, q1 = sm.last[tid];
-        double p = B.m_p11[u];
-        for (int q = sm.first[tid]; q <= q1; q++) {
-            p += sm.m_vms[q];
-            sm.m_p11[q] = p;
         }
-        B.m_p11_nx[u] = p;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) sm.wsum[warp] = incl;
+        __syncthreads();
+        int woff = 0, M = 0;
+#pragma unroll
+        for (int w = 0; w < GTF_SEND_THREADS / 32; w++) {
+            if (w < warp) woff += sm.wsum[w];
+            M += sm.wsum[w];
+        }
+        if (M) {                                                     // (uniform over the CTA)
+            if (tid == 0) sm.base = atomicAdd(&K.counts[PK_MSG], M); // one global atomic per tile
+            {
+                int pos = woff + incl - cnt;
+#pragma unroll
+                for (int j = 0; j < GTF_SEND_EPT; j++)
+                    if ((mymask >> j) & 1u) {
+                        sm.m_le[pos] = (uint16_t)(e0 + j); sm.m_src[pos] = sm.esrc[e0 + j];
+                        pos++;
+                    }
+            }
+            __syncthreads();
+            // ---- phase 2
+            double wq[GTF_SEND_MPT];
+#pragma unroll
+            for (int k = 0; k < GTF_SEND_MPT; k++) {
+                const int q = tid + k * GTF_SEND_THREADS;
+                wq[k] = 0.0;
+                if (q < M) {
+                    const int sl = sm.m_src[q];
+                    const double2 *rp = reinterpret_cast<const double2 *>(K.orec + o_base + sm.m_le[q]);   // one sector, in successor order
+                    const double2 r0 = rp[0], r1 = rp[1];
+                    const double2 ab = st.ab[sl];
+                    wq[k] = r1.y;
+                    sm.m_vms[q] = gtf_var_ms_pre(ab.x, ab.y, r0.y, r0.x, r1.x, st.srec[sl].z, g.endcap);
+                    if (q == 0 || sm.m_src[q - 1] != sl) sm.first[sl] = (uint16_t)q;
+                    if (q == M - 1 || sm.m_src[q + 1] != sl) sm.last[sl] = (uint16_t)q;
+                }
+            }
+            __syncthreads();
+            // ---- phase 3
+            if (tid < ns && sm.first[tid] != 0xffff) {
+                const int q1 = sm.last[tid];
+                double p = st.p11[ppad + tid];
+                for (int q = sm.first[tid]; q <= q1; q++) {
+                    p += sm.m_vms[q];
+                    sm.m_p11[q] = p;
+                }
+                B.m_p11_nx[u0 + tid] = p;
+            }
+            __syncthreads();
+            // ---- phase 4
+            const int base = sm.base;
+#pragma unroll
+            for (int k = 0; k < GTF_SEND_MPT; k++) {
+                const int q = tid + k * GTF_SEND_THREADS;
+                if (q < M) {
+                    const int gq = base + q, le = sm.m_le[q];
+                    const bool has = __double_as_longlong(wq[k]) != GTF_NO_TSE_BITS;
+                    K.msg_desc[gq] = make_int4(st.slot[epad + le] | (has ? 0 : (int)0x80000000), u0 + sm.m_src[q], st.dst[epad + le], 0);
+                    K.msg_w[gq] = has ? wq[k] : NAN;
+                    K.msg_p11[gq] = sm.m_p11[q];
+                    K.msg_vms[gq] = sm.m_vms[q];
+                }
+            }
+        }
+        __syncthreads();       // every read of this stage and of the work arrays is done: the next trip may overwrite them
+        d_cur = d_nxt;
+        d_nxt = d_nn;
     }
-    __syncthreads();
-    // ---- phase 4
-    const int base = sm.base;
-    for (int q = tid; q < M; q += GTF_SEND_THREADS) {
-        const int gq = base + q;
-        K.msg_desc[gq] = make_int4(sm.m_slot[q], u0 + sm.m_src[q], sm.m_dst[q], 0);
-        K.msg_w[gq] = sm.m_w[q];
-        K.msg_p11[gq] = sm.m_p11[q];
-        K.msg_vms[gq] = sm.m_vms[q];
-    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ k_exec
