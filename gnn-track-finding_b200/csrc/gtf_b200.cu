@@ -112,6 +112,9 @@ extern "C" int gtf_batch_create(int32_t N, int32_t E, int32_t S, int device, gtf
     memset((void *)b, 0, sizeof(*b));
     b->N = N; b->E = E; b->S = S; b->device = device;
     b->capN = N; b->capE = E; b->capS = S;
+    if (const char *fg = getenv("GTF_L2_FETCH")) {   // experiment switch: L2 -> DRAM fetch granularity (32 / 64 / 128 B)
+        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg)) != cudaSuccess) cudaGetLastError();
+    }
     int rc = batch_alloc(b);
     if (rc) {                      // every pointer is zero-initialised: a partial batch is safe to destroy
         const std::string msg = g_err;

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBat
     int t = blockIdx.x;
     const int4 zero4 = make_int4(0, 0, 0, 0);
     int4 d_cur = t < n_tiles ? tdesc[t] : zero4;
-    int4 d_nxt = t + G < n_tiles ? tdesc[t + G] : zero4;
+    int4 d_nxt = tdesc[min(t + G, n_tiles - 1)];
     if (t < n_tiles) send_prefetch(B, K, S.st[0], &S.full[0], d_cur, tid);
     for (int it = 0; t < n_tiles; t += G, it++) {
         const int s = it & 1;
@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBat
         const int tn = t + G;
         if (tn < n_tiles) send_prefetch(B, K, S.st[s ^ 1], &S.full[s ^ 1], d_nxt, tid);
         else asm volatile("cp.async.commit_group;" ::: "memory");
-        const int4 d_nn = tn + G < n_tiles ? tdesc[tn + G] : zero4;     // descriptor after next: a register prefetch
+        const int4 d_nn = tdesc[min(tn + G, n_tiles - 1)];             // descriptor after next: a register prefetch, first
+                                                                       // touched when the trip ends (no select on it here)
         asm volatile("cp.async.wait_group 1;" ::: "memory");          // this tile's (a, b) gathers (issued one trip ago)
         mbar_wait(&S.full[s], (unsigned)(it >> 1) & 1u);
         const int u0 = d_cur.x, ns = d_cur.y, o_base = d_cur.z, ne = d_cur.w;
@@ -789,9 +790,19 @@ template <int G> __device__ __forceinline__ void grp_shfl_info(const GtfInfo &in
 #endif
 static_assert(GTF_HV_WARPS * 32 >= GTF_MAXD * (GTF_MAXD - 1) / 2, "one thread per entry of the pair table");
 #ifndef GTF_HV_MINB
-#define GTF_HV_MINB 4
+#define GTF_HV_MINB 5
 #endif
-struct HvStage { double v[13][32]; }; // a b c tau p00 p01 p11 p22 + GtfPairGeo (I T Q A C) of the warp's 32 entries
+// per-warp staging of the 32 dict entries a warp works on, indexed by (group base + DICT POSITION): lanes keep their entry
+// in slot order (as loaded) and only this index carries the dict order, so nothing is ever permuted between lanes
+struct HvWarp {
+    double st[8][32];   // a b c tau p00 p01 p11 p22
+    double pg[5][32];   // GtfPairGeo: I T Q A C
+    double inf[8][32];  // information form: s00 s01 s11 sq v0 v1 vc vt
+    double pr[32];      // prior after the re-weighting (merged_prior sums, clustering.py:234,266)
+    double xs[32];      // w * likelihood of the active entries (denominator of the re-weighting, in dict order)
+    double park[4][32]; // w, likelihood, prior, edge weight of MY entry while the clustering needs the registers
+    int rk[32];         // dict stamps / source indices (to rank the entries)
+};
 
 template <int G>
 __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch B, DevPack Kin, Prog P, GtfGeom g, int bin,
@@ -799,12 +810,12 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
 {
     DevPack K = Kin;
     K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
-    constexpr int NG = 32 / G;                                   // nodes per warp
     constexpr int MAXN = G == 4 ? 4 : G == 8 ? 8 : 15;           // largest dict that can cluster in this bin
     constexpr int R = (MAXN * (MAXN - 1) / 2 + G - 1) / G;       // pair rounds
+    constexpr int NG = 32 / G;                                   // nodes per warp
     const unsigned FULL = 0xffffffffu;
     __shared__ unsigned int s_cnt[GTF_NCOUNTERS];
-    __shared__ HvStage s_stage[GTF_HV_WARPS];
+    __shared__ HvWarp s_warp[GTF_HV_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gl = lane % G, gbase = lane - gl;
     const unsigned gmask = G == 32 ? FULL : (((1u << G) - 1u) << gbase);
@@ -819,7 +830,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
     __syncthreads();
     const int count = K.counts[PK_HV0 + bin];
     const int32_t *list = K.hv_list + (size_t)bin * B.N;
-    HvStage &ss = s_stage[warp];
+    HvWarp &W = s_warp[warp];
     unsigned n_act = 0, n_chg = 0, n_off = 0, n_deact = 0, n_merged = 0, referr = 0;
     const int nwarps = gridDim.x * GTF_HV_WARPS;
     for (int base = (blockIdx.x * GTF_HV_WARPS + warp) * NG; base < count; base += nwarps * NG) {
@@ -844,7 +855,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             n += cnt;
         }
         const bool valid = gv && gl < n;
-        // ---- weight record, flags
+        // ---- weight record, tag, geometry, flags of my entry
         double w = 0.0, lik = 0.0, prior = 0.0, sx = 0.0, ew = 0.0;
         int rank = 0x7fffffff, side = 0, lrn = -1, lay = -1000 - lane, src = 0, rank0 = 0, tag0 = 0;
         unsigned f = 0;
@@ -865,15 +876,16 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             if (prior != prior) { side = 0; lrn = 0; }        // entry just written by the extrapolation: no side / lr_layer_norm yet
             if (!bm_get(K.pres0, slot)) f |= H_NEW;
         }
+        const int nmax = (int)__reduce_max_sync(FULL, (unsigned)n);
         // ---- new entries enter the dict in ascending source order (extrapolate...py:419-447)
         const unsigned newm = __ballot_sync(FULL, (f & H_NEW) != 0);
         if (newm) {
             const int nxt = gv ? B.uts_next[i] : 0;
+            __syncwarp();
+            W.rk[lane] = src;
+            __syncwarp();
             int before = 0;
-            for (int t = 0; t < G; t++) {
-                const int sk = __shfl_sync(FULL, src, t, G);
-                before += ((newm >> (gbase + t)) & 1u) && sk < src;
-            }
+            for (int t = 0; t < nmax; t++) before += ((newm >> (gbase + t)) & 1u) && W.rk[gbase + t] < src;
             if (f & H_NEW) rank = nxt + before;
             const int nnew = __popc(newm & gmask);
             if (nnew) {
@@ -881,51 +893,53 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
                 nf |= NF_DICT | NF_HASUTS;
             }
         }
-        // ---- bring the entries into dict order (ascending stamp): lane k of the group holds dict position k
-        const int nmax = (int)__reduce_max_sync(FULL, (unsigned)n);
-        {
-            int pos = 0;
-            for (int t = 0; t < nmax; t++) {
-                const int rt = __shfl_sync(FULL, rank, t, G);
-                pos += (t < n) && rt < rank;
-            }
-            if (!valid) pos = gl;
-            int inv = gl;
-            for (int t = 0; t < nmax; t++) {
-                const int pt = __shfl_sync(FULL, pos, t, G);
-                if (t < n && pt == gl) inv = t;
-            }
-            slot = __shfl_sync(FULL, slot, inv, G); f = __shfl_sync(FULL, f, inv, G);
-            rank = __shfl_sync(FULL, rank, inv, G); lay = __shfl_sync(FULL, lay, inv, G);
-            src = __shfl_sync(FULL, src, inv, G);
-            const int sl2 = __shfl_sync(FULL, side | (lrn << 8), inv, G);
-            side = (int)(int8_t)(sl2 & 0xff); lrn = sl2 >> 8;
-            w = __shfl_sync(FULL, w, inv, G); lik = __shfl_sync(FULL, lik, inv, G);
-            prior = __shfl_sync(FULL, prior, inv, G); sx = __shfl_sync(FULL, sx, inv, G);
-            ew = __shfl_sync(FULL, ew, inv, G);
-            rank0 = __shfl_sync(FULL, rank0, inv, G); tag0 = __shfl_sync(FULL, tag0, inv, G);
-        }
-        // ---- state record of my entry, node coordinates
-        GtfState mine;
-        mine.a = mine.b = mine.c = mine.tau = mine.p00 = mine.p01 = mine.p11 = mine.p22 = 0.0;
-        double sz = 0.0, sr = 0.0;
-        NodeXYZR X;
-        X.x = X.y = X.z = X.r = 0.0;
-        if (gv) X = K.xyzr[i];
+        // ---- dict position of my entry (ascending stamp)
+        __syncwarp();
+        W.rk[lane] = rank;
+        __syncwarp();
+        int pos = 0;
+        for (int t = 0; t < nmax; t++) pos += (t < n) && W.rk[gbase + t] < rank;
+        if (!valid) pos = gl;
+        const int dpos = gbase + pos;
+        const unsigned lastm = __ballot_sync(FULL, valid && pos == n - 1) & gmask;      // the lane holding the LAST dict key
+        const int lastlane = lastm ? __ffs(lastm) - 1 : gbase;
+        // ---- state record of my entry -> shared, with the per-entry parts of the pair chi2 and the information form
+        double nodex = 0.0;
         const bool cl_node = G < 32 && gv && (nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT) && n >= 3 && n <= GTF_MAXD; // clustering.py:207
-        if (valid && cl_node) {
-            const double2 *st = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)slot);
-            const double2 v0 = __ldcs(st + 0), v1 = __ldcs(st + 1), v2 = __ldcs(st + 2), v3 = __ldcs(st + 3);
-            mine.a = v0.x; mine.b = v0.y; mine.c = v1.x; mine.tau = v1.y;
-            mine.p00 = v2.x; mine.p01 = v2.y; mine.p11 = v3.x; mine.p22 = v3.y;
-            if (src >= 0) { const NodeXYZR S = K.xyzr[src]; sz = S.z; sr = S.r; }
+        const bool cl_any = G < 32 && __any_sync(FULL, cl_node);
+        {
+            NodeXYZR X;
+            X.x = X.y = X.z = X.r = 0.0;
+            if (gv) X = K.xyzr[i];
+            nodex = X.x;
+            if (cl_any) {
+                GtfState mine;
+                mine.a = mine.b = mine.c = mine.tau = mine.p00 = mine.p01 = mine.p11 = mine.p22 = 0.0;
+                double sz = 0.0, sr = 0.0;
+                if (valid && cl_node) {
+                    const double2 *stp = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)slot);
+                    const double2 v0 = __ldcs(stp + 0), v1 = __ldcs(stp + 1), v2 = __ldcs(stp + 2), v3 = __ldcs(stp + 3);
+                    mine.a = v0.x; mine.b = v0.y; mine.c = v1.x; mine.tau = v1.y;
+                    mine.p00 = v2.x; mine.p01 = v2.y; mine.p11 = v3.x; mine.p22 = v3.y;
+                    if (src >= 0) { const NodeXYZR Sx = K.xyzr[src]; sz = Sx.z; sr = Sx.r; }
+                }
+                GtfPairGeo pg;
+                gtf_pair_geo(sx, sz, sr, X.z, X.r, g, pg);
+                GtfInfo mi;
+                gtf_to_info(mine, mi);
+                W.st[0][dpos] = mine.a; W.st[1][dpos] = mine.b; W.st[2][dpos] = mine.c; W.st[3][dpos] = mine.tau;
+                W.st[4][dpos] = mine.p00; W.st[5][dpos] = mine.p01; W.st[6][dpos] = mine.p11; W.st[7][dpos] = mine.p22;
+                W.pg[0][dpos] = pg.I; W.pg[1][dpos] = pg.T; W.pg[2][dpos] = pg.Q; W.pg[3][dpos] = pg.A; W.pg[4][dpos] = pg.C;
+                W.inf[0][dpos] = mi.s00; W.inf[1][dpos] = mi.s01; W.inf[2][dpos] = mi.s11; W.inf[3][dpos] = mi.sq;
+                W.inf[4][dpos] = mi.v0; W.inf[5][dpos] = mi.v1; W.inf[6][dpos] = mi.vc; W.inf[7][dpos] = mi.vt;
+            }
         }
-        const double nodex = X.x;
         const bool okd = (nf & (NF_OK | NF_MULTI | NF_DICT)) == (NF_OK | NF_MULTI | NF_DICT);
         const bool oku = (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS);
         const unsigned m3 = H_PRES | H_EX | H_ACT;
         const unsigned samelay = __match_any_sync(FULL, lay) & gmask;
         const unsigned samex = __match_any_sync(FULL, __double_as_longlong(sx)) & gmask;
+        const bool isleft = sx < nodex;
 #pragma unroll
         for (int pass = 0; pass < 2; pass++) {
             // helper.py:30-63 compute_prior_probabilities
@@ -937,22 +951,22 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             // helper.py:99-200 side norm + reweight + prune
             {
                 const bool el = oku && (f & m3) == m3;
-                const bool left = el && sx < nodex;
+                const bool left = el && isleft;
                 const unsigned elm = __ballot_sync(FULL, el), leftm = __ballot_sync(FULL, left);
                 const unsigned grpm = samex & (left ? leftm : (elm & ~leftm));
                 const bool first = el && (__ffs(grpm) - 1 == lane);             // distinct x per side: len(set(coords))
                 const int normL = __popc(__ballot_sync(FULL, first && left) & gmask);
                 const int normR = __popc(__ballot_sync(FULL, first && !left) & gmask);
-                const unsigned lf = __shfl_sync(FULL, f, max(n - 1, 0), G);     // stale `neighbour_num`: LAST dict key
+                const unsigned lf = __shfl_sync(FULL, f, lastlane);             // stale `neighbour_num`: LAST dict key
                 const bool any_el = (elm & gmask) != 0;
                 if (any_el && !(lf & H_EX) && gl == 0) referr |= GTF_REF_KEY;
                 const bool last_active = (lf & (H_EX | H_ACT)) == (H_EX | H_ACT);
-                const double x = el ? w * lik : 0.0;                            // denominator in dict order (helper.py:165-169)
+                __syncwarp();
+                W.xs[dpos] = el ? w * lik : 0.0;                                // denominator in dict order (helper.py:165-169)
+                __syncwarp();
                 double denom = 0.0;
-                for (int q = 0; q < nmax; q++) {
-                    const double xq = __shfl_sync(FULL, x, q, G);
-                    if (q < n) denom += xq;
-                }
+                for (int q = 0; q < nmax; q++)
+                    if (q < n) denom += W.xs[gbase + q];
                 if (el) {
                     const int norm = last_active ? (left ? normL : normR) : 1;
                     double rw = (w * lik * prior) / denom;
@@ -969,21 +983,16 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         GtfState merged;
         merged.a = merged.b = merged.c = merged.tau = merged.p00 = merged.p01 = merged.p11 = merged.p22 = 0.0;
         double mprior = 0.0;
-        if (G < 32 && __any_sync(FULL, cl_node)) {
+        if (cl_any) {
             double thr = P.cl_kl;
             if (P.use_lut && gv) {
                 const double ev = B.emp_var[i];
                 const int lb = (ev == ev) ? (int)floor(ev / 0.05) : 27;
                 thr = P.lut[max(0, min(27, lb))];
             }
-            __syncwarp();
-            ss.v[0][lane] = mine.a; ss.v[1][lane] = mine.b; ss.v[2][lane] = mine.c; ss.v[3][lane] = mine.tau;
-            ss.v[4][lane] = mine.p00; ss.v[5][lane] = mine.p01; ss.v[6][lane] = mine.p11; ss.v[7][lane] = mine.p22;
-            {
-                GtfPairGeo pg;
-                gtf_pair_geo(sx, sz, sr, X.z, X.r, g, pg);
-                ss.v[8][lane] = pg.I; ss.v[9][lane] = pg.T; ss.v[10][lane] = pg.Q; ss.v[11][lane] = pg.A; ss.v[12][lane] = pg.C;
-            }
+            // my entry's weights leave the registers while the clustering runs
+            W.park[0][lane] = w; W.park[1][lane] = lik; W.park[2][lane] = prior; W.park[3][lane] = ew;
+            W.pr[dpos] = prior;
             __syncwarp();
             const int npairs = cl_node ? n * (n - 1) / 2 : 0;
             const int rmax = ((int)__reduce_max_sync(FULL, (unsigned)npairs) + G - 1) / G;
@@ -1000,14 +1009,13 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
                         HV_PAIR_DECODE(p, pi, pj);
                         const int li = gbase + pi, lj = gbase + pj;
                         GtfState si, sj;
-                        si.a = ss.v[0][li]; si.b = ss.v[1][li]; si.c = ss.v[2][li]; si.tau = ss.v[3][li];
-                        si.p00 = ss.v[4][li]; si.p01 = ss.v[5][li]; si.p11 = ss.v[6][li]; si.p22 = ss.v[7][li];
-                        sj.a = ss.v[0][lj]; sj.b = ss.v[1][lj]; sj.c = ss.v[2][lj]; sj.tau = ss.v[3][lj];
-                        sj.p00 = ss.v[4][lj]; sj.p01 = ss.v[5][lj]; sj.p11 = ss.v[6][lj]; sj.p22 = ss.v[7][lj];
+                        si.a = W.st[0][li]; si.b = W.st[1][li]; si.p00 = W.st[4][li]; si.p01 = W.st[5][li]; si.p11 = W.st[6][li];
+                        sj.a = W.st[0][lj]; sj.b = W.st[1][lj]; sj.p00 = W.st[4][lj]; sj.p01 = W.st[5][lj]; sj.p11 = W.st[6][lj];
+                        si.c = si.tau = si.p22 = sj.c = sj.tau = sj.p22 = 0.0;   // (not part of the pairwise chi2)
                         GtfPairGeo gi, gj;
-                        gi.I = ss.v[8][li]; gi.T = ss.v[9][li]; gi.Q = ss.v[10][li]; gi.A = ss.v[11][li]; gi.C = ss.v[12][li];
-                        gj.I = ss.v[8][lj]; gj.T = ss.v[9][lj]; gj.Q = ss.v[10][lj]; gj.A = ss.v[11][lj]; gj.C = ss.v[12][lj];
-                        const double v = gtf_pair_chi2_pre(si, sj, X.x, gi, gj, g);
+                        gi.I = W.pg[0][li]; gi.T = W.pg[1][li]; gi.Q = W.pg[2][li]; gi.A = W.pg[3][li]; gi.C = W.pg[4][li];
+                        gj.I = W.pg[0][lj]; gj.T = W.pg[1][lj]; gj.Q = W.pg[2][lj]; gj.A = W.pg[3][lj]; gj.C = W.pg[4][lj];
+                        const double v = gtf_pair_chi2_pre(si, sj, nodex, gi, gj, g);
                         pv[r] = v;
                         if (v != 0.0) {               // np.nonzero keeps NaN, drops +-0 (clustering.py:119)
                             nz_any = true;
@@ -1046,49 +1054,70 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
                     HV_PAIR_DECODE((int)p2, idx1, jj);
                 }
             }
-            unsigned rem = go ? (((1u << n) - 1u) & ~gone) : 0u;
+            unsigned rem = go ? (((1u << n) - 1u) & ~gone) : 0u;   // (bits = dict positions)
             if (go && rem == 0) {                           // np.min([]) at :252
                 if (gl == 0) referr |= GTF_REF_EMPTY_MIN;
                 go = false;
             }
             if (__any_sync(FULL, go)) {
-                GtfInfo mine_i, M, t;
-                gtf_to_info(mine, mine_i);
-                grp_shfl_info<G>(mine_i, idx0, M);          // clustering.py:231-233: Sigma^-1 = S_i + S_j
-                grp_shfl_info<G>(mine_i, idx1, t);
-                gtf_info_add(M, t);
+                GtfInfo M;
+                {
+                    const int l0 = gbase + idx0, l1 = gbase + idx1;  // clustering.py:231-233: Sigma^-1 = S_i + S_j
+                    M.s00 = W.inf[0][l0]; M.s01 = W.inf[1][l0]; M.s11 = W.inf[2][l0]; M.sq = W.inf[3][l0];
+                    M.v0 = W.inf[4][l0]; M.v1 = W.inf[5][l0]; M.vc = W.inf[6][l0]; M.vt = W.inf[7][l0];
+                    M.s00 += W.inf[0][l1]; M.s01 += W.inf[1][l1]; M.s11 += W.inf[2][l1]; M.sq += W.inf[3][l1];
+                    M.v0 += W.inf[4][l1]; M.v1 += W.inf[5][l1]; M.vc += W.inf[6][l1]; M.vt += W.inf[7][l1];
+                    mprior = W.pr[l0] + W.pr[l1];                    // :234
+                }
                 gtf_from_info(M, merged);
-                mprior = __shfl_sync(FULL, prior, idx0, G) + __shfl_sync(FULL, prior, idx1, G); // :234
                 bool live = go;
                 clustered = go;
+                const bool mine_in = valid && cl_node;
                 while (__any_sync(FULL, live)) {
-                    const bool have = live && gl < n && ((rem >> gl) & 1u);
-                    const double kl = have ? gtf_kl_info(mine, mine_i, merged, M) : INFINITY; // clustering.py:107-112
+                    const bool have = live && mine_in && ((rem >> pos) & 1u);
+                    double kl = INFINITY;                            // clustering.py:107-112, both inverses at hand
+                    if (have) {
+                        const double tr = (W.st[4][dpos] - merged.p00) * (M.s00 - W.inf[0][dpos]) + (W.st[6][dpos] - merged.p11) * (M.s11 - W.inf[2][dpos]) +
+                                          (W.st[7][dpos] - merged.p22) * (M.sq - W.inf[3][dpos]);
+                        const double d0 = W.st[0][dpos] - merged.a, d1 = W.st[1][dpos] - merged.b, d2 = W.st[3][dpos] - merged.tau;
+                        kl = tr + (d0 * d0 * (W.inf[0][dpos] + M.s00) + 2.0 * d0 * d1 * (W.inf[1][dpos] + M.s01) + d1 * d1 * (W.inf[2][dpos] + M.s11) +
+                                   d2 * d2 * (W.inf[3][dpos] + M.sq));
+                    }
                     const bool nan_kl = (__ballot_sync(FULL, have && kl != kl) & gmask) != 0;  // list.index(nan) -> ValueError
-                    double bv;
-                    const int bk = grp_argmin<G>(kl, have, gmask, gbase, bv);                  // list.index: first occurrence
+                    // arg-min; list.index: the FIRST occurrence in dict order among equal values
+                    const unsigned long long kk = have ? dbl_key(kl) : ~0ull;
+                    const unsigned long long mk = grp_min_u64<G>(kk);
+                    const unsigned tie = __ballot_sync(FULL, have && kk == mk) & gmask;
+                    int bk = __shfl_sync(FULL, pos, tie ? __ffs(tie) - 1 : lane);
+                    if (__any_sync(FULL, (tie & (tie - 1)) != 0)) {     // (warp-uniform: the reduction shuffles across groups)
+                        const int bmin = (int)grp_min_u32<G>(have && kk == mk ? (unsigned)pos : 99u);
+                        if (tie & (tie - 1)) bk = bmin;
+                    }
+                    if (!tie) bk = -1;
+                    const double bv = key_dbl(mk);
                     const bool absorb = live && !nan_kl && bk >= 0 && bv < thr;                // clustering.py:261
-                    grp_shfl_info<G>(mine_i, max(bk, 0), t);
-                    const double pk = __shfl_sync(FULL, prior, max(bk, 0), G);
                     if (live && nan_kl) {
                         if (gl == 0) referr |= GTF_REF_NAN_INDEX;
                         clustered = false;
                         live = false;
                     } else if (absorb) {
-                        gtf_info_add(M, t);                 // :263-265 merge_states(entry, merged)
+                        const int lb = gbase + bk;                   // :263-265 merge_states(entry, merged)
+                        M.s00 += W.inf[0][lb]; M.s01 += W.inf[1][lb]; M.s11 += W.inf[2][lb]; M.sq += W.inf[3][lb];
+                        M.v0 += W.inf[4][lb]; M.v1 += W.inf[5][lb]; M.vc += W.inf[6][lb]; M.vt += W.inf[7][lb];
                         gtf_from_info(M, merged);
-                        mprior = pk + mprior;               // :266
+                        mprior = W.pr[lb] + mprior;                  // :266
                         rem &= ~(1u << bk);
-                        if (rem == 0) live = false;         // :283
+                        if (rem == 0) live = false;                  // :283
                     } else
                         live = false;
                 }
                 // un-absorbed components: their in-edge is deactivated (clustering.py:297-321)
-                if (clustered && gl < n && ((rem >> gl) & 1u) && (f & H_EX)) {
+                if (clustered && valid && ((rem >> pos) & 1u) && (f & H_EX)) {
                     f &= ~H_ACT;
                     n_deact++;
                 }
             }
+            w = W.park[0][lane]; lik = W.park[1][lane]; prior = W.park[2][lane]; ew = W.park[3][lane];
         }
         // ---- degree (helper.py:67-73), mixture weights (helper.py:76-94), priors
         const unsigned actm = __ballot_sync(FULL, (f & (H_PRES | H_EX | H_ACT)) == (H_PRES | H_EX | H_ACT)) & gmask;
@@ -1110,8 +1139,8 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             double2 *m = reinterpret_cast<double2 *>(K.meta + slot);
             __stcs(m + 0, make_double2(w, lik));
             __stcs(m + 1, make_double2(prior, ew));              // ew: helper.py:180
-            const int t1 = tag_pack(side, lrn);
-            if (rank != rank0 || t1 != tag0) *reinterpret_cast<int2 *>(tag_p(K, slot)) = make_int2(rank, t1);
+            const int tw = tag_pack(side, lrn);
+            if (rank != rank0 || tw != tag0) *reinterpret_cast<int2 *>(tag_p(K, slot)) = make_int2(rank, tw);
             if ((f & H_ACT0) && !(f & H_ACT)) bm_clear(K.act_nx, slot);
         }
         if (gv && gl == 0) {
