@@ -110,6 +110,15 @@ class EventBatch(object):
     def sync(self):
         L.check(self.lib.gtf_batch_sync(self.h))
 
+    def near_threshold(self):
+        """boundary-flip candidates of the most recent stage call / iteration: (count, [(kind, index, value, threshold)])
+        -- decisions taken within 1e-9 relative of their threshold; kind indexes lib.NEAR_KINDS, index is a
+        slot (gate, reweight) or a node (cluster)"""
+        rec = (L.NearRec * 256)()
+        n = ctypes.c_int64(0)
+        L.check(self.lib.gtf_batch_near_threshold(self.h, rec, 256, ctypes.byref(n)))
+        return n.value, [(r.kind, r.index, r.value, r.threshold) for r in rec[:min(n.value, 256)]]
+
     def device_bytes(self):
         return int(self.lib.gtf_batch_device_bytes(self.h))
 

@@ -143,7 +143,8 @@ static int batch_alloc(gtf_batch *b)
     DA(b->n_dead, 1);
     DA(d.slot_p11, E); DA(d.slot_vms, E); DA(d.node_p11tot, N);
     DA(d.has_merged_nx, N); DA(d.m_p11_nx, N);
-    DA(d.counters, GTF_NCOUNTERS);
+    DA(d.counters, GTF_NCOUNTERS_ALL);
+    DA(d.near_log, GTF_NEAR_LOG);
     {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
@@ -177,7 +178,7 @@ static int batch_alloc(gtf_batch *b)
     DA(b->sort_keys, N); DA(b->sort_vals, N); DA(b->sort_keys2, N); DA(b->sort_vals2, N);
     DA(b->pv_xy, N); DA(b->pv_zr, N); DA(b->acc_now, N); DA(b->tags_a, N); DA(b->tags_b, N);
     DA(b->tile_begin, (int64_t)N + 2); DA(b->stile_begin, 4 * ((int64_t)N + 2)); // at most one tile per node (+ sentinel); int4 per k_send tile
-    CK(cudaMallocHost((void **)&b->h_counters, sizeof(unsigned long long) * GTF_NCOUNTERS));
+    CK(cudaMallocHost((void **)&b->h_counters, sizeof(unsigned long long) * GTF_NCOUNTERS_ALL));
     CK(cudaMallocHost((void **)&b->h_tiles, sizeof(int32_t) * 5 * ((size_t)N + 2)));
     CK(cudaFuncSetAttribute(k_send, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SendSmem)));
     CK(cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
@@ -195,7 +196,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (int f = 0; f < GTF_NFIELDS; f++) cudaFree(b->f[f]);
     DevBatch &d = b->d;
     void *extra[] = {d.sub_nalive, d.node_ok, b->n_dead, d.slot_p11, d.slot_vms, d.node_p11tot, d.has_merged_nx, d.m_p11_nx,
-                     d.counters, b->accepted_total, b->cand_root, b->sub_has_inactive, b->sub_first, b->sort_keys,
+                     d.counters, d.near_log, b->accepted_total, b->cand_root, b->sub_has_inactive, b->sub_first, b->sort_keys,
                      b->sort_vals, b->sort_keys2, b->sort_vals2, b->pv_xy, b->pv_zr, b->acc_now, b->tags_a, b->tags_b,
                      b->tile_begin, b->sort_tmp, b->cand_rows};
     for (void *p : extra) cudaFree(p);
@@ -323,6 +324,22 @@ extern "C" int gtf_batch_device_ptr(gtf_batch *b, int f, void **dptr)
     if (f == GTF_F_alive || f == GTF_F_sub_state || f == GTF_F_sub) b->derived_dirty = true;
     if (f == GTF_F_has_merged || f == GTF_F_uts_next || f == GTF_F_has_uts || f == GTF_F_m_p11) b->force_pending = true;
     *dptr = b->f[f];
+    return 0;
+}
+extern "C" int gtf_batch_near_threshold(gtf_batch *b, gtf_near_rec *out, int cap, int64_t *n)
+{
+    if (!b || !n) return fail(GTF_E_ARG, "gtf_batch_near_threshold: null argument");
+    CK(cudaSetDevice(b->device));
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, b->d.counters + CNT_NEAR, sizeof(cnt), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    *n = (int64_t)cnt;
+    int k = (int)std::min<unsigned long long>(cnt, (unsigned long long)GTF_NEAR_LOG);
+    if (cap < k) k = cap;
+    if (out && k > 0) {
+        CK(cudaMemcpyAsync(out, b->d.near_log, sizeof(gtf_near_rec) * (size_t)k, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
     return 0;
 }
 extern "C" int gtf_batch_sync(gtf_batch *b)
@@ -535,12 +552,12 @@ extern "C" int gtf_batch_load_events(gtf_batch *b, const gtf_events *ev)
 // ------------------------------------------------------------------------------------------------ stats
 static int counters_reset(gtf_batch *b)
 {
-    CK(cudaMemsetAsync(b->d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS, b->stream));
+    CK(cudaMemsetAsync(b->d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS_ALL, b->stream));
     return 0;
 }
 static int counters_read(gtf_batch *b, gtf_stats *st)
 {
-    CK(cudaMemcpyAsync(b->h_counters, b->d.counters, sizeof(unsigned long long) * GTF_NCOUNTERS, cudaMemcpyDeviceToHost,
+    CK(cudaMemcpyAsync(b->h_counters, b->d.counters, sizeof(unsigned long long) * GTF_NCOUNTERS_ALL, cudaMemcpyDeviceToHost,
                        b->stream));
     CK(cudaStreamSynchronize(b->stream));
     if (st) {
@@ -552,6 +569,7 @@ static int counters_read(gtf_batch *b, gtf_stats *st)
         st->active_edges = (int64_t)b->h_counters[CNT_ACTIVE];
         st->active_changed = (int64_t)b->h_counters[CNT_CHANGED];
         st->ref_errors = (int64_t)b->h_counters[CNT_REFERR];
+        st->near_threshold = (int64_t)b->h_counters[CNT_NEAR];
     }
     return 0;
 }
@@ -819,7 +837,7 @@ static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int r
     DevBatch &d = b->d;
     const size_t words = ((size_t)b->E + 31) / 32 + 2;
     cudaStream_t s0 = b->stream;
-    CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS, s0));
+    CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS_ALL, s0));
     if (timed) CK(cudaEventRecord(b->evk[0], s0));
     {
         const int nthr = (int)std::max<size_t>(words, (size_t)b->N);
@@ -1423,4 +1441,111 @@ extern "C" int gtf_kl_pairs(int device, const double *mean, const double *cov, c
     CKF(cudaMemcpy(out, d_out, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost));
 #undef CKF
     return done(0);
+}
+
+// ------------------------------------------------------------------------------------------------ stand-alone helpers
+// The pure helper functions of the reference (clustering/clustering.py:11-124, extrapolate_merged_states.py:26) for
+// callers that use them outside the stages: tiny inputs, one launch each, same device arithmetic as the kernels.
+struct SmallBuf {       // device scratch for a handful of doubles, freed on scope exit
+    double *d = nullptr;
+    ~SmallBuf() { if (d) cudaFree(d); }
+};
+__global__ void k_pairwise_chi2(const double *sv, const double *cov, const double *node, const double *nbr, int n, GtfGeom g, double *out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n * n) return;
+    const int i = p / n, j = p % n;
+    double v = 0.0;
+    if (j < i) {        // lower triangle, zeros elsewhere (clustering.py:80-86)
+        GtfState si, sj;
+        si.a = sv[3 * i]; si.b = sv[3 * i + 1]; si.p00 = cov[9 * i]; si.p01 = cov[9 * i + 1]; si.p11 = cov[9 * i + 4];
+        sj.a = sv[3 * j]; sj.b = sv[3 * j + 1]; sj.p00 = cov[9 * j]; sj.p01 = cov[9 * j + 1]; sj.p11 = cov[9 * j + 4];
+        si.c = si.tau = si.p22 = sj.c = sj.tau = sj.p22 = 0.0;
+        v = gtf_pair_chi2(si, sj, node[0], node[2], node[3], nbr[4 * i], nbr[4 * i + 2], nbr[4 * i + 3], nbr[4 * j], nbr[4 * j + 2],
+                          nbr[4 * j + 3], g);
+    }
+    out[p] = v;
+}
+extern "C" int gtf_pairwise_chi2(int device, int32_t n, const double *edge_svs, const double *edge_covs, const double *node_coords,
+                                 const double *neighbour_coords, double sigma0rz, double sigma0rz2, double endcap_boundary, double *out)
+{
+    if (n < 0 || !edge_svs || !edge_covs || !node_coords || !neighbour_coords || !out) return fail(GTF_E_ARG, "gtf_pairwise_chi2: bad argument");
+    if (gtf_device_count() <= device || device < 0) return fail(GTF_E_CUDA, "gtf_pairwise_chi2: no such CUDA device");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(device));
+    SmallBuf B;
+    const size_t nin = (size_t)n * 16 + 4, nout = (size_t)n * n;
+    CK(cudaMalloc((void **)&B.d, sizeof(double) * (nin + nout)));
+    double *sv = B.d, *cov = sv + 3 * n, *node = cov + 9 * n, *nbr = node + 4, *o = B.d + nin;
+    CK(cudaMemcpy(sv, edge_svs, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(cov, edge_covs, sizeof(double) * 9 * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(node, node_coords, sizeof(double) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(nbr, neighbour_coords, sizeof(double) * 4 * n, cudaMemcpyHostToDevice));
+    GtfGeom g;
+    g.sigma0xy = 0.0; g.sigma0rz = sigma0rz; g.sigma0rz2 = sigma0rz2; g.endcap = endcap_boundary;
+    k_pairwise_chi2<<<(unsigned)((nout + 127) / 128), 128>>>(sv, cov, node, nbr, n, g, o);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, o, sizeof(double) * nout, cudaMemcpyDeviceToHost));
+    return 0;
+}
+__global__ void k_merge_states(const double *in, double *out) { gtf_merge_general(in, in + 3, in + 12, in + 15, out, out + 3); }
+extern "C" int gtf_merge_states(int device, const double *mean1, const double *cov1, const double *mean2, const double *cov2,
+                                double *merged_mean, double *merged_cov)
+{
+    if (!mean1 || !cov1 || !mean2 || !cov2 || !merged_mean || !merged_cov) return fail(GTF_E_ARG, "gtf_merge_states: null argument");
+    if (gtf_device_count() <= device || device < 0) return fail(GTF_E_CUDA, "gtf_merge_states: no such CUDA device");
+    CK(cudaSetDevice(device));
+    SmallBuf B;
+    CK(cudaMalloc((void **)&B.d, sizeof(double) * 36));
+    double h[24], o[12];
+    memcpy(h, mean1, 24); memcpy(h + 3, cov1, 72); memcpy(h + 12, mean2, 24); memcpy(h + 15, cov2, 72);
+    CK(cudaMemcpy(B.d, h, sizeof(h), cudaMemcpyHostToDevice));
+    k_merge_states<<<1, 1>>>(B.d, B.d + 24);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(o, B.d + 24, sizeof(o), cudaMemcpyDeviceToHost));
+    memcpy(merged_mean, o, 24); memcpy(merged_cov, o + 3, 72);
+    return 0;
+}
+// in: node xyzr[4], neighbour xyzr[4], state[3], block covariance (p00 p01 p11 p22), chi2 cut; out: gtf_edge_result as doubles
+__global__ void k_extrapolate_one(const double *in, GtfGeom g, double *out)
+{
+    const double a = in[8], b = in[9];
+    const double dr = in[7] - in[3], dz = in[6] - in[2];
+    const double var_ms = gtf_var_ms(a, b, in[4], dr, dz, in[2], g.endcap);       // extrapolate...py:114-124
+    const double p11 = in[14] + var_ms;                                           // :127-128 (the caller's matrix is updated too)
+    GtfExtrapOut o;
+    gtf_extrapolate(in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], a, b, in[10], in[11], in[12], p11, in[15], var_ms, in[16], g, o);
+    out[0] = o.pass; out[1] = o.chi2; out[2] = var_ms;
+    if (o.pass) {
+        out[3] = o.lik; out[4] = o.s.a; out[5] = o.s.b; out[6] = o.s.c; out[7] = o.s.tau;
+        out[8] = o.s.p00; out[9] = o.s.p01; out[10] = o.s.p11; out[11] = o.s.p22;
+    }
+}
+extern "C" int gtf_extrapolate_validate(int device, const double *node_xyzr, const double *neighbour_xyzr, const double *state,
+                                        double *state_cov, double chi2_cut, const gtf_geom *g, gtf_edge_result *out)
+{
+    if (!node_xyzr || !neighbour_xyzr || !state || !state_cov || !g || !out) return fail(GTF_E_ARG, "gtf_extrapolate_validate: null argument");
+    if (gtf_device_count() <= device || device < 0) return fail(GTF_E_CUDA, "gtf_extrapolate_validate: no such CUDA device");
+    if (state_cov[2] != 0.0 || state_cov[5] != 0.0 || state_cov[6] != 0.0 || state_cov[7] != 0.0)
+        return fail(GTF_E_ARG, "gtf_extrapolate_validate: the covariance must have the block form every stored state has "
+                               "(row / column 2 zero off the diagonal: helper.py:423-425, extrapolate_merged_states.py:363-365)");
+    CK(cudaSetDevice(device));
+    SmallBuf B;
+    CK(cudaMalloc((void **)&B.d, sizeof(double) * 32));
+    double h[17], o[12] = {0};
+    memcpy(h, node_xyzr, 32); memcpy(h + 4, neighbour_xyzr, 32); memcpy(h + 8, state, 24);
+    h[11] = state_cov[0]; h[12] = state_cov[1]; h[14] = state_cov[4]; h[15] = state_cov[8]; h[13] = 0.0; h[16] = chi2_cut;
+    CK(cudaMemcpy(B.d, h, sizeof(h), cudaMemcpyHostToDevice));
+    k_extrapolate_one<<<1, 1>>>(B.d, geom_of(g), B.d + 20);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(o, B.d + 20, sizeof(o), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->pass = (int32_t)o[0]; out->chi2 = o[1]; out->var_ms = o[2];
+    state_cov[4] += o[2];             // `merged_cov[1, 1] += var_ms` mutates the caller's matrix (quirk 2)
+    if (out->pass) {
+        out->likelihood = o[3];
+        out->state[0] = o[4]; out->state[1] = o[5]; out->state[2] = o[6]; out->tau = o[7];
+        out->cov[0] = o[8]; out->cov[1] = o[9]; out->cov[2] = o[10]; out->cov[3] = o[11];
+    }
+    return 0;
 }

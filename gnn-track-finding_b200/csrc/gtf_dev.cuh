@@ -32,7 +32,9 @@ struct DevBatch {
     uint8_t *has_merged_nx;
     double *m_p11_nx;
     unsigned long long *counters; // [GTF_NCOUNTERS]
+    gtf_near_rec *near_log;       // [GTF_NEAR_LOG] decisions within 1e-9 relative of their threshold (counters[CNT_NEAR] counts them)
 };
+#define GTF_NEAR_LOG 256
 
 // ---- packed iteration layout (gtf_iter.cuh): per-slot records + bitmaps, built from / written back to the SoA
 // fields by k_pack_* / k_unpack_slots.  The SoA arrays stay the exchange format of the C-ABI.
@@ -94,8 +96,21 @@ struct DevPack {
 };
 
 enum {
-    CNT_MERGED = 0, CNT_DEACT, CNT_SENT, CNT_GATED, CNT_RWOFF, CNT_ACTIVE, CNT_CHANGED, CNT_REFERR, GTF_NCOUNTERS
+    CNT_MERGED = 0, CNT_DEACT, CNT_SENT, CNT_GATED, CNT_RWOFF, CNT_ACTIVE, CNT_CHANGED, CNT_REFERR, GTF_NCOUNTERS,
+    CNT_NEAR = GTF_NCOUNTERS, GTF_NCOUNTERS_ALL     // (CNT_NEAR is bumped in global memory directly: a rare event)
 };
+// a decision `value (<|<=) threshold` was just taken: note it when it is a boundary-flip candidate
+__device__ __forceinline__ void near_note(const DevBatch &B, int kind, int index, double value, double threshold)
+{
+    if (fabs(value - threshold) <= GTF_NEAR_RTOL * fabs(threshold)) {
+        const unsigned long long k = atomicAdd(&B.counters[CNT_NEAR], 1ull);
+        if (k < GTF_NEAR_LOG) {
+            gtf_near_rec r;
+            r.kind = kind; r.index = index; r.value = value; r.threshold = threshold;
+            B.near_log[k] = r;
+        }
+    }
+}
 
 // per-node program executed by the tile kernel
 enum { PG_ACT = 0, PG_PRES = 1, PG_REC = 2, PG_NODE = 3, PG_N = 4 };

@@ -198,13 +198,13 @@ __global__ void k_begin(DevBatch B, DevPack K, int words)
 //                                active successors, summed left to right (quirk 2); the total stays on the node
 //   phase 4  thread per message: coalesced append to the global source-major list k_exec consumes densely
 #ifndef GTF_SEND_THREADS
-#define GTF_SEND_THREADS 256
+#define GTF_SEND_THREADS 128
 #endif
 #ifndef GTF_SEND_EPT
 #define GTF_SEND_EPT 3                                   // out-edges per thread
 #endif
 #ifndef GTF_SEND_MINB
-#define GTF_SEND_MINB 4
+#define GTF_SEND_MINB 8
 #endif
 #define GTF_SEND_EDGES (GTF_SEND_THREADS * GTF_SEND_EPT)
 #define GTF_SEND_SRCS (GTF_SEND_THREADS - 1)             // (+1 offsets: one per thread; <= 255: uint8 source index)
@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
             bm_clear(K.act_nx, s); // :393
             gated++;
         }
+        near_note(B, GTF_NEAR_GATE, s, o.chi2, chi2_cut);
         q = qn;
     }
     if (sent) atomicAdd(&s_cnt[CNT_SENT], sent);
@@ -556,7 +557,7 @@ __device__ __forceinline__ void lent_prior(LEnt &a, LEnt &b, int n)
     if (ea) a.prior = same ? 0.5 : 1.0; // helper.py:61: 1/len(group)
     if (eb) b.prior = same ? 0.5 : 1.0;
 }
-__device__ __forceinline__ void lent_reweight(unsigned int *cnt, LEnt &a, LEnt &b, int n, double nodex, double thr)
+__device__ __forceinline__ void lent_reweight(const DevBatch &B, unsigned int *cnt, LEnt &a, LEnt &b, int n, double nodex, double thr)
 {
     const unsigned m3 = H_PRES | H_EX | H_ACT;
     const bool ea = (a.f & m3) == m3, eb = n == 2 && (b.f & m3) == m3;
@@ -577,6 +578,7 @@ __device__ __forceinline__ void lent_reweight(unsigned int *cnt, LEnt &a, LEnt &
         if (norm != 1) rw = rw / (double)norm;
         a.lrn = norm; a.side = la ? 1 : 2; a.w = rw; a.ew = rw;
         a.f |= H_RW;
+        near_note(B, GTF_NEAR_REWEIGHT, a.s, rw, thr);
         if (rw < thr) { a.f &= ~H_ACT; off++; }
     }
     if (eb) {
@@ -584,6 +586,7 @@ __device__ __forceinline__ void lent_reweight(unsigned int *cnt, LEnt &a, LEnt &
         if (norm != 1) rw = rw / (double)norm;
         b.lrn = norm; b.side = lb ? 1 : 2; b.w = rw; b.ew = rw;
         b.f |= H_RW;
+        near_note(B, GTF_NEAR_REWEIGHT, b.s, rw, thr);
         if (rw < thr) { b.f &= ~H_ACT; off++; }
     }
     if (off) atomicAdd(&cnt[CNT_RWOFF], off);
@@ -674,9 +677,9 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
                 if (n) {
                     const double nodex = B.x[i];
                     if (rdict) lent_prior(a, b, n);
-                    if (ruts) lent_reweight(s_cnt, a, b, n, nodex, P.rw_thr);
+                    if (ruts) lent_reweight(B, s_cnt, a, b, n, nodex, P.rw_thr);
                     if (rdict) lent_prior(a, b, n);
-                    if (ruts) lent_reweight(s_cnt, a, b, n, nodex, P.rw_thr);
+                    if (ruts) lent_reweight(B, s_cnt, a, b, n, nodex, P.rw_thr);
                 }
                 if (rdict) {
                     if (n == 0) atomicOr(&s_cnt[CNT_REFERR], (unsigned)GTF_REF_ZERO_DIV);
@@ -974,6 +977,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
                     lrn = norm; side = left ? 1 : 2;
                     w = rw; ew = rw;
                     f |= H_RW;
+                    near_note(B, GTF_NEAR_REWEIGHT, slot, rw, P.rw_thr);
                     if (rw < P.rw_thr) { f &= ~H_ACT; n_off++; }
                 }
             }
@@ -1029,6 +1033,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             if (cl_node && !nz_any && gl == 0) referr |= GTF_REF_EMPTY_MIN;    // np.min([]) -> ValueError
             const double best = key_dbl(grp_min_u64<G>(dbl_key(lbest)));
             bool go = cl_node && nz_any && !nan_any && best < P.cl_chi2;       // clustering.py:228 (nan < thr is False)
+            if (cl_node && nz_any && !nan_any && gl == 0) near_note(B, GTF_NEAR_CLUSTER_CHI2, i, best, P.cl_chi2);
             // np.where(distances == smallest): all tied positions in row-major order (clustering.py:122-123)
             unsigned t1 = 1u << 30, t2 = 1u << 30, nm = 0, gone = 0;
 #pragma unroll
@@ -1096,6 +1101,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
                     if (!tie) bk = -1;
                     const double bv = key_dbl(mk);
                     const bool absorb = live && !nan_kl && bk >= 0 && bv < thr;                // clustering.py:261
+                    if (live && !nan_kl && bk >= 0 && gl == 0) near_note(B, GTF_NEAR_CLUSTER_KL, i, bv, thr);
                     if (live && nan_kl) {
                         if (gl == 0) referr |= GTF_REF_NAN_INDEX;
                         clustered = false;

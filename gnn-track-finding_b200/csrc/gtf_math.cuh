@@ -354,6 +354,21 @@ GTF_HD double gtf_kl_general(const double *m1, const double *c1, const double *m
     return tr + (t0 * d0 + t1 * d1 + t2 * d2);
 }
 
+// clustering.py:97-105 merge_states for GENERAL 3x3 covariances (the stand-alone helper; the kernels use the block form)
+GTF_HD void gtf_merge_general(const double *m1, const double *c1, const double *m2, const double *c2, double *mm, double *mc)
+{
+    double i1[9], i2[9], sum[9];
+    gtf_inv3_general(c1, i1);
+    gtf_inv3_general(c2, i2);
+    for (int k = 0; k < 9; k++) sum[k] = i1[k] + i2[k];
+    gtf_inv3_general(sum, mc);
+    double v[3];
+    for (int r = 0; r < 3; r++)
+        v[r] = (i1[3 * r] * m1[0] + i1[3 * r + 1] * m1[1] + i1[3 * r + 2] * m1[2]) +
+               (i2[3 * r] * m2[0] + i2[3 * r + 1] * m2[1] + i2[3 * r + 2] * m2[2]);
+    for (int r = 0; r < 3; r++) mm[r] = mc[3 * r] * v[0] + mc[3 * r + 1] * v[1] + mc[3 * r + 2] * v[2];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Candidate quality gate (extract/extract_track_candidates.py:172-328).
 

@@ -130,7 +130,7 @@ __device__ __forceinline__ void node_prior(TileSmem &sm, int b0, int b1, int lan
 
 // helper.py:99-200 calculate_side_norm_factor + reweight for one node
 __device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int n, double nodex, double thr, int lane,
-                                              double *edge_w_tile, double *lrn_tile)
+                                              double *edge_w_tile, double *lrn_tile, const DevBatch &B, int s0)
 {
     const unsigned m = F_PRES | F_EX | F_ACT;
     int nl = 0, nr = 0, normL = 0, normR = 0;
@@ -174,6 +174,7 @@ __device__ __forceinline__ void node_reweight(TileSmem &sm, int b0, int b1, int 
             sm.w[ls] = rw;
             edge_w_tile[ls] = rw; // helper.py:180 edge attribute (coalesced: consecutive lanes, consecutive slots)
             unsigned f = sm.flags[ls] | F_RW;
+            near_note(B, GTF_NEAR_REWEIGHT, s0 + ls, rw, thr);
             if (rw < thr) { f &= ~F_ACT; off++; } else f |= F_ACT;
             sm.flags[ls] = (uint8_t)f;
         }
@@ -219,7 +220,8 @@ __device__ __forceinline__ void shfl_info(const GtfInfo &in, int src, GtfInfo &o
 template <class SM>
 __device__ __forceinline__ bool node_cluster(SM &sm, double *Dw, int b0, int n, double nx, double nz, double nr_,
                                              double chi2_thr, double kl_thr, const GtfGeom &g, int lane,
-                                             GtfState &merged, double &mprior, const double *gz, const double *gr)
+                                             GtfState &merged, double &mprior, const double *gz, const double *gr,
+                                             const DevBatch &B, int node)
 {
     if (n < 3 || n > GTF_MAXD) return false; // clustering.py:207
     const unsigned FULL = 0xffffffffu;
@@ -249,6 +251,7 @@ __device__ __forceinline__ bool node_cluster(SM &sm, double *Dw, int b0, int n, 
     if (nan_any) return false; // np.min -> nan, `nan < thr` False
     double best;
     warp_argmin(lbest, true, best);
+    if (lane == 0) near_note(B, GTF_NEAR_CLUSTER_CHI2, node, best, chi2_thr);
     if (!(best < chi2_thr)) return false; // clustering.py:228
     // np.where(distances == smallest): all tied positions in row-major order (clustering.py:122-123)
     int p1 = 1 << 30, nm = 0;
@@ -302,6 +305,7 @@ __device__ __forceinline__ bool node_cluster(SM &sm, double *Dw, int b0, int n, 
         }
         double bv;
         int bk = warp_argmin(kl, have, bv);                  // list.index: first occurrence
+        if (bk >= 0 && lane == 0) near_note(B, GTF_NEAR_CLUSTER_KL, node, bv, kl_thr);
         if (bk < 0 || !(bv < kl_thr)) break;                 // clustering.py:261
         shfl_info(mine_i, bk, t);                            // :263-265 merge_states(entry, merged)
         gtf_info_add(M, t);
@@ -378,7 +382,7 @@ __device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch B
         } else if (op == OP_RW) {
             if (uts && (nf & (NF_OK | NF_MULTI | NF_HASUTS)) == (NF_OK | NF_MULTI | NF_HASUTS)) {
                 if (n < 0) n = node_build_order(sm, b0, b1, lane);
-                node_reweight(sm, b0, b1, n, B.x[i], P.rw_thr, lane, ew_base, lrn_base);
+                node_reweight(sm, b0, b1, n, B.x[i], P.rw_thr, lane, ew_base, lrn_base, B, s0);
             }
         } else if (op == OP_CLUSTER) {
             if ((nf & (NF_OK | NF_DICT)) == (NF_OK | NF_DICT)) {
@@ -389,7 +393,7 @@ __device__ __noinline__ void node_program_generic(TileSmem &sm, const DevBatch B
                     int bin = (ev == ev) ? (int)floor(ev / 0.05) : 27;
                     thr = P.lut[max(0, min(27, bin))];
                 }
-                clustered = node_cluster(sm, sm.D[warp], b0, n, B.x[i], B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior, B.z, B.r);
+                clustered = node_cluster(sm, sm.D[warp], b0, n, B.x[i], B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior, B.z, B.r, B, i);
             }
         } else if (op == OP_DEGREE) {
             int deg = 0;
@@ -532,6 +536,7 @@ __device__ __forceinline__ void node_program_fast(SM &sm, const DevBatch &B, con
                         w = rw;
                         B.edge_w[s0 + ls] = rw; // helper.py:180
                         f |= F_RW;
+                        near_note(B, GTF_NEAR_REWEIGHT, s0 + ls, rw, P.rw_thr);
                         if (rw < P.rw_thr) f &= ~F_ACT; else f |= F_ACT;
                     }
                     int off = __popc(__ballot_sync(FULL, el && !(f & F_ACT)));
@@ -549,7 +554,7 @@ __device__ __forceinline__ void node_program_fast(SM &sm, const DevBatch &B, con
                     int bin = (ev == ev) ? (int)floor(ev / 0.05) : 27;
                     thr = P.lut[max(0, min(27, bin))];
                 }
-                clustered = node_cluster(sm, scratch, b0, n, nodex, B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior, B.z, B.r);
+                clustered = node_cluster(sm, scratch, b0, n, nodex, B.z[i], B.r[i], P.cl_chi2, thr, g, lane, merged, mprior, B.z, B.r, B, i);
                 if (valid) f = sm.flags[ls];
             }
         } else if (op == OP_DEGREE) {
@@ -695,6 +700,7 @@ __global__ void __launch_bounds__(GTF_TILE_THREADS, GTF_TILE_MINB) k_tile(DevBat
             gtf_extrapolate(sm.srcx[ls], B.y[u], B.z[u], B.r[u], B.x[v], B.y[v], B.z[v], B.r[v], B.m_a[u],
                             B.m_b[u], B.m_c[u], B.m_p00[u], B.m_p01[u], B.slot_p11[s], B.m_p22[u], B.slot_vms[s],
                             P.chi2_cut, g, o);
+            near_note(B, GTF_NEAR_GATE, s, o.chi2, P.chi2_cut);
             B.uts_chi2[s] = o.chi2;
             if (o.pass) {
                 int rs = B.rev_slot[s];

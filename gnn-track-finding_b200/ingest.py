@@ -11,6 +11,14 @@ Follows utilities/helper.py:524-545 (load_nodes_edges) and :465-520 (construct_g
 import numpy as np
 
 
+def radius_like_reference(x, y):
+    """r = np.sqrt(row.x**2 + row.y**2) evaluated row by row (helper.py:12-13, :532): a scalar `**2` goes through libm's
+    pow(), which is not always the correctly rounded x*x -- 16 of the 30,387 radii of the shipped event differ in the last
+    bit from sqrt(x*x + y*y).  The radius is an INPUT of the arithmetic, so ingest reproduces the reference's bits."""
+    import math
+    return np.array([math.sqrt(math.pow(a, 2) + math.pow(b, 2)) for a, b in zip(x.tolist(), y.tolist())], np.float64)
+
+
 def load_event_csv(event_prefix, min_volume, max_volume, truth=None):
     """event_prefix: path prefix such that prefix+'nodes.csv' / prefix+'edges.csv' exist (the reference passes
     '<dir>/event_1_filtered_graph_').  Returns a synth-style event dict (synth.event_to_host consumes it);
@@ -33,8 +41,9 @@ def load_event_csv(event_prefix, min_volume, max_volume, truth=None):
     pos[idx] = np.arange(len(idx))
     ok = (pos[n1] >= 0) & (pos[n2] >= 0)
     ev = {
-        "x": x, "y": y, "z": z, "r": np.sqrt(x * x + y * y),
+        "x": x, "y": y, "z": z, "r": radius_like_reference(x, y),
         "layer": (layer_id % 100).astype(np.int32), "volume": (layer_id // 1000).astype(np.int32),
+        "layer_id_mod1000": (layer_id % 1000).astype(np.int32),
         "truth": np.full(len(idx), -1, np.int64) if truth is None else np.asarray(truth, np.int64)[keep],
         "edge_a": pos[n1[ok]].astype(np.int32), "edge_b": pos[n2[ok]].astype(np.int32),   # add_edge(node1, node2) first
         "node_idx": idx,

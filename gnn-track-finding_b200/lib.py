@@ -21,10 +21,18 @@ class Geom(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in ("nodes_merged", "edges_deactivated", "edges_sent", "edges_gated",
-                                               "edges_reweight_off", "active_edges", "active_changed", "ref_errors")]
+                                               "edges_reweight_off", "active_edges", "active_changed", "ref_errors",
+                                               "near_threshold")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class NearRec(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("index", ctypes.c_int32), ("value", ctypes.c_double), ("threshold", ctypes.c_double)]
+
+
+NEAR_KINDS = ("gate chi2 <= chi2CutFactor", "reweight < threshold", "cluster chi2 < chi2_threshold", "cluster KL < KL_threshold")
 
 
 class IterParams(ctypes.Structure):
@@ -94,6 +102,7 @@ def lib():
         "gtf_batch_load_events": (ctypes.c_int, [vp, ctypes.POINTER(Events)]),
         "gtf_candidates_device": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]),
         "gtf_batch_sync": (ctypes.c_int, [vp]),
+        "gtf_batch_near_threshold": (ctypes.c_int, [vp, ctypes.POINTER(NearRec), ctypes.c_int, ctypes.POINTER(i64)]),
         "gtf_batch_stream": (ctypes.c_int, [vp, ctypes.POINTER(vp)]),
         "gtf_batch_device_bytes": (i64, [vp]),
         "gtf_batch_iteration_launches": (i64, [vp]),
@@ -115,6 +124,8 @@ def lib():
         "gtf_batch_timing": (ctypes.c_int, [vp, dp, dp, dp, ctypes.POINTER(ctypes.c_int)]),
         "gtf_batch_timing_kernels": (ctypes.c_int, [vp, dp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
         "gtf_kl_pairs": (ctypes.c_int, [ctypes.c_int, dp, dp, ctypes.POINTER(i32), i32, dp, i64, ctypes.POINTER(i64)]),
+        "gtf_pairwise_chi2": (ctypes.c_int, [ctypes.c_int, i32, dp, dp, dp, dp, dbl, dbl, dbl, dp]),
+        "gtf_merge_states": (ctypes.c_int, [ctypes.c_int, dp, dp, dp, dp, dp, dp]),
         "gtf_components": (ctypes.c_int, [vp]),
         "gtf_extract": (ctypes.c_int, [vp, pg, dbl, ctypes.c_int, dbl, dbl, ctypes.POINTER(i32),
                                        ctypes.POINTER(ctypes.c_uint8), dp, dp]),

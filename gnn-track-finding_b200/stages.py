@@ -160,3 +160,113 @@ def KLDistance_pairs(means, covs, offsets, device=0):
     if n.value:
         L.check(lib.gtf_kl_pairs(*args, out.ctypes.data_as(dp), n.value, ctypes.byref(n)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's stand-alone helpers (clustering/clustering.py:11-124, extrapolate_merged_states.py:26) under their own
+# names and argument order.  The arithmetic runs on the GPU through the C-ABI (one tiny launch per call: they exist for
+# callers that use the helpers directly -- the stages above never go through them).
+def _dp(a):
+    import ctypes
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def calc_pairwise_distances_chi2(num_edges, edge_svs, edge_covs, node_coords, neighbour_coords, sigma0rz, sigma0rz2,
+                                 endcap_boundary, device=0):
+    """clustering.py:80 -- (num_edges, num_edges) matrix, lower triangle = mahalanobis_distance(i, j < i), zeros elsewhere"""
+    from . import lib as L
+    n = int(num_edges)
+    sv = np.ascontiguousarray(np.asarray(edge_svs, np.float64).reshape(n, 3))
+    cv = np.ascontiguousarray(np.asarray(edge_covs, np.float64).reshape(n, 9))
+    nd = np.ascontiguousarray(np.asarray(node_coords, np.float64).reshape(4))
+    nb = np.ascontiguousarray(np.asarray(neighbour_coords, np.float64).reshape(n, 4))
+    out = np.zeros((n, n))
+    L.check(L.lib().gtf_pairwise_chi2(device, n, _dp(sv), _dp(cv), _dp(nd), _dp(nb), sigma0rz, sigma0rz2, endcap_boundary, _dp(out)))
+    return out
+
+
+def mahalanobis_distance(mean1, cov1, mean2, cov2, node_coords, neighbour1_coords, neighbour2_coords, sigma0rz, sigma0rz2,
+                         endcap_boundary, device=0):
+    """clustering.py:11"""
+    return calc_pairwise_distances_chi2(2, [mean2, mean1], [cov2, cov1], node_coords, [neighbour2_coords, neighbour1_coords],
+                                        sigma0rz, sigma0rz2, endcap_boundary, device)[1, 0]
+
+
+def KLDistance(mean1, cov1, mean2, cov2, device=0):
+    """clustering.py:90 (the "trace" of the element-wise product, pinned by the reference's shipped CSV)"""
+    return float(KLDistance_pairs([mean2, mean1], [cov2, cov1], [0, 2], device)[0])
+
+
+def merge_states(mean1, cov1, mean2, cov2, device=0):
+    """clustering.py:97 -- inverse-variance weighting; returns (merged_mean (3,), merged_cov (3, 3))"""
+    from . import lib as L
+    a = [np.ascontiguousarray(np.asarray(v, np.float64).reshape(-1)) for v in (mean1, cov1, mean2, cov2)]
+    mm, mc = np.zeros(3), np.zeros((3, 3))
+    L.check(L.lib().gtf_merge_states(device, _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(mm), _dp(mc)))
+    return mm, mc
+
+
+def calc_dist_to_merged_state(num_edges, edge_svs, edge_covs, merged_mean, merged_cov, device=0):
+    """clustering.py:107 -- list of KLDistance(component i, merged state)"""
+    n = int(num_edges)
+    if n == 0:
+        return []
+    means = np.empty((2 * n, 3))
+    covs = np.empty((2 * n, 9))
+    means[0::2], means[1::2] = np.asarray(merged_mean, np.float64).reshape(3), np.asarray(edge_svs, np.float64).reshape(n, 3)
+    covs[0::2], covs[1::2] = np.asarray(merged_cov, np.float64).reshape(9), np.asarray(edge_covs, np.float64).reshape(n, 9)
+    return [float(v) for v in KLDistance_pairs(means, covs, np.arange(0, 2 * n + 1, 2), device)]
+
+
+def get_smallest_dist_idx(distances):
+    """clustering.py:114 -- list: (min, first index of it); matrix: min over the NON-ZERO entries and every position holding
+    it as [rows..., cols...] (ties give more than two indices; the caller uses the first two).  Index logic only."""
+    if isinstance(distances, list):
+        smallest = np.min(distances)
+        return smallest, distances.index(smallest)
+    distances = np.asarray(distances)
+    smallest = np.min(distances[np.nonzero(distances)])
+    rows, cols = np.where(distances == smallest)
+    return smallest, np.concatenate((rows, cols), axis=None)
+
+
+def extrapolate_validate(subGraph, node_num, node_attr, neighbour_num, neighbour_attr, chi2CutFactor, state_to_extrapolate,
+                         state_cov, sigma0xy, sigma0rz, sigma0rz2, endcap_boundary, is_merged_state=False, device=0):
+    """extrapolate_merged_states.py:26 for one edge node -> neighbour.  Like the reference it mutates `state_cov[1, 1]`
+    (+= var_ms) and, on gate failure, sets the edge's `activated` to 0.  Returns the reference's 6-tuple."""
+    import ctypes
+    from . import lib as L
+
+    def xyzr(attr):
+        gm = attr["GNN_Measurement"]
+        return np.array([gm.x, gm.y, gm.z, gm.r], np.float64)
+
+    class EdgeResult(ctypes.Structure):
+        _fields_ = [("pass_", ctypes.c_int32), ("pad", ctypes.c_int32), ("chi2", ctypes.c_double), ("var_ms", ctypes.c_double),
+                    ("likelihood", ctypes.c_double), ("state", ctypes.c_double * 3), ("tau", ctypes.c_double),
+                    ("cov", ctypes.c_double * 4)]
+
+    nd, nb = xyzr(node_attr), xyzr(neighbour_attr)
+    st = np.ascontiguousarray(np.asarray(state_to_extrapolate, np.float64).reshape(3))
+    cov = np.ascontiguousarray(np.asarray(state_cov, np.float64).reshape(9))
+    res = EdgeResult()
+    geom = L.Geom(sigma0xy, sigma0rz, sigma0rz2, endcap_boundary)
+    fn = L.lib().gtf_extrapolate_validate
+    fn.restype = ctypes.c_int
+    L.check(fn(ctypes.c_int(device), _dp(nd), _dp(nb), _dp(st), _dp(cov), ctypes.c_double(chi2CutFactor), ctypes.byref(geom),
+               ctypes.byref(res)))
+    state_cov[1, 1] = cov[4]                                  # in-place accumulation on the caller's matrix (quirk 2)
+    same = subGraph.nodes[node_num]["truth_particle"] == subGraph.nodes[neighbour_num]["truth_particle"]
+    if not res.pass_:
+        subGraph[node_num][neighbour_num]["activated"] = 0
+        return None, res.chi2, 0 if same else 1, 1, 0, 0
+    updated_state = np.array(list(res.state))
+    p00, p01, p11, p22 = list(res.cov)
+    updated_cov = np.array([[p00, p01, 0.0], [p01, p11, 0.0], [0.0, 0.0, p22]])
+    return {"xy": (nd[0], nd[1]), "zr": (nd[2], nd[3]), "xyzr": (nd[0], nd[1], nd[2], nd[3]),
+            "edge_state_vector": updated_state, "edge_covariance": updated_cov,
+            "joint_vector": [updated_state[0], updated_state[1], res.tau],
+            "joint_vector_covariance": updated_cov,           # the same object, as in the reference (quirk 4)
+            "likelihood": res.likelihood,
+            "mixture_weight": subGraph.nodes[node_num]["track_state_estimates"][neighbour_num]["mixture_weight"]}, \
+        res.chi2, 0, 0, 1 if same else 0, 1

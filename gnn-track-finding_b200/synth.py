@@ -197,8 +197,86 @@ def degree_stats(ev):
 # native (networkx-free) construction of the flat layout for synthetic events
 
 
-def event_to_host(ev, event_id=0):
+def reorder_slots_pyset(hb, node_ids):
+    """Re-order every node's in-slots (= the key order of its seeded state dict) the way the reference does:
+    helper.py:280 iterates `set(nx.all_neighbors(G, node))`, i.e. the order is CPython's set-iteration order of the
+    neighbour IDS, filled from the predecessors (ascending node order inside the sub-graph copy, event_conversion.py:84)
+    followed by the successors (adjacency insertion order), and the list is then REVERSED (helper.py:350-351) before the
+    entries are inserted.  This runs under the same interpreter, so Python's own `set`
+    gives exactly that order (host-side ingest logic; no arithmetic).  `node_ids[i]` = graph id of node row i."""
+    N, E = len(hb["x"]), len(hb["in_src"])
+    in_off, in_src = hb["in_off"], hb["in_src"]
+    out_off, out_slot, slot_dst = hb["out_off"], hb["out_slot"], hb["slot_dst"]
+    ids = [int(v) for v in node_ids]
+    new_of_old = np.empty(E, np.int64)
+    for v in range(N):
+        s0, s1 = int(in_off[v]), int(in_off[v + 1])
+        if s1 - s0 <= 1:
+            new_of_old[s0:s1] = np.arange(s0, s1)
+            continue
+        srcs = in_src[s0:s1].tolist()
+        slot_of = {ids[u]: s0 + k for k, u in enumerate(srcs)}
+        succ = [ids[int(slot_dst[out_slot[o]])] for o in range(int(out_off[v]), int(out_off[v + 1]))]
+        order = [k for k in set([ids[u] for u in sorted(srcs)] + succ) if k in slot_of][::-1]   # `keys.reverse()`, helper.py:351
+        for k, key in enumerate(order):
+            new_of_old[slot_of[key]] = s0 + k
+    out = dict(hb)
+    perm = np.empty(E, np.int64)          # perm[new] = old
+    perm[new_of_old] = np.arange(E)
+    out["in_src"] = in_src[perm]
+    out["slot_dst"] = slot_dst[perm]
+    out["out_slot"] = new_of_old[out_slot].astype(np.int32)
+    rs = hb["rev_slot"][perm]
+    out["rev_slot"] = np.where(rs >= 0, new_of_old[np.maximum(rs, 0)], -1).astype(np.int32)
+    return out
+
+
+def networkx_subgraph_order(n, src, dst, ids):
+    """Node order of the sub-graph list `[G.subgraph(c).copy() for c in nx.weakly_connected_components(G)]`
+    (event_conversion.py:84) without networkx: components in the order of their first node; inside a component networkx
+    (3.x: `_plain_bfs` returns its `seen` set, `subgraph` filters with `set(nodes)` and iterates THAT set when it is smaller
+    than half the graph) yields the nodes in CPython set-iteration order of the ids, inserted in BFS order (successors, then
+    predecessors, adjacency insertion order).  Host-side ingest logic under the same interpreter: Python's own `set` is used.
+    src / dst: directed edges in insertion order as node rows 0..n-1; ids[row] = graph id.  Returns (order, sub_of_row)."""
+    succ = [[] for _ in range(n)]
+    pred = [[] for _ in range(n)]
+    for a, b in zip(src.tolist(), dst.tolist()):
+        succ[a].append(b)
+        pred[b].append(a)
+    ids = [int(v) for v in ids]
+    row_of = {k: r for r, k in enumerate(ids)}
+    seen_all = np.zeros(n, bool)
+    order, sub_of = [], np.zeros(n, np.int64)
+    n_sub = 0
+    for v in range(n):
+        if seen_all[v]:
+            continue
+        seen = {ids[v]}
+        nextlevel = [v]
+        while nextlevel:
+            thislevel, nextlevel = nextlevel, []
+            for u in thislevel:
+                for w in succ[u] + pred[u]:
+                    if ids[w] not in seen:
+                        seen.add(ids[w])
+                        nextlevel.append(w)
+        nodes = set(k for k in seen)                        # nx.filters.show_nodes: set(nbunch_iter(c)) -- filled one by one
+                                                            # from a generator (set(seen) would copy the table layout)
+        if 2 * len(nodes) < n:
+            rows = [row_of[k] for k in nodes]
+        else:
+            rows = sorted(row_of[k] for k in nodes)         # FilterAtlas falls back to the graph's own node order
+        seen_all[rows] = True
+        sub_of[rows] = n_sub
+        order += rows
+        n_sub += 1
+    return np.array(order, np.int64), sub_of
+
+
+def event_to_host(ev, event_id=0, dict_order="insertion"):
     """Flat host batch (topology + hit arrays) of one synthetic event, no networkx involved.
+    dict_order="pyset": the orders the REFERENCE's ingest produces for this event (networkx_subgraph_order for the nodes,
+    reorder_slots_pyset for the state dicts); needs ev["node_idx"] when the graph ids are not 0..n-1.
 
     Orders are *defined* here (they are inputs of the algorithm, SURVEY.md §7 "Order as data"):
       * sub-graphs = weakly connected components, ordered by their smallest hit id; nodes inside a
@@ -230,6 +308,8 @@ def event_to_host(ev, event_id=0):
     comp_rank = np.argsort(np.argsort(comp_min))          # sub-graph index by smallest member
     sub_of = comp_rank[comp]
     order = np.lexsort((np.arange(n), sub_of))            # new position -> old id
+    if dict_order == "pyset":
+        order, sub_of = networkx_subgraph_order(n, src, dst, ev["node_idx"] if "node_idx" in ev else np.arange(n))
     newpos = np.empty(n, np.int64)
     newpos[order] = np.arange(n)
     S = ncomp
@@ -264,7 +344,7 @@ def event_to_host(ev, event_id=0):
     sub_off = np.zeros(S + 1, np.int64)
     np.add.at(sub_off, sub_sorted + 1, 1)
     sub_off = np.cumsum(sub_off)
-    return {
+    hb = {
         "x": ev["x"][order], "y": ev["y"][order], "z": ev["z"][order], "r": ev["r"][order],
         "layer": ev["layer"][order].astype(np.int32), "volume": ev["volume"][order].astype(np.int32),
         "truth": ev["truth"][order], "orig_id": order.astype(np.int64),
@@ -275,6 +355,10 @@ def event_to_host(ev, event_id=0):
         "out_off": out_off.astype(np.int32), "out_slot": out_slot.astype(np.int32),
         "rev_slot": rev_slot.astype(np.int32),
     }
+    if dict_order == "pyset":
+        ids = ev["node_idx"] if "node_idx" in ev else np.arange(n)
+        hb = reorder_slots_pyset(hb, np.asarray(ids)[order])
+    return hb
 
 
 _NODE_IDX = ("in_src", "slot_dst")

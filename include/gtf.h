@@ -56,7 +56,22 @@ typedef struct {
     int64_t active_edges;       /* existing edges with activated == 1 after the call */
     int64_t active_changed;     /* edges whose flag changed in the call (convergence test) */
     int64_t ref_errors;         /* OR of GTF_REF_* */
+    int64_t near_threshold;     /* decisions taken within GTF_NEAR_RTOL (1e-9 relative) of their threshold in this call: the
+                                   "boundary flip candidates" of SURVEY.md 8d; the records are read with
+                                   gtf_batch_near_threshold */
 } gtf_stats;
+
+/* one decision whose value lies within 1e-9 relative of its threshold (an fp64 implementation with a different operation
+ * order may take it the other way) */
+#define GTF_NEAR_RTOL 1e-9
+#define GTF_NEAR_GATE 0         /* chi2 <= chi2CutFactor     extrapolate_merged_states.py:298   index = slot */
+#define GTF_NEAR_REWEIGHT 1     /* reweight < 0.1            utilities/helper.py:186            index = slot */
+#define GTF_NEAR_CLUSTER_CHI2 2 /* smallest_dist < chi2_thr  clustering/clustering.py:228       index = node */
+#define GTF_NEAR_CLUSTER_KL 3   /* smallest_dist < KL_thr    clustering/clustering.py:261       index = node */
+typedef struct {
+    int32_t kind, index;
+    double value, threshold;
+} gtf_near_rec;
 
 typedef struct {
     double chi2_cut;            /* extrapolation gate            run_gnn_trackml_mod.sh:28  (2.0)   */
@@ -107,6 +122,9 @@ typedef struct {
     const int32_t *out_off, *out_slot; /* [N+1], [E] out-CSR by source, successor order   extrapolate...py:430          */
 } gtf_events;
 int gtf_batch_load_events(gtf_batch *b, const gtf_events *ev);
+/* the boundary-flip candidates of the most recent stage call / iteration on this batch: up to `cap` records into `out`
+ * (the library keeps the first 256), *n = how many the call counted */
+int gtf_batch_near_threshold(gtf_batch *b, gtf_near_rec *out, int cap, int64_t *n);
 int gtf_batch_sync(gtf_batch *b);
 int gtf_batch_stream(gtf_batch *b, void **cuda_stream);
 int64_t gtf_batch_device_bytes(const gtf_batch *b);
@@ -199,6 +217,28 @@ int gtf_candidates_device(gtf_batch *b, int32_t **rows_dev, int64_t *n_rows);
  * out == NULL: count only).  Needs no batch. */
 int gtf_kl_pairs(int device, const double *mean, const double *cov, const int32_t *off, int32_t n_groups, double *out,
                  int64_t cap, int64_t *n_pairs);
+
+/* ---- the reference's stand-alone helper functions (tiny inputs, one launch each; same device arithmetic as the kernels) --- */
+/* clustering/clustering.py:80-86 calc_pairwise_distances_chi2 (= :11-78 mahalanobis_distance for every pair j < i):
+ * edge_svs f64[n][3], edge_covs f64[n][3][3] (only the symmetric [0:2, 0:2] block enters), node_coords (x, y, z, r),
+ * neighbour_coords f64[n][4]; out f64[n][n], lower triangle filled, zeros elsewhere.  Needs no batch. */
+int gtf_pairwise_chi2(int device, int32_t n, const double *edge_svs, const double *edge_covs, const double *node_coords,
+                      const double *neighbour_coords, double sigma0rz, double sigma0rz2, double endcap_boundary, double *out);
+/* clustering/clustering.py:97-105 merge_states for general 3x3 covariances (row-major f64[9]) */
+int gtf_merge_states(int device, const double *mean1, const double *cov1, const double *mean2, const double *cov2,
+                     double *merged_mean, double *merged_cov);
+/* extrapolate/extrapolate_merged_states.py:26-402 extrapolate_validate for ONE edge node -> neighbour: state (a, b, c) and its
+ * covariance (row-major f64[9], block form) at `node`; like the reference it adds the multiple-scattering variance to
+ * state_cov[1][1] IN PLACE (:127-128) before extrapolating.  pass == 0: chi2 > cut, the caller deactivates the edge (:393). */
+typedef struct {
+    int32_t pass, pad;
+    double chi2, var_ms, likelihood;
+    double state[3];   /* updated (a, b, c) = edge_state_vector                       */
+    double tau;        /* joint_vector = (state[0], state[1], tau)                    */
+    double cov[4];     /* p00 p01 p11 p22 of edge_covariance = joint_vector_covariance */
+} gtf_edge_result;
+int gtf_extrapolate_validate(int device, const double *node_xyzr, const double *neighbour_xyzr, const double *state,
+                             double *state_cov, double chi2_cut, const gtf_geom *g, gtf_edge_result *out);
 
 #ifdef __cplusplus
 }

@@ -96,7 +96,11 @@ def snapshot_graphs(graphs):
 def make(name):
     kw = EVENTS[name]
     ev = synth.barrel_event(**kw)
-    graphs = nxio.events_to_graphs(ev)
+    make_from_graphs(name, {"ev_" + k: v for k, v in ev.items()}, nxio.events_to_graphs(ev), name in COMPACT)
+
+
+def make_from_graphs(name, extra, graphs, compact):
+    """seed the given (unseeded) sub-graph list with the reference, run its schedule, write tests/golden/<name>.npz"""
     t0 = time.time()
     graphs = rh.seed_graphs(graphs)
     t_seed = time.time() - t0
@@ -106,15 +110,15 @@ def make(name):
     t0 = time.time()
     out = rh.reference_schedule(graphs)
     t_sched = time.time() - t0
-    data = {"ev_" + k: v for k, v in ev.items()}
+    data = dict(extra)
     for k in TOPO:
         data["topo_" + k] = canon[k]
     data["meta_times"] = np.array([t_seed, t_sched])
 
     def put(stage, st, extra=None):
-        keep = MUTABLE if name not in COMPACT else ["alive", "sub_state", "active", "has_merged", "m_a", "m_b", "m_c",
-                                                     "m_p00", "m_p01", "m_p11", "m_p22", "uts_present", "tse_present",
-                                                     "degree", "has_uts", "m_prior"]
+        keep = MUTABLE if not compact else ["alive", "sub_state", "active", "has_merged", "m_a", "m_b", "m_c",
+                                            "m_p00", "m_p01", "m_p11", "m_p22", "uts_present", "tse_present",
+                                            "degree", "has_uts", "m_prior"]
         for f in keep:
             data["%s/%s" % (stage, f)] = st[f]
         for k, v in (extra or {}).items():
@@ -139,6 +143,7 @@ def make(name):
             snap = snapshot_graphs(rem) if rem else None
             if snap is not None:
                 state = canonicalize(canon, snap, state, {"fragment": fr})
+                state["alive"][acc > 0] = 0      # (a sub-graph that became a fragment keeps its rows; its accepted nodes are gone)
             else:
                 state = {k: v.copy() for k, v in state.items()}
                 state["alive"][acc > 0] = 0

@@ -38,3 +38,38 @@ def test_shipped_event_statistics():
     assert abs(deg.mean() - 2.4) < 0.05
     full = ingest.load_event_csv(REF_EVENT, 0, 99)
     assert len(full["x"]) == 55701
+
+
+def shipped_event_from_fixture():
+    """the csv_* arrays of tests/golden/shipped_vol79.npz = what ingest.load_event_csv reads from the shipped files"""
+    import golden_util as gu
+    fx = gu.load("shipped_vol79")
+    ev = {k: fx["csv_" + k] for k in ("x", "y", "z", "layer", "volume", "edge_a", "edge_b", "node_idx")}
+    ev["r"] = ingest.radius_like_reference(ev["x"], ev["y"])
+    ev["truth"] = np.full(len(ev["x"]), -1, np.int64)
+    return fx, ev
+
+
+def test_native_ingest_reproduces_the_reference_graph_of_the_shipped_event():
+    """nodes.csv / edges.csv -> flat layout without pandas / networkx.  Against the graph the
+    UNMODIFIED reference builds from the same files (helper.py:524-545 load_nodes_edges, :465-520 construct_graph,
+    event_conversion.py:76-96; tests/golden/make_shipped_golden.py): node order, sub-graph split and order, successor order
+    and the state-dict order (CPython set iteration of the neighbour ids, helper.py:280) are all identical."""
+    fx, ev = shipped_event_from_fixture()
+    hb = synth.event_to_host(ev, 0, dict_order="pyset")
+    assert len(hb["x"]) == 30387 and len(hb["in_src"]) == 73230
+    assert np.array_equal(ev["node_idx"][hb["orig_id"]], fx["topo_orig_id"])          # node order, sub-graphs concatenated
+    for k in ("x", "y", "z", "r", "layer", "volume", "sub", "sub_off", "in_off", "in_src", "slot_dst", "out_off", "out_slot", "rev_slot"):
+        assert np.array_equal(hb[k], fx["topo_" + k]), k
+    # the default (insertion-order) layout is a different, equally valid labelling of the same graph: set iteration
+    # re-orders nodes inside small sub-graphs and the neighbours inside the state dicts
+    hb_ins = synth.event_to_host(ev, 0)
+    assert not np.array_equal(hb_ins["orig_id"], hb["orig_id"]) and np.array_equal(np.sort(hb_ins["orig_id"]), np.sort(hb["orig_id"]))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EVENT + "nodes.csv"), reason="reference data only in the build container")
+def test_fixture_holds_the_shipped_files_content():
+    fx, _ = shipped_event_from_fixture()
+    ev = ingest.load_event_csv(REF_EVENT, 7, 9)
+    for k in ("x", "y", "z", "layer", "volume", "edge_a", "edge_b", "node_idx"):
+        assert np.array_equal(ev[k], fx["csv_" + k]), k

@@ -68,7 +68,7 @@ def test_extract(name, prev, stage):
 
 
 @pytest.mark.parametrize("name", FIX + ["barrel100_cfg1"])
-def test_full_schedule_chained(name):
+def test_full_schedule_chained(name, rtol=1e-7):
     """run_gnn_trackml_mod.sh:71-148 schedule, chained from the seeds: every decision bit-exact"""
     fx = gu.load(name)
     ob = ol.OracleBatch(blank_seed(gu.stage_batch(fx, "seed")))
@@ -76,7 +76,7 @@ def test_full_schedule_chained(name):
     W = ("alive", "active", "merged", "degree")
 
     def chk(stage):
-        assert gu.compare_states(ob.hb, gu.stage_batch(fx, stage), W, rtol=1e-7) == [], stage
+        assert gu.compare_states(ob.hb, gu.stage_batch(fx, stage), W, rtol=rtol) == [], stage
 
     chk("seed")
     ob.cluster(0, 1.0, 2.0)
@@ -229,3 +229,13 @@ def test_cfg2_size_schedule_chained_vs_reference():
     """BASELINE configs[1] size (1000 tracks, 10k hits, 100k directed edges) through the reference's own schedule,
     chained from the seeds: every decision and candidate set bit-exact (COMPACT fixture, 222 s of reference time)"""
     test_full_schedule_chained("barrel1000_cfg2")
+
+
+def test_shipped_event_schedule_chained_vs_reference():
+    """the reference's SHIPPED TrackML-derived event (volumes 7-9: 30,387 hits, 73,230 directed edges, mean in-degree 2.4,
+    thousands of tiny sub-graphs) through the reference's own schedule: every decision and candidate set bit-exact.
+    Values: everything within 1e-9 except merged_cov[1,1] of 16 nodes (<= 4.1e-7): the reference's close-pair merge
+    (extract_track_candidates.py:101-118) writes the pair's midpoint into `GNN_Measurement` of a SHALLOW graph copy, i.e. into
+    the object the remaining graph shares, so those hits move for every later extrapolation even when the candidate is
+    rejected; the hit record here is immutable (not reproduced; no decision of this event depends on it)"""
+    test_full_schedule_chained("shipped_vol79", rtol=1e-6)
