@@ -15,7 +15,7 @@ value    device-resident throughput of that step, CUDA events on the batch strea
 loop     second device-resident figure: a COMMITTED 10-iteration gtf_iterate from the post-cluster state.
 e2e      the same metric through the public API from HOST buffers, every step a NEW batch: pinned host event arrays
          (hits + the two CSR orders, 44 B/hit + 8 B/edge) -> gtf_batch_load_events (H2D + device-side initialisation)
-         -> seed -> cluster(seeds) -> gtf_iterate until the active-edge set stops changing (<= 10) -> candidate
+         -> gtf_seed_cluster (seed + cluster on the seeds) -> gtf_iterate until the active-edge set stops changing (<= 10) -> candidate
          extraction -> candidate table (event, candidate, node) back on the host; at N > 1 the tables of all ranks are
          gathered on rank 0 with NCCL inside the timed region.  e2e.value = edge-iterations of all iterations / time.
 roofline algorithmic bytes / the summed CUDA-event durations of all kernels of the iteration vs the measured HBM copy
@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-loop", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches of the end-to-end pipeline (copy/compute overlap)")
+    ap.add_argument("--e2e-chunks", type=int, default=1, help="sub-batches per step of the end-to-end pipeline")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (0: min(steps, 10))")
     return ap.parse_args()
 
@@ -260,8 +260,7 @@ class E2EChunk(object):
 
     def run(self, to_host):
         b = self.b
-        b.seed(want_stats=False)
-        c1 = b.cluster("track_state_estimates", SCHED["chi2_c1"], SCHED["kl_c1"])
+        c1 = b.seed_cluster(SCHED["chi2_c1"], SCHED["kl_c1"])     # event_conversion.py:87-96 + iteration 1 (cluster on the seeds)
         st = b.iterate(max_iter=MAX_ITER, stop_when_converged=True, chi2_cut=SCHED["chi2_cut"], cluster_chi2=SCHED["chi2_c3"],
                        cluster_kl=SCHED["kl_c3"])
         b.extract(want_arrays=False)
@@ -275,15 +274,15 @@ class E2EChunk(object):
         return t
 
 
-def e2e_loop(chunks, steps, torch, dist, rank):
-    """per step: a NEW batch per chunk from pinned HOST event arrays -> candidate table on the host (rank 0).  All loads are
-    issued first (asynchronous, one stream per chunk), so chunk k+1's copies overlap chunk k's kernels."""
+def e2e_loop(sets, steps, torch, dist, rank):
+    """per step: a NEW batch from pinned HOST event arrays -> candidate table on the host (rank 0).  `sets` = two identical
+    lists of chunks (double buffering): while one set's kernels run, the other set's host->device copies and device-side
+    initialisation for the NEXT step are already in flight on their own streams.  Every timed step holds exactly one load
+    and one run of the whole batch; the first load of the timed region is not overlapped with anything."""
     from gtf_b200 import shard
     info = {}
 
-    def one():
-        for c in chunks:
-            c.load()
+    def run(chunks):
         if dist is None:
             for c in chunks:
                 c.run(True)
@@ -297,14 +296,23 @@ def e2e_loop(chunks, steps, torch, dist, rank):
             return table.shape[0]
         return 0
 
-    one()
+    def loop(n):
+        rows = 0
+        for c in sets[0]:
+            c.load()
+        for s in range(n):
+            if s + 1 < n:
+                for c in sets[(s + 1) & 1]:
+                    c.load()                     # next step's batch: asynchronous, other streams
+            rows = run(sets[s & 1])
+        return rows
+
+    loop(2)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
-    rows = 0
-    for _ in range(steps):
-        rows = one()
+    rows = loop(steps)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -425,15 +433,17 @@ def main():
     if not a.no_e2e:
         nch = max(1, min(a.e2e_chunks, len(my_ids)))
         per = [my_ids[k::nch] for k in range(nch)]
-        chunks = [E2EChunk(concat_events(pool, ids), local, torch) for ids in per]
+        sets = [[E2EChunk(concat_events(pool, ids), local, torch) for ids in per] for _ in range(2)]
+        chunks = sets[0]
         barrier()
         esteps = a.e2e_steps or min(a.steps, 10)
-        e2e_ms, rows, info = e2e_loop(chunks, esteps, torch, dist, rank)
+        e2e_ms, rows, info = e2e_loop(sets, esteps, torch, dist, rank)
         e2e = {"ms": e2e_ms / esteps, "steps": esteps, "h2d": sum(c.h2d for c in chunks), "rows": sum(c.n_rows for c in chunks),
                "edge_iters": sum(c.edge_iters for c in chunks), "iters": max(c.iters for c in chunks), "gather": info,
                "gathered_rows": rows}
-        for c in chunks:
-            c.b.close()
+        for cs in sets:
+            for c in cs:
+                c.b.close()
     red = torch.tensor([ms, e2e["ms"] if e2e else 0.0, loop["ms"] if loop else 0.0], device="cuda", dtype=torch.float64)
     tot = torch.tensor([float(n_active), float(b.E), float(len(my_ids)), float(e2e["edge_iters"] if e2e else 0),
                         float(e2e["h2d"] if e2e else 0), float(e2e["rows"] if e2e else 0), float(loop["edge_iterations"] if loop else 0)],
@@ -501,8 +511,9 @@ def main():
                           "d2h_bytes_per_step": 12.0 * e2e_rows, "ms_per_step": e2e_ms, "steps": e2e["steps"],
                           "events_per_s": n_ev_all / (e2e_ms / 1e3), "edge_iterations_per_step": e2e_edges,
                           "iterations_to_converge": e2e["iters"], "candidate_rows": e2e_rows, "chunks": min(a.e2e_chunks, len(my_ids)),
-                          "path": "pinned host event arrays -> gtf_batch_load_events -> gtf_seed_all -> gtf_cluster -> gtf_iterate "
-                                  "(until converged) -> gtf_extract -> candidate table on the host"
+                          "path": "pinned host event arrays -> gtf_batch_load_events -> gtf_seed_cluster -> gtf_iterate (until converged) "
+                                  "-> gtf_extract -> candidate table on the host; the next step's load overlaps this step's kernels "
+                                  "(two batch objects)"
                                   + (" of rank 0 via NCCL all-gather" if world > 1 else "")}
             if world > 1:
                 out["e2e"]["nccl_gather"] = {"rows_per_rank": e2e["gather"].get("counts"), "bytes_per_rank": e2e["gather"].get("bytes"),

@@ -173,6 +173,16 @@ class EventBatch(object):
         L.check(self.lib.gtf_seed_all(self.h, ctypes.byref(self.geom), ctypes.byref(st)))
         return self._done(st)
 
+    def seed_cluster(self, chi2_threshold, KL_threshold, KL_lut=None):
+        """seed() followed by cluster('track_state_estimates', ...) as one pass over the freshly seeded dicts"""
+        st = L.Stats()
+        lut = None
+        if KL_lut is not None:
+            lut = np.ascontiguousarray(KL_lut, np.float64)
+            lut = lut.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        L.check(self.lib.gtf_seed_cluster(self.h, ctypes.byref(self.geom), chi2_threshold, KL_threshold, lut, ctypes.byref(st)))
+        return self._done(st)
+
     def cluster(self, track_state_key, chi2_threshold, KL_threshold, KL_lut=None):
         st = L.Stats()
         lut = None

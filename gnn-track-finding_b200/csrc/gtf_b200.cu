@@ -32,6 +32,11 @@ static int fail(int code, const std::string &msg)
         if (r__) return r__; \
     } while (0)
 
+struct Prog;
+struct GtfGeom;
+static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre_passes, gtf_stats *st);
+static const bool g_tile_cluster = getenv("GTF_TILE_CLUSTER") != nullptr;   // debugging: cluster() on the seeds with the per-stage kernel
+
 struct FieldInfo { const char *name; int elem; char ext; };
 static const FieldInfo g_fields[GTF_NFIELDS] = {
 #define EXT_N 'N'
@@ -725,6 +730,7 @@ extern "C" int gtf_cluster(gtf_batch *b, int key, double chi2_thr, double kl_thr
     P.cl_chi2 = chi2_thr;
     P.cl_kl = kl_thr;
     if (kl_lut) { P.use_lut = 1; memcpy(P.lut, kl_lut, sizeof(double) * 28); }
+    if (key == GTF_KEY_TSE && !g_tile_cluster) return cluster_seeds_packed(b, P, geom_of(g), 0, st);
     TRY(launch_tile(b, P, geom_of(g)));
     return st ? counters_read(b, st) : 0;   // st == NULL: no read-back, the call stays asynchronous
 }
@@ -792,6 +798,7 @@ static Prog fused_prog(const gtf_iter_params *p)
     P.cl_chi2 = p->cluster_chi2;
     P.cl_kl = p->cluster_kl;
     P.rw_thr = p->reweight_threshold;
+    P.pre_passes = 2;
     if (p->kl_lut) { P.use_lut = 1; memcpy(P.lut, p->kl_lut, sizeof(double) * 28); }
     return P;
 }
@@ -829,26 +836,12 @@ template <int G> static void launch_hv(gtf_batch *b, cudaStream_t s, const Prog 
 {
     k_hv<G><<<b->n_sm * GTF_HV_MINB, GTF_HV_WARPS * 32, 0, s>>>(b->d, b->k, P, gg, bin, mo);
 }
-// the kernel launches of one iteration (k_begin .. k_hv / k_big), issued on the batch stream (and forked onto the side
-// streams for the independent bins); also the body that is captured into a CUDA graph
-static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int record_chi2, bool commit, bool timed)
+// k_node2 + the cooperative bins (k_hv<4|8|16|32>, k_big) of one pass over the packed dict entries
+static int issue_node_kernels(gtf_batch *b, const Prog &P, const GtfGeom &gg, bool commit, bool timed)
 {
     DevPack &k = b->k;
     DevBatch &d = b->d;
-    const size_t words = ((size_t)b->E + 31) / 32 + 2;
     cudaStream_t s0 = b->stream;
-    CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS_ALL, s0));
-    if (timed) CK(cudaEventRecord(b->evk[0], s0));
-    {
-        const int nthr = (int)std::max<size_t>(words, (size_t)b->N);
-        k_begin<<<(nthr + 255) / 256, 256, 0, s0>>>(d, k, (int)words);
-    }
-    if (b->n_stiles)
-        k_send<<<std::min(b->n_stiles, b->n_sm * GTF_SEND_MINB), GTF_SEND_THREADS, sizeof(SendSmem), s0>>>(
-            d, k, reinterpret_cast<const int4 *>(b->stile_begin), b->n_stiles, gg);
-    if (timed) CK(cudaEventRecord(b->evk[1], s0));
-    if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * GTF_EXEC_WAVES, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg, record_chi2);
-    if (timed) CK(cudaEventRecord(b->evk[2], s0));
     if (b->N) k_node2<<<(b->N + GTF_NODE2_THREADS - 1) / GTF_NODE2_THREADS, GTF_NODE2_THREADS, 0, s0>>>(d, k, P);
     if (timed) CK(cudaEventRecord(b->evk[3], s0));
     CK(cudaGetLastError());
@@ -872,6 +865,29 @@ static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int r
         CK(cudaStreamWaitEvent(s0, b->ev_join2, 0));
         CK(cudaStreamWaitEvent(s0, b->ev_join3, 0));
     }
+    return 0;
+}
+// the kernel launches of one iteration (k_begin .. k_hv / k_big), issued on the batch stream (and forked onto the side
+// streams for the independent bins); also the body that is captured into a CUDA graph
+static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int record_chi2, bool commit, bool timed)
+{
+    DevPack &k = b->k;
+    DevBatch &d = b->d;
+    const size_t words = ((size_t)b->E + 31) / 32 + 2;
+    cudaStream_t s0 = b->stream;
+    CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS_ALL, s0));
+    if (timed) CK(cudaEventRecord(b->evk[0], s0));
+    {
+        const int nthr = (int)std::max<size_t>(words, (size_t)b->N);
+        k_begin<<<(nthr + 255) / 256, 256, 0, s0>>>(d, k, (int)words);
+    }
+    if (b->n_stiles)
+        k_send<<<std::min(b->n_stiles, b->n_sm * GTF_SEND_MINB), GTF_SEND_THREADS, sizeof(SendSmem), s0>>>(
+            d, k, reinterpret_cast<const int4 *>(b->stile_begin), b->n_stiles, gg);
+    if (timed) CK(cudaEventRecord(b->evk[1], s0));
+    if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * GTF_EXEC_WAVES, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg, record_chi2);
+    if (timed) CK(cudaEventRecord(b->evk[2], s0));
+    TRY_(issue_node_kernels(b, P, gg, commit, timed));
     if (timed) CK(cudaEventRecord(b->evk[4], s0));
     b->launches_per_iter = 1 + (b->n_stiles ? 1 : 0) + (b->E ? 1 : 0) + (b->N ? 6 : 0); // k_begin, k_send, k_exec, k_node2 + k_hv x4 + k_big
     return 0;
@@ -942,6 +958,68 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
     }
     if (st) return counters_read(b, st);
     return 0;
+}
+
+// cluster() on the SEED dict (clustering.py:149-376 with 'track_state_estimates') on the packed node kernels: the seed
+// entries are packed like updated states (slot order = dict order), k_node2 / k_hv / k_big run without the re-weighting
+// (pre_passes (prior) passes first: 0 = the stage as the reference defines it, 1 = preceded by the seed's own
+// compute_prior_probabilities), then activation flags, weights and priors go back to the fields.
+static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre_passes, gtf_stats *st)
+{
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
+    TRY_(soa_for_stage(b, true));                 // every field current; the packed records are about to hold the seed dict
+    if (b->derived_dirty) TRY_(recount_subs(b));
+    DevPack &k = b->k;
+    DevBatch &d = b->d;
+    cudaStream_t s0 = b->stream;
+    P.key = GTF_KEY_TSE;
+    P.pre_passes = pre_passes;
+    {
+        int n = 0;
+        if (pre_passes) P.ops[n++] = OP_PRIOR;
+        P.ops[n++] = OP_CLUSTER; P.ops[n++] = OP_DEGREE; P.ops[n++] = OP_WEIGHTS; P.ops[n++] = OP_PRIOR; P.ops[n] = OP_END;
+    }
+    const size_t words = ((size_t)b->E + 31) / 32 + 2;
+    CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS_ALL, s0));
+    CK(cudaMemsetAsync(k.counts + PK_MISSING, 0, sizeof(int), s0));
+    CK(cudaMemsetAsync(k.counts + PK_FORCE, 0xff, sizeof(int), s0));       // every node is evaluated
+    b->force_dev = 1;
+    if (b->N) k_pack_nodes<<<(b->N + 256) / 256, 256, 0, s0>>>(d, k, 1, 1);
+    if (b->E) k_pack_tse<<<(b->E + 255) / 256, 256, 0, s0>>>(d, k);
+    {
+        const int nthr = (int)std::max<size_t>(words, (size_t)b->N);
+        k_begin<<<(nthr + 255) / 256, 256, 0, s0>>>(d, k, (int)words);
+    }
+    CK(cudaGetLastError());
+    TRY_(issue_node_kernels(b, P, gg, true, false));
+    // commit: the next activation bitmap and the carried merged_cov[1,1] become current
+    std::swap(k.act, k.act_nx);
+    std::swap(b->f[GTF_F_m_p11], *(void **)&d.m_p11_nx);
+    sync_dev_view(b);
+    b->parity ^= 1;
+    if (b->E) k_unpack_tse<<<(b->E + 255) / 256, 256, 0, s0>>>(b->d, k);
+    CK(cudaGetLastError());
+    // what is where now: activation bits + merged records are current on both sides after the unpack below; the dict-entry
+    // records hold the SEED dict, so the updated-state groups are re-packed from the fields before the next iteration
+    b->soa_stale[PG_ACT] = false; b->pack_stale[PG_ACT] = false; b->exists_stale = false;
+    b->pack_stale[PG_PRES] = b->pack_stale[PG_REC] = true;
+    b->soa_stale[PG_PRES] = b->soa_stale[PG_REC] = false;
+    b->soa_stale[PG_NODE] = true; b->pack_stale[PG_NODE] = false;
+    b->pack_static_stale = true;                  // the carried seed weights (per-out-edge records) changed
+    b->force_pending = true;
+    b->have_last_prog = false;
+    return st ? counters_read(b, st) : 0;
+}
+extern "C" int gtf_seed_cluster(gtf_batch *b, const gtf_geom *g, double chi2_threshold, double kl_threshold, const double *kl_lut,
+                                gtf_stats *st)
+{
+    TRY(gtf_seed(b, g));
+    CK(cudaMemsetAsync(b->f[GTF_F_active], 1, (size_t)(b->E ? b->E : 0), b->stream));
+    Prog P = make_prog(GTF_KEY_TSE, 0, {OP_END});
+    P.cl_chi2 = chi2_threshold;
+    P.cl_kl = kl_threshold;
+    if (kl_lut) { P.use_lut = 1; memcpy(P.lut, kl_lut, sizeof(double) * 28); }
+    return cluster_seeds_packed(b, P, geom_of(g), 1, st);
 }
 
 extern "C" int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st)

@@ -127,6 +127,7 @@ struct Prog {
     int key;          // working dict: GTF_KEY_TSE / GTF_KEY_UTS
     int wb;           // WB_* mask
     int use_lut;
+    int pre_passes;   // (prior, reweight) passes before the clustering in the packed node kernels: 2 = the fused iteration
     double chi2_cut, cl_chi2, cl_kl, rw_thr;
     double lut[28];
 };

@@ -171,6 +171,55 @@ __global__ void k_unpack_slots(DevBatch B, DevPack K, int do_act, int do_pres, i
     }
 }
 
+// the SEED dict (track_state_estimates) in the packed layout, so that cluster() on the seeds runs on the fast node kernels:
+// every in-slot's entry in slot order (= dict order, stamp = slot index), bitmaps, geometry
+__global__ void k_pack_tse(DevBatch B, DevPack K)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool in = s < B.E;
+    int src = -1, dst = 0;
+    if (in) { src = B.in_src[s]; dst = B.slot_dst[s]; }
+    const bool ex = in && src >= 0 && B.alive[src] && B.alive[dst];
+    const bool pres = in && B.tse_present[s] != 0;
+    const unsigned mex = __ballot_sync(0xffffffffu, ex);
+    const unsigned mact = __ballot_sync(0xffffffffu, in && B.active[s] == 1);
+    const unsigned mpres = __ballot_sync(0xffffffffu, pres);
+    const unsigned min_ = __ballot_sync(0xffffffffu, in);
+    if (lane == 0 && min_) {
+        K.act[s >> 5] = mact; K.exists[s >> 5] = mex; K.pres[s >> 5] = mpres;
+        if (mex != min_) atomicAdd(&K.counts[PK_MISSING], __popc(min_ & ~mex));
+    }
+    if (!in) return;
+    GeoRec gr;
+    gr.sx = src >= 0 ? B.x[src] : 0.0;
+    gr.lay = src >= 0 ? B.layer[src] : -1;
+    gr.src = src;
+    (*geo_p(K, s)) = gr;
+    if (pres) {
+        double2 *st = reinterpret_cast<double2 *>(K.state + 8 * (size_t)s);
+        st[0] = make_double2(B.tse_a[s], B.tse_b[s]);
+        st[1] = make_double2(B.tse_c[s], B.tse_tau[s]);
+        st[2] = make_double2(B.tse_p00[s], B.tse_p01[s]);
+        st[3] = make_double2(B.tse_p11[s], B.tse_p22[s]);
+        MetaRec m;
+        m.w = B.tse_w[s]; m.lik = 0.0; m.prior = B.tse_prior[s]; m.ew = 0.0;
+        K.meta[s] = m;
+        TagRec t;
+        t.rank = s; t.side = 0; t.pad = 0; t.lrn = -1;
+        (*tag_p(K, s)) = t;
+    }
+}
+__global__ void k_unpack_tse(DevBatch B, DevPack K)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B.E) return;
+    B.active[s] = bm_get(K.act, s) ? 1 : 0;
+    if (B.tse_present[s]) {
+        const MetaRec m = K.meta[s];
+        B.tse_w[s] = m.w; B.tse_prior[s] = m.prior;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ k_begin
 // start of an iteration: next activation bitmap := current, snapshot of the presence bitmap, list counters := 0,
 // accumulated p11 of the nodes carried over (k_send overwrites the ones that send; quirk 2)
@@ -658,7 +707,8 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
                 a.rank0 = b.rank0 = a.tag0 = b.tag0 = 0;
                 if (n >= 1) lent_load(B, K, e0, a);
                 if (n == 2) lent_load(B, K, e1, b);
-                if (B.has_uts[i]) nf |= NF_HASUTS | NF_DICT;
+                if (P.key == GTF_KEY_TSE) nf |= NF_DICT;          // every seeded node holds the dict (clustering.py:198)
+                else if (B.has_uts[i]) nf |= NF_HASUTS | NF_DICT;
                 const int nnew = ((a.f & H_NEW) != 0) + ((b.f & H_NEW) != 0);
                 if (nnew) { // new entries enter the dict in ascending source order (extrapolate...py:419-447)
                     const int nxt = B.uts_next[i];
@@ -674,7 +724,7 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
                 if (n == 2 && b.rank < a.rank) { LEnt t = a; a = b; b = t; } // dict order
                 const bool rdict = (nf & (NF_MULTI | NF_DICT)) == (NF_MULTI | NF_DICT);
                 const bool ruts = (nf & (NF_MULTI | NF_HASUTS)) == (NF_MULTI | NF_HASUTS);
-                if (n) {
+                if (n && P.pre_passes) {
                     const double nodex = B.x[i];
                     if (rdict) lent_prior(a, b, n);
                     if (ruts) lent_reweight(B, s_cnt, a, b, n, nodex, P.rw_thr);
@@ -842,7 +892,12 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         const int i = gv ? list[idx] : 0;
         int b0 = 0, b1 = 0;
         unsigned nf = 0;
-        if (gv) { b0 = B.in_off[i]; b1 = B.in_off[i + 1]; nf = B.node_ok[i] | (B.has_uts[i] ? (NF_HASUTS | NF_DICT) : 0u); }
+        if (gv) {
+            b0 = B.in_off[i]; b1 = B.in_off[i + 1];
+            nf = B.node_ok[i];
+            if (P.key == GTF_KEY_TSE) nf |= NF_DICT;                 // every seeded node holds the dict (clustering.py:198)
+            else if (B.has_uts[i]) nf |= NF_HASUTS | NF_DICT;
+        }
         // ---- the node's bits: my entry = the gl-th present slot; totals over the slots that hold no entry
         int slot = -1, n = 0, deg_np = 0, chg_np = 0;
         for (int c = b0; c < b1; c += 32) {
@@ -943,8 +998,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         const unsigned samelay = __match_any_sync(FULL, lay) & gmask;
         const unsigned samex = __match_any_sync(FULL, __double_as_longlong(sx)) & gmask;
         const bool isleft = sx < nodex;
-#pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
+        for (int pass = 0; pass < P.pre_passes; pass++) {                 // (2 in the iteration; 0 / 1 for cluster() on the seeds)
             // helper.py:30-63 compute_prior_probabilities
             {
                 const bool el = (f & m3) == m3;
@@ -952,7 +1006,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
                 if (okd && el) prior = HV_RECIP(__popc(samelay & elm));
             }
             // helper.py:99-200 side norm + reweight + prune
-            {
+            if (__any_sync(FULL, oku)) {
                 const bool el = oku && (f & m3) == m3;
                 const bool left = el && isleft;
                 const unsigned elm = __ballot_sync(FULL, el), leftm = __ballot_sync(FULL, left);
@@ -1200,7 +1254,7 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack Kin, Prog P, Gtf
         if (lane == 0) {
             sm.nbeg[0] = 0; sm.nbeg[1] = (uint16_t)d;
             unsigned nf = NF_DICT | B.node_ok[i];
-            if (B.has_uts[i]) nf |= NF_HASUTS;
+            if (P.key == GTF_KEY_UTS && B.has_uts[i]) nf |= NF_HASUTS;
             sm.nflags[0] = (uint8_t)nf;
         }
         for (int ls = lane; ls < d; ls += 32) {
@@ -1240,7 +1294,7 @@ __global__ void __launch_bounds__(32) k_big(DevBatch B, DevPack Kin, Prog P, Gtf
         // the generic program writes mo[k][i]: point every mo[k] at a shared scratch (biased by -i), copy out afterwards
         double *mo[8];
         for (int k = 0; k < 8; k++) mo[k] = mscr + k - i;
-        node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, true, hm_s - i, mo, lrn_s, ew_s);
+        node_program_generic(sm, B, P, g, i, 0, gs0, 0, lane, P.key == GTF_KEY_UTS, hm_s - i, mo, lrn_s, ew_s);
         __syncwarp();
         if (lane == 0) {
             if (sm.nflags[0] & NF_CLUSTERED) {

@@ -28,8 +28,9 @@ def reference_schedule(b, P=DEFAULTS, seed=True):
 def converged_schedule(b, P=DEFAULTS, max_iter=10, seed=True):
     """seed, cluster(seeds), fused iterations until the active-edge bitmap stops changing, extract."""
     if seed:
-        b.seed()
-    b.cluster("track_state_estimates", P["chi2_c1"], P["kl_c1"])
+        b.seed_cluster(P["chi2_c1"], P["kl_c1"])
+    else:
+        b.cluster("track_state_estimates", P["chi2_c1"], P["kl_c1"])
     stats = b.iterate(max_iter=max_iter, stop_when_converged=True, chi2_cut=P["chi2_cut"], cluster_chi2=P["chi2_c3"],
                       cluster_kl=P["kl_c3"])
     n, acc, pxy, pzr = b.extract(P["pval"], P["numhits"], P["sep3d"], P["merge_dist"])

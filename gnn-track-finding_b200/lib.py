@@ -108,6 +108,7 @@ def lib():
         "gtf_batch_iteration_launches": (i64, [vp]),
         "gtf_seed": (ctypes.c_int, [vp, pg]),
         "gtf_seed_all": (ctypes.c_int, [vp, pg, ps]),
+        "gtf_seed_cluster": (ctypes.c_int, [vp, pg, dbl, dbl, dp, ps]),
         "gtf_initialize_edge_activation": (ctypes.c_int, [vp]),
         "gtf_compute_prior_probabilities": (ctypes.c_int, [vp, ctypes.c_int]),
         "gtf_compute_mixture_weights": (ctypes.c_int, [vp, ctypes.c_int, ps]),

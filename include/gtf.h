@@ -137,6 +137,10 @@ int gtf_seed(gtf_batch *b, const gtf_geom *g);
 /* event_conversion.py:87-96 in one call: gtf_seed + initialize_edge_activation + compute_prior_probabilities(seeds) +
  * compute_mixture_weights(seeds) + node degrees (the last three as one kernel launch) */
 int gtf_seed_all(gtf_batch *b, const gtf_geom *g, gtf_stats *st);
+/* gtf_seed_all followed by gtf_cluster('track_state_estimates', ...) -- event_conversion.py:87-96 + iteration 1 of
+ * run_gnn_trackml_mod.sh:89 -- as ONE pass of the packed node kernels over the freshly seeded dicts */
+int gtf_seed_cluster(gtf_batch *b, const gtf_geom *g, double chi2_threshold, double kl_threshold, const double *kl_lut,
+                     gtf_stats *st);
 /* utilities/helper.py:24-25 initialize_edge_activation */
 int gtf_initialize_edge_activation(gtf_batch *b);
 /* utilities/helper.py:30-63 compute_prior_probabilities(GraphList, key) */

@@ -275,3 +275,26 @@ def test_shipped_event_native_ingest_to_candidates_vs_reference():
         ob.cluster(1, 1000.0, 100.0)
     b.iterate(max_iter=3, stop_when_converged=False)
     assert gu.compare_states(state_of(b), ob.hb, ("active", "merged", "uts", "degree", "edge_w"), rtol=1e-7) == []
+
+
+def test_seed_cluster_equals_seed_then_cluster():
+    """gtf_seed_cluster (one pass of the packed node kernels over the freshly seeded dicts) = gtf_seed_all followed by
+    gtf_cluster on the seeds, against the reference fixtures and bit for bit against the two-call form (scalar and LUT mode)"""
+    for name in ("barrel25_deg6", "barrel40_eta1", "barrel1000_cfg2"):
+        fx = gu.load(name)
+        hb = blank_seed(gu.stage_batch(fx, "seed"))
+        a = gtf_b200.EventBatch(hb)
+        sa = a.seed_cluster(1.0, 2.0)
+        what = ALL if name != "barrel1000_cfg2" else ("alive", "active", "merged", "degree")
+        assert gu.compare_states(state_of(a), gu.stage_batch(fx, "c1"), what) == [], name
+        c = gtf_b200.EventBatch(hb)
+        c.seed()
+        sc = c.cluster("track_state_estimates", 1.0, 2.0)
+        ga, gc = state_of(a), state_of(c)
+        for k in ga:
+            assert np.array_equal(ga[k], gc[k], equal_nan=True), (name, k)
+        assert sa == sc
+    fx = gu.load("lut_barrel40")
+    a = gtf_b200.EventBatch(blank_seed(gu.stage_batch(fx, "seed")))
+    a.seed_cluster(1.0, 123.0, KL_lut=fx["lut_stress"])
+    assert gu.compare_states(state_of(a), gu.stage_batch(fx, "c1str"), ALL, rtol=gu.RTOL, chained=True) == []
