@@ -1290,7 +1290,10 @@ extern "C" int gtf_extract(gtf_batch *b, const gtf_geom *g, double pval_cut, int
 {
     if (!b || !g) return fail(GTF_E_ARG, "gtf_extract: null argument");
     CK(cudaSetDevice(b->device));
-    TRY_(soa_for_stage(b, true));   // removes nodes: the packed copy (existing-edge bitmap) is rebuilt afterwards
+    // extraction reads the activation flags and removes nodes: only the flag bytes are brought up to date; the dict-entry
+    // and merged-state records stay packed, the existing-edge bitmap is rebuilt from `alive` before the next iteration
+    TRY_(soa_sync(b, 1u << PG_ACT));
+    b->exists_stale = true;
     TRY(gtf_components(b));
     if (n_accepted) *n_accepted = 0;
     if (b->N == 0) return 0;
