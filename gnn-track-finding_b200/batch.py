@@ -138,6 +138,8 @@ class EventBatch(object):
 
     def _done(self, st):
         self.last_stats = st.as_dict()
+        if st.ref_errors & 64:
+            raise L.GtfError("a kernel index left its array (GTF_STATUS_BOUNDS; debug build)")
         if self.raise_ref_errors and st.ref_errors:
             for bit, exc, msg in _REF_EXC:
                 if st.ref_errors & bit:
@@ -235,9 +237,9 @@ class EventBatch(object):
         L.check(self.lib.gtf_iterate(self.h, ctypes.byref(p), ctypes.byref(self.geom), max_iter,
                                      1 if stop_when_converged else 0, stats, ctypes.byref(n)))
         out = [stats[i].as_dict() for i in range(n.value)]
-        for s in out:
-            if self.raise_ref_errors and s["ref_errors"]:
-                self._done(stats[out.index(s)])
+        for k, s in enumerate(out):
+            if (self.raise_ref_errors and s["ref_errors"]) or (s["ref_errors"] & 64):
+                self._done(stats[k])
         return out
 
     def iterate_dry(self, chi2_cut=2.0, cluster_chi2=1000.0, cluster_kl=100.0, reweight_threshold=0.1, KL_lut=None,

@@ -99,6 +99,13 @@ enum {
     CNT_MERGED = 0, CNT_DEACT, CNT_SENT, CNT_GATED, CNT_RWOFF, CNT_ACTIVE, CNT_CHANGED, CNT_REFERR, GTF_NCOUNTERS,
     CNT_NEAR = GTF_NCOUNTERS, GTF_NCOUNTERS_ALL     // (CNT_NEAR is bumped in global memory directly: a rare event)
 };
+// in-kernel bounds checks of the debug build (compute-sanitizer is not available on the pool): a violated condition sets a
+// status bit that every stats read-back returns; the release build compiles them away
+#ifdef GTF_DEBUG_BOUNDS
+#define GTF_BOUND(B, cond) do { if (!(cond)) atomicOr(&(B).counters[CNT_REFERR], (unsigned long long)GTF_STATUS_BOUNDS); } while (0)
+#else
+#define GTF_BOUND(B, cond) ((void)0)
+#endif
 // a decision `value (<|<=) threshold` was just taken: note it when it is a boundary-flip candidate
 __device__ __forceinline__ void near_note(const DevBatch &B, int kind, int index, double value, double threshold)
 {

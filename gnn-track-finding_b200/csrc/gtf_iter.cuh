@@ -371,9 +371,11 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBat
         mbar_wait(&S.full[s], (unsigned)(it >> 1) & 1u);
         const int u0 = d_cur.x, ns = d_cur.y, o_base = d_cur.z, ne = d_cur.w;
         const int epad = o_base & 3, upad = u0 & 15, ppad = u0 & 1;
+        GTF_BOUND(B, ns >= 1 && ns <= GTF_SEND_SRCS && ne >= 0 && ne <= GTF_SEND_EDGES && u0 >= 0 && u0 + ns <= B.N && o_base >= 0 && o_base + ne <= B.E);
         // ---- phase 0
         if (tid < ns) {
             const int my_off = st.srec[tid].off - o_base, my_end = st.srec[tid + 1].off - o_base;
+            GTF_BOUND(B, my_off >= 0 && my_off <= my_end && my_end <= ne);
             sm.ok[tid] = st.hm[upad + tid] && (st.nok[upad + tid] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI);
             sm.first[tid] = 0xffff;
             for (int o = my_off; o < my_end; o++) sm.esrc[o] = (uint8_t)tid;
@@ -387,6 +389,7 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBat
         for (int j = 0; j < GTF_SEND_EPT; j++) {
             if (e0 + j < ne) {
                 const int sl = st.slot[epad + e0 + j];
+                GTF_BOUND(B, sl >= 0 && sl < B.E && sm.esrc[e0 + j] < ns);
                 if (sm.ok[sm.esrc[e0 + j]] && bm_get(K.act, sl) && (K.all_exist || bm_get(K.exists, sl))) { mymask |= 1u << j; cnt++; }
             }
         }
@@ -411,6 +414,7 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBat
 #pragma unroll
                 for (int j = 0; j < GTF_SEND_EPT; j++)
                     if ((mymask >> j) & 1u) {
+                        GTF_BOUND(B, pos >= 0 && pos < M && M <= ne);
                         sm.m_le[pos] = (uint16_t)(e0 + j); sm.m_src[pos] = sm.esrc[e0 + j];
                         pos++;
                     }
@@ -452,6 +456,7 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBat
                 const int q = tid + k * GTF_SEND_THREADS;
                 if (q < M) {
                     const int gq = base + q, le = sm.m_le[q];
+                    GTF_BOUND(B, gq >= 0 && gq < B.E && le < ne && st.dst[epad + le] >= 0 && st.dst[epad + le] < B.N);
                     const bool has = __double_as_longlong(wq[k]) != GTF_NO_TSE_BITS;
                     K.msg_desc[gq] = make_int4(st.slot[epad + le] | (has ? 0 : (int)0x80000000), u0 + sm.m_src[q], st.dst[epad + le], 0);
                     K.msg_w[gq] = has ? wq[k] : NAN;
@@ -500,6 +505,7 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
     };
     auto load = [&](int q, const int4 d, In &x) {
         const int u = d.y, v = d.z;
+        GTF_BOUND(B, u >= 0 && u < B.N && v >= 0 && v < B.N);
         const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
         x.sraw = d.x;
         x.ux = U.x; x.uy = U.y; x.uz = U.z; x.ur = U.r; x.vx = V.x; x.vy = V.y; x.vz = V.z; x.vr = V.r;
@@ -517,6 +523,7 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
     while (q < count) {
         const int s = cur.sraw & 0x7fffffff;
         const bool notse = cur.sraw < 0;
+        GTF_BOUND(B, s >= 0 && s < B.E);
         const double w = cur.w, p = cur.p, vms = cur.vms, p00 = cur.p00, p01 = cur.p01, p22 = cur.p22;
         const double dr = cur.vr - cur.ur, dz = cur.vz - cur.uz, uz = cur.uz, vz = cur.vz;
         GtfJac J;
@@ -697,6 +704,7 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
             }
         } else if (np > 2 && (nf & NF_OK)) {
             const int bin = np <= 4 ? 0 : np <= 8 ? 1 : np <= 16 ? 2 : np <= 32 ? 3 : 4;
+            GTF_BOUND(B, np <= b1 - b0);
             s_list[bin][atomicAdd(&s_n[bin], 1)] = i;
         } else {
             if (nf & NF_OK) {
@@ -705,6 +713,8 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
                 a.f = 0; b.f = 0; a.s = b.s = b0; a.lay = b.lay = -1; a.sx = b.sx = 0; a.w = b.w = a.lik = b.lik = 0;
                 a.prior = b.prior = a.ew = b.ew = 0; a.side = b.side = a.rank = b.rank = 0; a.lrn = b.lrn = -1;
                 a.rank0 = b.rank0 = a.tag0 = b.tag0 = 0;
+                GTF_BOUND(B, n < 1 || (e0 >= b0 && e0 < b1));
+                GTF_BOUND(B, n < 2 || (e1 > e0 && e1 < b1));
                 if (n >= 1) lent_load(B, K, e0, a);
                 if (n == 2) lent_load(B, K, e1, b);
                 if (P.key == GTF_KEY_TSE) nf |= NF_DICT;          // every seeded node holds the dict (clustering.py:198)
@@ -913,6 +923,8 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             n += cnt;
         }
         const bool valid = gv && gl < n;
+        GTF_BOUND(B, !gv || (i >= 0 && i < B.N && n <= G && n >= 3));
+        GTF_BOUND(B, !valid || (slot >= b0 && slot < b1));
         // ---- weight record, tag, geometry, flags of my entry
         double w = 0.0, lik = 0.0, prior = 0.0, sx = 0.0, ew = 0.0;
         int rank = 0x7fffffff, side = 0, lrn = -1, lay = -1000 - lane, src = 0, rank0 = 0, tag0 = 0;
@@ -958,6 +970,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         int pos = 0;
         for (int t = 0; t < nmax; t++) pos += (t < n) && W.rk[gbase + t] < rank;
         if (!valid) pos = gl;
+        GTF_BOUND(B, pos >= 0 && pos < G);
         const int dpos = gbase + pos;
         const unsigned lastm = __ballot_sync(FULL, valid && pos == n - 1) & gmask;      // the lane holding the LAST dict key
         const int lastlane = lastm ? __ffs(lastm) - 1 : gbase;
@@ -1107,6 +1120,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             gone = grp_or_u32<G>(gone);
             int idx0 = 0, idx1 = 0;
             if (go) {
+                GTF_BOUND(B, (int)pfirst < n * (n - 1) / 2);
                 HV_PAIR_DECODE((int)pfirst, idx0, idx1);       // unique minimum: idx = [row, col]
                 if (nm > 1) {                               // ties: idx = [rows..., cols...] -> idx[1] is the SECOND ROW
                     int jj;
@@ -1154,6 +1168,7 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
                     }
                     if (!tie) bk = -1;
                     const double bv = key_dbl(mk);
+                    GTF_BOUND(B, bk < n);
                     const bool absorb = live && !nan_kl && bk >= 0 && bv < thr;                // clustering.py:261
                     if (live && !nan_kl && bk >= 0 && gl == 0) near_note(B, GTF_NEAR_CLUSTER_KL, i, bv, thr);
                     if (live && nan_kl) {

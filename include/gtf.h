@@ -38,6 +38,8 @@ extern "C" {
 /* not a reference error: gtf_extract met a component of more than 64 nodes that could still be one-hit-per-layer (a
  * detector with > 62 distinct (volume, layer) ids); the call fails with GTF_E_DEGREE instead of skipping it silently */
 #define GTF_STATUS_CAND_OVERFLOW 32
+/* debug builds only (nvcc -DGTF_DEBUG_BOUNDS, tools/debug_bounds.sh): an index computed inside a kernel left its array */
+#define GTF_STATUS_BOUNDS 64
 
 typedef struct gtf_batch gtf_batch;
 
