@@ -17,7 +17,8 @@ e2e      the same metric through the public API from HOST buffers, every step a 
          (hits + the two CSR orders, 44 B/hit + 8 B/edge) -> gtf_batch_load_events (H2D + device-side initialisation)
          -> gtf_seed_cluster (seed + cluster on the seeds) -> gtf_iterate until the active-edge set stops changing (<= 10) -> candidate
          extraction -> candidate table (event, candidate, node) back on the host; at N > 1 the tables of all ranks are
-         gathered on rank 0 with NCCL inside the timed region.  e2e.value = edge-iterations of all iterations / time.
+         gathered on rank 0 with NCCL inside the timed region.  The next step's load (a second batch object, a helper
+         thread for its host side) overlaps the current step.  e2e.value = edge-iterations of all iterations / time.
 roofline algorithmic bytes / the summed CUDA-event durations of all kernels of the iteration vs the measured HBM copy
          bandwidth in MEASURED_PEAKS.json.  Two units: SURVEY.md 8d's 264 B per active edge (`frac`), and the strict count
          that charges the 153 B read only to edges that carry a message and the 89 B write only to messages that pass
@@ -281,33 +282,49 @@ def e2e_loop(sets, steps, torch, dist, rank):
     and one run of the whole batch; the first load of the timed region is not overlapped with anything."""
     from gtf_b200 import shard
     info = {}
+    prof = {"load_issue": 0.0, "run": 0.0, "gather": 0.0}       # host wall clock per phase (GTF_E2E_PROFILE=1 prints it)
 
     def run(chunks):
+        t0 = time.perf_counter()
         if dist is None:
             for c in chunks:
                 c.run(True)
+            prof["run"] += time.perf_counter() - t0
             return sum(c.n_rows for c in chunks)
         parts = [c.run(False) for c in chunks]
         parts = [torch.as_tensor(p, device="cuda") for p in parts if p is not None]
         mine = torch.cat(parts) if parts else torch.zeros((0, 3), dtype=torch.int32, device="cuda")
+        t1 = time.perf_counter()
         table = shard.gather_candidates(mine, sort=False, info=info)     # NCCL: counts all-gather + padded table all-gather
+        prof["run"] += t1 - t0
+        prof["gather"] += time.perf_counter() - t1
         if rank == 0:
             assert table.shape[0] == sum(info["counts"])
             return table.shape[0]
         return 0
 
+    def load(chunks):
+        t0 = time.perf_counter()
+        for c in chunks:
+            c.load()
+        prof["load_issue"] += time.perf_counter() - t0
+
+    from concurrent.futures import ThreadPoolExecutor
+    loader = ThreadPoolExecutor(1)               # the host side of a load (tile tables, ~60 driver calls) runs beside the schedule
+
     def loop(n):
         rows = 0
-        for c in sets[0]:
-            c.load()
+        load(sets[0])
         for s in range(n):
-            if s + 1 < n:
-                for c in sets[(s + 1) & 1]:
-                    c.load()                     # next step's batch: asynchronous, other streams
+            nxt = loader.submit(load, sets[(s + 1) & 1]) if s + 1 < n else None   # next step's batch: own streams, own thread
             rows = run(sets[s & 1])
+            if nxt is not None:
+                nxt.result()
         return rows
 
     loop(2)
+    for k in prof:
+        prof[k] = 0.0
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -317,6 +334,9 @@ def e2e_loop(sets, steps, torch, dist, rank):
     if dist is not None:
         dist.barrier()
     ms = (time.perf_counter() - t0) * 1e3
+    if os.environ.get("GTF_E2E_PROFILE"):
+        sys.stderr.write("rank %d e2e ms/step: total %.2f, of which host time in load_events %.2f, schedule %.2f, gather %.2f\n" % (
+            rank, ms / steps, *(1e3 * prof[k] / steps for k in ("load_issue", "run", "gather"))))
     return ms, rows, info
 
 
