@@ -807,11 +807,11 @@ static int ensure_packed(gtf_batch *b)
 {
     if (b->derived_dirty) TRY(recount_subs(b));
     const bool st = b->pack_static_stale;
-    const bool any = st || b->exists_stale || b->pack_stale[0] || b->pack_stale[1] || b->pack_stale[2] || b->pack_stale[PG_NODE];
+    const bool any = st || b->pack_out_stale || b->exists_stale || b->pack_stale[0] || b->pack_stale[1] || b->pack_stale[2] || b->pack_stale[PG_NODE];
     if (!any) return 0;
     b->force_pending = true; // the packed state changes from outside: the next committed iteration evaluates every node
     DevPack &k = b->k;
-    if (st) {
+    if (st || b->pack_out_stale) {
         if (b->E) k_pack_out<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, k);
     }
     if (b->N && (st || b->pack_stale[PG_NODE]))
@@ -829,6 +829,7 @@ static int ensure_packed(gtf_batch *b)
     }
     CK(cudaGetLastError());
     b->pack_static_stale = false;
+    b->pack_out_stale = false;
     for (int q = 0; q < PG_N; q++) b->pack_stale[q] = false;
     return 0;
 }
@@ -960,6 +961,12 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
     return 0;
 }
 
+__global__ void k_count_flags(const uint8_t *f, int n, unsigned long long *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned m = __ballot_sync(0xffffffffu, i < n && f[i] != 0);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
 // cluster() on the SEED dict (clustering.py:149-376 with 'track_state_estimates') on the packed node kernels: the seed
 // entries are packed like updated states (slot order = dict order), k_node2 / k_hv / k_big run without the re-weighting
 // (pre_passes (prior) passes first: 0 = the stage as the reference defines it, 1 = preceded by the seed's own
@@ -980,6 +987,16 @@ static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre
         P.ops[n++] = OP_CLUSTER; P.ops[n++] = OP_DEGREE; P.ops[n++] = OP_WEIGHTS; P.ops[n++] = OP_PRIOR; P.ops[n] = OP_END;
     }
     const size_t words = ((size_t)b->E + 31) / 32 + 2;
+    // does any node hold updated states?  (`has_uts` is current: soa_for_stage above)
+    bool uts_empty = true;
+    if (b->N) {
+        CK(cudaMemsetAsync(b->n_dead, 0, sizeof(unsigned long long), s0));
+        k_count_flags<<<(b->N + 255) / 256, 256, 0, s0>>>((const uint8_t *)b->f[GTF_F_has_uts], b->N, b->n_dead);
+        unsigned long long nu = 0;
+        CK(cudaMemcpyAsync(&nu, b->n_dead, sizeof(nu), cudaMemcpyDeviceToHost, s0));
+        CK(cudaStreamSynchronize(s0));
+        uts_empty = nu == 0;
+    }
     CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long) * GTF_NCOUNTERS_ALL, s0));
     CK(cudaMemsetAsync(k.counts + PK_MISSING, 0, sizeof(int), s0));
     CK(cudaMemsetAsync(k.counts + PK_FORCE, 0xff, sizeof(int), s0));       // every node is evaluated
@@ -999,13 +1016,21 @@ static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre
     b->parity ^= 1;
     if (b->E) k_unpack_tse<<<(b->E + 255) / 256, 256, 0, s0>>>(b->d, k);
     CK(cudaGetLastError());
-    // what is where now: activation bits + merged records are current on both sides after the unpack below; the dict-entry
-    // records hold the SEED dict, so the updated-state groups are re-packed from the fields before the next iteration
+    // what is where now: activation bits are current on both sides, the merged records are newer in the packed copy, the
+    // geometry / node records were just rebuilt; the per-out-edge records carry the OLD seed weights.  The dict-entry
+    // records hold the SEED dict: when the batch has no updated states at all (fresh events: the usual case) the presence
+    // bitmap is simply cleared -- absent entries are never read --, otherwise the updated-state groups are re-packed from
+    // the fields before the next iteration.
     b->soa_stale[PG_ACT] = false; b->pack_stale[PG_ACT] = false; b->exists_stale = false;
-    b->pack_stale[PG_PRES] = b->pack_stale[PG_REC] = true;
     b->soa_stale[PG_PRES] = b->soa_stale[PG_REC] = false;
+    if (uts_empty) {
+        CK(cudaMemsetAsync(k.pres, 0, sizeof(uint32_t) * words, s0));
+        b->pack_stale[PG_PRES] = b->pack_stale[PG_REC] = false;
+    } else
+        b->pack_stale[PG_PRES] = b->pack_stale[PG_REC] = true;
     b->soa_stale[PG_NODE] = true; b->pack_stale[PG_NODE] = false;
-    b->pack_static_stale = true;                  // the carried seed weights (per-out-edge records) changed
+    b->pack_static_stale = false;
+    b->pack_out_stale = true;                     // the carried seed weights (per-out-edge records) changed
     b->force_pending = true;
     b->have_last_prog = false;
     return st ? counters_read(b, st) : 0;

@@ -199,6 +199,7 @@ struct gtf_batch {
     DevPack k;
     bool exists_stale;         // alive flags changed since the existing-edge bitmap was built
     bool pack_static_stale;    // topology / coordinates / seed weights changed since the static part was built
+    bool pack_out_stale;       // only the per-out-edge records (carried seed weights) are out of date
     bool pack_stale[4], soa_stale[4]; // per group (PG_ACT, PG_PRES, PG_REC, PG_NODE): which side holds the newer state
     cudaStream_t stream3;
     cudaEvent_t ev_fork2, ev_join2, ev_join3;

@@ -159,15 +159,18 @@ __global__ void k_unpack_slots(DevBatch B, DevPack K, int do_act, int do_pres, i
     if (do_act) B.active[s] = bm_get(K.act, s) ? 1 : 0;
     if (do_pres) B.uts_present[s] = bm_get(K.pres, s) ? 1 : 0;
     if (do_rec) {
-        const double2 *st = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)s);
-        double2 v0 = st[0], v1 = st[1], v2 = st[2], v3 = st[3];
-        B.uts_a[s] = v0.x; B.uts_b[s] = v0.y; B.uts_c[s] = v1.x; B.uts_tau[s] = v1.y;
-        B.uts_p00[s] = v2.x; B.uts_p01[s] = v2.y; B.uts_p11[s] = v3.x; B.uts_p22[s] = v3.y;
         const MetaRec m = K.meta[s];
-        B.uts_w[s] = m.w; B.uts_lik[s] = m.lik; B.uts_prior[s] = m.prior; B.edge_w[s] = m.ew;
-        const TagRec t = (*tag_p(K, s));
-        B.uts_rank[s] = t.rank; B.uts_side[s] = t.side;
-        if (t.lrn >= 0) B.uts_lrn[s] = t.lrn == 0 ? NAN : (double)t.lrn;
+        B.edge_w[s] = m.ew;
+        if (bm_get(K.pres, s)) {         // (records of absent entries are scratch: cluster() on the seed dict borrows them)
+            const double2 *st = reinterpret_cast<const double2 *>(K.state + 8 * (size_t)s);
+            double2 v0 = st[0], v1 = st[1], v2 = st[2], v3 = st[3];
+            B.uts_a[s] = v0.x; B.uts_b[s] = v0.y; B.uts_c[s] = v1.x; B.uts_tau[s] = v1.y;
+            B.uts_p00[s] = v2.x; B.uts_p01[s] = v2.y; B.uts_p11[s] = v3.x; B.uts_p22[s] = v3.y;
+            B.uts_w[s] = m.w; B.uts_lik[s] = m.lik; B.uts_prior[s] = m.prior;
+            const TagRec t = (*tag_p(K, s));
+            B.uts_rank[s] = t.rank; B.uts_side[s] = t.side;
+            if (t.lrn >= 0) B.uts_lrn[s] = t.lrn == 0 ? NAN : (double)t.lrn;
+        }
     }
 }
 
@@ -195,19 +198,20 @@ __global__ void k_pack_tse(DevBatch B, DevPack K)
     gr.lay = src >= 0 ? B.layer[src] : -1;
     gr.src = src;
     (*geo_p(K, s)) = gr;
+    MetaRec m;                          // (the edge attribute `mixture_weight` rides in the record of every slot)
+    m.w = 0.0; m.lik = 0.0; m.prior = 0.0; m.ew = B.edge_w[s];
     if (pres) {
         double2 *st = reinterpret_cast<double2 *>(K.state + 8 * (size_t)s);
         st[0] = make_double2(B.tse_a[s], B.tse_b[s]);
         st[1] = make_double2(B.tse_c[s], B.tse_tau[s]);
         st[2] = make_double2(B.tse_p00[s], B.tse_p01[s]);
         st[3] = make_double2(B.tse_p11[s], B.tse_p22[s]);
-        MetaRec m;
-        m.w = B.tse_w[s]; m.lik = 0.0; m.prior = B.tse_prior[s]; m.ew = 0.0;
-        K.meta[s] = m;
-        TagRec t;
-        t.rank = s; t.side = 0; t.pad = 0; t.lrn = -1;
-        (*tag_p(K, s)) = t;
+        m.w = B.tse_w[s]; m.prior = B.tse_prior[s];
     }
+    K.meta[s] = m;
+    TagRec t;
+    t.rank = s; t.side = 0; t.pad = 0; t.lrn = -1;
+    (*tag_p(K, s)) = t;
 }
 __global__ void k_unpack_tse(DevBatch B, DevPack K)
 {

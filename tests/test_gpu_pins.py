@@ -294,6 +294,16 @@ def test_seed_cluster_equals_seed_then_cluster():
         for k in ga:
             assert np.array_equal(ga[k], gc[k], equal_nan=True), (name, k)
         assert sa == sc
+        # and the packed iteration picks both up identically (after gtf_seed_cluster the dict-entry records still hold the
+        # seed dict and only the presence bitmap is cleared; after the two-call form everything is re-packed)
+        a2 = gtf_b200.EventBatch(hb)
+        a2.seed_cluster(1.0, 2.0)
+        ia = a2.iterate(max_iter=2, stop_when_converged=False)
+        ic = c.iterate(max_iter=2, stop_when_converged=False)
+        assert ia == ic
+        ga, gc = state_of(a2), state_of(c)
+        for k in ga:
+            assert np.array_equal(ga[k], gc[k], equal_nan=True), (name, k, "after two iterations")
     fx = gu.load("lut_barrel40")
     a = gtf_b200.EventBatch(blank_seed(gu.stage_batch(fx, "seed")))
     a.seed_cluster(1.0, 123.0, KL_lut=fx["lut_stress"])
