@@ -34,7 +34,7 @@ static int fail(int code, const std::string &msg)
 
 struct Prog;
 struct GtfGeom;
-static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre_passes, gtf_stats *st);
+static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre_passes, gtf_stats *st, const gtf_geom *seed_first = nullptr);
 static const bool g_tile_cluster = getenv("GTF_TILE_CLUSTER") != nullptr;   // debugging: cluster() on the seeds with the per-stage kernel
 
 struct FieldInfo { const char *name; int elem; char ext; };
@@ -635,20 +635,49 @@ static int launch_prefix(gtf_batch *b, const GtfGeom &g)
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ seeding
-__global__ void k_seed_slots(DevBatch B, GtfGeom g)
+// pack != 0: the entry also goes straight into the packed layout (what k_pack_tse would build from the fields afterwards:
+// state / weight / tag / geometry records, activation = presence = every slot, existing-edge bits), for gtf_seed_cluster
+__global__ void k_seed_slots(DevBatch B, DevPack K, GtfGeom g, int pack)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= B.E) return;
-    int i = B.slot_dst[s], b0 = B.in_off[i], d = B.in_off[i + 1] - b0, k = s - b0;
-    int key = B.in_src[s], other = B.in_src[b0 + d - 1 - k]; // quirk 5: tau of the mirrored neighbour
-    double zA = B.z[i], rA = B.r[i];
-    double dz = B.z[other] - zA, dr = B.r[other] - rA;
-    double vt = gtf_var_tau(dz, dr, zA, B.z[other], g);
+    const bool in = s < B.E;
+    int key = -1, i = 0;
     GtfState o;
-    gtf_seed_entry(B.x[i], B.y[i], zA, rA, B.x[key], B.y[key], B.z[key], B.r[key], dz / dr, vt * vt, g, o);
-    B.tse_present[s] = 1;
-    B.tse_a[s] = o.a; B.tse_b[s] = o.b; B.tse_c[s] = o.c; B.tse_tau[s] = o.tau;
-    B.tse_p00[s] = o.p00; B.tse_p01[s] = o.p01; B.tse_p11[s] = o.p11; B.tse_p22[s] = o.p22;
+    if (in) {
+        i = B.slot_dst[s];
+        int b0 = B.in_off[i], d = B.in_off[i + 1] - b0, k = s - b0;
+        key = B.in_src[s];
+        int other = B.in_src[b0 + d - 1 - k]; // quirk 5: tau of the mirrored neighbour
+        double zA = B.z[i], rA = B.r[i];
+        double dz = B.z[other] - zA, dr = B.r[other] - rA;
+        double vt = gtf_var_tau(dz, dr, zA, B.z[other], g);
+        gtf_seed_entry(B.x[i], B.y[i], zA, rA, B.x[key], B.y[key], B.z[key], B.r[key], dz / dr, vt * vt, g, o);
+        B.tse_present[s] = 1;
+        B.tse_a[s] = o.a; B.tse_b[s] = o.b; B.tse_c[s] = o.c; B.tse_tau[s] = o.tau;
+        B.tse_p00[s] = o.p00; B.tse_p01[s] = o.p01; B.tse_p11[s] = o.p11; B.tse_p22[s] = o.p22;
+    }
+    if (!pack) return;
+    const bool ex = in && key >= 0 && B.alive[key] && B.alive[i];
+    const unsigned mex = __ballot_sync(0xffffffffu, ex), min_ = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && min_) {
+        K.act[s >> 5] = min_; K.pres[s >> 5] = min_; K.exists[s >> 5] = mex;       // initialize_edge_activation: all 1
+        if (mex != min_) atomicAdd(&K.counts[PK_MISSING], __popc(min_ & ~mex));
+    }
+    if (!in) return;
+    GeoRec gr;
+    gr.sx = B.x[key]; gr.lay = B.layer[key]; gr.src = key;
+    K.aux[s].g = gr;
+    double2 *st = reinterpret_cast<double2 *>(K.state + 8 * (size_t)s);
+    st[0] = make_double2(o.a, o.b);
+    st[1] = make_double2(o.c, o.tau);
+    st[2] = make_double2(o.p00, o.p01);
+    st[3] = make_double2(o.p11, o.p22);
+    MetaRec m;
+    m.w = B.tse_w[s]; m.lik = 0.0; m.prior = B.tse_prior[s]; m.ew = B.edge_w[s];
+    K.meta[s] = m;
+    TagRec t;
+    t.rank = s; t.side = 0; t.pad = 0; t.lrn = -1;
+    K.aux[s].t = t;
 }
 // np.var of the xy edge gradients (helper.py:446), in set-iteration order = reversed slot order
 __global__ void k_seed_nodes(DevBatch B)
@@ -674,7 +703,7 @@ extern "C" int gtf_seed(gtf_batch *b, const gtf_geom *g)
     CK(cudaSetDevice(b->device));
     TRY_(soa_for_stage(b, true));
     GtfGeom gg = geom_of(g);
-    if (b->E) k_seed_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, gg);
+    if (b->E) k_seed_slots<<<(b->E + 255) / 256, 256, 0, b->stream>>>(b->d, b->k, gg, 0);
     if (b->N) k_seed_nodes<<<(b->N + 255) / 256, 256, 0, b->stream>>>(b->d);
     CK(cudaGetLastError());
     return 0;
@@ -971,7 +1000,7 @@ __global__ void k_count_flags(const uint8_t *f, int n, unsigned long long *out)
 // entries are packed like updated states (slot order = dict order), k_node2 / k_hv / k_big run without the re-weighting
 // (pre_passes (prior) passes first: 0 = the stage as the reference defines it, 1 = preceded by the seed's own
 // compute_prior_probabilities), then activation flags, weights and priors go back to the fields.
-static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre_passes, gtf_stats *st)
+static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre_passes, gtf_stats *st, const gtf_geom *seed_first)
 {
     if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
     TRY_(soa_for_stage(b, true));                 // every field current; the packed records are about to hold the seed dict
@@ -1002,7 +1031,13 @@ static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre
     CK(cudaMemsetAsync(k.counts + PK_FORCE, 0xff, sizeof(int), s0));       // every node is evaluated
     b->force_dev = 1;
     if (b->N) k_pack_nodes<<<(b->N + 256) / 256, 256, 0, s0>>>(d, k, 1, 1);
-    if (b->E) k_pack_tse<<<(b->E + 255) / 256, 256, 0, s0>>>(d, k);
+    if (seed_first) {
+        // gtf_seed_cluster: helper.py:238-452 + :24-25 with the entries written to the fields AND the packed records at once
+        CK(cudaMemsetAsync(b->f[GTF_F_active], 1, (size_t)(b->E ? b->E : 0), s0));
+        if (b->E) k_seed_slots<<<(b->E + 255) / 256, 256, 0, s0>>>(d, k, geom_of(seed_first), 1);
+        if (b->N) k_seed_nodes<<<(b->N + 255) / 256, 256, 0, s0>>>(d);
+    } else if (b->E)
+        k_pack_tse<<<(b->E + 255) / 256, 256, 0, s0>>>(d, k);
     {
         const int nthr = (int)std::max<size_t>(words, (size_t)b->N);
         k_begin<<<(nthr + 255) / 256, 256, 0, s0>>>(d, k, (int)words);
@@ -1038,13 +1073,14 @@ static int cluster_seeds_packed(gtf_batch *b, Prog P, const GtfGeom &gg, int pre
 extern "C" int gtf_seed_cluster(gtf_batch *b, const gtf_geom *g, double chi2_threshold, double kl_threshold, const double *kl_lut,
                                 gtf_stats *st)
 {
-    TRY(gtf_seed(b, g));
-    CK(cudaMemsetAsync(b->f[GTF_F_active], 1, (size_t)(b->E ? b->E : 0), b->stream));
+    if (!b || !g) return fail(GTF_E_ARG, "gtf_seed_cluster: null argument");
+    if (!b->finalized) return fail(GTF_E_STATE, "batch not finalized");
+    CK(cudaSetDevice(b->device));
     Prog P = make_prog(GTF_KEY_TSE, 0, {OP_END});
     P.cl_chi2 = chi2_threshold;
     P.cl_kl = kl_threshold;
     if (kl_lut) { P.use_lut = 1; memcpy(P.lut, kl_lut, sizeof(double) * 28); }
-    return cluster_seeds_packed(b, P, geom_of(g), 1, st);
+    return cluster_seeds_packed(b, P, geom_of(g), 1, st, g);
 }
 
 extern "C" int gtf_iterate_dry(gtf_batch *b, const gtf_iter_params *p, const gtf_geom *g, gtf_stats *st)

@@ -13,8 +13,7 @@ def t(fn):
 for rep in range(3):
     rows = []
     rows.append(("load_events", t(c.load)[0]))
-    rows.append(("seed", t(lambda: b.seed(want_stats=False))[0]))
-    rows.append(("cluster(seeds)", t(lambda: b.cluster("track_state_estimates", 1.0, 2.0))[0]))
+    rows.append(("seed_cluster", t(lambda: b.seed_cluster(1.0, 2.0))[0]))
     ms, st = t(lambda: b.iterate(max_iter=10, stop_when_converged=True))
     rows.append(("iterate x%d" % len(st), ms))
     rows.append(("extract", t(lambda: b.extract(want_arrays=False))[0]))
