@@ -159,7 +159,7 @@ static int batch_alloc(gtf_batch *b)
         // packed iteration layout (gtf_iter.cuh)
         DevPack &k = b->k;
         const int64_t words = ((int64_t)E + 31) / 32 + 2;
-        DA(k.out_dst, E); DA(k.orec, E); DA(k.aux, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N); DA(k.srec, (int64_t)N + 1);
+        DA(k.out_dst, E); DA(k.orec, E); DA(k.aux, E); DA(k.xyzr, N); DA(k.mrec, N); DA(k.mrec_nx, N); DA(k.srec, (int64_t)N + 1); DA(k.mab, N);
         DA(k.act, words); DA(k.act_nx, words); DA(k.pres, words); DA(k.exists, words); DA(k.pres0, words);
         DA(k.state, (int64_t)E * 8); DA(k.meta, E);
         DA(k.msg_desc, E); DA(k.msg_w, E);
@@ -207,7 +207,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     for (void *p : extra) cudaFree(p);
     {
         DevPack &k = b->k;
-        void *pk[] = {k.srec, k.mrec, k.mrec_nx, k.out_dst, k.orec, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
+        void *pk[] = {k.mab, k.srec, k.mrec, k.mrec_nx, k.out_dst, k.orec, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
                       k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         for (int c = 0; c < 2; c++)
@@ -880,6 +880,7 @@ static int issue_node_kernels(gtf_batch *b, const Prog &P, const GtfGeom &gg, bo
         mo.hm = commit ? d.has_merged : d.has_merged_nx;
         mo.rec = commit ? k.mrec : k.mrec_nx;
         mo.p11 = d.m_p11_nx; // k_begin / k_send wrote every node's accumulated value there; a new cluster replaces it
+        mo.ab = commit ? k.mab : nullptr;
         // the bins are independent (disjoint nodes): run them side by side
         CK(cudaEventRecord(b->ev_fork2, s0));
         CK(cudaStreamWaitEvent(b->stream2, b->ev_fork2, 0));

@@ -81,6 +81,8 @@ struct DevPack {
     NodeXYZR *xyzr;              // [N]
     SrcRec *srec;                // [N + 1]
     MergedRec *mrec, *mrec_nx;   // [N] merged state of every node (64 B: two whole sectors); _nx: shadow for uncommitted passes
+    double2 *mab;                // [N] compact copy of the COMMITTED merged (a, b): what k_send needs of a source, contiguous
+                                 // per tile (a 16 B gather out of the 64 B records costs a 64 B DRAM fetch per source)
     int all_exist;               // every slot is an existing edge (no ghost slot, no removed node): set on the device from counts[PK_MISSING]
     // mutable slot state
     uint32_t *act, *act_nx, *pres, *exists; // bitmaps over slots, 2 zero words of padding
@@ -107,16 +109,23 @@ enum {
 #define GTF_BOUND(B, cond) ((void)0)
 #endif
 // a decision `value (<|<=) threshold` was just taken: note it when it is a boundary-flip candidate
+#ifdef GTF_NEAR_NOINLINE      // (measured: a real call costs the hot kernels more than the inlined rare path, 0.138 vs 0.134 ms in k_exec)
+#define GTF_NEAR_ATTR __noinline__
+#else
+#define GTF_NEAR_ATTR __forceinline__
+#endif
+__device__ GTF_NEAR_ATTR void near_log(unsigned long long *counters, gtf_near_rec *log, int kind, int index, double value, double threshold)
+{
+    const unsigned long long k = atomicAdd(&counters[CNT_NEAR], 1ull);
+    if (k < GTF_NEAR_LOG) {
+        gtf_near_rec r;
+        r.kind = kind; r.index = index; r.value = value; r.threshold = threshold;
+        log[k] = r;
+    }
+}
 __device__ __forceinline__ void near_note(const DevBatch &B, int kind, int index, double value, double threshold)
 {
-    if (fabs(value - threshold) <= GTF_NEAR_RTOL * fabs(threshold)) {
-        const unsigned long long k = atomicAdd(&B.counters[CNT_NEAR], 1ull);
-        if (k < GTF_NEAR_LOG) {
-            gtf_near_rec r;
-            r.kind = kind; r.index = index; r.value = value; r.threshold = threshold;
-            B.near_log[k] = r;
-        }
-    }
+    if (fabs(value - threshold) <= GTF_NEAR_RTOL * fabs(threshold)) near_log(B.counters, B.near_log, kind, index, value, threshold);
 }
 
 // per-node program executed by the tile kernel

@@ -142,6 +142,7 @@ __global__ void k_pack_nodes(DevBatch B, DevPack K, int do_static, int do_merged
         m.a = B.m_a[i]; m.b = B.m_b[i]; m.c = B.m_c[i]; m.p00 = B.m_p00[i]; m.p01 = B.m_p01[i]; m.p22 = B.m_p22[i];
         m.prior = B.m_prior[i]; m.cl_p11 = NAN;
         K.mrec[i] = m;
+        K.mab[i] = make_double2(m.a, m.b);
     }
 }
 __global__ void k_unpack_nodes(DevBatch B, DevPack K)
@@ -326,7 +327,12 @@ __device__ __forceinline__ void send_prefetch(const DevBatch &B, const DevPack &
         const int ua = u0 & ~15, un = ((u0 + ns + 15) & ~15) - ua;
         const int pa = u0 & ~1, pn = ((u0 + ns + 1) & ~1) - pa;
         const unsigned b_edges = 4u * on, b_src = 16u * (ns + 1), b_fl = (unsigned)un, b_p = 8u * pn;
+#ifndef GTF_SEND_GATHER_AB
+        mbar_expect_tx(bar, 2 * b_edges + b_src + 2 * b_fl + b_p + 16u * ns);
+        bulk_g2s(st.ab, K.mab + u0, 16u * ns, bar);      // merged (a, b) of the tile's sources: compact array
+#else
         mbar_expect_tx(bar, 2 * b_edges + b_src + 2 * b_fl + b_p);
+#endif
         if (on) {
             bulk_g2s(st.slot, B.out_slot + oa, b_edges, bar);
             bulk_g2s(st.dst, K.out_dst + oa, b_edges, bar);
@@ -336,8 +342,10 @@ __device__ __forceinline__ void send_prefetch(const DevBatch &B, const DevPack &
         bulk_g2s(st.nok, B.node_ok + ua, b_fl, bar);
         bulk_g2s(st.p11, B.m_p11 + pa, b_p, bar);
     }
+#ifdef GTF_SEND_GATHER_AB
     if (tid < ns)                                        // merged (a, b): first 16 B of the 64 B node record
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&st.ab[tid])), "l"(K.mrec + u0 + tid) : "memory");
+#endif
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
@@ -790,6 +798,7 @@ struct MergedOut {
     uint8_t *hm;      // has_merged flags to set
     MergedRec *rec;   // merged-state records to write (in place when the pass is committed, shadow otherwise)
     double *p11;      // accumulated merged_cov[1,1] of the next state
+    double2 *ab;      // compact (a, b) of the committed state (k_send), NULL in uncommitted passes
 };
 __device__ __forceinline__ void merged_store(const MergedOut &MO, int i, const GtfState &m, double mprior)
 {
@@ -799,6 +808,7 @@ __device__ __forceinline__ void merged_store(const MergedOut &MO, int i, const G
     r[1] = make_double2(m.c, m.p00);
     r[2] = make_double2(m.p01, m.p22);
     r[3] = make_double2(mprior, m.p11);
+    if (MO.ab) MO.ab[i] = make_double2(m.a, m.b);
     MO.p11[i] = m.p11;
 }
 // the node was evaluated and formed no cluster: remember that (static nodes are skipped later, see k_node2)
