@@ -587,7 +587,9 @@ struct LEnt {          // one dict entry of a light node
 };
 // second word of the tag record: side in byte 0, lr_layer_norm code in the upper half
 __device__ __forceinline__ int tag_pack(int side, int lrn) { return (side & 0xff) | (lrn << 16); }
-__device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, int s, LEnt &e)
+// `pf`: the entry's flag bits when the caller already holds the bitmap windows they live in (H_EX | H_ACT | H_ACT0 | H_ORIG |
+// H_NEW), or ~0u: test the bitmaps here
+__device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, int s, LEnt &e, unsigned pf = ~0u)
 {
     const double2 m0 = __ldcs(reinterpret_cast<const double2 *>(K.meta + s));
     const double2 m1 = __ldcs(reinterpret_cast<const double2 *>(K.meta + s) + 1);
@@ -601,12 +603,26 @@ __device__ __forceinline__ void lent_load(const DevBatch &B, const DevPack &K, i
     e.rank0 = tg.x;
     e.sx = gr.sx + 0.0; e.lay = gr.lay;
     unsigned f = H_PRES;
-    if (K.all_exist || bm_get(K.exists, s)) f |= H_EX;
-    if (bm_get(K.act_nx, s)) f |= H_ACT | H_ACT0;
-    if (bm_get(K.act, s)) f |= H_ORIG;
+    if (pf != ~0u)
+        f |= pf;
+    else {
+        if (K.all_exist || bm_get(K.exists, s)) f |= H_EX;
+        if (bm_get(K.act_nx, s)) f |= H_ACT | H_ACT0;
+        if (bm_get(K.act, s)) f |= H_ORIG;
+        if (!bm_get(K.pres0, s)) f |= H_NEW;
+    }
     if (e.prior != e.prior) { e.side = 0; e.lrn = 0; }   // entry just written by the extrapolation: no side / lr_layer_norm yet
-    if (!bm_get(K.pres0, s)) f |= H_NEW;
     e.f = f;
+}
+// flag bits of the entry at bit `k` of the bitmap windows (existing, next activation, activation, presence snapshot)
+__device__ __forceinline__ unsigned win_flags(unsigned exw, unsigned anw, unsigned a0w, unsigned p0w, int k)
+{
+    unsigned f = 0;
+    if ((exw >> k) & 1u) f |= H_EX;
+    if ((anw >> k) & 1u) f |= H_ACT | H_ACT0;
+    if ((a0w >> k) & 1u) f |= H_ORIG;
+    if (!((p0w >> k) & 1u)) f |= H_NEW;
+    return f;
 }
 __device__ __forceinline__ void lent_store(const DevBatch &B, const DevPack &K, const LEnt &e)
 {
@@ -683,23 +699,28 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
         unsigned nf = B.node_ok[i];
         const int b0 = B.in_off[i], b1 = B.in_off[i + 1];
         int np = 0, e0 = -1, e1 = -1, deg = 0, chg = 0;
-        unsigned a0_any = 0;
+        unsigned a0_any = 0, f0 = 0, f1 = 0;          // f0 / f1: flag bits of the first two entries, cut out of the windows
         for (int c = b0; c < b1; c += 32) {
             const int nb = min(32, b1 - c);
             const unsigned mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
             const unsigned ex = K.all_exist ? mask : (bm_win(K.exists, c) & mask);
             const unsigned pr = bm_win(K.pres, c) & mask;
-            const unsigned an = bm_win(K.act_nx, c) & ex, a0 = bm_win(K.act, c) & ex;
+            const unsigned p0 = bm_win(K.pres0, c);
+            const unsigned anr = bm_win(K.act_nx, c), a0r = bm_win(K.act, c);
+            const unsigned an = anr & ex, a0 = a0r & ex;
             deg += __popc(an);
             chg += __popc(an ^ a0);
             a0_any |= a0;
             if (pr) {
                 if (np == 0) {
-                    e0 = c + __ffs(pr) - 1;
+                    const int k0 = __ffs(pr) - 1;
+                    e0 = c + k0; f0 = win_flags(ex, anr, a0r, p0, k0);
                     const unsigned r = pr & (pr - 1);
-                    if (r) e1 = c + __ffs(r) - 1;
-                } else if (np == 1)
-                    e1 = c + __ffs(pr) - 1;
+                    if (r) { const int k1 = __ffs(r) - 1; e1 = c + k1; f1 = win_flags(ex, anr, a0r, p0, k1); }
+                } else if (np == 1) {
+                    const int k1 = __ffs(pr) - 1;
+                    e1 = c + k1; f1 = win_flags(ex, anr, a0r, p0, k1);
+                }
                 np += __popc(pr);
             }
         }
@@ -727,8 +748,8 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
                 a.rank0 = b.rank0 = a.tag0 = b.tag0 = 0;
                 GTF_BOUND(B, n < 1 || (e0 >= b0 && e0 < b1));
                 GTF_BOUND(B, n < 2 || (e1 > e0 && e1 < b1));
-                if (n >= 1) lent_load(B, K, e0, a);
-                if (n == 2) lent_load(B, K, e1, b);
+                if (n >= 1) lent_load(B, K, e0, a, f0);
+                if (n == 2) lent_load(B, K, e1, b, f1);
                 if (P.key == GTF_KEY_TSE) nf |= NF_DICT;          // every seeded node holds the dict (clustering.py:198)
                 else if (B.has_uts[i]) nf |= NF_HASUTS | NF_DICT;
                 const int nnew = ((a.f & H_NEW) != 0) + ((b.f & H_NEW) != 0);
@@ -924,16 +945,23 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
         }
         // ---- the node's bits: my entry = the gl-th present slot; totals over the slots that hold no entry
         int slot = -1, n = 0, deg_np = 0, chg_np = 0;
+        unsigned fw = 0;                                          // flag bits of my entry, cut out of the windows
         for (int c = b0; c < b1; c += 32) {
             const int nb = min(32, b1 - c);
             const unsigned mask = nb == 32 ? FULL : ((1u << nb) - 1u);
             const unsigned ex = K.all_exist ? mask : (bm_win(K.exists, c) & mask);
             const unsigned pr = bm_win(K.pres, c) & mask;
-            const unsigned an = bm_win(K.act_nx, c) & ex, a0 = bm_win(K.act, c) & ex;
+            const unsigned p0 = bm_win(K.pres0, c);
+            const unsigned anr = bm_win(K.act_nx, c), a0r = bm_win(K.act, c);
+            const unsigned an = anr & ex, a0 = a0r & ex;
             deg_np += __popc(an & ~pr);
             chg_np += __popc((an ^ a0) & ~pr);
             const int cnt = __popc(pr);
-            if (slot < 0 && gl < n + cnt) slot = c + (int)__fns(pr, 0, gl - n + 1);
+            if (slot < 0 && gl < n + cnt) {
+                const int k = (int)__fns(pr, 0, gl - n + 1);
+                slot = c + k;
+                fw = win_flags(ex, anr, a0r, p0, k);
+            }
             n += cnt;
         }
         const bool valid = gv && gl < n;
@@ -953,12 +981,8 @@ __global__ void __launch_bounds__(GTF_HV_WARPS * 32, GTF_HV_MINB) k_hv(DevBatch 
             lrn = tg.y >> 16;
             const GeoRec gr = ld_geo(geo_p(K, slot));
             sx = gr.sx + 0.0; lay = gr.lay; src = gr.src;
-            f = H_PRES;
-            if (K.all_exist || bm_get(K.exists, slot)) f |= H_EX;
-            if (bm_get(K.act_nx, slot)) f |= H_ACT | H_ACT0;
-            if (bm_get(K.act, slot)) f |= H_ORIG;
+            f = H_PRES | fw;
             if (prior != prior) { side = 0; lrn = 0; }        // entry just written by the extrapolation: no side / lr_layer_norm yet
-            if (!bm_get(K.pres0, slot)) f |= H_NEW;
         }
         const int nmax = (int)__reduce_max_sync(FULL, (unsigned)n);
         // ---- new entries enter the dict in ascending source order (extrapolate...py:419-447)
