@@ -24,8 +24,12 @@ for case in range(n_cases):
     hb = synth.concat_host_batches(hbs)
     hb.pop("truth"); hb.pop("orig_id")
     ob = ol.OracleBatch(hb); ob.seed(); ob.cluster(0, 1.0, 2.0)
-    b = gtf_b200.EventBatch(hb); b.raise_ref_errors = False
-    b.seed(); b.cluster(0, 1.0, 2.0)
+    if rng.random() < 0.5:          # full upload + two calls, or device-side ingest + the fused seed / cluster pass
+        b = gtf_b200.EventBatch(hb); b.raise_ref_errors = False
+        b.seed(); b.cluster(0, 1.0, 2.0)
+    else:
+        b = gtf_b200.EventBatch.with_capacity(len(hb["x"]) + 5, len(hb["in_src"]) + 9, len(hb["sub_event"]) + 1); b.raise_ref_errors = False
+        b.load_events(hb); b.seed_cluster(1.0, 2.0)
     plan = rng.choice(["single", "burst", "mixed"])
     n_it = 5
     for _ in range(n_it):
