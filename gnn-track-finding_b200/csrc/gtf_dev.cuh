@@ -35,6 +35,7 @@ struct DevBatch {
     gtf_near_rec *near_log;       // [GTF_NEAR_LOG] decisions within 1e-9 relative of their threshold (counters[CNT_NEAR] counts them)
 };
 #define GTF_NEAR_LOG 256
+#define GTF_LOOP_BURST 32      // iterations of gtf_iterate queued between two host read-backs
 
 // ---- packed iteration layout (gtf_iter.cuh): per-slot records + bitmaps, built from / written back to the SoA
 // fields by k_pack_* / k_unpack_slots.  The SoA arrays stay the exchange format of the C-ABI.
@@ -71,7 +72,10 @@ struct __align__(32) MergedRec {  // merged_state / merged_cov / merged_prior of
 static_assert(sizeof(MetaRec) == 32 && sizeof(AuxRec) == 32 && sizeof(NodeXYZR) == 32 && sizeof(OutRec) == 32 && sizeof(MergedRec) == 64,
               "packed records are whole 32 B sectors");
 
-enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_FORCE = 7, PK_NCOUNTS = 8 };
+enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_FORCE = 7,
+       PK_STOP = 8,   // the committed loop of gtf_iterate has converged on the device: queued iterations do nothing
+       PK_DONE = 9,   // iterations of that loop that ran
+       PK_NCOUNTS = 10 };
 
 struct DevPack {
     // static, derived from the topology and the hit coordinates
@@ -94,7 +98,7 @@ struct DevPack {
     double *msg_w;               // [E] mixture weight carried by the message (extrapolate...py:384)
     double *msg_p11, *msg_vms;   // [E] merged_cov[1,1] as the edge sees it (quirk 2), its multiple-scattering term
     int32_t *hv_list;            // [(HV_BINS + 1) * N] cooperative nodes binned by dict size: <=4, <=8, <=16, <=32, more
-    int *counts;                 // [PK_NCOUNTS] messages, 4 bins, big, missing slots, 'evaluate every node' flag
+    int *counts;                 // [PK_NCOUNTS] messages, 4 bins, big, missing slots, 'evaluate every node' flag, loop stop / done
 };
 
 enum {
@@ -190,6 +194,8 @@ struct gtf_batch {
     int32_t *stile_begin;      // k_send tiles as int4 (first source, sources, first out-edge, out-edges): whole sources,
                                // <= GTF_SEND_SRCS sources and <= GTF_SEND_EDGES out-edges
     unsigned long long *h_counters; // pinned
+    unsigned long long *loop_stats, *h_loop_stats; // [GTF_LOOP_BURST][GTF_NCOUNTERS_ALL] per-iteration counters of a queued loop (device, pinned)
+    int *h_loop_done;          // pinned
     int64_t dev_bytes;
     // extraction scratch
     uint8_t *accepted_total;   // [N] nodes accepted by any gtf_extract so far
@@ -219,6 +225,7 @@ struct gtf_batch {
     Prog last_prog;
     GtfGeom last_geom;
     bool use_graph;            // replay the iteration from a CUDA graph (GTF_GRAPH=0: plain launches)
+    bool fused_sx;             // k_send + k_exec as the one warp-specialised kernel k_sx (GTF_FUSED_SX=1)
     int parity;                // which half of the ping-pong pairs (act / act_nx, m_p11 / m_p11_nx) is current
     IterGraph graphs[2][2];    // [committed][parity]
     double t_k[5];             // send, exec, node, heavy, (spare)

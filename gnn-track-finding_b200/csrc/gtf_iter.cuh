@@ -228,12 +228,27 @@ __global__ void k_unpack_tse(DevBatch B, DevPack K)
 // ------------------------------------------------------------------------------------------------ k_begin
 // start of an iteration: next activation bitmap := current, snapshot of the presence bitmap, list counters := 0,
 // accumulated p11 of the nodes carried over (k_send overwrites the ones that send; quirk 2)
-__global__ void k_begin(DevBatch B, DevPack K, int words)
+__global__ void k_begin(DevBatch B, DevPack K, int words, int reset_counters)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= PK_BIG) K.counts[t] = 0;
+    if (K.counts[PK_STOP]) return;       // a queued iteration after the loop converged: empty lists, nothing else happens
     if (t < words) { K.act_nx[t] = K.act[t]; K.pres0[t] = K.pres[t]; }
     if (t < B.N) B.m_p11_nx[t] = B.m_p11[t];
-    if (t <= PK_BIG) K.counts[t] = 0;
+    if (reset_counters && t < GTF_NCOUNTERS_ALL) B.counters[t] = 0;
+}
+// end of a queued iteration of gtf_iterate: its counters go to the loop's table; converged = no activation flag changed
+__global__ void k_iter_end(const unsigned long long *counters, unsigned long long *table, int *counts, int stop_when_converged)
+{
+    const int t = threadIdx.x;
+    if (counts[PK_STOP]) return;
+    const int it = counts[PK_DONE];
+    if (t < GTF_NCOUNTERS_ALL) table[(size_t)it * GTF_NCOUNTERS_ALL + t] = counters[t];
+    __syncwarp();
+    if (t == 0) {
+        counts[PK_DONE] = it + 1;
+        if (stop_when_converged && counters[CNT_CHANGED] == 0) counts[PK_STOP] = 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ k_send
@@ -349,22 +364,13 @@ __device__ __forceinline__ void send_prefetch(const DevBatch &B, const DevPack &
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBatch B, DevPack Kin, const int4 *__restrict__ tdesc, int n_tiles,
-                                                                         GtfGeom g)
+// the tile loop of k_send
+__device__ __forceinline__ void send_tiles(const DevBatch &B, const DevPack &K, SendSmem &S, const int4 *__restrict__ tdesc, int n_tiles,
+                                           const GtfGeom &g, const int tid)
 {
-    DevPack K = Kin;
-    K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
-    extern __shared__ __align__(16) unsigned char send_raw[];
-    SendSmem &S = *reinterpret_cast<SendSmem *>(send_raw);
     SendWork &sm = S.w;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
-    if (tid == 0) {
-        mbar_init(&S.full[0], 1);
-        mbar_init(&S.full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
     int t = blockIdx.x;
     const int4 zero4 = make_int4(0, 0, 0, 0);
     int4 d_cur = t < n_tiles ? tdesc[t] : zero4;
@@ -484,6 +490,24 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBat
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
+__global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBatch B, DevPack Kin, const int4 *__restrict__ tdesc, int n_tiles,
+                                                                         GtfGeom g)
+{
+    if (Kin.counts[PK_STOP]) return;
+    DevPack K = Kin;
+    K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
+    extern __shared__ __align__(16) unsigned char send_raw[];
+    SendSmem &S = *reinterpret_cast<SendSmem *>(send_raw);
+    if (threadIdx.x == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    send_tiles(B, K, S, tdesc, n_tiles, g, threadIdx.x);
+}
+
+
 // ------------------------------------------------------------------------------------------------ k_exec
 // thread per message: extrapolate, chi2 gate, Kalman update (extrapolate_merged_states.py:26-402); writes the state
 // record and the weight record of the receiving dict entry, clears the activation bit of a gated edge.
@@ -576,6 +600,374 @@ __global__ void __launch_bounds__(GTF_EXEC_THREADS, GTF_EXEC_MINB) k_exec(DevBat
     if (gated) atomicAdd(&s_cnt[CNT_GATED], gated);
     __syncthreads();
     flush_counters(s_cnt, B.counters, tid);
+}
+
+// ------------------------------------------------------------------------------------------------ k_sx
+// k_send and k_exec as ONE warp-specialised kernel: the message list never goes to global memory (40 B written and 40 B read
+// back per message: a fifth of the iteration's DRAM traffic) and the memory-bound scan overlaps the fp64-bound update on the
+// same SM.  A CTA = one SCANNING warp group (warps 0-3, 40 registers after setmaxnreg.dec) + one EXECUTING warp group
+// (warps 4-7: the k_exec message program, 120 registers after setmaxnreg.inc -- the pool is the CTA's own 256 x 80);
+// three CTAs per SM.
+//   scan     twelve scanning warps per SM cannot hide a tile's dependent global loads the way k_send's 32 do, so the tile loop
+//            is a two-stage software pipeline: trip i runs stage A of tile i+1 (flags -> ordered compaction -> descriptors
+//            into the ring, per-message OutRec gathers STARTED with cp.async straight into the ring slots) around stage B
+//            of tile i (gathers landed a trip ago: Highland terms, per-source running sums, publish); the bitmap words A
+//            tests are loaded before B and used after it, the tile inputs arrive by cp.async.bulk two trips ahead.
+//   ring     shared memory, GTF_RING entries of 48 B: (slot | no-seed-entry bit, source, destination) + the OutRec gathered
+//            in place, rewritten by stage B to (var_ms, merged_cov[1,1] as the edge sees it, -, carried weight).  The scanners
+//            publish `tail`; executing warp w takes the chunks of 32 consecutive positions c = w, w + 4, ...: dense warps
+//            whatever the tiles' message counts are.
+//   execute  software-pipelined like k_exec: the next chunk's ring entries and the gathers they index are fetched between
+//            the Jacobian half and the covariance half of the current one when the chunk is already there, otherwise at the
+//            top of the next trip.
+#ifndef GTF_SX_CTAS
+#define GTF_SX_CTAS 3
+#endif
+#ifndef GTF_SX_SCAN_REGS
+#define GTF_SX_SCAN_REGS 40
+#endif
+#ifndef GTF_SX_EXEC_REGS
+#define GTF_SX_EXEC_REGS 120
+#endif
+#define GTF_STR2(x) #x
+#define GTF_STR(x) GTF_STR2(x)
+#define GTF_RING 800                                     // >= 2 GTF_SEND_EDGES (a tile not yet published + the next one's bound) + 31
+                                                         // (an incomplete chunk nobody can take yet): the scanners never wait for
+                                                         // space that only they could free
+struct __align__(32) SxRec { double vms, p11, rdz, w; }; // as gathered: OutRec (sin_t, xk, rdz, w)
+struct SxRing {
+    SxRec rec[GTF_RING];
+    int4 desc[GTF_RING];
+    int tail, done;                                      // messages published so far; no more will come
+    int cons_next[4];                                    // per executing warp: first ring position it has not released yet
+};
+struct SxWork {                                          // per tile in flight (stage A of tile i+1 / stage B of tile i)
+    uint16_t first[GTF_SEND_SRCS + 1], last[GTF_SEND_SRCS + 1];
+    uint8_t m_src[GTF_SEND_EDGES];
+};
+struct __align__(32) SxSmem {
+    SxRing ring;
+    SendStage st[4];
+    SxWork w[2];
+    int4 tdesc[8];                                       // descriptors of tiles i .. i+4 (cp.async, two trips before their first use)
+    uint64_t full[4];
+    uint8_t esrc[GTF_SEND_EDGES], ok[GTF_SEND_SRCS + 1];
+    int wsum[4];
+    unsigned int cnt[GTF_NCOUNTERS];
+};
+static_assert((sizeof(SxSmem) + 1024) * GTF_SX_CTAS <= 228 * 1024, "k_sx: shared memory of the resident CTAs (228 KB per SM, 1 KB reserved per CTA)");
+static_assert(sizeof(OutRec) == sizeof(SxRec) && GTF_RING >= 2 * GTF_SEND_EDGES + 31 && GTF_RING % 32 == 0, "ring");
+__device__ __forceinline__ int ld_acq_s(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_rel_s(int *p, int v)
+{
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sx_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the scanning warp group only
+
+// the scanning warp group of k_sx.  Trip i: compaction of tile i+1 (its activation words were loaded a trip ago), the words of
+// tile i+2, then the messages of tile i (their record gathers were started a trip ago); tile i+3's inputs are on their way.
+__device__ __forceinline__ void sx_scan(const DevBatch &B, const DevPack &K, SxSmem &S, const int4 *__restrict__ tdesc, int n_tiles,
+                                        const GtfGeom &g, const int tid)
+{
+    SxRing &R = S.ring;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int n_my = (n_tiles - (int)blockIdx.x + G - 1) / G;          // tiles of this CTA: blockIdx.x + j G
+    if (tid < 5 && tid < n_my) S.tdesc[tid] = tdesc[blockIdx.x + tid * G];
+    sx_sync();
+    // the bulk copies complete on their stage's mbarrier; no cp.async group belongs to them
+    auto prefetch = [&](int j) {
+        if (tid == 0) {
+            const int4 d = S.tdesc[j & 7];
+            SendStage &st = S.st[j & 3];
+            uint64_t *bar = &S.full[j & 3];
+            const int u0 = d.x, ns = d.y, o0 = d.z, ne = d.w;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const int oa = o0 & ~3, on = ((o0 + ne + 3) & ~3) - oa;
+            const int ua = u0 & ~15, un = ((u0 + ns + 15) & ~15) - ua;
+            const int pa = u0 & ~1, pn = ((u0 + ns + 1) & ~1) - pa;
+            const unsigned b_edges = 4u * on, b_src = 16u * (ns + 1), b_fl = (unsigned)un, b_p = 8u * pn;
+            mbar_expect_tx(bar, 2 * b_edges + b_src + 2 * b_fl + b_p + 16u * ns);
+            bulk_g2s(st.ab, K.mab + u0, 16u * ns, bar);
+            if (on) {
+                bulk_g2s(st.slot, B.out_slot + oa, b_edges, bar);
+                bulk_g2s(st.dst, K.out_dst + oa, b_edges, bar);
+            }
+            bulk_g2s(st.srec, K.srec + u0, b_src, bar);
+            bulk_g2s(st.hm, B.has_merged + ua, b_fl, bar);
+            bulk_g2s(st.nok, B.node_ok + ua, b_fl, bar);
+            bulk_g2s(st.p11, B.m_p11 + pa, b_p, bar);
+        }
+    };
+    const int e0 = tid * GTF_SEND_EPT;
+    unsigned wa[GTF_SEND_EPT];                           // activation words of this thread's out-edges of the tile in stage A
+    // every thread observes the stage's mbarrier itself (visibility of the asynchronous-proxy writes), then reads the words
+    auto act_words = [&](int j) {
+        const int4 d = S.tdesc[j & 7];
+        mbar_wait(&S.full[j & 3], (unsigned)(j >> 2) & 1u);
+        const SendStage &st = S.st[j & 3];
+        const int epad = d.z & 3, ne = d.w;
+#pragma unroll
+        for (int k = 0; k < GTF_SEND_EPT; k++) {
+            wa[k] = 0;
+            if (e0 + k < ne) {
+                const int sl = st.slot[epad + e0 + k];
+                GTF_BOUND(B, sl >= 0 && sl < B.E);
+                wa[k] = K.act[sl >> 5];
+            }
+        }
+    };
+    for (int j = 0; j < 3 && j < n_my; j++) prefetch(j);
+    act_words(0);
+    int tail = 0;                                        // ring position after the last tile that went through stage A
+    int M_b = 0, base_b = 0;                             // messages of the tile in stage B and their first ring position
+    for (int i = -1; i < n_my; i++) {
+        if (tid == 0 && i + 5 < n_my && i >= 0)           // descriptor of tile i+5: part of this trip's cp.async group, complete
+                                                         // before stage B of the next trip, first read two trips from now
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&S.tdesc[(i + 5) & 7])), "l"(tdesc + blockIdx.x + (i + 5) * G) : "memory");
+        if (i + 3 < n_my && i >= 0) prefetch(i + 3);     // (its stage was last read by tile i-1: done before the previous trip's last barrier)
+        // ---- stage A, tile i+1: which sources send at all, ordered compaction, descriptors and record gathers into the ring
+        const bool has_a = i + 1 < n_my;
+        int M_a = 0;
+        if (has_a) {
+            const int4 d = S.tdesc[(i + 1) & 7];
+            const int u0a = d.x, nsa = d.y, oba = d.z, nea = d.w, epad = d.z & 3;
+            GTF_BOUND(B, nsa >= 1 && nsa <= GTF_SEND_SRCS && nea >= 0 && nea <= GTF_SEND_EDGES && u0a >= 0 && u0a + nsa <= B.N && oba >= 0 && oba + nea <= B.E);
+            SendStage &sa = S.st[(i + 1) & 3];
+            SxWork &Wa = S.w[(i + 1) & 1];
+            if (tid < nsa) {
+                const int upad = u0a & 15;
+                const int my_off = sa.srec[tid].off - oba, my_end = sa.srec[tid + 1].off - oba;
+                GTF_BOUND(B, my_off >= 0 && my_off <= my_end && my_end <= nea);
+                S.ok[tid] = sa.hm[upad + tid] && (sa.nok[upad + tid] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI);
+                Wa.first[tid] = 0xffff;
+                for (int o = my_off; o < my_end; o++) S.esrc[o] = (uint8_t)tid;
+            }
+            if (tid == 0)                                                // room for the tile's messages (at most nea)?
+                for (;;) {
+                    const int head = min(min(ld_acq_s(&R.cons_next[0]), ld_acq_s(&R.cons_next[1])),
+                                         min(ld_acq_s(&R.cons_next[2]), ld_acq_s(&R.cons_next[3])));
+                    if (tail + nea - head <= GTF_RING) break;
+                    __nanosleep(100);
+                }
+            sx_sync();
+            int cnt = 0;
+            unsigned mymask = 0;
+#pragma unroll
+            for (int j = 0; j < GTF_SEND_EPT; j++) {
+                if (e0 + j < nea && S.ok[S.esrc[e0 + j]]) {
+                    const int sl = sa.slot[epad + e0 + j];
+                    if (((wa[j] >> (sl & 31)) & 1u) && (K.all_exist || bm_get(K.exists, sl))) { mymask |= 1u << j; cnt++; }
+                }
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, dd);
+                if (lane >= dd) incl += v;
+            }
+            if (lane == 31) S.wsum[warp] = incl;
+            sx_sync();
+            int woff = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                if (w < warp) woff += S.wsum[w];
+                M_a += S.wsum[w];
+            }
+            int pos = woff + incl - cnt;
+#pragma unroll
+            for (int j = 0; j < GTF_SEND_EPT; j++)
+                if ((mymask >> j) & 1u) {
+                    GTF_BOUND(B, pos >= 0 && pos < M_a && M_a <= nea);
+                    const int rp = (tail + pos) % GTF_RING, le = e0 + j, src = S.esrc[le];
+                    GTF_BOUND(B, sa.dst[epad + le] >= 0 && sa.dst[epad + le] < B.N);
+                    Wa.m_src[pos] = (uint8_t)src;
+                    R.desc[rp] = make_int4(sa.slot[epad + le], u0a + src, sa.dst[epad + le], 0);
+                    const unsigned dsts = smem_u32(&R.rec[rp]);
+                    const OutRec *gp = K.orec + oba + le;            // one sector, in successor order
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n cp.async.cg.shared.global [%2], [%3], 16;"
+                                 ::"r"(dsts), "l"(gp), "r"(dsts + 16), "l"(reinterpret_cast<const char *>(gp) + 16) : "memory");
+                    pos++;
+                }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // ---- the activation words of tile i+2 travel while stage B runs
+        if (i + 2 < n_my) act_words(i + 2);
+        // ---- stage B, tile i: its record gathers are the group before the one just committed
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        sx_sync();       // tile i's gathers, tile i+1's compaction and work arrays are complete
+        if (i >= 0 && M_b) {
+            SendStage &sb = S.st[i & 3];
+            SxWork &Wb = S.w[i & 1];
+            const int4 d = S.tdesc[i & 7];
+            const int u0 = d.x, ns = d.y, ppad = d.x & 1;
+#pragma unroll
+            for (int k = 0; k < GTF_SEND_MPT; k++) {
+                const int q = tid + k * GTF_SEND_THREADS;
+                if (q < M_b) {
+                    const int rp = (base_b + q) % GTF_RING;
+                    const int sl = Wb.m_src[q];
+                    const SxRec r = R.rec[rp];       // (sin_t, xk, rdz, w)
+                    const double2 ab = sb.ab[sl];
+                    R.rec[rp].vms = gtf_var_ms_pre(ab.x, ab.y, r.p11, r.vms, r.rdz, sb.srec[sl].z, g.endcap);
+                    if (__double_as_longlong(r.w) == GTF_NO_TSE_BITS) { R.rec[rp].w = NAN; R.desc[rp].x |= (int)0x80000000; }
+                    if (q == 0 || Wb.m_src[q - 1] != sl) Wb.first[sl] = (uint16_t)q;
+                    if (q == M_b - 1 || Wb.m_src[q + 1] != sl) Wb.last[sl] = (uint16_t)q;
+                }
+            }
+            sx_sync();
+            if (tid < ns && Wb.first[tid] != 0xffff) {               // quirk 2: summed in successor order
+                const int q1 = Wb.last[tid];
+                double p = sb.p11[ppad + tid];
+                int rp = (base_b + Wb.first[tid]) % GTF_RING;
+                for (int q = Wb.first[tid]; q <= q1; q++) {
+                    p += R.rec[rp].vms;
+                    R.rec[rp].p11 = p;
+                    rp = rp + 1 == GTF_RING ? 0 : rp + 1;
+                }
+                B.m_p11_nx[u0 + tid] = p;
+            }
+            sx_sync();   // (also ends the trip: every read of tile i's stage and work arrays is done)
+            if (tid == 0) st_rel_s(&R.tail, base_b + M_b);          // the tile's messages are complete: publish them
+        }
+        base_b = tail;
+        M_b = M_a;
+        tail += M_a;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (tid == 0) st_rel_s(&R.done, 1);
+}
+
+// entries of chunk c that can be taken: 32, fewer for the last chunk, 0 = not there yet (only when !block), -1 = none will come
+__device__ __forceinline__ int sx_chunk(SxRing &R, int c, bool block, int lane)
+{
+    int n = 0;
+    if (lane == 0) {
+        unsigned ns = 128;
+        for (;;) {
+            const int done = ld_acq_s(&R.done);
+            const int tail = ld_acq_s(&R.tail);
+            if (tail >= 32 * (c + 1)) { n = 32; break; }
+            if (done) { n = tail > 32 * c ? tail - 32 * c : -1; break; }
+            if (!block) break;
+            __nanosleep(ns);                             // (a starved warp must not take issue slots from the scanners)
+            if (ns < 2048) ns *= 2;
+        }
+    }
+    n = __shfl_sync(0xffffffffu, n, 0);
+    __syncwarp();                                        // (orders the other lanes' ring reads after lane 0's acquire)
+    return n;
+}
+__global__ void __launch_bounds__(256, GTF_SX_CTAS) k_sx(DevBatch B, DevPack Kin, const int4 *__restrict__ tdesc, int n_tiles, double chi2_cut,
+                                                         GtfGeom g, int record_chi2)
+{
+    static_assert(GTF_SEND_THREADS == 128, "one warp group scans");
+    if (Kin.counts[PK_STOP]) return;
+    extern __shared__ __align__(32) unsigned char sx_raw[];
+    SxSmem &S = *reinterpret_cast<SxSmem *>(sx_raw);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        mbar_init(&S.full[2], 1);
+        mbar_init(&S.full[3], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.ring.tail = 0; S.ring.done = 0;
+    }
+    if (tid < 4) S.ring.cons_next[tid] = 32 * tid;
+    if (tid < GTF_NCOUNTERS) S.cnt[tid] = 0;
+    __syncthreads();
+    if (tid < 128) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " GTF_STR(GTF_SX_SCAN_REGS) ";");
+        DevPack K = Kin;
+        K.all_exist = Kin.counts[PK_MISSING] == 0;
+        sx_scan(B, K, S, tdesc, n_tiles, g, tid);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " GTF_STR(GTF_SX_EXEC_REGS) ";");
+        const DevPack &K = Kin;
+        SxRing &R = S.ring;
+        const int lane = tid & 31, w = (tid >> 5) - 4;
+        unsigned gated = 0, sent = 0;
+        struct In {
+            int sraw;
+            double ux, uy, uz, ur, vx, vy, vz, vr, a, b, c, p00, p01, p22, w, p, vms;
+        };
+        auto load = [&](int pos, In &x) {
+            const int rp = pos % GTF_RING;
+            const int4 d = R.desc[rp];
+            const int u = d.y, v = d.z;
+            GTF_BOUND(B, u >= 0 && u < B.N && v >= 0 && v < B.N);
+            const NodeXYZR U = K.xyzr[u], V = K.xyzr[v];
+            x.sraw = d.x;
+            x.ux = U.x; x.uy = U.y; x.uz = U.z; x.ur = U.r; x.vx = V.x; x.vy = V.y; x.vz = V.z; x.vr = V.r;
+            const double2 *mr = reinterpret_cast<const double2 *>(K.mrec + u);
+            const double2 r0 = mr[0], r1 = mr[1], r2 = mr[2];
+            x.a = r0.x; x.b = r0.y; x.c = r1.x; x.p00 = r1.y; x.p01 = r2.x; x.p22 = r2.y;
+            const SxRec r = R.rec[rp];
+            x.w = r.w; x.p = r.p11; x.vms = r.vms;
+        };
+        In cur;
+        int c = w;                                       // this warp's chunk
+        int n_cur = 0;                                   // its entries, 0: not loaded yet
+        for (;;) {
+            if (n_cur == 0) {
+                n_cur = sx_chunk(R, c, true, lane);
+                if (n_cur < 0) break;
+                if (lane < n_cur) load(32 * c + lane, cur);
+            }
+            const bool mine = lane < n_cur;
+            const int s = cur.sraw & 0x7fffffff;
+            const bool notse = cur.sraw < 0;
+            GTF_BOUND(B, !mine || (s >= 0 && s < B.E));
+            const double cw = cur.w, p = cur.p, vms = cur.vms, p00 = cur.p00, p01 = cur.p01, p22 = cur.p22;
+            const double dr = cur.vr - cur.ur, dz = cur.vz - cur.uz, uz = cur.uz, vz = cur.vz;
+            GtfJac J;
+            if (mine) gtf_extrap_jac(cur.ux, cur.uy, cur.vx, cur.vy, cur.a, cur.b, cur.c, J);
+            // the ring entries of chunk c are in registers: release them, then look for the next chunk without waiting
+            __syncwarp();
+            if (lane == 0) st_rel_s(&R.cons_next[w], 32 * (c + 4));
+            const int n_nxt = sx_chunk(R, c + 4, false, lane);
+            if (lane < n_nxt) load(32 * (c + 4) + lane, cur);
+#ifdef GTF_SX_NOEXEC
+            if (mine && J.f00 == 1.2345e-300) {
+#else
+            if (mine) {
+#endif
+                GtfExtrapOut o;
+                gtf_extrap_update(J, dr, dz, uz, vz, p00, p01, p, p22, vms, chi2_cut, g, o);
+                if (record_chi2) B.uts_chi2[s] = o.chi2;
+                sent++;
+                if (o.pass) {
+                    if (notse) atomicOr(&S.cnt[CNT_REFERR], (unsigned)GTF_REF_NO_TSE);
+                    double2 *st = reinterpret_cast<double2 *>(K.state + 8 * (size_t)s);
+                    __stcs(st + 0, make_double2(o.s.a, o.s.b));
+                    __stcs(st + 1, make_double2(o.s.c, o.s.tau));
+                    __stcs(st + 2, make_double2(o.s.p00, o.s.p01));
+                    __stcs(st + 3, make_double2(o.s.p11, o.s.p22));
+                    double2 *m = reinterpret_cast<double2 *>(K.meta + s);     // (see k_exec)
+                    __stcs(m + 0, make_double2(cw, o.lik));
+                    __stcs(m + 1, make_double2(NAN, NAN));
+                    bm_set(K.pres, s);
+                } else {
+                    bm_clear(K.act_nx, s); // :393
+                    gated++;
+                }
+                near_note(B, GTF_NEAR_GATE, s, o.chi2, chi2_cut);
+            }
+            c += 4;
+            if (n_nxt < 0) break;
+            n_cur = n_nxt;
+        }
+        if (sent) atomicAdd(&S.cnt[CNT_SENT], sent);
+        if (gated) atomicAdd(&S.cnt[CNT_GATED], gated);
+    }
+    __syncthreads();
+    flush_counters(S.cnt, B.counters, tid);
 }
 
 // ------------------------------------------------------------------------------------------------ k_node
@@ -684,6 +1076,7 @@ __device__ __forceinline__ void lent_reweight(const DevBatch &B, unsigned int *c
 #endif
 __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(DevBatch B, DevPack Kin, Prog P)
 {
+    if (Kin.counts[PK_STOP]) return;
     DevPack K = Kin;
     K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
     __shared__ unsigned int s_cnt[GTF_NCOUNTERS];

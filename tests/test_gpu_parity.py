@@ -160,6 +160,62 @@ def test_fused_iterate_vs_oracle(n_events, n_tracks, eta):
     assert np.array_equal(lab, ob.cca())
 
 
+def same_state(a, c, rtol=1e-9):
+    """integer / flag fields identical, value fields within rtol (two separately compiled kernels may contract their
+    multiply-adds differently); returns the offending fields"""
+    bad = []
+    for f in a:
+        x, y = np.asarray(a[f]), np.asarray(c[f])
+        if x.dtype.kind != "f":
+            if not np.array_equal(x, y):
+                bad.append(f)
+            continue
+        nx, ny = np.isnan(x), np.isnan(y)
+        if not np.array_equal(nx, ny):
+            bad.append(f + " (NaN pattern)")
+            continue
+        d = np.abs(x[~nx] - y[~ny])
+        if d.size and not (d <= rtol * np.maximum(np.abs(x[~nx]), 1e-300)).all():
+            bad.append("%s (max rel %.3g)" % (f, float((d / np.maximum(np.abs(x[~nx]), 1e-300)).max())))
+    return bad
+
+
+def test_fused_send_execute_kernel_equals_the_two_kernel_path(monkeypatch):
+    """GTF_FUSED_SX=1: k_send + k_exec as the one warp-specialised kernel k_sx (scanning / executing warp groups, message ring
+    in shared memory).  Same iterations on the same event through both paths: every flag / order / counter identical, values
+    to 1e-9 (measured: 1e-11); and the fused path against the oracle.  A tile whose every out-edge carries a message (first iteration: all
+    edges active) fills the ring to its bound."""
+    hb = synth_batch(3, 400, 2050, eta_max=1.0)
+    ob = ol.OracleBatch(hb)
+    ob.seed()
+    ob.cluster(0, 1.0, 2.0)
+    ref = gpu_batch(hb)
+    monkeypatch.setenv("GTF_FUSED_SX", "1")
+    fus = gpu_batch(hb)
+    monkeypatch.delenv("GTF_FUSED_SX")
+    for b in (ref, fus):
+        b.seed()
+        b.cluster(0, 1.0, 2.0)
+    assert fus.iteration_launches() == 0
+    for it in range(4):
+        ob.extrapolate_stage(2.0)
+        ob.cluster(1, 1000.0, 100.0)
+        s_ref = ref.iterate(max_iter=1, stop_when_converged=False)[0]
+        l0 = fus.iteration_launches()
+        s_fus = fus.iterate(max_iter=1, stop_when_converged=False)[0]
+        assert fus.iteration_launches() - l0 == 9       # k_begin, k_sx, k_node2, k_hv x 4, k_big, k_iter_end
+        assert s_ref == s_fus, (it, s_ref, s_fus)
+        c = state_of(fus)
+        assert same_state(state_of(ref), c) == [], it
+        bad = gu.compare_states(c, ob.hb, ALL, rtol=1e-7)
+        assert bad == [], (it, bad)
+    # uncommitted passes and a longer committed loop through the fused kernel
+    d1 = fus.iterate_dry(want_stats=True)
+    assert d1 == ref.iterate_dry(want_stats=True)
+    assert fus.iterate(max_iter=6)[-1] == ref.iterate(max_iter=6)[-1]
+    assert same_state(state_of(ref), state_of(fus)) == []
+
+
 def test_iterate_dry_is_idempotent_and_matches_commit():
     hb = synth_batch(2, 300, 2100)
     b = gpu_batch(hb)

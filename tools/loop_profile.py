@@ -1,0 +1,25 @@
+"""Per-iteration kernel times of the committed loop (128-event batch): where do the later iterations spend their time?
+  python tools/loop_profile.py [events] [iterations]"""
+import sys, os, json
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import numpy as np
+import gtf_b200, bench
+ne = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+nit = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+hb = bench.build_batch(ne, 1000, 3000, 16)
+b = gtf_b200.EventBatch(hb)
+for rep in range(2):           # second pass: warm
+    b.seed_cluster(1.0, 2.0)
+    rows = []
+    for it in range(nit):
+        b.set_timing(True)
+        st = b.iterate(max_iter=1, stop_when_converged=False)[0]
+        kt = b.timing_kernels()
+        rows.append({"iteration": it + 1, "ms": {k: round(kt[k], 4) for k in ("k_send", "k_exec", "k_node2", "k_hv")},
+                     "total_ms": round(sum(kt[k] for k in ("k_send", "k_exec", "k_node2", "k_hv")), 4),
+                     "edges_sent": st["edges_sent"], "active_edges": st["active_edges"], "active_changed": st["active_changed"],
+                     "nodes_merged": st["nodes_merged"]})
+    b.set_timing(False)
+for r in rows:
+    print(json.dumps(r))
+print(json.dumps({"loop_ms": round(sum(r["total_ms"] for r in rows), 3)}))

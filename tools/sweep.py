@@ -35,11 +35,27 @@ def point(n_tracks, degree, n_events, steps=20):
     for _ in range(steps):
         b.iterate_dry()
     kt = b.timing_kernels()
+    b.set_timing(False)
     kern = {k: kt[k] for k in ("k_send", "k_exec", "k_node2", "k_hv")}
     it_ms = sum(kern.values())
+    # the iteration as a user runs it (CUDA graph replay, or the single cooperative launch for small batches): wall clock
+    import time
+    for _ in range(5):
+        b.iterate_dry()
+    b.sync()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        b.iterate_dry()
+    b.sync()
+    wall_ms = (time.perf_counter() - t0) / 200 * 1e3
+    l0 = b.iteration_launches()
+    b.iterate_dry()
+    launches = b.iteration_launches() - l0
     deg = np.diff(hb["in_off"])
     out = {"tracks_per_event": n_tracks, "events": n_events, "target_degree": degree, "hits": b.N, "directed_edges": b.E,
            "mean_degree": float(deg.mean()), "active_edges": n_active, "kernels_ms": kern, "iteration_ms": it_ms,
+           "iteration_ms_as_launched": wall_ms, "launches_per_iteration": launches,
+           "roofline_frac_as_launched": bench.B_ALG * n_active / (wall_ms / 1e3) / 1e9 / PEAK,
            "active_edge_iterations_per_s": n_active / (it_ms / 1e3),
            "all_edges_per_s": b.E / (it_ms / 1e3),
            "roofline_frac": bench.B_ALG * n_active / (it_ms / 1e3) / 1e9 / PEAK}
