@@ -169,6 +169,7 @@ static int batch_alloc(gtf_batch *b)
         DA(k.msg_desc, E); DA(k.msg_w, E);
         DA(k.msg_p11, E); DA(k.msg_vms, E);
         DA(k.hv_list, (int64_t)(HV_BINS + 1) * N);
+        DA(k.c_edge, E); DA(k.c_rng, N);
         DA(k.counts, PK_NCOUNTS);
         b->pack_static_stale = true;
         b->exists_stale = true;
@@ -218,11 +219,12 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     {
         DevPack &k = b->k;
         void *pk[] = {k.mab, k.srec, k.mrec, k.mrec_nx, k.out_dst, k.orec, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
-                      k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.counts, b->stile_begin};
+                      k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.c_edge, k.c_rng, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         for (int c = 0; c < 2; c++)
             for (int q = 0; q < 2; q++)
-                if (b->graphs[c][q].exec) cudaGraphExecDestroy(b->graphs[c][q].exec);
+                for (int v = 0; v < 2; v++)
+                    if (b->graphs[c][q][v].exec) cudaGraphExecDestroy(b->graphs[c][q][v].exec);
         if (b->stream3) cudaStreamDestroy(b->stream3);
         if (b->ev_fork2) cudaEventDestroy(b->ev_fork2);
         if (b->ev_join2) cudaEventDestroy(b->ev_join2);
@@ -913,7 +915,7 @@ static int issue_node_kernels(gtf_batch *b, const Prog &P, const GtfGeom &gg, bo
 }
 // the kernel launches of one iteration (k_begin .. k_hv / k_big), issued on the batch stream (and forked onto the side
 // streams for the independent bins); also the body that is captured into a CUDA graph
-static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int record_chi2, bool commit, bool timed)
+static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int record_chi2, bool commit, bool timed, bool sparse = false)
 {
     DevPack &k = b->k;
     DevBatch &d = b->d;
@@ -935,13 +937,16 @@ static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int r
         if (b->n_stiles)
             k_send<<<std::min(b->n_stiles, b->n_sm * GTF_SEND_MINB), GTF_SEND_THREADS, sizeof(SendSmem), s0>>>(
                 d, k, reinterpret_cast<const int4 *>(b->stile_begin), b->n_stiles, gg);
+        // inside a committed loop, once k_compact_out has listed the few out-edges still active (PK_SPARSE, decided on the
+        // device), k_send returns at once and k_send_sparse sends; otherwise it is k_send_sparse that returns at once
+        if (sparse && b->N) k_send_sparse<<<(b->N + 255) / 256, 256, 0, s0>>>(d, k, gg);
         if (timed) CK(cudaEventRecord(b->evk[1], s0));
         if (b->E) k_exec<<<b->n_sm * GTF_EXEC_MINB * GTF_EXEC_WAVES, GTF_EXEC_THREADS, 0, s0>>>(d, k, P.chi2_cut, gg, record_chi2);
         if (timed) CK(cudaEventRecord(b->evk[2], s0));
     }
     TRY_(issue_node_kernels(b, P, gg, commit, timed));
     if (timed) CK(cudaEventRecord(b->evk[4], s0));
-    b->launches_per_iter = 1 + (b->n_stiles ? 1 : 0) + (!b->fused_sx && b->E ? 1 : 0) + (b->N ? 6 : 0); // k_begin, k_sx | k_send, k_exec, k_node2 + k_hv x4 + k_big
+    b->launches_per_iter = 1 + (b->n_stiles ? 1 : 0) + (!b->fused_sx && b->E ? 1 : 0) + (b->N ? 6 : 0) + (sparse && !b->fused_sx && b->N ? 1 : 0); // k_begin, k_sx | k_send, k_exec, k_node2 + k_hv x4 + k_big
     return 0;
 }
 // one iteration on the packed layout.  commit: the next state becomes the current one (merged states are written in
@@ -949,7 +954,7 @@ static int issue_iteration(gtf_batch *b, const Prog &P, const GtfGeom &gg, int r
 // buffers and nothing the next pass reads is changed (profiling / benchmark entry point).
 // The launch sequence is replayed from a CUDA graph (one per {committed, not} x {ping-pong parity}, re-captured when
 // the parameters change): nine dependent launches cost more than the kernels themselves on a single event.
-static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom &gg, gtf_stats *st, bool commit)
+static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom &gg, gtf_stats *st, bool commit, bool sparse = false)
 {
     TRY(ensure_packed(b));
     DevPack &k = b->k;
@@ -979,23 +984,33 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
             b->t_count++;
         }
     } else {
-        IterGraph &G = b->graphs[commit ? 1 : 0][b->parity];
+        IterGraph &G = b->graphs[commit ? 1 : 0][b->parity][sparse ? 1 : 0];
+        // the captured arguments hold sizes and pointers, not the tile tables' contents: a new batch of the same shape in the same
+        // batch object replays the graph as it is; another shape updates the instantiated graph in place (cudaGraphExecUpdate:
+        // tens of microseconds instead of an instantiation per graph and per loaded batch)
         const bool same = G.exec && memcmp(&G.P, &P, sizeof(Prog)) == 0 && memcmp(&G.g, &gg, sizeof(GtfGeom)) == 0 &&
                           G.record_chi2 == p->record_chi2 && G.n_stiles == b->n_stiles && G.stile == (const void *)b->stile_begin &&
-                          G.topo_gen == b->topo_gen;
+                          G.N == b->N && G.E == b->E && G.S == b->S && G.n_tiles == b->n_tiles;
         if (!same) {
-            if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
             cudaGraph_t graph = nullptr;
             CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
-            int r = issue_iteration(b, P, gg, p->record_chi2, commit, false);
+            int r = issue_iteration(b, P, gg, p->record_chi2, commit, false, sparse);
             cudaError_t e = cudaStreamEndCapture(s0, &graph);
             if (r) { if (graph) cudaGraphDestroy(graph); return r; }
             if (e != cudaSuccess) return fail(GTF_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-            e = cudaGraphInstantiate(&G.exec, graph, 0);
+            if (G.exec) {
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(G.exec, graph, &info) != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaGraphExecDestroy(G.exec);
+                    G.exec = nullptr;
+                }
+            }
+            if (!G.exec) e = cudaGraphInstantiate(&G.exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return fail(GTF_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
             G.P = P; G.g = gg; G.record_chi2 = p->record_chi2; G.n_stiles = b->n_stiles; G.stile = (const void *)b->stile_begin;
-            G.topo_gen = b->topo_gen;
+            G.N = b->N; G.E = b->E; G.S = b->S; G.n_tiles = b->n_tiles;
         }
         CK(cudaGraphLaunch(G.exec, s0));
     }
@@ -1168,11 +1183,17 @@ extern "C" int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geo
         DevPack &k = b->k;
         cudaStream_t s0 = b->stream;
         bool stopped = false;
+        const bool may_compact = !b->fused_sx && max_iter >= 3 && b->N && b->E;   // (worth one more pass over the out-edges)
+        CK(cudaMemsetAsync(k.counts + PK_SPARSE, 0, 2 * sizeof(int), s0));
         while (it < max_iter && !stopped) {
             const int burst = std::min(max_iter - it, (int)GTF_LOOP_BURST);
             CK(cudaMemsetAsync(k.counts + PK_STOP, 0, 2 * sizeof(int), s0));   // stop flag, iterations done
             for (int q = 0; q < burst; q++) {
-                TRY(iterate_packed(b, p, geom_of(g), nullptr, true));
+                if (may_compact && it + q == 1) {        // after the loop's first iteration (the ping-pong pairs are swapped:
+                    k_compact_out<<<(b->N + 255) / 256, 256, 0, s0>>>(b->d, k);   // k.act is the current bitmap)
+                    b->launches++;
+                }
+                TRY(iterate_packed(b, p, geom_of(g), nullptr, true, may_compact && it + q >= 1));
                 k_iter_end<<<1, 32, 0, s0>>>(b->d.counters, b->loop_stats, k.counts, stop_when_converged);
                 b->launches++;
             }
@@ -1181,6 +1202,7 @@ extern "C" int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geo
                                cudaMemcpyDeviceToHost, s0));
             CK(cudaMemcpyAsync(b->h_loop_done, k.counts + PK_DONE, sizeof(int), cudaMemcpyDeviceToHost, s0));
             CK(cudaMemsetAsync(k.counts + PK_STOP, 0, sizeof(int), s0));
+            if (it + burst >= max_iter) CK(cudaMemsetAsync(k.counts + PK_SPARSE, 0, sizeof(int), s0));
             CK(cudaStreamSynchronize(s0));
             const int done = *b->h_loop_done;
             if (done < 1 || done > burst) return fail(GTF_E_STATE, "gtf_iterate: loop bookkeeping out of range");
@@ -1202,6 +1224,7 @@ extern "C" int gtf_iterate(gtf_batch *b, const gtf_iter_params *p, const gtf_geo
                 }
             }
             it += done;
+            if (done < burst) CK(cudaMemsetAsync(k.counts + PK_SPARSE, 0, sizeof(int), s0));
             stopped = done < burst || (stop_when_converged && b->h_loop_stats[(size_t)(done - 1) * GTF_NCOUNTERS_ALL + CNT_CHANGED] == 0);
         }
     }
@@ -1714,6 +1737,35 @@ extern "C" int gtf_merge_states(int device, const double *mean1, const double *c
     CK(cudaGetLastError());
     CK(cudaMemcpy(o, B.d + 24, sizeof(o), cudaMemcpyDeviceToHost));
     memcpy(merged_mean, o, 24); memcpy(merged_cov, o + 3, 72);
+    return 0;
+}
+// parabolic-model seeding of the KL look-up-table training pipeline (learn_KL_parabolic_model/.../utils.py:221-299): thread per
+// (node, neighbour) pair
+__global__ void k_seed_parabolic(const double *node_xy, const double *nbr_xy, int64_t n, double s0, double sA, double sB, double *sv, double *cov)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s[3], c[9];
+    gtf_seed_parabolic(node_xy[2 * i], node_xy[2 * i + 1], nbr_xy[2 * i], nbr_xy[2 * i + 1], s0, sA, sB, s, c);
+    for (int k = 0; k < 3; k++) sv[3 * i + k] = s[k];
+    for (int k = 0; k < 9; k++) cov[9 * i + k] = c[k];
+}
+extern "C" int gtf_seed_parabolic_pairs(int device, int64_t n, const double *node_xy, const double *nbr_xy, double sigma0, double sigmaA,
+                                        double sigmaB, double *state, double *cov)
+{
+    if (n < 0 || !node_xy || !nbr_xy || !state || !cov) return fail(GTF_E_ARG, "gtf_seed_parabolic_pairs: bad argument");
+    if (gtf_device_count() <= device || device < 0) return fail(GTF_E_CUDA, "gtf_seed_parabolic_pairs: no such CUDA device");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(device));
+    SmallBuf B;
+    CK(cudaMalloc((void **)&B.d, sizeof(double) * (size_t)n * 16));
+    double *dn = B.d, *db = dn + 2 * n, *ds = db + 2 * n, *dc = ds + 3 * n;
+    CK(cudaMemcpy(dn, node_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db, nbr_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+    k_seed_parabolic<<<(unsigned)((n + 127) / 128), 128>>>(dn, db, n, sigma0, sigmaA, sigmaB, ds, dc);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(state, ds, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cov, dc, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
     return 0;
 }
 // in: node xyzr[4], neighbour xyzr[4], state[3], block covariance (p00 p01 p11 p22), chi2 cut; out: gtf_edge_result as doubles

@@ -75,7 +75,9 @@ static_assert(sizeof(MetaRec) == 32 && sizeof(AuxRec) == 32 && sizeof(NodeXYZR) 
 enum { HV_BINS = 4, PK_MSG = 0, PK_HV0 = 1, PK_BIG = 5, PK_MISSING = 6, PK_FORCE = 7,
        PK_STOP = 8,   // the committed loop of gtf_iterate has converged on the device: queued iterations do nothing
        PK_DONE = 9,   // iterations of that loop that ran
-       PK_NCOUNTS = 10 };
+       PK_SPARSE = 10, // the loop's out-edges have been compacted to the active ones: k_send_sparse sends, k_send does nothing
+       PK_CLIST = 11, // entries of the compacted list handed out so far
+       PK_NCOUNTS = 12 };
 
 struct DevPack {
     // static, derived from the topology and the hit coordinates
@@ -97,6 +99,10 @@ struct DevPack {
     int4 *msg_desc;              // [E] (slot, source, destination, -); slot bit 31: the source has no seed entry for this neighbour
     double *msg_w;               // [E] mixture weight carried by the message (extrapolate...py:384)
     double *msg_p11, *msg_vms;   // [E] merged_cov[1,1] as the edge sees it (quirk 2), its multiple-scattering term
+    // the ACTIVE out-edges of every source, compacted inside a committed loop once few are left (activation only ever
+    // falls inside a loop): k_compact_out -> k_send_sparse
+    int4 *c_edge;                // [E] (slot, destination, out-edge index, -), a source's edges contiguous and in successor order
+    int2 *c_rng;                 // [N] (first entry, entries) of the source in c_edge
     int32_t *hv_list;            // [(HV_BINS + 1) * N] cooperative nodes binned by dict size: <=4, <=8, <=16, <=32, more
     int *counts;                 // [PK_NCOUNTS] messages, 4 bins, big, missing slots, 'evaluate every node' flag, loop stop / done
 };
@@ -173,7 +179,7 @@ struct IterGraph {
     GtfGeom g;
     int record_chi2, n_stiles;
     const void *stile;
-    int topo_gen;              // batch topology generation the kernel arguments (N, E, grids) were captured for
+    int N, E, S, n_tiles;      // batch shape the kernel arguments (sizes, grids) were captured for
 };
 
 struct gtf_batch {
@@ -227,7 +233,7 @@ struct gtf_batch {
     bool use_graph;            // replay the iteration from a CUDA graph (GTF_GRAPH=0: plain launches)
     bool fused_sx;             // k_send + k_exec as the one warp-specialised kernel k_sx (GTF_FUSED_SX=1)
     int parity;                // which half of the ping-pong pairs (act / act_nx, m_p11 / m_p11_nx) is current
-    IterGraph graphs[2][2];    // [committed][parity]
+    IterGraph graphs[2][2][2]; // [committed][parity][sparse-send variant]
     double t_k[5];             // send, exec, node, heavy, (spare)
     // optional per-kernel timing of the iteration (CUDA events on the batch stream)
     bool timing;

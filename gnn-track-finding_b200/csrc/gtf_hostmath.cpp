@@ -46,6 +46,10 @@ void gtfh_merge(const double *s1, const double *s2, double *out8)
     out8[4] = m.p00; out8[5] = m.p01; out8[6] = m.p11; out8[7] = m.p22;
 }
 double gtfh_kl(const double *s1, const double *s2) { return gtf_kl(st(s1), st(s2)); }
+void gtfh_seed_parabolic(const double *node_xy, const double *nbr_xy, double s0, double sA, double sB, double *sv3, double *cov9)
+{
+    gtf_seed_parabolic(node_xy[0], node_xy[1], nbr_xy[0], nbr_xy[1], s0, sA, sB, sv3, cov9);
+}
 double gtfh_kl_general(const double *m1, const double *c1, const double *m2, const double *c2) { return gtf_kl_general(m1, c1, m2, c2); }
 }
 

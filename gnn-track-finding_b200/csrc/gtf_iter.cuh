@@ -493,7 +493,7 @@ __device__ __forceinline__ void send_tiles(const DevBatch &B, const DevPack &K, 
 __global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBatch B, DevPack Kin, const int4 *__restrict__ tdesc, int n_tiles,
                                                                          GtfGeom g)
 {
-    if (Kin.counts[PK_STOP]) return;
+    if (Kin.counts[PK_STOP] | Kin.counts[PK_SPARSE]) return;
     DevPack K = Kin;
     K.all_exist = Kin.counts[PK_MISSING] == 0; // every slot is an existing edge (counted when the bitmaps were packed)
     extern __shared__ __align__(16) unsigned char send_raw[];
@@ -507,6 +507,97 @@ __global__ void __launch_bounds__(GTF_SEND_THREADS, GTF_SEND_MINB) k_send(DevBat
     send_tiles(B, K, S, tdesc, n_tiles, g, threadIdx.x);
 }
 
+
+// ------------------------------------------------------------------------------------------------ k_send_sparse
+// Late iterations of a committed loop: a few percent of the edges are still active, yet the tiled k_send scans every
+// out-edge (0.12 ms per 12.8 M edges whatever they carry).  Inside one loop an activation flag only ever falls (the kernels
+// clear bits, nothing sets one), so the out-edges active after the loop's first iteration are a superset of everything later
+// iterations can send: k_compact_out lists them once per source (successor order kept), k_send_sparse walks the lists --
+// thread per source: the running sum of quirk 2 is sequential per source anyway.  Chosen on the device (PK_SPARSE): the
+// lists are only built when fewer than a quarter of the slots are active.
+__global__ void k_compact_out(DevBatch B, DevPack Kin)
+{
+    DevPack K = Kin;
+    if (K.counts[PK_STOP]) return;
+    const unsigned long long active = B.counters[CNT_ACTIVE];      // of the iteration that just ended
+    if (active * 4ull > (unsigned long long)B.E) return;           // (uniform over the grid)
+    K.all_exist = Kin.counts[PK_MISSING] == 0;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    if (u == 0) K.counts[PK_SPARSE] = 1;
+    int n = 0, o0 = 0, o1 = 0;
+    if (u < B.N) {
+        o0 = K.srec[u].off; o1 = K.srec[u + 1].off;
+        for (int o = o0; o < o1; o++) {
+            const int sl = B.out_slot[o];
+            n += bm_get(K.act, sl) && (K.all_exist || bm_get(K.exists, sl));
+        }
+    }
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    int base = 0;
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 31 && tot) base = atomicAdd(&K.counts[PK_CLIST], tot);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - n;
+    if (u < B.N) {
+        K.c_rng[u] = make_int2(base, n);
+        if (n)
+            for (int o = o0; o < o1; o++) {
+                const int sl = B.out_slot[o];
+                if (bm_get(K.act, sl) && (K.all_exist || bm_get(K.exists, sl))) K.c_edge[base++] = make_int4(sl, K.out_dst[o], o, 0);
+            }
+    }
+}
+__global__ void __launch_bounds__(256) k_send_sparse(DevBatch B, DevPack K, GtfGeom g)
+{
+    if (K.counts[PK_STOP] | !K.counts[PK_SPARSE]) return;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    int n = 0;
+    int2 rng = make_int2(0, 0);
+    unsigned live = 0;                                   // which of the source's first 32 listed edges are still active (later
+                                                         // ones are tested again in the second pass: the bitmap does not change)
+    if (u < B.N && B.has_merged[u] && (B.node_ok[u] & (NF_OK | NF_MULTI)) == (NF_OK | NF_MULTI)) {
+        rng = K.c_rng[u];
+        for (int k = 0; k < rng.y; k++) {
+            const bool a = bm_get(K.act, K.c_edge[rng.x + k].x);
+            if (a && k < 32) live |= 1u << k;
+            n += a;
+        }
+    }
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    int base = 0;
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 31 && tot) base = atomicAdd(&K.counts[PK_MSG], tot);   // one global atomic per warp
+    int gq = __shfl_sync(0xffffffffu, base, 31) + incl - n;
+    if (!n) return;
+    const double2 ab = K.mab[u];
+    const double z = K.srec[u].z;
+    double p = B.m_p11[u];
+    for (int k = 0; k < rng.y; k++) {
+        const int4 e = K.c_edge[rng.x + k];
+        if (k < 32 ? !((live >> k) & 1u) : !bm_get(K.act, e.x)) continue;
+        const double2 *rp = reinterpret_cast<const double2 *>(K.orec + e.z);
+        const double2 r0 = rp[0], r1 = rp[1];            // (sin_t, xk), (rdz, w)
+        const double vms = gtf_var_ms_pre(ab.x, ab.y, r0.y, r0.x, r1.x, z, g.endcap);
+        p += vms;                                        // quirk 2: summed in successor order
+        const bool has = __double_as_longlong(r1.y) != GTF_NO_TSE_BITS;
+        GTF_BOUND(B, gq >= 0 && gq < B.E && e.y >= 0 && e.y < B.N);
+        K.msg_desc[gq] = make_int4(e.x | (has ? 0 : (int)0x80000000), u, e.y, 0);
+        K.msg_w[gq] = has ? r1.y : NAN;
+        K.msg_p11[gq] = p;
+        K.msg_vms[gq] = vms;
+        gq++;
+    }
+    B.m_p11_nx[u] = p;
+}
 
 // ------------------------------------------------------------------------------------------------ k_exec
 // thread per message: extrapolate, chi2 gate, Kalman update (extrapolate_merged_states.py:26-402); writes the state

@@ -108,6 +108,38 @@ GTF_HD void gtf_seed_entry(double xA, double yA, double zA, double rA, double xk
 }
 
 // ------------------------------------------------------------------------------------------------
+// Parabolic-model seeding of the KL look-up-table training pipeline, one (node, neighbour) pair:
+// learn_KL_parabolic_model/src/generate_training_data/utils.py:221-299 (compute_track_state_estimates) with :197-218
+// (rotate_track: the origin -> node edge becomes the x axis) -- NOT the seeding of the reconstruction (gtf_seed_entry):
+// H rows are (x^2, x, 1) without the 1/2, the measurement errors are S = diag(sigma0^2, sigmaA^2, sigmaB^2) and the
+// covariance H^-1 S H^-T is a FULL 3x3 matrix (row-major cov9).
+GTF_HD void gtf_seed_parabolic(double xn, double yn, double xb, double yb, double sigma0, double sigmaA, double sigmaB,
+                               double *sv3, double *cov9)
+{
+    const double two_pi = 2.0 * 3.14159265358979323846;
+    double ang = atan2(yn - 0.0, xn - 0.0);                       // :191-194 getAngleBetweenPoints((0, 0), node)
+    while (ang < 0.0) ang += two_pi;                              // :184-187 angle_trunc
+    const double angle = two_pi - ang;                            // :209
+    const double ca = cos(angle), sa = sin(angle);
+    const double xr_n = xn * ca - yn * sa, yr_n = xn * sa + yn * ca;   // :214-216
+    const double xr_b = xb * ca - yb * sa, yr_b = xb * sa + yb * ca;
+    const double xr_0 = 0.0 * ca - 0.0 * sa;
+    const double x0 = xr_0 - xr_n, xB = xr_b - xr_n, mB = yr_b - yr_n; // :262-269 translate: the node becomes the origin
+    // H = [[x0^2, x0, 1], [0, 0, 1], [xB^2, xB, 1]] (:281-283), closed-form inverse
+    const double iD = 1.0 / (x0 * xB * (x0 - xB));
+    const double h[3][3] = {{xB * iD, (x0 - xB) * iD, -x0 * iD},
+                            {-(xB * xB) * iD, (xB * xB - x0 * x0) * iD, (x0 * x0) * iD},
+                            {0.0, 1.0, 0.0}};
+    const double m[3] = {0.0, 0.0, mB};                           // :280 [m_0, m_A, m_B]
+    const double S[3] = {sigma0 * sigma0, sigmaA * sigmaA, sigmaB * sigmaB};
+    for (int i = 0; i < 3; i++) {
+        sv3[i] = h[i][0] * m[0] + h[i][1] * m[1] + h[i][2] * m[2];     // :287
+        for (int j = 0; j < 3; j++)
+            cov9[3 * i + j] = h[i][0] * S[0] * h[j][0] + h[i][1] * S[1] * h[j][1] + h[i][2] * S[2] * h[j][2];   // :288
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Extrapolate + chi2 gate + Kalman update for one edge u -> v (extrapolate_merged_states.py:26-402).
 struct GtfExtrapOut {
     double chi2, lik, var_ms;

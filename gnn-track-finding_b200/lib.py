@@ -127,6 +127,7 @@ def lib():
         "gtf_kl_pairs": (ctypes.c_int, [ctypes.c_int, dp, dp, ctypes.POINTER(i32), i32, dp, i64, ctypes.POINTER(i64)]),
         "gtf_pairwise_chi2": (ctypes.c_int, [ctypes.c_int, i32, dp, dp, dp, dp, dbl, dbl, dbl, dp]),
         "gtf_merge_states": (ctypes.c_int, [ctypes.c_int, dp, dp, dp, dp, dp, dp]),
+        "gtf_seed_parabolic_pairs": (ctypes.c_int, [ctypes.c_int, i64, dp, dp, dbl, dbl, dbl, dp, dp]),
         "gtf_components": (ctypes.c_int, [vp]),
         "gtf_extract": (ctypes.c_int, [vp, pg, dbl, ctypes.c_int, dbl, dbl, ctypes.POINTER(i32),
                                        ctypes.POINTER(ctypes.c_uint8), dp, dp]),

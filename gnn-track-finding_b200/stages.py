@@ -206,6 +206,50 @@ def merge_states(mean1, cov1, mean2, cov2, device=0):
     return mm, mc
 
 
+def seed_parabolic_pairs(node_xy, nbr_xy, sigma0=4.0, sigmaA=0.1, sigmaB=0.1, device=0):
+    """learn_KL_parabolic_model/src/generate_training_data/utils.py:221-299 for n (node, neighbour) pairs on the GPU:
+    (edge_state_vector (n, 3), edge_covariance (n, 3, 3))"""
+    from . import lib as L
+    a = np.ascontiguousarray(np.asarray(node_xy, np.float64).reshape(-1, 2))
+    b = np.ascontiguousarray(np.asarray(nbr_xy, np.float64).reshape(-1, 2))
+    if a.shape != b.shape:
+        raise ValueError("node_xy and nbr_xy must hold the same number of pairs")
+    n = a.shape[0]
+    sv, cov = np.zeros((n, 3)), np.zeros((n, 3, 3))
+    if n:
+        L.check(L.lib().gtf_seed_parabolic_pairs(device, n, _dp(a), _dp(b), sigma0, sigmaA, sigmaB, _dp(sv), _dp(cov)))
+    return sv, cov
+
+
+def compute_track_state_estimates_parabolic(GraphList, device=0):
+    """The seeding of the KL look-up-table training pipeline under the reference's name and attributes
+    (learn_KL_parabolic_model/.../utils.py:221: `compute_track_state_estimates(GraphList)`): every node gets
+    `track_state_estimates` = {neighbour: {'edge_state_vector', 'edge_covariance'}} over nx.all_neighbors (dict order = the
+    REVERSED neighbour order, :254-255) and `xy_edge_gradient_mean_var`.  One kernel launch for all pairs of all graphs; the
+    gradient mean / variance is two numpy reductions per node, as in the reference (:296)."""
+    import networkx as nx
+    pairs, nxy, bxy = [], [], []
+    for gi, G in enumerate(GraphList):
+        for node in G.nodes():
+            m = G.nodes[node]["GNN_Measurement"]
+            nbrs = list(nx.all_neighbors(G, node))
+            grads = []
+            for k in nbrs:
+                b = G.nodes[k]["GNN_Measurement"]
+                grads.append((m.y - b.y) / (m.x - b.x))
+            for k in reversed(nbrs):
+                b = G.nodes[k]["GNN_Measurement"]
+                pairs.append((gi, node, k))
+                nxy.append((m.x, m.y))
+                bxy.append((b.x, b.y))
+            G.nodes[node]["track_state_estimates"] = {}
+            G.nodes[node]["xy_edge_gradient_mean_var"] = (np.mean(grads), np.var(grads))
+    sv, cov = seed_parabolic_pairs(nxy, bxy, device=device)
+    for (gi, node, k), s, c in zip(pairs, sv, cov):
+        GraphList[gi].nodes[node]["track_state_estimates"][k] = {"edge_state_vector": s, "edge_covariance": c}
+    return GraphList
+
+
 def calc_dist_to_merged_state(num_edges, edge_svs, edge_covs, merged_mean, merged_cov, device=0):
     """clustering.py:107 -- list of KLDistance(component i, merged state)"""
     n = int(num_edges)

@@ -233,6 +233,12 @@ int gtf_pairwise_chi2(int device, int32_t n, const double *edge_svs, const doubl
 /* clustering/clustering.py:97-105 merge_states for general 3x3 covariances (row-major f64[9]) */
 int gtf_merge_states(int device, const double *mean1, const double *cov1, const double *mean2, const double *cov2,
                      double *merged_mean, double *merged_cov);
+/* learn_KL_parabolic_model/src/generate_training_data/utils.py:221-299 compute_track_state_estimates (with :197-218
+ * rotate_track) -- the PARABOLIC-model seeding behind the KL look-up-table training data, not the seeding of the reconstruction
+ * (gtf_seed): for each of the n (node, neighbour) pairs (xy f64[n][2] each) the `edge_state_vector` f64[n][3] and the full
+ * `edge_covariance` f64[n][3][3] = H^-1 diag(sigma0^2, sigmaA^2, sigmaB^2) H^-T (the reference: 4.0, 0.1, 0.1).  Needs no batch. */
+int gtf_seed_parabolic_pairs(int device, int64_t n, const double *node_xy, const double *nbr_xy, double sigma0, double sigmaA,
+                             double sigmaB, double *state, double *cov);
 /* extrapolate/extrapolate_merged_states.py:26-402 extrapolate_validate for ONE edge node -> neighbour: state (a, b, c) and its
  * covariance (row-major f64[9], block form) at `node`; like the reference it adds the multiple-scattering variance to
  * state_cov[1][1] IN PLACE (:127-128) before extrapolating.  pass == 0: chi2 > cut, the caller deactivates the edge (:393). */

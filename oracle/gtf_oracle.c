@@ -1061,3 +1061,47 @@ int gtfo_tag_propagation(gtfo_arrays *A, double threshold, int32_t *tags, int ma
     free(work); free(next);
     return sweeps;
 }
+
+/* learn_KL_parabolic_model/src/generate_training_data/utils.py:221-299 compute_track_state_estimates for ONE
+ * (node, neighbour) pair, with :197-218 rotate_track (coords = [neighbours..., node, (0, 0)]: p1 = origin, p2 = node):
+ * literal -- rotation of every point by 2 pi - atan2, translation, H built as written, np.linalg.inv -> inv_n,
+ * H_inv . m and H_inv . S . H_inv^T as matrix products.  sv[3], cov[9] row-major. */
+void gtfo_seed_parabolic(const double node_xy[2], const double nbr_xy[2], double sigma0, double sigmaA, double sigmaB,
+                         double sv[3], double cov[9])
+{
+    const double pi = 3.14159265358979323846;
+    const double p1[2] = {0.0, 0.0};
+    double a = atan2(node_xy[1] - p1[1], node_xy[0] - p1[0]);    /* :191-194 */
+    while (a < 0.0) a += pi * 2;                                  /* :184-187 */
+    const double angle = 2 * pi - a;                              /* :209 */
+    const double pts[3][2] = {{nbr_xy[0], nbr_xy[1]}, {node_xy[0], node_xy[1]}, {0.0, 0.0}};
+    double rot[3][2];
+    for (int k = 0; k < 3; k++) {                                 /* :213-217 */
+        rot[k][0] = pts[k][0] * cos(angle) - pts[k][1] * sin(angle);
+        rot[k][1] = pts[k][0] * sin(angle) + pts[k][1] * cos(angle);
+    }
+    const double x_trans = rot[1][0], y_trans = rot[1][1];        /* :261-262 rotated_coords[-2] = the node */
+    double tr[3][2];
+    for (int k = 0; k < 3; k++) { tr[k][0] = rot[k][0] - x_trans; tr[k][1] = rot[k][1] - y_trans; }
+    const double x_0 = tr[2][0], x_B = tr[0][0], m_B = tr[0][1];  /* :273, :277-279 */
+    const double meas[3] = {0.0, 0.0, m_B};
+    const double H[9] = {x_0 * x_0, x_0, 1, 0, 0, 1, x_B * x_B, x_B, 1};   /* :281-283 */
+    double Hi[9];
+    inv_n(H, Hi, 3);                                              /* :286 */
+    const double S[9] = {sigma0 * sigma0, 0, 0, 0, sigmaA * sigmaA, 0, 0, 0, sigmaB * sigmaB};
+    for (int i = 0; i < 3; i++) {
+        sv[i] = 0.0;
+        for (int k = 0; k < 3; k++) sv[i] += Hi[3 * i + k] * meas[k];      /* :287 */
+    }
+    double HS[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            HS[3 * i + j] = 0.0;
+            for (int k = 0; k < 3; k++) HS[3 * i + j] += Hi[3 * i + k] * S[3 * k + j];
+        }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            cov[3 * i + j] = 0.0;
+            for (int k = 0; k < 3; k++) cov[3 * i + j] += HS[3 * i + k] * Hi[3 * j + k];   /* :288 */
+        }
+}

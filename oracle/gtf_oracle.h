@@ -69,4 +69,7 @@ double gtfo_mahalanobis(const double m1[3], const double c1[9], const double m2[
                         const double node[4], const double nb1[4], const double nb2[4], double sigma0rz,
                         double sigma0rz2, double endcap);
 double gtfo_chi2_sf(double x, double k);
+/* learn_KL_parabolic_model/src/generate_training_data/utils.py:221-299 for one (node, neighbour) pair */
+void gtfo_seed_parabolic(const double node_xy[2], const double nbr_xy[2], double sigma0, double sigmaA, double sigmaB,
+                         double sv[3], double cov[9]);
 #endif

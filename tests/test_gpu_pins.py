@@ -1,6 +1,8 @@
 """GPU parity against the round-2 reference pins (tests/golden/make_lut_tag_golden.py, make_golden.py barrel1000_cfg2):
 LUT-threshold mode vs the reference's cluster() with a per-node KL_threshold, emp_var vs helper.py:446, tag propagation
 vs the unmodified tag_propagation.py, a cfg2-size event through the reference's own schedule.  All through the C-ABI."""
+import os
+
 import numpy as np
 import pytest
 
@@ -138,6 +140,19 @@ def test_load_events_equals_full_upload_and_batch_reuse():
     assert np.array_equal(torch.as_tensor(t, device="cuda").cpu().numpy(), ref1[3])
     b.load_events(hb2)
     same(run(b), ref2)
+    b.load_events(hb1)
+    same(run(b), ref1)
+    # the same SHAPE with other hits: the captured iteration graphs are replayed as they are (sizes and pointers are equal,
+    # the tile tables and everything else they read live in device memory) -- no state of the previous events may show
+    hb3 = {k: np.array(v, copy=True) for k, v in hb1.items()}
+    rng = np.random.default_rng(5)
+    for f in ("x", "y", "z"):
+        hb3[f] = hb3[f] + rng.normal(size=len(hb3[f])) * 0.05
+    hb3["r"] = np.sqrt(hb3["x"] ** 2 + hb3["y"] ** 2)
+    ref3 = run(gtf_b200.EventBatch(hb3))
+    assert not np.array_equal(ref3[2]["m_a"], ref1[2]["m_a"], equal_nan=True)
+    b.load_events(hb3)
+    same(run(b), ref3)
     b.load_events(hb1)
     same(run(b), ref1)
 
@@ -308,3 +323,39 @@ def test_seed_cluster_equals_seed_then_cluster():
     a = gtf_b200.EventBatch(blank_seed(gu.stage_batch(fx, "seed")))
     a.seed_cluster(1.0, 123.0, KL_lut=fx["lut_stress"])
     assert gu.compare_states(state_of(a), gu.stage_batch(fx, "c1str"), ALL, rtol=gu.RTOL, chained=True) == []
+
+
+def test_parabolic_seeding_of_the_lut_training_pipeline_vs_reference():
+    """learn_KL_parabolic_model/src/generate_training_data/utils.py:221-299 (compute_track_state_estimates with rotate_track):
+    the kernel behind gtf_seed_parabolic_pairs against the outputs of the UNMODIFIED reference function on a toy graph
+    (tests/golden/make_parabolic_golden.py): state vectors and full 3x3 covariances to 1e-9 (measured 1e-14), and the
+    reference-named graph wrapper: same dict keys in the same order, same xy_edge_gradient_mean_var."""
+    import networkx as nx
+    from gtf_b200 import stages
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "parabolic_seed.npz"))
+    sv, cov = stages.seed_parabolic_pairs(fx["node_xy"], fx["nbr_xy"])
+    assert np.abs(sv - fx["state"]).max() <= 1e-9 * np.abs(fx["state"]).max()
+    assert (np.abs(cov - fx["cov"]) <= 1e-9 * np.abs(fx["cov"])).all()
+    assert (sv[:, 2] == 0).all()
+
+    class M:
+        def __init__(self, x, y):
+            self.x, self.y = x, y
+    G = nx.DiGraph()
+    xy = {}
+    for n, p in zip(fx["node"], fx["node_xy"]):
+        xy[int(n)] = p
+    for n in range(int(fx["n_nodes"])):
+        G.add_node(n, GNN_Measurement=M(*xy[n]))
+    G.add_edges_from((int(u), int(v)) for u, v in fx["edges"])
+    stages.compute_track_state_estimates_parabolic([G])
+    i = 0
+    for n, mv in zip(fx["grad_node"], fx["grad_mean_var"]):
+        a = G.nodes[int(n)]
+        assert np.allclose(a["xy_edge_gradient_mean_var"], mv, rtol=1e-12, atol=0)
+        for k, e in a["track_state_estimates"].items():
+            assert (int(fx["node"][i]), int(fx["nbr"][i])) == (int(n), int(k))
+            assert np.allclose(e["edge_state_vector"], fx["state"][i], rtol=1e-9, atol=1e-300)
+            assert np.allclose(e["edge_covariance"], fx["cov"][i], rtol=1e-9, atol=0)
+            i += 1
+    assert i == len(fx["node"])

@@ -216,3 +216,23 @@ def test_general_kl_known_answer_from_reference_csv(hm):
     got = np.sort(np.array(out))
     assert len(got) == 7574
     assert gu.rel_err(got, fx["kl_sorted"]) <= 1e-9
+
+
+def test_parabolic_seeding_algebra_and_oracle_vs_reference(hm):
+    """learn_KL_parabolic_model/.../utils.py:221-299: the kernel's closed-form inverse (gtf_seed_parabolic in gtf_math.cuh, host
+    build) and the oracle's literal restatement (np.linalg.inv -> pivoted Gauss-Jordan) against the unmodified reference's
+    outputs (tests/golden/parabolic_seed.npz): 1e-9 (measured 1e-14)."""
+    fx = np.load(os.path.join(gu.REPO, "tests", "golden", "parabolic_seed.npz"))
+    O = ol.lib()
+    sig = [dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, dp]
+    hm.gtfh_seed_parabolic.argtypes = sig
+    hm.gtfh_seed_parabolic.restype = None
+    O.gtfo_seed_parabolic.argtypes = sig
+    O.gtfo_seed_parabolic.restype = None
+    for fn in (hm.gtfh_seed_parabolic, O.gtfo_seed_parabolic):
+        for i in range(len(fx["node"])):
+            n, b = np.ascontiguousarray(fx["node_xy"][i]), np.ascontiguousarray(fx["nbr_xy"][i])
+            sv, cv = np.zeros(3), np.zeros(9)
+            fn(P(n), P(b), 4.0, 0.1, 0.1, P(sv), P(cv))
+            assert np.allclose(sv, fx["state"][i], rtol=1e-9, atol=1e-300)
+            assert np.allclose(cv, fx["cov"][i].ravel(), rtol=1e-9, atol=0)

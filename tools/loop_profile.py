@@ -23,3 +23,14 @@ for rep in range(2):           # second pass: warm
 for r in rows:
     print(json.dumps(r))
 print(json.dumps({"loop_ms": round(sum(r["total_ms"] for r in rows), 3)}))
+
+# the loop as a user runs it: one gtf_iterate call (device-side loop, sparse send from the second iteration on), wall clock
+import time
+for rep in range(3):
+    b.seed_cluster(1.0, 2.0)
+    b.sync()
+    t0 = time.perf_counter()
+    st = b.iterate(max_iter=nit, stop_when_converged=False)
+    b.sync()
+    ms = (time.perf_counter() - t0) * 1e3
+print(json.dumps({"gtf_iterate_wall_ms": round(ms, 3), "iterations": len(st), "launches": b.iteration_launches()}))
