@@ -447,8 +447,9 @@ def main():
             lms.append(e0.elapsed_time(e1))
             ledges = c1["active_edges"] + sum(s["active_edges"] for s in st[:-1])
         loop = {"iterations": MAX_ITER, "ms": min(lms), "edge_iterations": ledges, "value": ledges / (min(lms) / 1e3),
-                "unit": "edges/s", "note": "committed gtf_iterate x%d incl. one counter read-back per iteration; later iterations "
-                                           "skip nodes without an active in-edge" % MAX_ITER}
+                "unit": "edges/s", "note": "one committed gtf_iterate call, max_iter = %d: the loop runs on the device (one counter read-back at "
+                                           "the end), iterations after the first send from the compacted active out-edge lists and skip nodes "
+                                           "without an active in-edge" % MAX_ITER}
     e2e = None
     if not a.no_e2e:
         nch = max(1, min(a.e2e_chunks, len(my_ids)))

@@ -38,7 +38,7 @@ def point(n_tracks, degree, n_events, steps=20):
     b.set_timing(False)
     kern = {k: kt[k] for k in ("k_send", "k_exec", "k_node2", "k_hv")}
     it_ms = sum(kern.values())
-    # the iteration as a user runs it (CUDA graph replay, or the single cooperative launch for small batches): wall clock
+    # the iteration as a user runs it (CUDA graph replay): wall clock
     import time
     for _ in range(5):
         b.iterate_dry()
