@@ -169,7 +169,8 @@ static int batch_alloc(gtf_batch *b)
         DA(k.msg_desc, E); DA(k.msg_w, E);
         DA(k.msg_p11, E); DA(k.msg_vms, E);
         DA(k.hv_list, (int64_t)(HV_BINS + 1) * N);
-        DA(k.c_edge, E); DA(k.c_rng, N);
+        DA(k.c_edge, E); DA(k.c_rng, N); DA(k.node_static, N); DA(k.node_rest, N);
+        CK(cudaMemset(k.node_static, 0, (size_t)(N ? N : 1)));
         DA(k.counts, PK_NCOUNTS);
         b->pack_static_stale = true;
         b->exists_stale = true;
@@ -219,7 +220,7 @@ extern "C" int gtf_batch_destroy(gtf_batch *b)
     {
         DevPack &k = b->k;
         void *pk[] = {k.mab, k.srec, k.mrec, k.mrec_nx, k.out_dst, k.orec, k.aux, k.xyzr, k.act, k.act_nx, k.pres, k.exists, k.pres0, k.state, k.meta, k.msg_desc,
-                      k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.c_edge, k.c_rng, k.counts, b->stile_begin};
+                      k.msg_w, k.msg_p11, k.msg_vms, k.hv_list, k.c_edge, k.c_rng, k.node_static, k.node_rest, k.counts, b->stile_begin};
         for (void *p : pk) cudaFree(p);
         for (int c = 0; c < 2; c++)
             for (int q = 0; q < 2; q++)
@@ -973,7 +974,7 @@ static int iterate_packed(gtf_batch *b, const gtf_iter_params *p, const GtfGeom 
         if (commit) { b->last_prog = P; b->last_geom = gg; b->have_last_prog = true; b->force_pending = false; }
     }
     if (b->timing || !b->use_graph) {
-        TRY(issue_iteration(b, P, gg, p->record_chi2, commit, b->timing));
+        TRY(issue_iteration(b, P, gg, p->record_chi2, commit, b->timing, sparse));
         if (b->timing) {
             CK(cudaEventSynchronize(b->evk[4]));
             for (int q = 0; q < 4; q++) {

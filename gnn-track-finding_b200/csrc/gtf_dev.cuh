@@ -101,8 +101,11 @@ struct DevPack {
     double *msg_p11, *msg_vms;   // [E] merged_cov[1,1] as the edge sees it (quirk 2), its multiple-scattering term
     // the ACTIVE out-edges of every source, compacted inside a committed loop once few are left (activation only ever
     // falls inside a loop): k_compact_out -> k_send_sparse
-    int4 *c_edge;                // [E] (slot, destination, out-edge index, -), a source's edges contiguous and in successor order
+    int4 *c_edge;                // [E] (slot, destination, out-edge index, source), a source's edges contiguous and in successor order
     int2 *c_rng;                 // [N] (first entry, entries) of the source in c_edge
+    // nodes found without an active in-edge (k_node2): skipped without a scan until the next forced pass
+    uint8_t *node_static;        // [N]
+    double *node_rest;           // [N] their merged_cov[1,1] to restore every iteration (quirk 2), NaN: none
     int32_t *hv_list;            // [(HV_BINS + 1) * N] cooperative nodes binned by dict size: <=4, <=8, <=16, <=32, more
     int *counts;                 // [PK_NCOUNTS] messages, 4 bins, big, missing slots, 'evaluate every node' flag, loop stop / done
 };

@@ -547,10 +547,13 @@ __global__ void k_compact_out(DevBatch B, DevPack Kin)
         if (n)
             for (int o = o0; o < o1; o++) {
                 const int sl = B.out_slot[o];
-                if (bm_get(K.act, sl) && (K.all_exist || bm_get(K.exists, sl))) K.c_edge[base++] = make_int4(sl, K.out_dst[o], o, 0);
+                if (bm_get(K.act, sl) && (K.all_exist || bm_get(K.exists, sl))) K.c_edge[base++] = make_int4(sl, K.out_dst[o], o, u);
             }
     }
 }
+// thread per source walking its list.  (A thread per LISTED edge -- one coalesced 16 B read each, the earlier active successors'
+// terms recomputed -- was measured too: 78 vs 90 us per iteration with 0.9 M listed edges, but 0.06 ms SLOWER per iteration on the
+// bench schedule, where 2.6 M edges are listed and a source keeps several active successors.)
 __global__ void __launch_bounds__(256) k_send_sparse(DevBatch B, DevPack K, GtfGeom g)
 {
     if (K.counts[PK_STOP] | !K.counts[PK_SPARSE]) return;
@@ -1179,7 +1182,13 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
     __syncthreads();
     const int i = blockIdx.x * GTF_NODE2_THREADS + tid;
     unsigned n_act = 0, n_chg = 0;
-    if (i < B.N) {
+    const bool force = K.counts[PK_FORCE] != 0;
+    if (i < B.N && !force && K.node_static[i]) {
+        // found static by an earlier iteration: activation only ever falls, so it stays static until the next forced pass --
+        // no scan of its windows, only the restored merged_cov[1,1] (NaN: nothing to restore)
+        const double cp = K.node_rest[i];
+        if (cp == cp) B.m_p11_nx[i] = cp;
+    } else if (i < B.N) {
         unsigned nf = B.node_ok[i];
         const int b0 = B.in_off[i], b1 = B.in_off[i + 1];
         int np = 0, e0 = -1, e1 = -1, deg = 0, chg = 0;
@@ -1213,12 +1222,16 @@ __global__ void __launch_bounds__(GTF_NODE2_THREADS, GTF_NODE2_MINB) k_node2(Dev
         // skipped -- except that a cluster's merged_cov[1,1] is re-created by every evaluation while the node keeps
         // sending (quirk 2), so that value is restored.  After anything changed the packed state from outside, every
         // node is evaluated once (PK_FORCE).
-        const bool is_static = a0_any == 0 && !K.counts[PK_FORCE];
+        const bool is_static = a0_any == 0 && !force;
+        if (force) K.node_static[i] = 0;              // (a forced pass evaluates every node and forgets the marks)
         if (is_static) {
+            double cp = NAN;
             if (np > 2 && (nf & NF_OK)) {
-                const double cp = K.mrec[i].cl_p11;
+                cp = K.mrec[i].cl_p11;
                 if (cp == cp) B.m_p11_nx[i] = cp;
             }
+            K.node_static[i] = 1;
+            K.node_rest[i] = cp;
         } else if (np > 2 && (nf & NF_OK)) {
             const int bin = np <= 4 ? 0 : np <= 8 ? 1 : np <= 16 ? 2 : np <= 32 ? 3 : 4;
             GTF_BOUND(B, np <= b1 - b0);

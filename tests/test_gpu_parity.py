@@ -236,14 +236,17 @@ def test_iterate_dry_is_idempotent_and_matches_commit():
     assert s3 == s1
 
 
-@pytest.mark.parametrize("stop", [False, True])
-def test_device_side_loop_equals_single_iterations(stop):
+@pytest.mark.parametrize("stop,graph", [(False, "1"), (True, "1"), (False, "0")])
+def test_device_side_loop_equals_single_iterations(stop, graph, monkeypatch):
     """gtf_iterate(max_iter = 8) queues its iterations on the device (k_iter_end files the counters and raises the stop flag;
     from the second iteration on the few out-edges still active are sent by k_send_sparse from the compacted lists) -- against
     the same iterations issued one call at a time (one read-back each, tiled k_send throughout) and against the oracle:
     same counters per iteration, same number of iterations, identical flags and orders, values to 1e-12."""
     hb = synth_batch(3, 400, 2150, eta_max=1.0)
-    one, loop = gpu_batch(hb), gpu_batch(hb)
+    one = gpu_batch(hb)
+    monkeypatch.setenv("GTF_GRAPH", graph)           # 0: plain launches instead of graph replays (read when the batch is created)
+    loop = gpu_batch(hb)
+    monkeypatch.delenv("GTF_GRAPH")
     ob = ol.OracleBatch(hb)
     ob.seed()
     ob.cluster(0, 1.0, 2.0)

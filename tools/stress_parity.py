@@ -24,17 +24,32 @@ for case in range(n_cases):
     hb = synth.concat_host_batches(hbs)
     hb.pop("truth"); hb.pop("orig_id")
     ob = ol.OracleBatch(hb); ob.seed(); ob.cluster(0, 1.0, 2.0)
+    fused = rng.random() < 0.3       # send + execute as the one warp-specialised kernel (read when the batch is created)
+    if os.environ.get("GTF_STRESS_FUSED"):
+        fused = os.environ["GTF_STRESS_FUSED"] == "1"
+    os.environ["GTF_FUSED_SX"] = "1" if fused else "0"
     if rng.random() < 0.5:          # full upload + two calls, or device-side ingest + the fused seed / cluster pass
         b = gtf_b200.EventBatch(hb); b.raise_ref_errors = False
         b.seed(); b.cluster(0, 1.0, 2.0)
     else:
         b = gtf_b200.EventBatch.with_capacity(len(hb["x"]) + 5, len(hb["in_src"]) + 9, len(hb["sub_event"]) + 1); b.raise_ref_errors = False
         b.load_events(hb); b.seed_cluster(1.0, 2.0)
-    plan = rng.choice(["single", "burst", "mixed"])
+    plan = rng.choice(["single", "burst", "mixed", "loop", "loop"])
+    if os.environ.get("GTF_STRESS_PLAN"):            # (same random events, one plan for all: isolates a path)
+        plan = os.environ["GTF_STRESS_PLAN"]
     n_it = 5
+    if plan == "loop":               # the device-side loop: stop flag, sparse send, more iterations than one burst holds
+        cap = int(rng.choice([3, 7, 12, 40]))
+        st = b.iterate(max_iter=cap, stop_when_converged=True)
+        n_it = len(st)
+        assert n_it == cap or st[-1]["active_changed"] == 0, st[-1]
+        assert all(x["active_changed"] != 0 for x in st[:-1])
+        plan = "loop%d/%d" % (n_it, cap)
     for _ in range(n_it):
         ob.extrapolate_stage(2.0); ob.cluster(1, 1000.0, 100.0)
-    if plan == "single":
+    if plan.startswith("loop"):
+        pass
+    elif plan == "single":
         for _ in range(n_it): b.iterate(max_iter=1, stop_when_converged=False)
     elif plan == "burst":
         b.iterate(max_iter=n_it, stop_when_converged=False)
@@ -44,11 +59,12 @@ for case in range(n_cases):
         b.iterate(max_iter=1, stop_when_converged=False, want_stats=False)
         b.iterate_dry()
         b.iterate(max_iter=2, stop_when_converged=False)
-    bad = gu.compare_states(b.download(), ob.hb, WHAT, rtol=1e-7)
+    # (k_sx: separately compiled update code rounds 1e-11 differently per iteration; chained, 1.3e-7 was seen on m_c)
+    bad = gu.compare_states(b.download(), ob.hb, WHAT, rtol=2e-7 if fused else 1e-7)
     same_cca = bool(np.array_equal(b.CCA(), ob.cca()))
     deg_max = int(np.diff(hb["in_off"]).max())
-    print("case %d: events %d tracks %d degree %.0f (max in-degree %d) eta %.1f plan %-6s -> %s%s" %
-          (case, n_ev, tracks, deg, deg_max, eta, plan, "ok" if not bad else bad, "" if same_cca else " CCA DIFFERS"), flush=True)
+    print("case %d: events %d tracks %d degree %.0f (max in-degree %d) eta %.1f plan %-9s%s -> %s%s" %
+          (case, n_ev, tracks, deg, deg_max, eta, plan, " k_sx" if fused else "", "ok" if not bad else bad, "" if same_cca else " CCA DIFFERS"), flush=True)
     bad_total += bool(bad) + (not same_cca)
     b.close()
 print("stress parity:", "ALL OK" if bad_total == 0 else "%d FAILURES" % bad_total)
