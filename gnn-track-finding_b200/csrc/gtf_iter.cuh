@@ -1027,7 +1027,7 @@ __global__ void __launch_bounds__(256, GTF_SX_CTAS) k_sx(DevBatch B, DevPack Kin
             if (lane == 0) st_rel_s(&R.cons_next[w], 32 * (c + 4));
             const int n_nxt = sx_chunk(R, c + 4, false, lane);
             if (lane < n_nxt) load(32 * (c + 4) + lane, cur);
-#ifdef GTF_SX_NOEXEC
+#ifdef GTF_SX_NOEXEC                                     // ablation build (profiles/r02_k_sx.txt): scan + ring + gathers only
             if (mine && J.f00 == 1.2345e-300) {
 #else
             if (mine) {
