@@ -39,10 +39,13 @@ EVENTS = {
     "barrel40_eta1": dict(n_tracks=40, seed=2001, eta_max=1.0, target_degree=10.0),
     "barrel25_deg6": dict(n_tracks=25, seed=2002, eta_max=0.5, target_degree=6.0),
     "barrel100_cfg1": dict(n_tracks=100, seed=1000, eta_max=0.5, target_degree=10.0),
+    # small and dense (mean in-degree 16, maxima near 50: mostly fake edges, long merge chains): the shape on which the randomised
+    # sweep sees the largest value drift between oracle and kernels
+    "barrel60_deg16": dict(n_tracks=60, seed=3002, eta_max=0.5, target_degree=16.0),
     # BASELINE configs[1] size: 1000 tracks -> 10k hits / 100k directed edges (several minutes of reference time)
     "barrel1000_cfg2": dict(n_tracks=1000, seed=2000, eta_max=0.5, target_degree=10.0),
 }
-COMPACT = {"barrel100_cfg1", "barrel1000_cfg2"}   # decisions + merged states only (keeps the fixture small)
+COMPACT = {"barrel100_cfg1", "barrel1000_cfg2", "barrel60_deg16"}   # decisions + merged states only (keeps the fixture small)
 
 
 def canonicalize(canon, snap, prev, graphs_alive_subs):

@@ -95,7 +95,7 @@ def test_extract_vs_reference(name, prev, stage):
         assert gu.rel_err(np.sort(got[:, 1]), np.sort(want[:, 1])) <= 1e-8
 
 
-@pytest.mark.parametrize("name", FIX + ["barrel100_cfg1"])
+@pytest.mark.parametrize("name", FIX + ["barrel100_cfg1", "barrel60_deg16"])
 def test_full_schedule_vs_reference(name):
     """run_gnn_trackml_mod.sh schedule end to end on the GPU: decisions bit-exact at every stage"""
     fx = gu.load(name)

@@ -67,7 +67,7 @@ def test_extract(name, prev, stage):
         assert gu.rel_err(np.sort(got[:, 1]), np.sort(want[:, 1])) <= 1e-8
 
 
-@pytest.mark.parametrize("name", FIX + ["barrel100_cfg1"])
+@pytest.mark.parametrize("name", FIX + ["barrel100_cfg1", "barrel60_deg16"])
 def test_full_schedule_chained(name, rtol=1e-7):
     """run_gnn_trackml_mod.sh:71-148 schedule, chained from the seeds: every decision bit-exact"""
     fx = gu.load(name)

@@ -10,7 +10,7 @@ import golden_util as gu, oracle_lib as ol
 from test_oracle_golden import blank_seed
 
 gpu = "--gpu" in sys.argv
-names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["barrel25_deg6", "barrel40_eta1", "barrel100_cfg1", "barrel1000_cfg2", "shipped_vol79"]
+names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["barrel25_deg6", "barrel40_eta1", "barrel60_deg16", "barrel100_cfg1", "barrel1000_cfg2", "shipped_vol79"]
 FIELDS = ("m_a", "m_b", "m_c", "m_p00", "m_p01", "m_p11", "m_p22", "m_prior")
 
 
