@@ -172,3 +172,32 @@ def test_randomised_iteration_plans_vs_oracle(seed):
         b.iterate(max_iter=2, stop_when_converged=False)
     assert gu.compare_states(b.download(), ob.hb, ("alive", "active", "merged", "uts", "degree", "edge_w"), rtol=1e-7) == []
     assert np.array_equal(b.CCA(), ob.cca())
+
+
+def test_cfg1_toy_event_nan_regime_vs_oracle():
+    """BASELINE configs[0]: the 2-D toy event (z = r = 0 for every hit) through the 3-D path.  tau = dz / dr is 0 / 0, so every
+    slope, its variance and every KL are NaN: numpy semantics make each comparison false -- no cluster forms, no merged state,
+    no message -- and the device must land on exactly the oracle's state (NaN patterns included), without raising."""
+    from gtf_b200 import synth
+    ev = synth.toy_event(seed=3)
+    hb = synth.event_to_host(ev)
+    hb.pop("truth")
+    hb.pop("orig_id")
+    ob = ol.OracleBatch(hb)
+    ob.seed()
+    ob.cluster(0, 1.0, 2.0)
+    b = gtf_b200.EventBatch(hb)
+    b.seed()
+    st = b.cluster(0, 1.0, 2.0)
+    assert st["nodes_merged"] == 0 and st["ref_errors"] == 0
+    what = ("active", "merged", "tse", "uts", "degree", "edge_w")
+    assert gu.compare_states(b.download(), ob.hb, what) == []
+    got = b.download(["tse_tau", "tse_p22", "tse_a", "tse_present"])
+    assert np.isnan(got["tse_tau"][got["tse_present"] > 0]).all() and np.isfinite(got["tse_a"][got["tse_present"] > 0]).all()
+    for _ in range(2):
+        ob.extrapolate_stage(2.0)
+        ob.cluster(1, 1000.0, 100.0)
+        s = b.iterate(max_iter=1, stop_when_converged=False)[0]
+        assert s["edges_sent"] == 0 and s["active_edges"] == len(hb["in_src"]) and s["active_changed"] == 0
+        assert gu.compare_states(b.download(), ob.hb, what, rtol=1e-7) == []
+    assert np.array_equal(b.CCA(), ob.cca())

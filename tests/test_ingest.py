@@ -73,3 +73,29 @@ def test_fixture_holds_the_shipped_files_content():
     ev = ingest.load_event_csv(REF_EVENT, 7, 9)
     for k in ("x", "y", "z", "layer", "volume", "edge_a", "edge_b", "node_idx"):
         assert np.array_equal(ev[k], fx["csv_" + k]), k
+
+
+def test_cfg1_toy_event_shape_and_host_layout():
+    """BASELINE configs[0]: the 2-D toy detector of toyMC_model/track_simulation_xy.py:36-160 (88 straight tracks x 10 hits, the
+    collision point and every node on a long-dx edge removed), seeded: the event is deterministic, its edges join layers one or
+    two apart, and the host layout built from it is a consistent pair of CSR orders."""
+    from gtf_b200 import synth
+    ev, ev2 = synth.toy_event(seed=3), synth.toy_event(seed=3)
+    for k in ev:
+        assert np.array_equal(ev[k], ev2[k])
+    assert not np.array_equal(ev["y"], synth.toy_event(seed=4)["y"][:len(ev["y"])]) or len(ev["y"]) != len(synth.toy_event(seed=4)["y"])
+    n, e, mean_deg, frac = synth.degree_stats(ev)
+    assert 50 <= n <= 880 and e == 2 * len(ev["edge_a"]) and 1.0 < mean_deg < 10.0
+    dl = np.abs(ev["layer"][ev["edge_a"]] - ev["layer"][ev["edge_b"]])
+    assert dl.min() >= 1 and dl.max() <= 2 and (ev["edge_a"] != ev["edge_b"]).all()
+    assert (ev["z"] == 0).all() and (ev["r"] == 0).all() and (ev["layer"] >= 1).all()        # the collision point is gone
+    hb = synth.event_to_host(ev)
+    N, E = len(hb["x"]), len(hb["in_src"])
+    assert N == n and E == e
+    assert hb["in_off"][0] == 0 and hb["in_off"][-1] == E and hb["out_off"][0] == 0 and hb["out_off"][-1] == E
+    assert sorted(hb["out_slot"].tolist()) == list(range(E))                                   # every slot is somebody's out-edge
+    rs = hb["rev_slot"]
+    assert (rs >= 0).all() and np.array_equal(rs[rs], np.arange(E))                            # u->v and v->u cross-linked
+    assert np.array_equal(hb["slot_dst"], np.repeat(np.arange(N), np.diff(hb["in_off"])))
+    src_of_out = np.repeat(np.arange(N), np.diff(hb["out_off"]))
+    assert np.array_equal(hb["in_src"][hb["out_slot"]], src_of_out)
